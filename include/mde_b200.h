@@ -1,0 +1,151 @@
+/* mde_b200.h -- C ABI of the B200-native AdaBins head / loss / external-info path.
+ *
+ * One entry point per kernel group.  Plain pointers and sizes only (no torch types); every pointer is DEVICE
+ * memory owned by the caller (torch allocates; kernels never allocate or free); every call enqueues work on
+ * the given cudaStream_t and returns without synchronising (CUDA-graph capturable), unless noted.
+ * Return value: MDE_OK (0) or a negative MDE_ERR_* code; mde_error_string() names it.  There is no CPU
+ * fallback anywhere behind this header.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference tree
+ * DylanAuty/MDE-biological-vision-systems).
+ */
+#ifndef MDE_B200_H
+#define MDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mde_stream_t; /* cudaStream_t */
+
+enum {
+  MDE_OK = 0,
+  MDE_ERR_BAD_SHAPE = -1,   /* a size / stride / divisibility precondition failed */
+  MDE_ERR_BAD_POINTER = -2, /* null or misaligned pointer */
+  MDE_ERR_BAD_ARCH = -3,    /* device is not sm_100 */
+  MDE_ERR_LAUNCH = -4,      /* cudaGetLastError() != cudaSuccess after the launch */
+  MDE_ERR_UNSUPPORTED = -5, /* mode not implemented */
+  MDE_ERR_DRIVER = -6       /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+};
+
+enum { MDE_F32 = 0, MDE_F64 = 1 };
+enum { MDE_NORM_LINEAR = 0, MDE_NORM_SOFTMAX = 1, MDE_NORM_SIGMOID = 2 };
+
+int mde_version(void);
+const char* mde_error_string(int code);
+/* 0 if the current device is compute capability 10.x, MDE_ERR_BAD_ARCH otherwise. Synchronous, no launch. */
+int mde_check_device(void);
+/* Number of kernels launched through this library since load (the bench's "gpu_launches" evidence). */
+int64_t mde_launch_count(void);
+
+/* ---- K3: label -> embedding gather -------------------------------------------------------------------
+ * Replaces SemanticsLoader.get_semantics (ExternalInfoLoaders/SemanticsLoader.py:102-145) and
+ * InstanceSegmentationLoader.get_instance_segmentation (ExternalInfoLoaders/InstanceSegmentationLoader.py:89-121):
+ * clamp (labels outside [0, rows-1] -> background), table.index_select + permute to planar [B,D,H,W].
+ *   labels      int64 [B*HW]           (read)
+ *   labels_out  int64 [B*HW] or NULL   (clamped labels written back; may alias labels == in-place clamp)
+ *   table       [rows, D]  of out_dtype, row-major (or [B, rows, D] when table_image_stride != 0)
+ *   out         [B, D, HW] of out_dtype
+ *   background  >= 0: clamp target; < 0: no clamp, out-of-range labels raise *oob_flag (int32, may be NULL)
+ *               and produce zeros (the reference's index_select would raise IndexError).
+ */
+int mde_gather_embed(const int64_t* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
+                     int rows, int D, int background, int out_dtype, int64_t table_image_stride,
+                     int32_t* oob_flag, mde_stream_t stream);
+
+/* Per-image class histogram -> per-image table of area fractions count/HW (float64), the gather table of
+ * SemanticsLoader.get_semantics_inst_areas (SemanticsLoader.py:88-99).
+ *   counts int32 [B, rows] workspace (zeroed by the call); frac float64 [B, rows] output. */
+int mde_class_area_table(const int64_t* labels, int B, int64_t HW, int rows, int32_t* counts, double* frac,
+                         mde_stream_t stream);
+
+/* int64 -> float32 cast of instance areas (InstanceSegmentationLoader.py:112) */
+int mde_cast_i64_f32(const int64_t* in, float* out, int64_t n, mde_stream_t stream);
+
+/* ---- A3: per-pixel 1x1-conv MLP  C_in -> 10 -> 10 with ReLU (unet_adaptive_bins.py:146-174, used :196-228) ----
+ *   x [B, C_in, HW] float32 (C_in = 1 or 3), each input is divided by in_scale first (the /(H*W) of :219,:226; pass 1.0f for none)
+ *   w0 [H1, C_in], b0 [H1], w1 [H2, H1], b1 [H2]   (H1 = H2 = 10 in the reference; <= 16 supported)
+ *   out: written at channel offset of a [B, out_channels_total, HW] tensor (so the caller can write straight
+ *        into the concatenated encoder input):  out + (b*out_batch_stride + c*HW + p)                      */
+int mde_aux_mlp_fwd(const float* x, int64_t x_batch_stride, const float* w0, const float* b0, const float* w1,
+                    const float* b1, float* out, int64_t out_batch_stride, int B, int C_in, int H1, int H2,
+                    int64_t HW, float in_scale, mde_stream_t stream);
+/* backward: grad wrt x (may be NULL) and wrt the four parameter tensors (accumulated with atomics; caller zeroes) */
+int mde_aux_mlp_bwd(const float* x, int64_t x_batch_stride, const float* w0, const float* b0, const float* w1,
+                    const float* b1, const float* gout, int64_t gout_batch_stride, float* gx, float* gw0, float* gb0,
+                    float* gw1, float* gb1, int B, int C_in, int H1, int H2, int64_t HW, float in_scale,
+                    mde_stream_t stream);
+
+/* ---- K1b/K2 prologue: bin-width regressor + normalisation + cumsum (miniViT.py:17-21,35-45;
+ * unet_adaptive_bins.py:292-296).  t0 [B, E] rows at stride t0_stride (token 0 of the transformer output).
+ *   w1 [H,E] b1 [H] w2 [H,H] b2 [H] w3 [n_bins,H] b3 [n_bins]   (E = 128, H = 256 in the reference)
+ *   y_raw [B,n_bins] (pre-normalisation regressor output, kept for backward), widths_normed [B,n_bins],
+ *   edges [B,n_bins+1], centers [B,n_bins]                                                            */
+int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, int B, int E, int H, int n_bins,
+                           int norm_mode, float min_val, float max_val, float* y_raw, float* widths_normed,
+                           float* edges, float* centers, mde_stream_t stream);
+
+/* ---- K1d: range-attention contraction  y[b,n,p] = sum_k x[b,k,p] * q[b,n,k]  (layers.py:31-36) ----------
+ * x [B,K,P] float32 (NCHW with P = h*w), q [B,N,K] float32, y [B,N,P] float32.
+ * impl 0 = SIMT fp32 (exact fp32 FMA), impl 1 = TMA + tcgen05 TF32 (requires P % 128 == 0, K == 128, N % 16 == 0). */
+int mde_range_attention(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, int impl,
+                        mde_stream_t stream);
+
+/* ---- K2: streaming bin pipeline  pred[b,p] = sum_j softmax_j(logits[b,:,p]) * centers[b,j]
+ * (unet_adaptive_bins.py:286 Softmax(dim=1) and :298-300).  logits [B,n_bins,P], centers [B,n_bins], pred [B,P]. */
+int mde_bins_pred_fwd(const float* logits, const float* centers, float* pred, int B, int n_bins, int64_t P,
+                      mde_stream_t stream);
+/* 1x1 conv 128 -> n_bins (+bias) on the range-attention maps (unet_adaptive_bins.py:190,286), SIMT fp32.
+ * ram [B,K,P], w [n_bins,K], bias [n_bins] -> logits [B,n_bins,P] */
+int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* logits, int B, int K, int n_bins,
+                    int64_t P, mde_stream_t stream);
+
+/* ---- K1d+K1e+K2 fused: range attention -> conv_out -> softmax -> centre-weighted sum, nothing but pred is
+ * written (miniViT.py:33 + unet_adaptive_bins.py:286-300).  TMA-fed tcgen05 (TF32), accumulators in TMEM.
+ *   x [B,128,P] float32 (conv3x3 output, NCHW), wf [B,n_bins,128] float32 = (conv_out.weight @ queries[b]) * log2(e)
+ *   rounded to TF32 (mde_fold_queries produces it), biasf [n_bins] = bias*log2(e), centers [B,n_bins], pred [B,P].
+ * Requires P % 128 == 0, n_bins == 256. */
+int mde_head_chain_fwd(const float* x, const float* wf, const float* biasf, const float* centers, float* pred, int B,
+                       int n_bins, int64_t P, mde_stream_t stream);
+/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e ),  biasf = bias * log2e   (fp32 FMA) */
+int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride, float* wf,
+                     float* biasf, int B, int n_bins, int N, int K, mde_stream_t stream);
+
+/* out[i] = round-to-nearest TF32 of in[i] (so the tensor cores' operand truncation is exact for this tensor) */
+int mde_round_tf32(const float* in, float* out, int64_t n, mde_stream_t stream);
+/* bring-up knobs for the UMMA shared-memory descriptors (bytes) and the last barrier-timeout code (0 = none;
+ * synchronises the device).  Test/debug only. */
+int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version);
+int mde_tc_last_error(void);
+
+/* ---- A8': noAdaBins epilogue relu(x) + 1e-4 (unet_adaptive_bins.py:240-242) */
+int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_t stream);
+
+/* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
+ * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is
+ * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (zeroed by the call; holds
+ * {sum g, sum g^2, n} as float64 afterwards, which mde_silog_bwd reads).  loss: float32 scalar. */
+int64_t mde_silog_ws_bytes(void);
+int mde_silog_fwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W,
+                  int interpolate, void* ws, float* loss, mde_stream_t stream);
+/* grad_pred [B,1,h,w] (zeroed by the call, accumulated with atomics) given upstream scalar grad (device ptr) */
+int mde_silog_bwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W,
+                  int interpolate, const void* ws, const float* grad_loss, float* grad_pred, mde_stream_t stream);
+
+/* ---- K5: bin-centre chamfer loss (loss.py:33-46 -> pytorch3d.loss.chamfer_distance, K=1 squared L2 both ways,
+ * point mean, batch mean; targets < 1e-3 dropped).  edges [B,n_bins+1] float32 ascending; target [B,HW] float32.
+ * ws: >= mde_chamfer_ws_bytes(B,n_bins) bytes scratch (zeroed by the call; keeps per-image/per-centre statistics
+ * for mde_chamfer_bwd).  loss: float32 scalar (NaN if an image has no valid target, like the reference's 0/0). */
+int64_t mde_chamfer_ws_bytes(int B, int n_bins);
+int mde_chamfer_fwd(const float* edges, const float* target, int B, int n_bins, int64_t HW, float min_target,
+                    void* ws, float* loss, mde_stream_t stream);
+int mde_chamfer_bwd(const float* edges, int B, int n_bins, const void* ws, const float* grad_loss,
+                    float* grad_edges, mde_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDE_B200_H */

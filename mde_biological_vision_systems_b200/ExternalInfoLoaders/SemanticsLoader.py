@@ -1,0 +1,120 @@
+"""Drop-in for the reference's ExternalInfoLoaders/SemanticsLoader.py.
+
+``SemanticsLoader(args).get_semantics(batch) -> (semantics_raw, semantics)`` with the reference's mode strings
+(/root/reference/ExternalInfoLoaders/SemanticsLoader.py:34-145).  The reference gathers on the CPU and ships a
+25-channel float tensor over PCIe; here the int64 label map is what crosses the bus (25x less) and the clamp +
+table gather + NCHW permute run as one shared-memory-staged kernel on the GPU (ops.gather_embed).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from .. import ops
+
+_EMBEDDINGS = {
+    "glove": "ade20k_150_classes_glove_840b_300d_embeddings.npy",
+    "glove-25d": "ade20k_150_classes_glove_twitter_27b_25d_embeddings.npy",
+    "places-random": "ade20k_places_classes_25d_embeddings_random.npy",
+    "places-shuffled": "ade20k_places_classes_glove_twitter_27b_25d_embeddings_shuffled.npy",
+    "places": "ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy",
+}
+
+
+def _data_file(name):
+    """The reference opens ``data/<name>`` relative to the cwd; fall back to the copy shipped with this repo."""
+    local = os.path.join("data", name)
+    if os.path.exists(local):
+        return local
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "data", name)
+
+
+class SemanticsLoader():
+    def __init__(self, args, device=None):
+        self.args = args
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        self.embeddings_path = None
+        self.human_sizes_path = None
+        self.word_embeddings_semantics = None  # float64 host tensor, as in the reference
+        self.human_sizes = None
+        self._dev_tables = {}
+        self.set_semantics_path()
+        self.set_human_sizes_path()
+        self.load_word_embeddings()
+        self.load_human_sizes()
+
+    def set_semantics_path(self):
+        mode = self.args.use_semantics
+        if mode is None:
+            return
+        key = None
+        if mode == "glove":
+            key = "glove"
+        elif mode in ("glove-25d", "glove-25d-inst-areas"):
+            key = "glove-25d"
+        elif "ade20k-places" in mode:
+            if "random" in mode:
+                key = "places-random"
+            elif "glove-25d" in mode:
+                key = "places-shuffled" if "size_shuffled" in mode else "places"
+        if key is not None:
+            self.embeddings_path = _data_file(_EMBEDDINGS[key])
+
+    def set_human_sizes_path(self):
+        mode = self.args.use_semantics
+        if mode is not None and "human-sizes" in mode:
+            if "ade20k-places" not in mode:
+                sys.exit("Error: human-sizes not implemented for semantics other than ade20k-places.")
+            self.human_sizes_path = _data_file(
+                "ade20k_classes_abs_sizes_shuffled.npy" if "shuffled" in mode else "ade20k_classes_abs_sizes.npy")
+
+    def load_word_embeddings(self):
+        if self.embeddings_path is not None:
+            self.word_embeddings_semantics = torch.from_numpy(np.load(self.embeddings_path))
+
+    def load_human_sizes(self):
+        if self.human_sizes_path is not None:
+            self.human_sizes = torch.from_numpy(np.load(self.human_sizes_path))
+
+    def _table(self, name, host, dtype):
+        """Device copy of a table, converted once (float64 -> float32 rounding happens exactly once per entry, so
+        gathering the rounded table is bit-identical to the reference's gather-then-.float())."""
+        key = (name, dtype)
+        if key not in self._dev_tables:
+            self._dev_tables[key] = host.to(dtype).contiguous().to(self.device)
+        return self._dev_tables[key]
+
+    def get_semantics_inst_areas(self, semantics_raw):
+        rows = self.word_embeddings_semantics.shape[0]
+        return ops.class_area_fraction(semantics_raw, rows)
+
+    def get_semantics(self, batch):
+        """-> (semantics_raw [B,1,H,W] int64 on the device, clamped like the reference clamps the batch tensor;
+               semantics [B,C,H,W] on the device) or (None, None)."""
+        mode = self.args.use_semantics
+        if mode is None:
+            return None, None
+        host_raw = batch['semantics']
+        raw = host_raw.to(self.device, non_blocking=True).contiguous()
+        places = "ade20k-places" in mode
+        if "raw" in mode:
+            if places:  # clamp only, no gather
+                raw = raw.clamp_(max=100)
+                raw[raw < 0] = 100
+            semantics = ops.cast_i64_f32(raw)
+        else:
+            # places tables are float32 on return (.float() at :128-129); the 150-class tables stay float64
+            dtype = torch.float32 if places else torch.float64
+            table = self._table("emb", self.word_embeddings_semantics, dtype)
+            semantics = ops.gather_embed(raw, table, background=100 if places else None, write_back=places)
+        if "inst-areas" in mode:
+            semantics = torch.cat((semantics, self.get_semantics_inst_areas(raw)), dim=1)
+        if self.human_sizes is not None:
+            sizes = ops.gather_embed(raw, self._table("sizes", self.human_sizes, torch.float32), background=None)
+            semantics = torch.cat((semantics, sizes), dim=1)
+        if places and isinstance(host_raw, torch.Tensor) and not host_raw.is_cuda:
+            # mirror the reference's in-place clamp of the caller's batch tensor (SemanticsLoader.py:117-118)
+            host_raw[host_raw > 100] = 100
+            host_raw[host_raw < 0] = 100
+        return raw, semantics

@@ -1,0 +1,215 @@
+// A3 -- per-pixel 1x1-conv MLP  C_in -> 10 -> 10 (ReLU after both), forward and backward.
+//
+// Reference: nn.Sequential(Conv2d(C_in,10,1), ReLU, Conv2d(10,10,1), ReLU) built at
+// models/unet_adaptive_bins.py:146-174 and applied to area / size channels at :196-228.
+// HBM-bound streaming kernel: 4*C_in bytes in, 40 bytes out per pixel; the 150 (C_in = 3) weights live in
+// registers/shared memory; one thread owns 4 consecutive pixels (128-bit loads and stores per plane).
+// The output pointer addresses a channel slice of the concatenated encoder input, so no torch.cat copy follows.
+#include "common.cuh"
+
+namespace mde {
+
+constexpr int HID = 10;
+
+template <int CIN>
+struct MlpWeights {
+  float w0[HID * CIN], b0[HID], w1[HID * HID], b1[HID];
+};
+
+template <int CIN>
+__device__ __forceinline__ void load_weights(MlpWeights<CIN>& s, const float* w0, const float* b0, const float* w1,
+                                             const float* b1) {
+  for (int i = threadIdx.x; i < HID * CIN; i += blockDim.x) s.w0[i] = w0[i];
+  for (int i = threadIdx.x; i < HID * HID; i += blockDim.x) s.w1[i] = w1[i];
+  for (int i = threadIdx.x; i < HID; i += blockDim.x) {
+    s.b0[i] = b0[i];
+    s.b1[i] = b1[i];
+  }
+  __syncthreads();
+}
+
+template <int CIN, int VEC>
+__global__ void __launch_bounds__(256) aux_mlp_fwd_kernel(const float* __restrict__ x, long long xbs,
+                                                          const float* __restrict__ w0, const float* __restrict__ b0,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          float* __restrict__ out, long long obs, long long HW,
+                                                          float in_scale) {
+  __shared__ MlpWeights<CIN> sw;
+  load_weights<CIN>(sw, w0, b0, w1, b1);
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * xbs;
+  float* ob = out + (long long)b * obs;
+  const long long groups = HW / VEC;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long p = g * VEC;
+    float xin[CIN][VEC];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      if (VEC == 4) {
+        const float4 v = ldg_stream(reinterpret_cast<const float4*>(xb + (long long)c * HW + p));
+        xin[c][0] = v.x / in_scale; xin[c][1] = v.y / in_scale; xin[c][2] = v.z / in_scale; xin[c][3] = v.w / in_scale;
+      } else {
+        xin[c][0] = xb[(long long)c * HW + p] / in_scale;
+      }
+    }
+    float h[HID][VEC];
+#pragma unroll
+    for (int j = 0; j < HID; ++j)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float a = sw.b0[j];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) a = fmaf(sw.w0[j * CIN + c], xin[c][v], a);
+        h[j][v] = fmaxf(a, 0.f);
+      }
+#pragma unroll
+    for (int i = 0; i < HID; ++i) {
+      float o[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float a = sw.b1[i];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) a = fmaf(sw.w1[i * HID + j], h[j][v], a);
+        o[v] = fmaxf(a, 0.f);
+      }
+      if (VEC == 4) stg_stream(reinterpret_cast<float4*>(ob + (long long)i * HW + p), make_float4(o[0], o[1], o[2], o[3]));
+      else ob[(long long)i * HW + p] = o[0];
+    }
+  }
+}
+
+// Backward: recompute the hidden layer, accumulate parameter gradients per thread, reduce per block, one atomic
+// per parameter per block.
+template <int CIN>
+__global__ void __launch_bounds__(256) aux_mlp_bwd_kernel(const float* __restrict__ x, long long xbs,
+                                                          const float* __restrict__ w0, const float* __restrict__ b0,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          const float* __restrict__ gout, long long gbs, float* gx,
+                                                          float* gw0, float* gb0, float* gw1, float* gb1, int B,
+                                                          long long HW, float in_scale) {
+  __shared__ MlpWeights<CIN> sw;
+  load_weights<CIN>(sw, w0, b0, w1, b1);
+  float aw0[HID * CIN], ab0[HID], aw1[HID * HID], ab1[HID];
+#pragma unroll
+  for (int i = 0; i < HID * CIN; ++i) aw0[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < HID * HID; ++i) aw1[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < HID; ++i) ab0[i] = ab1[i] = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / HW, p = t - b * HW;
+    float xin[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) xin[c] = x[b * xbs + (long long)c * HW + p] / in_scale;
+    float h[HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+      float a = sw.b0[j];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) a = fmaf(sw.w0[j * CIN + c], xin[c], a);
+      h[j] = fmaxf(a, 0.f);
+    }
+    float gh[HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) gh[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < HID; ++i) {
+      float a = sw.b1[i];
+#pragma unroll
+      for (int j = 0; j < HID; ++j) a = fmaf(sw.w1[i * HID + j], h[j], a);
+      const float go = a > 0.f ? gout[b * gbs + (long long)i * HW + p] : 0.f;
+      ab1[i] += go;
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        aw1[i * HID + j] = fmaf(go, h[j], aw1[i * HID + j]);
+        gh[j] = fmaf(sw.w1[i * HID + j], go, gh[j]);
+      }
+    }
+    float gxin[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) gxin[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+      const float g = h[j] > 0.f ? gh[j] : 0.f;
+      ab0[j] += g;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        aw0[j * CIN + c] = fmaf(g, xin[c], aw0[j * CIN + c]);
+        gxin[c] = fmaf(sw.w0[j * CIN + c], g, gxin[c]);
+      }
+    }
+    if (gx) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) gx[b * xbs + (long long)c * HW + p] = gxin[c] / in_scale;
+    }
+  }
+  // block reduction: warp shuffle, then shared, then one atomic per parameter
+  __shared__ float red[8];
+  auto block_add = [&](float v, float* dst) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+      if (s != 0.f) atomicAdd(dst, s);
+    }
+    __syncthreads();
+  };
+#pragma unroll
+  for (int i = 0; i < HID * CIN; ++i) block_add(aw0[i], gw0 + i);
+#pragma unroll
+  for (int i = 0; i < HID; ++i) block_add(ab0[i], gb0 + i);
+#pragma unroll
+  for (int i = 0; i < HID * HID; ++i) block_add(aw1[i], gw1 + i);
+#pragma unroll
+  for (int i = 0; i < HID; ++i) block_add(ab1[i], gb1 + i);
+}
+
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+int mde_aux_mlp_fwd(const float* x, int64_t xbs, const float* w0, const float* b0, const float* w1, const float* b1,
+                    float* out, int64_t obs, int B, int C_in, int H1, int H2, int64_t HW, float in_scale,
+                    mde_stream_t stream) {
+  if (!x || !w0 || !b0 || !w1 || !b1 || !out) return MDE_ERR_BAD_POINTER;
+  if (H1 != HID || H2 != HID || (C_in != 1 && C_in != 3)) return MDE_ERR_UNSUPPORTED;
+  if (B <= 0 || HW <= 0 || B > 65535) return MDE_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (HW % 4 == 0) && (xbs % 4 == 0) && (obs % 4 == 0) && aligned(x, 16) && aligned(out, 16);
+  const long long groups = vec ? HW / 4 : HW;
+  long long gx = (groups + 255) / 256;
+  if (gx > 4096) gx = 4096;
+  dim3 grid((unsigned)gx, (unsigned)B);
+  if (C_in == 1) {
+    if (vec) aux_mlp_fwd_kernel<1, 4><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, out, obs, HW, in_scale);
+    else aux_mlp_fwd_kernel<1, 1><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, out, obs, HW, in_scale);
+  } else {
+    if (vec) aux_mlp_fwd_kernel<3, 4><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, out, obs, HW, in_scale);
+    else aux_mlp_fwd_kernel<3, 1><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, out, obs, HW, in_scale);
+  }
+  return check_launch();
+}
+
+int mde_aux_mlp_bwd(const float* x, int64_t xbs, const float* w0, const float* b0, const float* w1, const float* b1,
+                    const float* gout, int64_t gbs, float* gx, float* gw0, float* gb0, float* gw1, float* gb1, int B,
+                    int C_in, int H1, int H2, int64_t HW, float in_scale, mde_stream_t stream) {
+  if (!x || !w0 || !b0 || !w1 || !b1 || !gout || !gw0 || !gb0 || !gw1 || !gb1) return MDE_ERR_BAD_POINTER;
+  if (H1 != HID || H2 != HID || (C_in != 1 && C_in != 3)) return MDE_ERR_UNSUPPORTED;
+  if (B <= 0 || HW <= 0) return MDE_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = MDE_NUM_SMS * 4;
+  if (C_in == 1)
+    aux_mlp_bwd_kernel<1><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, gout, gbs, gx, gw0, gb0, gw1, gb1, B, HW, in_scale);
+  else
+    aux_mlp_bwd_kernel<3><<<grid, 256, 0, st>>>(x, xbs, w0, b0, w1, b1, gout, gbs, gx, gw0, gb0, gw1, gb1, B, HW, in_scale);
+  return check_launch();
+}
+
+}  // extern "C"

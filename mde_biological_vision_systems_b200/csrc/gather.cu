@@ -1,0 +1,231 @@
+// K3 -- label -> embedding gather (shared-memory-staged table, planar NCHW stores), class-area table, casts.
+//
+// Reference semantics: ExternalInfoLoaders/SemanticsLoader.py:102-145 and
+// ExternalInfoLoaders/InstanceSegmentationLoader.py:89-121 (clamp, index_select, permute to [B,D,H,W]).
+// HBM-bound: per pixel 8 B of int64 label in, D*sizeof(T) out (108 B/px for the fp32 GloVe-25d case).
+// Layout: one thread owns 4 consecutive pixels -> one 32 B label read and one 16 B store per channel plane,
+// so a warp writes 512 contiguous bytes per plane (fully coalesced); the table sits in shared memory with an odd
+// row pitch (D = 25 or 3) so distinct labels in a warp hit distinct banks.
+#include "common.cuh"
+
+namespace mde {
+
+unsigned long long g_launch_count = 0;
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+    stg_stream(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+  }
+};
+template <>
+struct Vec4<double> {
+  static __device__ __forceinline__ void store(double* p, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+  }
+};
+
+__device__ __forceinline__ int clamp_label(long long l, int rows, int background, bool& oob) {
+  if (l < 0 || l > (long long)(rows - 1)) {
+    if (background >= 0) return background;
+    oob = true;
+    return -1;
+  }
+  return (int)l;
+}
+
+// VEC = 4: HW % 4 == 0 and 16/32-byte aligned pointers; VEC = 1: generic scalar path.
+template <typename T, int VEC, bool SMEM>
+__global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __restrict__ labels,
+                                                            long long* labels_out, const T* __restrict__ table,
+                                                            T* __restrict__ out, long long HW, int rows, int D,
+                                                            int background, long long table_image_stride,
+                                                            int* oob_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* stab = reinterpret_cast<T*>(smem_raw);
+  const int b = blockIdx.y;
+  const T* tab = table + (long long)b * table_image_stride;
+  if (SMEM) {
+    for (int i = threadIdx.x; i < rows * D; i += blockDim.x) stab[i] = tab[i];
+    __syncthreads();
+    tab = stab;
+  }
+  const long long* lab = labels + (long long)b * HW;
+  long long* lab_out = labels_out ? labels_out + (long long)b * HW : nullptr;
+  T* o = out + (long long)b * D * HW;
+  const long long groups = HW / VEC;
+  bool oob = false;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long p = g * VEC;
+    if (VEC == 4) {
+      const longlong2 a = *reinterpret_cast<const longlong2*>(lab + p);
+      const longlong2 c = *reinterpret_cast<const longlong2*>(lab + p + 2);
+      const int l0 = clamp_label(a.x, rows, background, oob), l1 = clamp_label(a.y, rows, background, oob);
+      const int l2 = clamp_label(c.x, rows, background, oob), l3 = clamp_label(c.y, rows, background, oob);
+      if (lab_out) {
+        *reinterpret_cast<longlong2*>(lab_out + p) = make_longlong2(l0 < 0 ? a.x : l0, l1 < 0 ? a.y : l1);
+        *reinterpret_cast<longlong2*>(lab_out + p + 2) = make_longlong2(l2 < 0 ? c.x : l2, l3 < 0 ? c.y : l3);
+      }
+      const T* r0 = tab + (l0 < 0 ? 0 : l0) * D;
+      const T* r1 = tab + (l1 < 0 ? 0 : l1) * D;
+      const T* r2 = tab + (l2 < 0 ? 0 : l2) * D;
+      const T* r3 = tab + (l3 < 0 ? 0 : l3) * D;
+      const T z = T(0);
+#pragma unroll 5
+      for (int d = 0; d < D; ++d) {
+        Vec4<T>::store(o + (long long)d * HW + p, l0 < 0 ? z : r0[d], l1 < 0 ? z : r1[d], l2 < 0 ? z : r2[d],
+                       l3 < 0 ? z : r3[d]);
+      }
+    } else {
+      const long long raw = lab[p];
+      const int l = clamp_label(raw, rows, background, oob);
+      if (lab_out) lab_out[p] = l < 0 ? raw : l;
+      const T* r = tab + (l < 0 ? 0 : l) * D;
+      for (int d = 0; d < D; ++d) o[(long long)d * HW + p] = l < 0 ? T(0) : r[d];
+    }
+  }
+  if (oob && oob_flag) atomicExch(oob_flag, 1);
+}
+
+template <typename T>
+static int launch_gather(const int64_t* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
+                         int rows, int D, int background, int64_t tis, int32_t* oob_flag, cudaStream_t st) {
+  const size_t tab_bytes = (size_t)rows * D * sizeof(T);
+  const bool smem = tab_bytes <= 48 * 1024;
+  const bool vec = (HW % 4 == 0) && aligned(labels, 16) && aligned(out, 16) && (!labels_out || aligned(labels_out, 16));
+  const long long groups = vec ? HW / 4 : HW;
+  long long gx = (groups + 256 * 4 - 1) / (256 * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 65535) gx = 65535;
+  dim3 grid((unsigned)gx, (unsigned)B);
+  const size_t sm = smem ? tab_bytes : 0;
+  const long long* L = reinterpret_cast<const long long*>(labels);
+  long long* LO = reinterpret_cast<long long*>(labels_out);
+  const T* Tb = reinterpret_cast<const T*>(table);
+  T* O = reinterpret_cast<T*>(out);
+#define MDE_GATHER_LAUNCH(V, S) \
+  gather_embed_kernel<T, V, S><<<grid, 256, sm, st>>>(L, LO, Tb, O, HW, rows, D, background, tis, oob_flag)
+  if (vec && smem) MDE_GATHER_LAUNCH(4, true);
+  else if (vec) MDE_GATHER_LAUNCH(4, false);
+  else if (smem) MDE_GATHER_LAUNCH(1, true);
+  else MDE_GATHER_LAUNCH(1, false);
+#undef MDE_GATHER_LAUNCH
+  return check_launch();
+}
+
+// ---- per-image class histogram -> area fraction table -------------------------------------------------------
+__global__ void __launch_bounds__(256) class_hist_kernel(const long long* __restrict__ labels, long long HW, int rows,
+                                                          int* __restrict__ counts) {
+  extern __shared__ int shist[];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) shist[i] = 0;
+  __syncthreads();
+  const long long* lab = labels + (long long)b * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const long long l = lab[p];
+    if (l >= 0 && l < rows) atomicAdd(&shist[(int)l], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows; i += blockDim.x)
+    if (shist[i]) atomicAdd(&counts[b * rows + i], shist[i]);
+}
+
+__global__ void class_frac_kernel(const int* __restrict__ counts, double* __restrict__ frac, int n, long long HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // python: label_area = count / total_area  (int / int true division -> float64)
+  if (i < n) frac[i] = (double)counts[i] / (double)HW;
+}
+
+__global__ void cast_i64_f32_kernel(const long long* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];  // round-to-nearest-even, as Tensor.float()
+}
+
+__global__ void relu_eps_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float eps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaxf(x[i], 0.f) + eps;
+}
+
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+int mde_version(void) { return 100; }
+
+int64_t mde_launch_count(void) { return (int64_t)g_launch_count; }
+
+const char* mde_error_string(int code) {
+  switch (code) {
+    case MDE_OK: return "ok";
+    case MDE_ERR_BAD_SHAPE: return "bad shape / stride / divisibility";
+    case MDE_ERR_BAD_POINTER: return "null or misaligned pointer";
+    case MDE_ERR_BAD_ARCH: return "device is not sm_100 (B200)";
+    case MDE_ERR_LAUNCH: return "kernel launch failed";
+    case MDE_ERR_UNSUPPORTED: return "unsupported mode";
+    case MDE_ERR_DRIVER: return "CUDA driver entry point unavailable";
+  }
+  return "unknown error";
+}
+
+int mde_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return MDE_ERR_BAD_ARCH;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return MDE_ERR_BAD_ARCH;
+  return major == 10 ? MDE_OK : MDE_ERR_BAD_ARCH;
+}
+
+int mde_gather_embed(const int64_t* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
+                     int rows, int D, int background, int out_dtype, int64_t table_image_stride, int32_t* oob_flag,
+                     mde_stream_t stream) {
+  if (!labels || !table || !out) return MDE_ERR_BAD_POINTER;
+  if (B < 0 || HW < 0 || rows <= 0 || D <= 0 || background >= rows || B > 65535) return MDE_ERR_BAD_SHAPE;
+  if (B == 0 || HW == 0) return MDE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == MDE_F32)
+    return launch_gather<float>(labels, labels_out, table, out, B, HW, rows, D, background, table_image_stride, oob_flag, st);
+  if (out_dtype == MDE_F64)
+    return launch_gather<double>(labels, labels_out, table, out, B, HW, rows, D, background, table_image_stride, oob_flag, st);
+  return MDE_ERR_UNSUPPORTED;
+}
+
+int mde_class_area_table(const int64_t* labels, int B, int64_t HW, int rows, int32_t* counts, double* frac,
+                         mde_stream_t stream) {
+  if (!labels || !counts || !frac) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || HW <= 0 || rows <= 0 || rows > 8192 || B > 65535) return MDE_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * rows, st);
+  long long gx = (HW + 256 * 16 - 1) / (256 * 16);
+  if (gx > 1024) gx = 1024;
+  class_hist_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, rows * sizeof(int), st>>>(
+      reinterpret_cast<const long long*>(labels), HW, rows, counts);
+  int rc = check_launch();
+  if (rc) return rc;
+  class_frac_kernel<<<(B * rows + 255) / 256, 256, 0, st>>>(counts, frac, B * rows, HW);
+  return check_launch();
+}
+
+int mde_cast_i64_f32(const int64_t* in, float* out, int64_t n, mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (n <= 0) return n == 0 ? MDE_OK : MDE_ERR_BAD_SHAPE;
+  long long gx = (n + 255) / 256;
+  if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;
+  cast_i64_f32_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(in), out, n);
+  return check_launch();
+}
+
+int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_t stream) {
+  if (!x || !y) return MDE_ERR_BAD_POINTER;
+  if (n <= 0) return n == 0 ? MDE_OK : MDE_ERR_BAD_SHAPE;
+  long long gx = (n + 255) / 256;
+  if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;
+  relu_eps_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(x, y, n, eps);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// K1d / K1d+K1e+K2 -- the range-attention contraction on tcgen05, stand-alone and fused with conv_out + softmax + bins.
+//
+// Reference: PixelWiseDotProduct (models/layers.py:31-36), conv_out + Softmax(dim=1)
+// (models/unet_adaptive_bins.py:190-191,286) and the centre-weighted sum (:298-300).
+//
+// One persistent, warp-specialised kernel (1 CTA / SM, 224 threads):
+//   warp 0      TMA producer for the activation tiles  x[b, k, p0:p0+128]  (NCHW, so the pixel axis is contiguous:
+//               the A operand is MN-major).  A tile is 128 pixels x 128 channels fp32 = 64 KB, streamed as four
+//               32-channel stages of 16 KB (four 32-pixel x 32-channel SWIZZLE_128B boxes each) through an NS-deep ring.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M = 128 pixels, N = NB, K = 8 per instruction,
+//               16 instructions per tile), accumulating in TMEM; two TMEM accumulator buffers so the epilogue of tile
+//               i overlaps the MMAs of tile i+1.
+//   warp 2      per-image weight loader (B operand, K-major, SWIZZLE_128B; re-loaded when the CTA crosses an image
+//               boundary) + TMEM allocation / release.
+//   warps 3-6   epilogue: tcgen05.ld 32 columns at a time (thread = pixel row), then either
+//                 EPI_STORE   : write y[b, n, p]                      (stand-alone range attention, N = 128)
+//                 EPI_SOFTMAX : online softmax over the NB = 256 logits and centre-weighted sum -> pred[b, p]
+//               so in the fused form neither the range-attention maps (29 MB/img) nor the logits / softmax
+//               (58 MB/img each) ever reach HBM: algorithmic traffic is 128*P*4 B in + P*4 B out per image.
+// In the fused form the two 1x1 contractions are folded by associativity, W'_b = W_out @ Q_b (tiny, exact fp32,
+// mde_fold_queries), pre-scaled by log2(e) and rounded to TF32 once, so the tensor cores run ONE K = 128 contraction
+// per pixel against the per-image 256 x 128 operand; the bias enters the softmax as exp2(b_j) factors.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mde {
+namespace tc {
+
+constexpr int TILE_M = 128;                      // pixels per tile (UMMA M)
+constexpr int KDIM = 128;                        // contraction length (channels)
+constexpr int KC = 32;                           // channels per stage = one 128-byte swizzle row per channel
+constexpr int STAGE_BYTES = TILE_M * KC * 4;     // 16384
+constexpr int BOX_BYTES = 32 * KC * 4;           // one 32-pixel x 32-channel box
+constexpr int NUM_THREADS = 224;
+constexpr int EPI_WARP0 = 3;
+enum { EPI_STORE = 0, EPI_SOFTMAX = 1 };
+
+struct DebugCfg {
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo, version;
+};
+static DebugCfg g_dbg = {4096, 1024, 16, 1024, 1};
+
+template <int NB>
+struct SmemPlan {
+  static constexpr int W_BYTES = NB * KDIM * 4;  // per-image B operand: 4 K-chunks x [NB rows][128 B]
+  static constexpr int NS = (NB == 256) ? 5 : 8;
+  static constexpr int RING_BYTES = NS * STAGE_BYTES;
+  static constexpr int CONST_BYTES = 2 * NB * 4;  // exp2(bias) and exp2(bias)*centre per bin
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = W_BYTES + RING_BYTES + CONST_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+template <int NB, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    head_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const float* __restrict__ biasf, const float* __restrict__ centers, float* __restrict__ out,
+                      int tiles_per_img, int total_tiles, long long P, DebugCfg dbg) {
+  using Plan = SmemPlan<NB>;
+  constexpr int NS = Plan::NS;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+  const uint32_t s_w = base;
+  const uint32_t s_ring = s_w + Plan::W_BYTES;
+  float* c_fac = reinterpret_cast<float*>(gbase + Plan::W_BYTES + Plan::RING_BYTES);  // [NB] exp2(bias)
+  float* c_cen = c_fac + NB;                                                            // [NB] exp2(bias)*centre
+  const uint32_t s_bar = s_ring + Plan::RING_BYTES + Plan::CONST_BYTES;
+  // barrier slots (8 B each)
+  const uint32_t bar_full = s_bar;                 // [NS]
+  const uint32_t bar_empty = s_bar + 8 * NS;       // [NS]
+  const uint32_t bar_wfull = s_bar + 16 * NS;      // [1]
+  const uint32_t bar_wempty = bar_wfull + 8;       // [1]
+  const uint32_t bar_accfull = bar_wempty + 8;     // [2]
+  const uint32_t bar_accempty = bar_accfull + 16;  // [2]
+  const uint32_t s_tmem_slot = bar_accempty + 16;  // uint32
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous tile range of this CTA (so it crosses at most one image boundary)
+  const int t_begin = (int)(((long long)total_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)total_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_wempty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accfull + 8 * i, 1);
+      mbar_init(bar_accempty + 8 * i, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+  }
+  constexpr uint32_t TMEM_COLS = (2 * NB <= 32) ? 32 : (2 * NB <= 64) ? 64 : (2 * NB <= 128) ? 128 : (2 * NB <= 256) ? 256 : 512;
+  if (warp == 2) {
+    tmem_alloc(s_tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= activation producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int img = t / tiles_per_img;
+        const int p0 = (t - img * tiles_per_img) * TILE_M;
+        for (int kc = 0; kc < KDIM / KC; ++kc) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+          mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+          const uint32_t dst = s_ring + stage * STAGE_BYTES;
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            tma_load_3d(dst + m * BOX_BYTES, &map_x, bar_full + 8 * stage, p0 + 32 * m, kc * KC, img);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= per-image weight loader =================
+    if (lane == 0) {
+      int cur = -1;
+      uint32_t wphase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int img = t / tiles_per_img;
+        if (img == cur) continue;
+        cur = img;
+        mbar_wait(bar_wempty, wphase ^ 1, 2);  // previous image's MMAs have drained
+        mbar_expect_tx(bar_wfull, Plan::W_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < KDIM / KC; ++kc)
+          tma_load_3d(s_w + kc * (NB * 128), &map_w, bar_wfull, kc * KC, 0, img);
+        wphase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_TF32, TILE_M, NB, /*A MN-major*/ 1, /*B K-major*/ 0);
+      uint32_t stage = 0, phase = 0, wphase = 0;
+      int cur = -1;
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int img = t / tiles_per_img;
+        if (img != cur) {
+          if (cur >= 0) umma_commit(bar_wempty);  // fires when every MMA that read the old weights is done
+          mbar_wait(bar_wfull, wphase, 3);
+          wphase ^= 1;
+          cur = img;
+        }
+        const uint32_t buf = it & 1;
+        mbar_wait(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * NB;
+        for (int kc = 0; kc < KDIM / KC; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase, 5);
+          tc_fence_after();
+          const uint32_t a_base = s_ring + stage * STAGE_BYTES;
+          const uint32_t b_base = s_w + kc * (NB * 128);
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {
+            // A (MN-major, SW128): one 8-channel K-atom = 8 rows x 128 B = 1024 B; 32-pixel MN-atoms 4096 B apart
+            const uint64_t adesc = make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B, dbg.version);
+            // B (K-major, SW128): 8 tf32 = 32 B along the 128-B swizzle row; 8-row atoms 1024 B apart
+            const uint64_t bdesc = make_smem_desc(b_base + j * 32, dbg.b_lbo, dbg.b_sbo, SWZ_128B, dbg.version);
+            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs complete
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(bar_accfull + 8 * buf);
+      }
+    }
+  } else {
+    // ================= epilogue warps (3..6) =================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    const int epi_tid = threadIdx.x - EPI_WARP0 * 32;
+    int cur = -1;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int img = t / tiles_per_img;
+      const int p0 = (t - img * tiles_per_img) * TILE_M;
+      if (EPI == EPI_SOFTMAX && img != cur) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading the old constants
+        for (int j = epi_tid; j < NB; j += 128) {
+          const float f = exp2f(biasf[j]);
+          c_fac[j] = f;
+          c_cen[j] = f * centers[(long long)img * NB + j];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      cur = img;
+      const uint32_t buf = it & 1;
+      mbar_wait(bar_accfull + 8 * buf, (it >> 1) & 1, 6);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * NB + ((uint32_t)(quarter * 32) << 16);
+      const long long pix = (long long)p0 + quarter * 32 + lane;
+      if (EPI == EPI_SOFTMAX) {
+        float m = -INFINITY, s = 0.f, ws = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 == NB) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+          }
+          float cm = __uint_as_float(r[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
+          if (cm > m) {
+            const float sc = ex2_approx(m - cm);  // 0 on the first chunk (m = -inf)
+            s *= sc;
+            ws *= sc;
+            m = cm;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(c_fac + c0 + i);
+            const float4 g = *reinterpret_cast<const float4*>(c_cen + c0 + i);
+            const float e0 = ex2_approx(__uint_as_float(r[i + 0]) - m);
+            const float e1 = ex2_approx(__uint_as_float(r[i + 1]) - m);
+            const float e2 = ex2_approx(__uint_as_float(r[i + 2]) - m);
+            const float e3 = ex2_approx(__uint_as_float(r[i + 3]) - m);
+            s = fmaf(e0, f.x, s);
+            ws = fmaf(e0, g.x, ws);
+            s = fmaf(e1, f.y, s);
+            ws = fmaf(e1, g.y, ws);
+            s = fmaf(e2, f.z, s);
+            ws = fmaf(e2, g.z, ws);
+            s = fmaf(e3, f.w, s);
+            ws = fmaf(e3, g.w, ws);
+          }
+        }
+        out[(long long)img * P + pix] = ws / s;
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 == NB) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+          }
+          float* dst = out + ((long long)img * NB + c0) * P + pix;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[(long long)i * P] = __uint_as_float(r[i]);  // 128 B per warp per row
+        }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int NB, int EPI>
+static int launch_chain(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
+                        long long P, cudaStream_t st) {
+  using Plan = SmemPlan<NB>;
+  if (P % TILE_M != 0) return MDE_ERR_BAD_SHAPE;
+  if (!aligned(x, 16) || !aligned(w, 16)) return MDE_ERR_BAD_POINTER;
+  CUtensorMap mx, mw;
+  {
+    const uint64_t dims[3] = {(uint64_t)P, (uint64_t)KDIM, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)P * 4, (uint64_t)P * KDIM * 4};
+    const uint32_t box[3] = {32, KC, 1};
+    if (!encode_f32(&mx, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)KDIM, (uint64_t)NB, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)KDIM * 4, (uint64_t)NB * KDIM * 4};
+    const uint32_t box[3] = {KC, NB, 1};
+    if (!encode_f32(&mw, w, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+  }
+  const int tiles_per_img = (int)(P / TILE_M);
+  const long long total = (long long)tiles_per_img * B;
+  if (total > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
+  const int grid = (int)(total < MDE_NUM_SMS ? total : MDE_NUM_SMS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL) !=
+        cudaSuccess)
+      return MDE_ERR_LAUNCH;
+    attr_set = true;
+  }
+  head_chain_kernel<NB, EPI><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
+                                                                      (int)total, P, g_dbg);
+  return check_launch();
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned int r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
+    out[i] = __uint_as_float(r);
+  }
+}
+
+}  // namespace tc
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+int mde_head_chain_fwd(const float* x, const float* wf, const float* biasf, const float* centers, float* pred, int B,
+                       int n_bins, int64_t P, mde_stream_t stream) {
+  if (!x || !wf || !biasf || !centers || !pred) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
+  if (n_bins != 256) return MDE_ERR_UNSUPPORTED;
+  return tc::launch_chain<256, tc::EPI_SOFTMAX>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
+}
+
+// stand-alone range attention on tensor cores (called by mde_range_attention(impl = 1)); q should be TF32-rounded
+int mde_range_attention_tc(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, cudaStream_t st) {
+  if (K != 128 || N != 128) return MDE_ERR_UNSUPPORTED;
+  return tc::launch_chain<128, tc::EPI_STORE>(x, q, nullptr, nullptr, y, B, P, st);
+}
+
+int mde_round_tf32(const float* in, float* out, int64_t n, mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (n <= 0) return n == 0 ? MDE_OK : MDE_ERR_BAD_SHAPE;
+  long long g = (n + 255) / 256;
+  if (g > MDE_NUM_SMS * 8) g = MDE_NUM_SMS * 8;
+  tc::round_tf32_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  return check_launch();
+}
+
+// debug/bring-up knobs for the UMMA shared-memory descriptors (bytes); version = descriptor version field
+int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version) {
+  tc::g_dbg.a_lbo = (uint32_t)a_lbo;
+  tc::g_dbg.a_sbo = (uint32_t)a_sbo;
+  tc::g_dbg.b_lbo = (uint32_t)b_lbo;
+  tc::g_dbg.b_sbo = (uint32_t)b_sbo;
+  tc::g_dbg.version = (uint32_t)version;
+  return MDE_OK;
+}
+
+// last barrier-timeout code recorded by a tcgen05 kernel of this file (0 = none). Synchronises the device.
+int mde_tc_last_error(void) {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, tc::g_tc_error, sizeof(int));
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+"""Offline, random-init EfficientNet backbones shaped like geffnet's ``tf_efficientnet_b{1,5}_ap``.
+
+The reference obtains its encoder with ``torch.hub.load('rwightman/gen-efficientnet-pytorch', ...)``
+(/root/reference/models/unet_adaptive_bins.py:318-324), which needs the network and an un-pinned
+third-party repository.  This module rebuilds the same *module tree* (child order ``conv_stem, bn1,
+act1, blocks[0..6], conv_head, bn2, act2, global_pool, classifier`` and geffnet parameter names) so that
+
+* ``Encoder`` (which walks ``_modules`` in order and keeps every intermediate, reference
+  ``unet_adaptive_bins.py:103-116``) sees the feature list the decoder indexes ([4],[5],[6],[8],[11]);
+* a real geffnet checkpoint can be dropped in with ``load_state_dict``.
+
+The backbone is *outside* the hot path: it is plain PyTorch/cuDNN passthrough and both
+sides of every parity test receive the same backbone object.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# (block type, repeats, kernel, stride, expansion, out channels) of EfficientNet-B0; every stage has se 0.25
+_B0_STAGES = (
+    ("ds", 1, 3, 1, 1, 16),
+    ("ir", 2, 3, 2, 6, 24),
+    ("ir", 2, 5, 2, 6, 40),
+    ("ir", 3, 3, 2, 6, 80),
+    ("ir", 3, 5, 1, 6, 112),
+    ("ir", 4, 5, 2, 6, 192),
+    ("ir", 1, 3, 1, 6, 320),
+)
+_SCALING = {  # name -> (width multiplier, depth multiplier)
+    "tf_efficientnet_b0_ap": (1.0, 1.0),
+    "tf_efficientnet_b1_ap": (1.0, 1.1),
+    "tf_efficientnet_b5_ap": (1.6, 2.2),
+}
+_BN_EPS = 1e-3  # TF-ported nets use eps 1e-3
+
+
+def _round_channels(ch, mult, divisor=8):
+    ch = ch * mult
+    new = max(divisor, int(ch + divisor / 2) // divisor * divisor)
+    if new < 0.9 * ch:
+        new += divisor
+    return new
+
+
+def _same_pad_amount(size, k, s):
+    return max((math.ceil(size / s) - 1) * s + k - size, 0)
+
+
+class SamePadConv2d(nn.Conv2d):
+    """TensorFlow 'SAME' convolution (asymmetric padding computed from the input size)."""
+
+    def __init__(self, cin, cout, kernel_size, stride=1, groups=1, bias=False):
+        super().__init__(cin, cout, kernel_size, stride, 0, 1, groups, bias)
+
+    def forward(self, x):
+        kh, kw = self.kernel_size
+        ph = _same_pad_amount(x.shape[-2], kh, self.stride[0])
+        pw = _same_pad_amount(x.shape[-1], kw, self.stride[1])
+        if ph or pw:
+            x = F.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+        return F.conv2d(x, self.weight, self.bias, self.stride, 0, 1, self.groups)
+
+
+def _conv(cin, cout, k, stride=1, groups=1, bias=False):
+    if stride == 1:  # symmetric padding is exact 'SAME' for odd kernels at stride 1
+        return nn.Conv2d(cin, cout, k, 1, k // 2, groups=groups, bias=bias)
+    return SamePadConv2d(cin, cout, k, stride, groups, bias)
+
+
+class SqueezeExcite(nn.Module):
+    def __init__(self, channels, reduced):
+        super().__init__()
+        self.conv_reduce = nn.Conv2d(channels, reduced, 1, bias=True)
+        self.act1 = nn.SiLU(inplace=True)
+        self.conv_expand = nn.Conv2d(reduced, channels, 1, bias=True)
+
+    def forward(self, x):
+        g = x.mean((2, 3), keepdim=True)
+        g = self.conv_expand(self.act1(self.conv_reduce(g)))
+        return x * torch.sigmoid(g)
+
+
+class DepthwiseSeparableConv(nn.Module):
+    def __init__(self, cin, cout, k, stride, se_ratio=0.25):
+        super().__init__()
+        self.has_residual = stride == 1 and cin == cout
+        self.conv_dw = _conv(cin, cin, k, stride, groups=cin)
+        self.bn1 = nn.BatchNorm2d(cin, eps=_BN_EPS)
+        self.act1 = nn.SiLU(inplace=True)
+        self.se = SqueezeExcite(cin, max(1, int(cin * se_ratio)))
+        self.conv_pw = nn.Conv2d(cin, cout, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout, eps=_BN_EPS)
+        self.act2 = nn.Identity()
+
+    def forward(self, x):
+        y = self.act1(self.bn1(self.conv_dw(x)))
+        y = self.bn2(self.conv_pw(self.se(y)))
+        return x + y if self.has_residual else y
+
+
+class InvertedResidual(nn.Module):
+    def __init__(self, cin, cout, k, stride, expand, se_ratio=0.25):
+        super().__init__()
+        mid = cin * expand
+        self.has_residual = stride == 1 and cin == cout
+        self.conv_pw = nn.Conv2d(cin, mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(mid, eps=_BN_EPS)
+        self.act1 = nn.SiLU(inplace=True)
+        self.conv_dw = _conv(mid, mid, k, stride, groups=mid)
+        self.bn2 = nn.BatchNorm2d(mid, eps=_BN_EPS)
+        self.act2 = nn.SiLU(inplace=True)
+        self.se = SqueezeExcite(mid, max(1, int(cin * se_ratio)))
+        self.conv_pwl = nn.Conv2d(mid, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout, eps=_BN_EPS)
+
+    def forward(self, x):
+        y = self.act1(self.bn1(self.conv_pw(x)))
+        y = self.act2(self.bn2(self.conv_dw(y)))
+        y = self.bn3(self.conv_pwl(self.se(y)))
+        return x + y if self.has_residual else y
+
+
+class GenEfficientNet(nn.Module):
+    """Module tree in geffnet order; ``forward`` is only used stand-alone (the Encoder walks children)."""
+
+    def __init__(self, width=1.0, depth=1.0, in_chans=3, num_classes=1000):
+        super().__init__()
+        stem = _round_channels(32, width)
+        self.conv_stem = SamePadConv2d(in_chans, stem, 3, 2)
+        self.bn1 = nn.BatchNorm2d(stem, eps=_BN_EPS)
+        self.act1 = nn.SiLU(inplace=True)
+        stages, cin = [], stem
+        for kind, reps, k, stride, expand, ch in _B0_STAGES:
+            cout = _round_channels(ch, width)
+            blocks = []
+            for r in range(int(math.ceil(reps * depth))):
+                s = stride if r == 0 else 1
+                if kind == "ds":
+                    blocks.append(DepthwiseSeparableConv(cin, cout, k, s))
+                else:
+                    blocks.append(InvertedResidual(cin, cout, k, s, expand))
+                cin = cout
+            stages.append(nn.Sequential(*blocks))
+        self.blocks = nn.Sequential(*stages)
+        head = _round_channels(1280, width)
+        self.conv_head = nn.Conv2d(cin, head, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(head, eps=_BN_EPS)
+        self.act2 = nn.SiLU(inplace=True)
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.classifier = nn.Linear(head, num_classes)
+        self.num_features = head
+
+    def forward(self, x):
+        x = self.act1(self.bn1(self.conv_stem(x)))
+        x = self.act2(self.bn2(self.conv_head(self.blocks(x))))
+        return self.classifier(self.global_pool(x).flatten(1))
+
+
+def build_backbone(name, seed=None):
+    """Random-init stand-in for ``torch.hub.load('rwightman/gen-efficientnet-pytorch', name)``."""
+    width, depth = _SCALING[name]
+    if seed is None:
+        return GenEfficientNet(width, depth)
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        return GenEfficientNet(width, depth)

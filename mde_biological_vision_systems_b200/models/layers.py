@@ -1,0 +1,44 @@
+"""Drop-in for the reference's models/layers.py (PatchTransformerEncoder, PixelWiseDotProduct).
+
+Same constructor signatures, forward contracts and state_dict keys (``embedding_convPxP.*``,
+``positional_encodings``, ``transformer_encoder.layers.{i}.*``) so reference checkpoints load unchanged
+(/root/reference/models/layers.py:5-36, model_io.py:36-72).
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class PatchTransformerEncoder(nn.Module):
+    """conv k=patch s=patch -> + positional rows -> 4 post-LN encoder layers; returns [S, N, E]
+    (reference layers.py:5-24).  The parameter containers are the stock torch modules so that key names, shapes
+    and default initialisation are identical to the reference's."""
+
+    def __init__(self, in_channels, patch_size=10, embedding_dim=128, num_heads=4):
+        super().__init__()
+        layer = nn.TransformerEncoderLayer(embedding_dim, num_heads, dim_feedforward=1024)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=4, enable_nested_tensor=False)
+        self.embedding_convPxP = nn.Conv2d(in_channels, embedding_dim, kernel_size=patch_size, stride=patch_size,
+                                           padding=0)
+        self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
+
+    def forward(self, x):
+        emb = self.embedding_convPxP(x).flatten(2)  # [N, E, S]
+        emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
+        return self.transformer_encoder(emb.permute(2, 0, 1))  # [S, N, E]
+
+
+class PixelWiseDotProduct(nn.Module):
+    """y[n, cout, h, w] = sum_c x[n, c, h, w] * K[n, cout, c]  (reference layers.py:27-36) on the tcgen05 /
+    SIMT contraction kernel (ops.range_attention -> mde_range_attention)."""
+
+    def __init__(self, impl="auto"):
+        super().__init__()
+        self.impl = impl
+
+    def forward(self, x, K):
+        n, c, h, w = x.size()
+        _, cout, ck = K.size()
+        assert c == ck, "Number of channels in x and Embedding dimension (at dim 2) of K matrix must match"
+        return ops.range_attention(x, K, impl=self.impl)

@@ -1,0 +1,39 @@
+"""Drop-in for the reference's models/miniViT.py (mViT head), /root/reference/models/miniViT.py:7-45."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .layers import PatchTransformerEncoder, PixelWiseDotProduct
+
+
+class mViT(nn.Module):
+    def __init__(self, in_channels, n_query_channels=128, patch_size=16, dim_out=256, embedding_dim=128, num_heads=4,
+                 norm='linear'):
+        super().__init__()
+        self.norm = norm
+        self.n_query_channels = n_query_channels
+        self.patch_transformer = PatchTransformerEncoder(in_channels, patch_size, embedding_dim, num_heads)
+        self.dot_product_layer = PixelWiseDotProduct()
+        self.conv3x3 = nn.Conv2d(in_channels, embedding_dim, kernel_size=3, stride=1, padding=1)
+        self.regressor = nn.Sequential(nn.Linear(embedding_dim, 256), nn.LeakyReLU(), nn.Linear(256, 256),
+                                       nn.LeakyReLU(), nn.Linear(256, dim_out))
+
+    # -- pieces shared by the reference-shaped forward() and the fused path of UnetAdaptiveBins ------------------
+    def tokens_and_features(self, x):
+        """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w])"""
+        tgt = self.patch_transformer(x.clone())
+        return tgt, self.conv3x3(x)
+
+    def bin_widths(self, tgt, min_val=None, max_val=None):
+        """regressor + normalisation on token 0 (miniViT.py:35-45); with min/max also edges and centres."""
+        r = self.regressor
+        return ops.regressor_bins(tgt[0], r[0].weight, r[0].bias, r[2].weight, r[2].bias, r[4].weight, r[4].bias,
+                                  self.norm, 0.0 if min_val is None else min_val, 1.0 if max_val is None else max_val)
+
+    def forward(self, x):
+        """-> (bin_widths_normed [N, dim_out], range_attention_maps [N, n_query, h, w]) as the reference."""
+        tgt, feat = self.tokens_and_features(x)
+        queries = tgt[1:self.n_query_channels + 1, ...].permute(1, 0, 2)
+        range_attention_maps = self.dot_product_layer(feat, queries)
+        widths_normed = self.bin_widths(tgt)[0]
+        return widths_normed, range_attention_maps

@@ -1,0 +1,281 @@
+"""Drop-in for the reference's models/unet_adaptive_bins.py.
+
+Keeps ``UnetAdaptiveBins.build()/forward() -> (bin_edges, pred)``, ``get_1x_lr_params/get_10x_lr_params``,
+``get_num_channels_to_add`` and every state_dict key (/root/reference/models/unet_adaptive_bins.py:119-395), while
+the head runs on the sm_100a kernels of this package:
+
+* external-info insertion at the input (:194-235): the 1x1-conv MLPs run as one streaming kernel each
+  (ops.aux_mlp) writing straight into the concatenated encoder input;
+* mViT + conv_out + softmax + bins (:285-302): ops.fold_queries + ops.head_chain (TMA + tcgen05, nothing but
+  ``pred`` written) or, when the fused kernel's shape constraints do not hold, range attention -> conv1x1 ->
+  ops.bins_pred (streaming);
+* noAdaBins epilogue (:240-242): ops.relu_eps.
+
+The EfficientNet encoder and DecoderBN bodies are outside the hot path and stay plain
+PyTorch/cuDNN modules; they only exist so the surface and the checkpoints match.
+"""
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .efficientnet import SamePadConv2d, build_backbone
+from .miniViT import mViT
+
+Conv2dSame = SamePadConv2d  # the reference exposes this name (unet_adaptive_bins.py:24-36)
+
+
+def _block(cin, cout):
+    return [nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(cout), nn.LeakyReLU()]
+
+
+class UpSampleBN(nn.Module):
+    """bilinear(align_corners) up-sample to the skip's size, concat, 2 x (conv3x3-BN-LeakyReLU); keys ``_net.{0,1,3,4}``."""
+
+    def __init__(self, skip_input, output_features):
+        super().__init__()
+        self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
+
+    def forward(self, x, concat_with):
+        x = F.interpolate(x, size=concat_with.shape[-2:], mode='bilinear', align_corners=True)
+        return self._net(torch.cat((x, concat_with), dim=1))
+
+
+class DecoderBN(nn.Module):
+    _SKIP_EXTRA = {2048: (64, 24, 16, 8), 1280: (0, 0, 0, 0)}  # B5 / B1 skip widths differ from the B1 defaults
+
+    def __init__(self, num_features=2048, num_classes=1, bottleneck_features=2048, mode="AdaBins"):
+        super().__init__()
+        f = int(num_features)
+        extra = self._SKIP_EXTRA[f]
+        self.conv2 = nn.Conv2d(bottleneck_features, f, kernel_size=1, stride=1, padding=1)
+        self.up1 = UpSampleBN(f + 112 + extra[0], f // 2)
+        self.up2 = UpSampleBN(f // 2 + 40 + extra[1], f // 4)
+        self.up3 = UpSampleBN(f // 4 + 24 + extra[2], f // 8)
+        self.up4 = UpSampleBN(f // 8 + 16 + extra[3], f // 16)
+        self.mode = mode
+        self.conv3 = nn.Conv2d(f // 16, num_classes if mode == "AdaBins" else 1, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, features):
+        s0, s1, s2, s3, bottleneck = features[4], features[5], features[6], features[8], features[11]
+        y = self.conv2(bottleneck)
+        for up, skip in ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0)):
+            y = up(y, skip)
+        return self.conv3(y)
+
+
+class Encoder(nn.Module):
+    """Walks the backbone's children in order and records every intermediate (the decoder indexes the list)."""
+
+    def __init__(self, backend):
+        super().__init__()
+        self.original_model = backend
+
+    def forward(self, x):
+        feats = [x]
+        for name, child in self.original_model._modules.items():
+            stages = child._modules.values() if name == 'blocks' else (child,)
+            for stage in stages:
+                feats.append(stage(feats[-1]))
+        return feats
+
+
+def _mlp(cin):
+    return nn.Sequential(nn.Conv2d(cin, 10, kernel_size=1), nn.ReLU(), nn.Conv2d(10, 10, kernel_size=1), nn.ReLU())
+
+
+class UnetAdaptiveBins(nn.Module):
+    def __init__(self, backend, n_bins=100, min_val=0.1, max_val=10, norm='linear', encoder_name="efficientnet-b5",
+                 semantics_mode=None, instance_segmentation_mode=None, insertion_point="before-attn", image="rgb"):
+        super().__init__()
+        self.num_classes = n_bins
+        self.min_val = min_val
+        self.max_val = max_val
+        self.encoder = Encoder(backend)
+        self.semantics_mode = semantics_mode
+        self.instance_segmentation_mode = instance_segmentation_mode
+        self.insertion_point = insertion_point
+        self.image = image
+        self.encoder_name = encoder_name
+        self.image_pre_encode = None
+        self.fused_head = True  # False: range attention -> conv1x1 -> streaming bins (three kernels)
+
+        self.num_decoded_channels = 128
+        extra = UnetAdaptiveBins.get_num_channels_to_add(encoder_name, semantics_mode, instance_segmentation_mode, image)
+        if insertion_point == "before-attn":
+            self.num_decoded_channels += extra
+
+        if semantics_mode is not None:
+            if semantics_mode == "glove-25d-inst-areas":
+                self.semantics_areas_fc = _mlp(1)
+            if "human-sizes" in semantics_mode:
+                self.semantics_absolute_sizes_fc = _mlp(3)
+        if instance_segmentation_mode is not None:
+            self.instance_areas_fc = _mlp(1)
+            if "human_sizes" in instance_segmentation_mode:
+                self.instance_absolute_sizes_fc = _mlp(3)
+
+        adabins = "noAdaBins" not in encoder_name
+        if adabins:
+            self.adaptive_bins_layer = mViT(self.num_decoded_channels, n_query_channels=128, patch_size=16,
+                                            dim_out=n_bins, embedding_dim=128, norm=norm)
+        if "efficientnet-b5" in encoder_name:
+            self.decoder = DecoderBN(num_classes=128, num_features=2048, bottleneck_features=2048)
+        elif "efficientnet-b1" in encoder_name:
+            self.decoder = DecoderBN(num_classes=128, num_features=1280, bottleneck_features=1280,
+                                     mode="AdaBins" if adabins else "noAdaBins")
+        if adabins:
+            self.conv_out = nn.Sequential(nn.Conv2d(128, n_bins, kernel_size=1, stride=1, padding=0), nn.Softmax(dim=1))
+
+    # ---- external-info insertion -------------------------------------------------------------------------------
+    @staticmethod
+    def _run_mlp(seq, x, in_div, out):
+        return ops.aux_mlp(x, seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, in_div=in_div, out=out)
+
+    def _external_channels(self, semantics, instance_labels, instance_areas, hw):
+        """The channel groups the reference concatenates (unet_adaptive_bins.py:194-228 / :244-282), in order, as
+        ("copy", tensor) or ("mlp", module, input tensor, divisor) items."""
+        items = []
+        if semantics is not None:
+            if self.semantics_mode == "glove-25d-inst-areas":
+                items.append(("copy", semantics[:, 0:25]))
+                items.append(("mlp", self.semantics_areas_fc, semantics[:, 25:26], 1.0))
+            elif "human-sizes" in self.semantics_mode:
+                items.append(("copy", semantics[:, 0:-3]))
+                items.append(("mlp", self.semantics_absolute_sizes_fc, semantics[:, -3:], 1.0))
+            else:
+                items.append(("copy", semantics))
+        if instance_labels is not None:
+            items.append(("copy", instance_labels))
+        if instance_areas is not None:
+            if "human_sizes" in self.instance_segmentation_mode:
+                items.append(("mlp", self.instance_areas_fc, instance_areas[:, 0:1], float(hw)))
+                items.append(("mlp", self.instance_absolute_sizes_fc, instance_areas[:, 1:4], 1.0))
+            else:
+                items.append(("mlp", self.instance_areas_fc, instance_areas, float(hw)))
+        return items
+
+    def _concat_external(self, x, items):
+        """One allocation for the widened tensor; pass-through groups are copied (with the .float() cast fused into
+        the copy), MLP groups are written in place by the streaming kernel."""
+        if not items:
+            return x
+        widths = [it[1].shape[1] if it[0] == "copy" else 10 for it in items]
+        b, c, h, w = x.shape
+        out = torch.empty((b, c + sum(widths), h, w), dtype=torch.float32, device=x.device)
+        out[:, :c].copy_(x)
+        ch = c
+        for it, wd in zip(items, widths):
+            dst = out[:, ch:ch + wd]
+            if it[0] == "copy":
+                dst.copy_(it[1])
+            else:
+                self._run_mlp(it[1], it[2], it[3], dst)
+            ch += wd
+        return out
+
+    # ---- head -------------------------------------------------------------------------------------------------
+    def _head(self, unet_out):
+        head = self.adaptive_bins_layer
+        conv = self.conv_out[0]
+        tgt, feat = head.tokens_and_features(unet_out)
+        _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
+        queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)  # [N, 128, E] view
+        if self.fused_head and ops.head_chain_supported(feat, self.num_classes):
+            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries)
+            pred = ops.head_chain(feat, wf, biasf, centers)
+        else:
+            ram = ops.range_attention(feat, queries)
+            pred = ops.bins_pred(ops.conv1x1(ram, conv.weight, conv.bias), centers)
+        return bin_edges, pred
+
+    def forward(self, x, semantics=None, instance_labels=None, instance_areas=None, **kwargs):
+        if self.insertion_point == "input":
+            items = self._external_channels(semantics, instance_labels, instance_areas, x.shape[2] * x.shape[3])
+            x = self._concat_external(x, items)
+        if self.image == "none":
+            if x.shape[1] <= 3:
+                sys.exit("Error: Add more auxiliary information at input if using no image")
+            x = x[:, 3:, :, :]
+
+        unet_out = self.decoder(self.encoder(x), **kwargs)
+
+        if "noAdaBins" in self.encoder_name:
+            return None, ops.relu_eps(unet_out, 0.0001)
+
+        if self.insertion_point == "before-attn":
+            size = unet_out.shape[-2:]
+            near = lambda t: None if t is None else F.interpolate(t, size=size, mode='nearest').float()
+            # NB: the reference's human-sizes branch here concatenates onto x instead of unet_out (a bug that makes
+            # that mode unusable, unet_adaptive_bins.py:253-259); this implementation concatenates onto unet_out.
+            items = self._external_channels(near(semantics), near(instance_labels), near(instance_areas),
+                                            x.shape[2] * x.shape[3])
+            unet_out = self._concat_external(unet_out, items)
+
+        return self._head(unet_out)
+
+    def get_1x_lr_params(self):  # lr/10 learning rate
+        return self.encoder.parameters()
+
+    def get_10x_lr_params(self):  # lr learning rate
+        modules = [self.decoder] if "noAdaBins" in self.encoder_name else \
+            [self.decoder, self.adaptive_bins_layer, self.conv_out]
+        for m in modules:
+            yield from m.parameters()
+
+    @classmethod
+    def build(cls, n_bins, encoder_name="efficientnet-b5", insertion_point="before-attn", **kwargs):
+        """Same call as the reference's build() (:315-360).  The backbone is the offline geffnet-shaped generator of
+        models/efficientnet.py (random init; a geffnet ``tf_efficientnet_b{1,5}_ap`` state_dict loads into it)."""
+        if "efficientnet-b5" in encoder_name:
+            basemodel_name = 'tf_efficientnet_b5_ap'
+        elif "efficientnet-b1" in encoder_name:
+            basemodel_name = 'tf_efficientnet_b1_ap'
+        else:
+            sys.exit("Error [models/unet_adaptive_bins.py]: encoder not recognised")
+        basemodel = build_backbone(basemodel_name)
+        basemodel.global_pool = nn.Identity()
+        basemodel.classifier = nn.Identity()
+
+        if insertion_point == "input":
+            extra = UnetAdaptiveBins.get_num_channels_to_add(
+                encoder_name=encoder_name, semantics_mode=kwargs.get('semantics_mode'),
+                instance_segmentation_mode=kwargs.get('instance_segmentation_mode'), image=kwargs.get('image', 'rgb'))
+            stem = basemodel.conv_stem
+            rgb_weights = stem.weight.detach().clone()
+            keep_rgb = kwargs.get('image', 'rgb') != "none"
+            if not keep_rgb and extra < 1:
+                sys.exit("Too few input channels - add more inputs")
+            # the reference hard-codes 32 stem filters here (:345); B5's 48 would not fit the next layer
+            new_stem = Conv2dSame((3 if keep_rgb else 0) + extra, 32, kernel_size=(3, 3), stride=(2, 2), bias=False)
+            if keep_rgb and rgb_weights.shape[0] == 32:
+                with torch.no_grad():
+                    new_stem.weight[:, 0:3] = rgb_weights
+            basemodel.conv_stem = new_stem
+
+        return cls(basemodel, n_bins=n_bins, encoder_name=encoder_name, insertion_point=insertion_point, **kwargs)
+
+    @staticmethod
+    def get_num_channels_to_add(encoder_name, semantics_mode, instance_segmentation_mode, image):
+        """Channel bookkeeping of the reference (:363-395): returns how many channels the external info adds."""
+        n = 0
+        if semantics_mode is not None:
+            if "raw" in semantics_mode:
+                n += 1
+            elif semantics_mode == "glove":
+                n += 300
+            elif "glove-25d" in semantics_mode:
+                n += 25
+            else:
+                sys.exit("Error [models/unet_adaptive_bins.py]: semantics mode not recognised")
+            n += 10 * (("inst-areas" in semantics_mode) + ("human-sizes" in semantics_mode))
+        if instance_segmentation_mode is not None:
+            if instance_segmentation_mode == "raw":
+                n += 1
+            elif instance_segmentation_mode == "coco" or "ade20k_swin" in instance_segmentation_mode:
+                n += 35  # 25 embedding channels + 10 from the area MLP
+            if "human_sizes" in instance_segmentation_mode:
+                n += 10
+        return n

@@ -1,0 +1,346 @@
+"""Thin Python layer over the C ABI (include/mde_b200.h): tensor checks, stream plumbing, autograd glue.
+
+Every function here launches hand-written sm_100a kernels from libmde_b200.so on torch's current CUDA stream.
+Inputs must be CUDA tensors; nothing here computes on the CPU or through a PyTorch substitute.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+LOG2E = 1.4426950408889634
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MdeError("mde_b200 operators take CUDA tensors only (no CPU fallback exists)")
+
+
+def launch_count():
+    return int(_lib.load(False).mde_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# K3: gathers
+# ------------------------------------------------------------------------------------------------------------
+def gather_embed(labels, table, background=None, write_back=False, out=None, table_image_stride=0):
+    """labels int64 [B,1,H,W]; table [rows,D] (f32/f64, CUDA) -> [B,D,H,W] of table.dtype.
+    background: clamp target for labels outside [0,rows-1] (None = no clamp; out-of-range raises IndexError like
+    the reference's index_select).  write_back=True stores the clamped labels into ``labels`` (the reference clamps
+    the batch tensor in place: SemanticsLoader.py:115-118)."""
+    lib = _lib.load()
+    _need_cuda(labels, table)
+    if labels.dtype != torch.int64 or labels.dim() != 4 or labels.shape[1] != 1 or not labels.is_contiguous():
+        raise ValueError("labels must be a contiguous int64 [B,1,H,W] tensor")
+    if table.dtype not in (torch.float32, torch.float64) or not table.is_contiguous():
+        raise ValueError("table must be contiguous float32/float64")
+    b, _, h, w = labels.shape
+    if table_image_stride:
+        rows, d = table.shape[1], table.shape[2]
+    else:
+        rows, d = table.shape
+    if out is None:
+        out = torch.empty((b, d, h, w), dtype=table.dtype, device=labels.device)
+    flag = None
+    if background is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=labels.device)
+    rc = lib.mde_gather_embed(_p(labels), _p(labels) if write_back else None, _p(table), _p(out), b, h * w, rows, d,
+                              -1 if background is None else int(background),
+                              0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
+    _lib.check(rc, "mde_gather_embed")
+    if flag is not None and int(flag.item()) != 0:
+        raise IndexError("index out of range in label gather (table has %d rows)" % rows)
+    return out
+
+
+def class_area_fraction(labels, rows):
+    """SemanticsLoader.get_semantics_inst_areas: float64 [B,1,H,W] of per-image class pixel fractions."""
+    lib = _lib.load()
+    _need_cuda(labels)
+    b, _, h, w = labels.shape
+    counts = torch.empty((b, rows), dtype=torch.int32, device=labels.device)
+    frac = torch.empty((b, rows, 1), dtype=torch.float64, device=labels.device)
+    _lib.check(lib.mde_class_area_table(_p(labels), b, h * w, rows, _p(counts), _p(frac), _s()), "mde_class_area_table")
+    return gather_embed(labels, frac, background=None, table_image_stride=rows)
+
+
+def cast_i64_f32(x):
+    lib = _lib.load()
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _lib.check(lib.mde_cast_i64_f32(_p(x), _p(out), x.numel(), _s()), "mde_cast_i64_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# A3: per-pixel MLP
+# ------------------------------------------------------------------------------------------------------------
+def _plane_view_ok(t):
+    b, c, h, w = t.shape
+    return t.stride(3) == 1 and t.stride(2) == w and t.stride(1) == h * w
+
+
+def _aux_mlp_launch(x, w0, b0, w1, b1, in_div, out):
+    lib = _lib.load()
+    b, c, h, w = x.shape
+    rc = lib.mde_aux_mlp_fwd(_p(x), x.stride(0), _p(w0), _p(b0), _p(w1), _p(b1), _p(out), out.stride(0), b, c,
+                             w0.shape[0], w1.shape[0], h * w, float(in_div), _s())
+    _lib.check(rc, "mde_aux_mlp_fwd")
+    return out
+
+
+class _AuxMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, in_div):
+        b, c, h, w = x.shape
+        out = torch.empty((b, w1.shape[0], h, w), dtype=torch.float32, device=x.device)
+        _aux_mlp_launch(x, w0, b0, w1, b1, in_div, out)
+        ctx.save_for_backward(x, w0, b0, w1, b1)
+        ctx.in_div = float(in_div)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        x, w0, b0, w1, b1 = ctx.saved_tensors
+        b, c, h, w = x.shape
+        if not _plane_view_ok(gout):
+            gout = gout.contiguous()
+        gw0, gb0, gw1, gb1 = (torch.zeros_like(t) for t in (w0, b0, w1, b1))
+        rc = lib.mde_aux_mlp_bwd(_p(x), x.stride(0), _p(w0), _p(b0), _p(w1), _p(b1), _p(gout), gout.stride(0), None,
+                                 _p(gw0), _p(gb0), _p(gw1), _p(gb1), b, c, w0.shape[0], w1.shape[0], h * w, ctx.in_div,
+                                 _s())
+        _lib.check(rc, "mde_aux_mlp_bwd")
+        return None, gw0, gb0, gw1, gb1, None
+
+
+def aux_mlp(x, w0, b0, w1, b1, in_div=1.0, out=None):
+    """relu(conv1x1(relu(conv1x1(x / in_div)))) with conv weights [10,C,1,1] / [10,10,1,1] (or 2-D).
+    ``out`` (a channel slice of a contiguous NCHW tensor) is only honoured when no gradient is being recorded."""
+    _need_cuda(x, w0, b0, w1, b1)
+    if x.dtype != torch.float32 or not _plane_view_ok(x):
+        x = x.float().contiguous()
+    w0f, w1f = w0.reshape(w0.shape[0], -1).contiguous(), w1.reshape(w1.shape[0], -1).contiguous()
+    b0, b1 = b0.contiguous(), b1.contiguous()
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (w0, b0, w1, b1))
+    if not needs_grad:
+        if out is None:
+            out = torch.empty((x.shape[0], w1f.shape[0], x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
+        elif not _plane_view_ok(out):
+            raise ValueError("out must be a channel slice of a contiguous NCHW tensor")
+        return _aux_mlp_launch(x, w0f.detach(), b0.detach(), w1f.detach(), b1.detach(), in_div, out)
+    res = _AuxMlp.apply(x, w0f, b0, w1f, b1, in_div)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# regressor + bins
+# ------------------------------------------------------------------------------------------------------------
+_NORM = {"linear": 0, "softmax": 1, "sigmoid": 2}
+
+
+def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val):
+    """t0 [B,E] (rows may be strided) -> (widths_normed [B,n], edges [B,n+1], centers [B,n], y_raw [B,n])."""
+    lib = _lib.load()
+    _need_cuda(t0, w1, w2, w3)
+    if t0.stride(1) != 1:
+        t0 = t0.contiguous()
+    b, e = t0.shape
+    hdim, n = w1.shape[0], w3.shape[0]
+    dev = t0.device
+    y_raw = torch.empty((b, n), dtype=torch.float32, device=dev)
+    wn = torch.empty((b, n), dtype=torch.float32, device=dev)
+    edges = torch.empty((b, n + 1), dtype=torch.float32, device=dev)
+    centers = torch.empty((b, n), dtype=torch.float32, device=dev)
+    rc = lib.mde_regressor_bins_fwd(_p(t0), t0.stride(0), _p(w1.contiguous()), _p(b1.contiguous()), _p(w2.contiguous()),
+                                    _p(b2.contiguous()), _p(w3.contiguous()), _p(b3.contiguous()), b, e, hdim, n,
+                                    _NORM.get(norm, 2), float(min_val), float(max_val), _p(y_raw), _p(wn), _p(edges),
+                                    _p(centers), _s())
+    _lib.check(rc, "mde_regressor_bins_fwd")
+    return wn, edges, centers, y_raw
+
+
+# ------------------------------------------------------------------------------------------------------------
+# range attention / conv_out / bins
+# ------------------------------------------------------------------------------------------------------------
+def round_tf32(x):
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(lib.mde_round_tf32(_p(x), _p(out), x.numel(), _s()), "mde_round_tf32")
+    return out
+
+
+def range_attention(x, queries, impl="auto"):
+    """y[b,n,h,w] = sum_k x[b,k,h,w] * queries[b,n,k]  (PixelWiseDotProduct).  impl: 'simt' (fp32 FMA),
+    'tc' (TMA + tcgen05 TF32) or 'auto' (tc when the shape allows)."""
+    lib = _lib.load()
+    _need_cuda(x, queries)
+    x = x.contiguous().float()
+    queries = queries.contiguous().float()
+    b, k, h, w = x.shape
+    n = queries.shape[1]
+    p = h * w
+    tc_ok = (p % 128 == 0) and k == 128 and n == 128
+    if impl == "auto":
+        impl = "tc" if tc_ok else "simt"
+    if impl == "tc" and not tc_ok:
+        raise _lib.MdeError("tcgen05 range attention needs K = N = 128 and h*w % 128 == 0")
+    y = torch.empty((b, n, h, w), dtype=torch.float32, device=x.device)
+    q = round_tf32(queries) if impl == "tc" else queries
+    rc = lib.mde_range_attention(_p(x), _p(q), _p(y), b, k, n, p, 1 if impl == "tc" else 0, _s())
+    _lib.check(rc, "mde_range_attention")
+    return y
+
+
+def conv1x1(ram, weight, bias):
+    """logits[b,j,h,w] = bias[j] + sum_n weight[j,n] ram[b,n,h,w]   (conv_out's Conv2d(128,n_bins,1), SIMT fp32)."""
+    lib = _lib.load()
+    ram = ram.contiguous()
+    b, k, h, w = ram.shape
+    wt = weight.reshape(weight.shape[0], -1).contiguous()
+    out = torch.empty((b, wt.shape[0], h, w), dtype=torch.float32, device=ram.device)
+    rc = lib.mde_conv1x1_fwd(_p(ram), _p(wt), _p(bias.contiguous()) if bias is not None else None, _p(out), b, k,
+                             wt.shape[0], h * w, _s())
+    _lib.check(rc, "mde_conv1x1_fwd")
+    return out
+
+
+def bins_pred(logits, centers):
+    """pred[b,0,h,w] = sum_j softmax_j(logits[b,:,h,w]) * centers[b,j]  (streaming K2 kernel)."""
+    lib = _lib.load()
+    logits = logits.contiguous()
+    b, n, h, w = logits.shape
+    pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.mde_bins_pred_fwd(_p(logits), _p(centers.contiguous()), _p(pred), b, n, h * w, _s()),
+               "mde_bins_pred_fwd")
+    return pred
+
+
+def fold_queries(w_out, bias, queries):
+    """wf[b] = tf32(log2e * w_out @ queries[b]) [B,n_bins,K];  biasf = log2e * bias.  queries [B,N,K] (strided ok)."""
+    lib = _lib.load()
+    wt = w_out.reshape(w_out.shape[0], -1).contiguous()
+    n_bins, n = wt.shape
+    if queries.stride(2) != 1 or queries.stride(1) != queries.shape[2]:
+        queries = queries.contiguous()
+    b, _, k = queries.shape
+    wf = torch.empty((b, n_bins, k), dtype=torch.float32, device=queries.device)
+    biasf = torch.empty((n_bins,), dtype=torch.float32, device=queries.device)
+    rc = lib.mde_fold_queries(_p(wt), _p(bias.contiguous()), _p(queries), queries.stride(0), _p(wf), _p(biasf), b, n_bins,
+                              n, k, _s())
+    _lib.check(rc, "mde_fold_queries")
+    return wf, biasf
+
+
+def head_chain(x, wf, biasf, centers):
+    """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x [B,128,h,w] -> [B,1,h,w]."""
+    lib = _lib.load()
+    x = x.contiguous()
+    b, k, h, w = x.shape
+    pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
+    rc = lib.mde_head_chain_fwd(_p(x), _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b, wf.shape[1], h * w, _s())
+    _lib.check(rc, "mde_head_chain_fwd")
+    return pred
+
+
+def head_chain_supported(x, n_bins):
+    return x.shape[1] == 128 and n_bins == 256 and (x.shape[2] * x.shape[3]) % 128 == 0
+
+
+def relu_eps(x, eps=1e-4):
+    lib = _lib.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(lib.mde_relu_eps_fwd(_p(x), _p(y), x.numel(), float(eps), _s()), "mde_relu_eps_fwd")
+    return y
+
+
+# ------------------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------------------
+class _SILog(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, interpolate):
+        lib = _lib.load()
+        b, _, h, w = pred.shape
+        hh, ww = target.shape[-2:]
+        ws = torch.empty(int(lib.mde_silog_ws_bytes()), dtype=torch.uint8, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        rc = lib.mde_silog_fwd(_p(pred), _p(target), _p(mask), b, h, w, hh, ww, 1 if interpolate else 0, _p(ws), _p(loss),
+                               _s())
+        _lib.check(rc, "mde_silog_fwd")
+        ctx.save_for_backward(pred, target, mask, ws)
+        ctx.interpolate = interpolate
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        pred, target, mask, ws = ctx.saved_tensors
+        b, _, h, w = pred.shape
+        hh, ww = target.shape[-2:]
+        gp = torch.empty_like(pred)
+        g = g.contiguous().float()
+        rc = lib.mde_silog_bwd(_p(pred), _p(target), _p(mask), b, h, w, hh, ww, 1 if ctx.interpolate else 0, _p(ws),
+                               _p(g), _p(gp), _s())
+        _lib.check(rc, "mde_silog_bwd")
+        return gp, None, None, None
+
+
+def silog(pred, target, mask=None, interpolate=True):
+    _need_cuda(pred, target, mask)
+    if pred.dim() != 4 or pred.shape[1] != 1 or target.dim() != 4 or target.shape[1] != 1:
+        raise ValueError("silog expects pred [B,1,h,w] and target [B,1,H,W]")
+    if mask is not None:
+        if mask.dtype != torch.bool and mask.dtype != torch.uint8:
+            raise ValueError("mask must be a bool tensor")
+        mask = mask.expand_as(target).contiguous()
+        mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    return _SILog.apply(pred.contiguous().float(), target.contiguous().float(), mask, bool(interpolate))
+
+
+class _Chamfer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, edges, target, min_target):
+        lib = _lib.load()
+        b, n1 = edges.shape
+        hw = target.numel() // b
+        ws = torch.empty(int(lib.mde_chamfer_ws_bytes(b, n1 - 1)), dtype=torch.uint8, device=edges.device)
+        loss = torch.empty((), dtype=torch.float32, device=edges.device)
+        rc = lib.mde_chamfer_fwd(_p(edges), _p(target), b, n1 - 1, hw, float(min_target), _p(ws), _p(loss), _s())
+        _lib.check(rc, "mde_chamfer_fwd")
+        ctx.save_for_backward(edges, ws)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        edges, ws = ctx.saved_tensors
+        b, n1 = edges.shape
+        ge = torch.empty_like(edges)
+        g = g.contiguous().float()
+        _lib.check(lib.mde_chamfer_bwd(_p(edges), b, n1 - 1, _p(ws), _p(g), _p(ge), _s()), "mde_chamfer_bwd")
+        return ge, None, None
+
+
+def bins_chamfer(edges, target_depth_maps, min_target=1e-3):
+    _need_cuda(edges, target_depth_maps)
+    if edges.dim() != 2 or target_depth_maps.shape[0] != edges.shape[0]:
+        raise ValueError("bins_chamfer expects edges [B,n_bins+1] and targets [B,...]")
+    return _Chamfer.apply(edges.contiguous().float(), target_depth_maps.contiguous().float(), min_target)
