@@ -110,12 +110,15 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
  * Requires P % 128 == 0, n_bins == 256. */
 int mde_head_chain_fwd(const float* x, const float* wf, const float* biasf, const float* centers, float* pred, int B,
                        int n_bins, int64_t P, mde_stream_t stream);
-/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e ),  biasf = bias * log2e   (fp32 FMA) */
+/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale ),  biasf = bias * log2e   (fp32 FMA).
+ * operand_scale = MDE_TF32_TRUNC_COMP compensates the mean mantissa loss of the OTHER operand, which the tensor
+ * core truncates (not rounds) to TF32 when it reads raw fp32 from shared memory; 1.0f disables it. */
+#define MDE_TF32_TRUNC_COMP 1.000352f
 int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride, float* wf,
-                     float* biasf, int B, int n_bins, int N, int K, mde_stream_t stream);
+                     float* biasf, int B, int n_bins, int N, int K, float operand_scale, mde_stream_t stream);
 
-/* out[i] = round-to-nearest TF32 of in[i] (so the tensor cores' operand truncation is exact for this tensor) */
-int mde_round_tf32(const float* in, float* out, int64_t n, mde_stream_t stream);
+/* out[i] = round-to-nearest TF32 of in[i]*scale (so the tensor cores' operand truncation is exact for this tensor) */
+int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stream_t stream);
 /* bring-up knobs for the UMMA shared-memory descriptors (bytes) and the last barrier-timeout code (0 = none;
  * synchronises the device).  Test/debug only. */
 int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version);

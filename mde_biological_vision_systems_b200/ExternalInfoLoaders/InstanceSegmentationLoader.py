@@ -21,6 +21,7 @@ class InstanceSegmentationLoader():
         self.background_class_num = None
         self.human_sizes = None
         self._dev_tables = {}
+        self.clamp_host_batch = False  # see SemanticsLoader: the clamp happens on the device copy
         self.set_embeddings_path()
         self.set_human_sizes_path()
         self.load_word_embeddings()
@@ -76,7 +77,7 @@ class InstanceSegmentationLoader():
         if self.human_sizes is not None:
             sizes = ops.gather_embed(raw, self._table("sizes", self.human_sizes, torch.float32), background=None)
             areas = torch.cat((areas, sizes), dim=1)
-        if isinstance(host_raw, torch.Tensor) and not host_raw.is_cuda:
+        if self.clamp_host_batch and isinstance(host_raw, torch.Tensor) and not host_raw.is_cuda:
             rows = self.word_embeddings_semantics.shape[0]
             host_raw[host_raw < 0] = bg
             host_raw[host_raw > rows - 1] = bg

@@ -39,6 +39,9 @@ class SemanticsLoader():
         self.word_embeddings_semantics = None  # float64 host tensor, as in the reference
         self.human_sizes = None
         self._dev_tables = {}
+        # The reference clamps batch['semantics'] in place on the host (SemanticsLoader.py:117-118).  Here the clamp runs
+        # on the GPU and the clamped map is what get_semantics returns; set this to also rewrite the caller's host tensor.
+        self.clamp_host_batch = False
         self.set_semantics_path()
         self.set_human_sizes_path()
         self.load_word_embeddings()
@@ -113,7 +116,7 @@ class SemanticsLoader():
         if self.human_sizes is not None:
             sizes = ops.gather_embed(raw, self._table("sizes", self.human_sizes, torch.float32), background=None)
             semantics = torch.cat((semantics, sizes), dim=1)
-        if places and isinstance(host_raw, torch.Tensor) and not host_raw.is_cuda:
+        if self.clamp_host_batch and places and isinstance(host_raw, torch.Tensor) and not host_raw.is_cuda:
             # mirror the reference's in-place clamp of the caller's batch tensor (SemanticsLoader.py:117-118)
             host_raw[host_raw > 100] = 100
             host_raw[host_raw < 0] = 100

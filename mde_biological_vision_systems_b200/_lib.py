@@ -31,8 +31,8 @@ SIGNATURES = {
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),
     "mde_head_chain_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
-    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _p]),
-    "mde_round_tf32": (_i32, [_p, _p, _i64, _p]),
+    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_round_tf32": (_i32, [_p, _p, _i64, _f32, _p]),
     "mde_tc_debug_config": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "mde_tc_last_error": (_i32, []),
     "mde_relu_eps_fwd": (_i32, [_p, _p, _i64, _f32, _p]),

@@ -290,7 +290,7 @@ __device__ __forceinline__ float tf32_rna(float v) {
 __global__ void __launch_bounds__(256) fold_queries_kernel(const float* __restrict__ w_out, const float* __restrict__ bias,
                                                            const float* __restrict__ q, long long qbs,
                                                            float* __restrict__ wf, float* __restrict__ biasf, int n_bins,
-                                                           int N, int K) {
+                                                           int N, int K, float operand_scale) {
   const float LOG2E = 1.4426950408889634f;
   const int b = blockIdx.y;
   const int j = blockIdx.x * 16 + (threadIdx.x >> 4);
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) fold_queries_kernel(const float* __restri
   for (int k = kl; k < K; k += 16) {
     float a = 0.f;
     for (int nn = 0; nn < N; ++nn) a = fmaf(wr[nn], qb[(long long)nn * K + k], a);
-    wf[((long long)b * n_bins + j) * K + k] = tf32_rna(a * LOG2E);
+    wf[((long long)b * n_bins + j) * K + k] = tf32_rna(a * LOG2E * operand_scale);
   }
   if (b == 0 && kl == 0) biasf[j] = bias[j] * LOG2E;
 }
@@ -370,11 +370,11 @@ int mde_range_attention(const float* x, const float* q, float* y, int B, int K, 
 }
 
 int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride, float* wf,
-                     float* biasf, int B, int n_bins, int N, int K, mde_stream_t stream) {
+                     float* biasf, int B, int n_bins, int N, int K, float operand_scale, mde_stream_t stream) {
   if (!w_out || !bias || !q || !wf || !biasf) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || B > 65535 || n_bins <= 0 || N <= 0 || K <= 0) return MDE_ERR_BAD_SHAPE;
   fold_queries_kernel<<<dim3((unsigned)((n_bins + 15) / 16), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
-      w_out, bias, q, q_batch_stride, wf, biasf, n_bins, N, K);
+      w_out, bias, q, q_batch_stride, wf, biasf, n_bins, N, K, operand_scale);
   return check_launch();
 }
 

@@ -313,10 +313,10 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
   return check_launch();
 }
 
-__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned int r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i]));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(in[i] * scale));
     out[i] = __uint_as_float(r);
   }
 }
@@ -342,12 +342,12 @@ int mde_range_attention_tc(const float* x, const float* q, float* y, int B, int 
   return tc::launch_chain<128, tc::EPI_STORE>(x, q, nullptr, nullptr, y, B, P, st);
 }
 
-int mde_round_tf32(const float* in, float* out, int64_t n, mde_stream_t stream) {
+int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stream_t stream) {
   if (!in || !out) return MDE_ERR_BAD_POINTER;
   if (n <= 0) return n == 0 ? MDE_OK : MDE_ERR_BAD_SHAPE;
   long long g = (n + 255) / 256;
   if (g > MDE_NUM_SMS * 8) g = MDE_NUM_SMS * 8;
-  tc::round_tf32_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  tc::round_tf32_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(in, out, n, scale);
   return check_launch();
 }
 

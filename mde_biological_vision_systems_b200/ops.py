@@ -11,6 +11,9 @@ import torch
 from . import _lib
 
 LOG2E = 1.4426950408889634
+# mean relative mantissa loss of an fp32 value truncated to TF32 is 2^-11 * E[1/m] = 3.52e-4 (m log-uniform in [1,2));
+# the tensor core truncates the raw-fp32 activation operand, so the pre-rounded weight operand is scaled up by it
+TF32_TRUNC_COMP = 1.000352
 
 
 def _s():
@@ -29,6 +32,46 @@ def _need_cuda(*ts):
 
 def launch_count():
     return int(_lib.load(False).mde_launch_count())
+
+
+# Optional per-kernel CUDA-event timing (bench.py's roofline numbers are measured live with this, on the launching
+# stream): timing("head_chain") returns a context manager that records an event pair when enabled, else a no-op.
+_TIMING = {"on": False, "records": []}
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING["on"]:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING["on"]:
+            self.end.record()
+            _TIMING["records"].append((self.name, self.start, self.end))
+        return False
+
+
+def timing(name):
+    return _Timed(name)
+
+
+def enable_kernel_timing(on=True):
+    _TIMING["on"] = bool(on)
+    _TIMING["records"] = []
+
+
+def kernel_times_ms():
+    """name -> list of per-launch durations (ms); call after torch.cuda.synchronize()."""
+    out = {}
+    for name, s, e in _TIMING["records"]:
+        out.setdefault(name, []).append(s.elapsed_time(e))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -55,9 +98,10 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
     flag = None
     if background is None:
         flag = torch.zeros(1, dtype=torch.int32, device=labels.device)
-    rc = lib.mde_gather_embed(_p(labels), _p(labels) if write_back else None, _p(table), _p(out), b, h * w, rows, d,
-                              -1 if background is None else int(background),
-                              0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
+    with timing("gather_embed"):
+        rc = lib.mde_gather_embed(_p(labels), _p(labels) if write_back else None, _p(table), _p(out), b, h * w, rows, d,
+                                  -1 if background is None else int(background),
+                                  0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
     _lib.check(rc, "mde_gather_embed")
     if flag is not None and int(flag.item()) != 0:
         raise IndexError("index out of range in label gather (table has %d rows)" % rows)
@@ -178,11 +222,11 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val):
 # ------------------------------------------------------------------------------------------------------------
 # range attention / conv_out / bins
 # ------------------------------------------------------------------------------------------------------------
-def round_tf32(x):
+def round_tf32(x, scale=1.0):
     lib = _lib.load()
     x = x.contiguous()
     out = torch.empty_like(x)
-    _lib.check(lib.mde_round_tf32(_p(x), _p(out), x.numel(), _s()), "mde_round_tf32")
+    _lib.check(lib.mde_round_tf32(_p(x), _p(out), x.numel(), float(scale), _s()), "mde_round_tf32")
     return out
 
 
@@ -202,7 +246,7 @@ def range_attention(x, queries, impl="auto"):
     if impl == "tc" and not tc_ok:
         raise _lib.MdeError("tcgen05 range attention needs K = N = 128 and h*w % 128 == 0")
     y = torch.empty((b, n, h, w), dtype=torch.float32, device=x.device)
-    q = round_tf32(queries) if impl == "tc" else queries
+    q = round_tf32(queries, TF32_TRUNC_COMP) if impl == "tc" else queries
     rc = lib.mde_range_attention(_p(x), _p(q), _p(y), b, k, n, p, 1 if impl == "tc" else 0, _s())
     _lib.check(rc, "mde_range_attention")
     return y
@@ -227,12 +271,13 @@ def bins_pred(logits, centers):
     logits = logits.contiguous()
     b, n, h, w = logits.shape
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=logits.device)
-    _lib.check(lib.mde_bins_pred_fwd(_p(logits), _p(centers.contiguous()), _p(pred), b, n, h * w, _s()),
-               "mde_bins_pred_fwd")
+    with timing("bins_pred"):
+        rc = lib.mde_bins_pred_fwd(_p(logits), _p(centers.contiguous()), _p(pred), b, n, h * w, _s())
+    _lib.check(rc, "mde_bins_pred_fwd")
     return pred
 
 
-def fold_queries(w_out, bias, queries):
+def fold_queries(w_out, bias, queries, operand_scale=TF32_TRUNC_COMP):
     """wf[b] = tf32(log2e * w_out @ queries[b]) [B,n_bins,K];  biasf = log2e * bias.  queries [B,N,K] (strided ok)."""
     lib = _lib.load()
     wt = w_out.reshape(w_out.shape[0], -1).contiguous()
@@ -243,7 +288,7 @@ def fold_queries(w_out, bias, queries):
     wf = torch.empty((b, n_bins, k), dtype=torch.float32, device=queries.device)
     biasf = torch.empty((n_bins,), dtype=torch.float32, device=queries.device)
     rc = lib.mde_fold_queries(_p(wt), _p(bias.contiguous()), _p(queries), queries.stride(0), _p(wf), _p(biasf), b, n_bins,
-                              n, k, _s())
+                              n, k, float(operand_scale), _s())
     _lib.check(rc, "mde_fold_queries")
     return wf, biasf
 
@@ -254,7 +299,8 @@ def head_chain(x, wf, biasf, centers):
     x = x.contiguous()
     b, k, h, w = x.shape
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
-    rc = lib.mde_head_chain_fwd(_p(x), _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b, wf.shape[1], h * w, _s())
+    with timing("head_chain"):
+        rc = lib.mde_head_chain_fwd(_p(x), _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b, wf.shape[1], h * w, _s())
     _lib.check(rc, "mde_head_chain_fwd")
     return pred
 
@@ -282,8 +328,9 @@ class _SILog(torch.autograd.Function):
         hh, ww = target.shape[-2:]
         ws = torch.empty(int(lib.mde_silog_ws_bytes()), dtype=torch.uint8, device=pred.device)
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
-        rc = lib.mde_silog_fwd(_p(pred), _p(target), _p(mask), b, h, w, hh, ww, 1 if interpolate else 0, _p(ws), _p(loss),
-                               _s())
+        with timing("silog_fwd"):
+            rc = lib.mde_silog_fwd(_p(pred), _p(target), _p(mask), b, h, w, hh, ww, 1 if interpolate else 0, _p(ws),
+                                   _p(loss), _s())
         _lib.check(rc, "mde_silog_fwd")
         ctx.save_for_backward(pred, target, mask, ws)
         ctx.interpolate = interpolate
@@ -323,7 +370,8 @@ class _Chamfer(torch.autograd.Function):
         hw = target.numel() // b
         ws = torch.empty(int(lib.mde_chamfer_ws_bytes(b, n1 - 1)), dtype=torch.uint8, device=edges.device)
         loss = torch.empty((), dtype=torch.float32, device=edges.device)
-        rc = lib.mde_chamfer_fwd(_p(edges), _p(target), b, n1 - 1, hw, float(min_target), _p(ws), _p(loss), _s())
+        with timing("chamfer_fwd"):
+            rc = lib.mde_chamfer_fwd(_p(edges), _p(target), b, n1 - 1, hw, float(min_target), _p(ws), _p(loss), _s())
         _lib.check(rc, "mde_chamfer_fwd")
         ctx.save_for_backward(edges, ws)
         return loss

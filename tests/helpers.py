@@ -57,3 +57,11 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12)))
+
+
+def rel_stats(a, b):
+    """(max, 99.9th percentile) of the element-wise relative error."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    r = np.abs(a - b) / np.maximum(np.abs(b), 1e-12)
+    return float(r.max()), float(np.quantile(r, 0.999))

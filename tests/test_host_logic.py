@@ -1,0 +1,102 @@
+"""CPU: drop-in surface, state_dict contract, C-ABI exports, and 'no fallback' behaviour."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from mde_biological_vision_systems_b200 import _lib, ops
+from mde_biological_vision_systems_b200.loss import BinsChamferLoss, SILogLoss
+from mde_biological_vision_systems_b200.models import UnetAdaptiveBins
+
+from helpers import ROOT, make_model
+
+CASES = {
+    "b1_plain": dict(encoder_name="efficientnet-b1", insertion_point="input", semantics_mode=None,
+                     instance_segmentation_mode=None),
+    "b1_cfg3": dict(encoder_name="efficientnet-b1", insertion_point="input", semantics_mode="glove-25d",
+                    instance_segmentation_mode="ade20k_swin_human_sizes"),
+    "b1_areas_before_attn": dict(encoder_name="efficientnet-b1", insertion_point="before-attn",
+                                 semantics_mode="glove-25d-inst-areas", instance_segmentation_mode="coco"),
+    "b5_plain": dict(encoder_name="efficientnet-b5", insertion_point="before-attn", semantics_mode=None,
+                     instance_segmentation_mode=None),
+    "b1_noadabins": dict(encoder_name="efficientnet-b1-noAdaBins", insertion_point="input", semantics_mode=None,
+                         instance_segmentation_mode=None),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_state_dict_keys_match_reference(case, golden_state_keys):
+    m = make_model(**CASES[case])
+    mine = {k: "x".join(map(str, v.shape)) or "scalar" for k, v in m.state_dict().items() if not k.startswith("encoder.")}
+    assert mine == golden_state_keys[case]
+
+
+def test_num_channels_to_add():
+    f = UnetAdaptiveBins.get_num_channels_to_add
+    assert f("efficientnet-b1", "glove-25d-ade20k-places", None, "rgb") == 25          # config 2 -> 28 inputs
+    assert f("efficientnet-b1", "glove-25d", "ade20k_swin_human_sizes", "rgb") == 70   # config 3 -> 73 inputs
+    assert f("efficientnet-b1", "glove-25d-inst-areas", "coco", "rgb") == 70
+    assert f("efficientnet-b1", "glove", None, "rgb") == 300
+    assert f("efficientnet-b1", "raw", None, "rgb") == 1
+    assert f("efficientnet-b1", None, None, "rgb") == 0
+    with pytest.raises(SystemExit):
+        f("efficientnet-b1", "one-hot-ade20k-places", None, "rgb")
+
+
+def test_build_surface():
+    m = UnetAdaptiveBins.build(n_bins=256, min_val=1e-3, max_val=10, norm="linear", encoder_name="efficientnet-b1",
+                               semantics_mode="glove-25d-ade20k-places", instance_segmentation_mode=None,
+                               insertion_point="input", image="rgb")
+    assert m.encoder.original_model.conv_stem.weight.shape == (32, 28, 3, 3)
+    n1 = sum(p.numel() for p in m.get_1x_lr_params())
+    n10 = sum(p.numel() for p in m.get_10x_lr_params())
+    assert n1 + n10 == sum(p.numel() for p in m.parameters())
+    assert SILogLoss().name == "SILog" and BinsChamferLoss().name == "ChamferLoss"
+    # geffnet child order (the Encoder indexes features by position)
+    names = list(m.encoder.original_model._modules.keys())
+    assert names == ["conv_stem", "bn1", "act1", "blocks", "conv_head", "bn2", "act2", "global_pool", "classifier"]
+
+
+def test_backbone_feature_shapes():
+    """features [4],[5],[6],[8],[11] = 16/24/40/112/1280 channels at /2 /4 /8 /16 /32 for B1."""
+    m = make_model(**CASES["b1_plain"])
+    with torch.no_grad():
+        feats = m.encoder(torch.zeros(1, 3, 64, 96))
+    got = [(feats[i].shape[1], feats[i].shape[2], feats[i].shape[3]) for i in (4, 5, 6, 8, 11)]
+    assert got == [(16, 32, 48), (24, 16, 24), (40, 8, 12), (112, 4, 6), (1280, 2, 3)]
+    with torch.no_grad():
+        out = m.decoder(feats)
+    assert out.shape == (1, 128, 32, 48)
+
+
+def test_abi_exports_every_declared_symbol():
+    """Every function declared in include/mde_b200.h is exported by the built library and bound in _lib.py."""
+    header = open(os.path.join(ROOT, "include", "mde_b200.h")).read()
+    declared = set(re.findall(r"\b(mde_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load(check_device=False).mde_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Operators refuse CPU tensors / a box without a B200 instead of silently computing elsewhere."""
+    if torch.cuda.is_available():
+        pytest.skip("only meaningful on a CPU-only box")
+    with pytest.raises(_lib.MdeError):
+        ops.silog(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 8, 8))
+    with pytest.raises(_lib.MdeError):
+        SILogLoss()(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mde_biological_vision_systems_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} mentions the oracle"
