@@ -88,6 +88,16 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
                            int norm_mode, float min_val, float max_val, float* y_raw, float* widths_normed,
                            float* edges, float* centers, mde_stream_t stream);
 
+/* ---- K1b: one post-LN transformer encoder layer (models/layers.py:8-9,23: nn.TransformerEncoderLayer(128, 4, 1024),
+ * ReLU, eps 1e-5, eval semantics).  Tokens x, y are [S, NB, E] row-major (row = s*NB + n), E = 128, E/heads = 32.
+ * Parameter tensors keep torch's layouts: in_w [3E,E], out_w [E,E], l1_w [FF,E], l2_w [E,FF].
+ * ws: mde_encoder_layer_ws_floats(S,NB,E,FF) floats of scratch.  y may not alias x. */
+int64_t mde_encoder_layer_ws_floats(int S, int NB, int E, int FF);
+int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const float* in_b, const float* out_w,
+                          const float* out_b, const float* ln1_w, const float* ln1_b, const float* l1_w, const float* l1_b,
+                          const float* l2_w, const float* l2_b, const float* ln2_w, const float* ln2_b, float* ws, int S,
+                          int NB, int E, int heads, int FF, float eps, mde_stream_t stream);
+
 /* ---- K1d: range-attention contraction  y[b,n,p] = sum_k x[b,k,p] * q[b,n,k]  (layers.py:31-36) ----------
  * x [B,K,P] float32 (NCHW with P = h*w), q [B,N,K] float32, y [B,N,P] float32.
  * impl 0 = SIMT fp32 (exact fp32 FMA), impl 1 = TMA + tcgen05 TF32 (requires P % 128 == 0, K == 128, N % 16 == 0). */
@@ -126,6 +136,14 @@ int mde_tc_last_error(void);
 
 /* ---- A8': noAdaBins epilogue relu(x) + 1e-4 (unet_adaptive_bins.py:240-242) */
 int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_t stream);
+
+/* ---- "next" row (f)1: DecoderBN up-sampling step (models/unet_adaptive_bins.py:51-54): bilinear align_corners=True
+ * resize of x [B,C1,h,w] to HxW fused with torch.cat((up_x, skip [B,C2,H,W]), 1) -> out [B,C1+C2,H,W]. */
+int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B, int C1, int C2, int h, int w, int H,
+                            int W, mde_stream_t stream);
+/* gradient of the resize part: gout [B,Ctot,H,W] (first C1 channels read) -> gx [B,C1,h,w]; deterministic gather */
+int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
+                     mde_stream_t stream);
 
 /* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
  * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is

@@ -205,9 +205,18 @@ __global__ void __launch_bounds__(256) bins_pred_kernel(const float* __restrict_
 // pixel_gemm (SIMT fp32): y[b,n,p] = bias[n] + sum_k W[b*wbs + n*K + k] * x[b,k,p]
 // CTA tile 64 (n) x 128 (p), K step 16; 256 threads, each 8 n x 4 p.
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float v) {
+  unsigned int r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// EPI 0: y = acc + bias[n];  EPI 1: y = tf32_rna(acc * out_scale)  (operand preparation for the tensor-core chain)
+template <int EPI>
 __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                          long long wbs, const float* __restrict__ bias,
-                                                         float* __restrict__ y, int K, int N, long long P) {
+                                                         float* __restrict__ y, int K, int N, long long P,
+                                                         float out_scale) {
   __shared__ __align__(16) float sx[16][128];
   __shared__ float sw[16][64 + 1];
   const int b = blockIdx.z;
@@ -264,46 +273,29 @@ __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict
   for (int i = 0; i < 8; ++i) {
     const int n = n0 + tn * 8 + i;
     if (n >= N) continue;
-    const float bv = bias ? bias[n] : 0.f;
+    const float bv = (EPI == 0 && bias) ? bias[n] : 0.f;
     const long long p = p0 + tp * 4;
     float* dst = yb + (long long)n * P + p;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = EPI == 0 ? acc[i][j] + bv : tf32_rna(acc[i][j] * out_scale);
     if (p + 3 < P && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-      *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0] + bv, acc[i][1] + bv, acc[i][2] + bv, acc[i][3] + bv);
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (p + j < P) dst[j] = acc[i][j] + bv;
+        if (p + j < P) dst[j] = o[j];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// fold_queries: wf[b,j,k] = tf32_rna( log2e * sum_n w_out[j,n] * q[b,n,k] ),  biasf[j] = log2e * bias[j]
-// grid (n_bins/16, B); block 256: thread -> (j local 0..15, k group)   (tiny: 8.4 MFLOP per image)
+// fold_queries: wf[b,j,k] = tf32_rna( log2e * scale * sum_n w_out[j,n] * q[b,n,k] ) is pixel_gemm<1> with x := q[b]
+// viewed as [n][k] ("pixels" = k); biasf[j] = log2e * bias[j]
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float v) {
-  unsigned int r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
-
-__global__ void __launch_bounds__(256) fold_queries_kernel(const float* __restrict__ w_out, const float* __restrict__ bias,
-                                                           const float* __restrict__ q, long long qbs,
-                                                           float* __restrict__ wf, float* __restrict__ biasf, int n_bins,
-                                                           int N, int K, float operand_scale) {
-  const float LOG2E = 1.4426950408889634f;
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * 16 + (threadIdx.x >> 4);
-  const int kl = threadIdx.x & 15;
-  if (j >= n_bins) return;
-  const float* wr = w_out + (long long)j * N;
-  const float* qb = q + (long long)b * qbs;
-  for (int k = kl; k < K; k += 16) {
-    float a = 0.f;
-    for (int nn = 0; nn < N; ++nn) a = fmaf(wr[nn], qb[(long long)nn * K + k], a);
-    wf[((long long)b * n_bins + j) * K + k] = tf32_rna(a * LOG2E * operand_scale);
-  }
-  if (b == 0 && kl == 0) biasf[j] = bias[j] * LOG2E;
+__global__ void scale_bias_kernel(const float* __restrict__ bias, float* __restrict__ biasf, int n, float s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) biasf[i] = bias[i] * s;
 }
 
 }  // namespace mde
@@ -347,7 +339,7 @@ static int launch_pixel_gemm(const float* x, const float* W, int64_t wbs, const 
                              int N, int64_t P, cudaStream_t st) {
   if (B > 65535) return MDE_ERR_BAD_SHAPE;
   dim3 grid((unsigned)((P + 127) / 128), (unsigned)((N + 63) / 64), (unsigned)B);
-  pixel_gemm_kernel<<<grid, 256, 0, st>>>(x, W, wbs, bias, y, K, N, P);
+  pixel_gemm_kernel<0><<<grid, 256, 0, st>>>(x, W, wbs, bias, y, K, N, P, 1.f);
   return check_launch();
 }
 
@@ -373,8 +365,14 @@ int mde_fold_queries(const float* w_out, const float* bias, const float* q, int6
                      float* biasf, int B, int n_bins, int N, int K, float operand_scale, mde_stream_t stream) {
   if (!w_out || !bias || !q || !wf || !biasf) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || B > 65535 || n_bins <= 0 || N <= 0 || K <= 0) return MDE_ERR_BAD_SHAPE;
-  fold_queries_kernel<<<dim3((unsigned)((n_bins + 15) / 16), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
-      w_out, bias, q, q_batch_stride, wf, biasf, n_bins, N, K, operand_scale);
+  if (q_batch_stride != (int64_t)N * K) return MDE_ERR_BAD_SHAPE;  // q[b] must be a dense [N,K] block
+  cudaStream_t st = (cudaStream_t)stream;
+  const float LOG2E = 1.4426950408889634f;
+  dim3 grid((unsigned)((K + 127) / 128), (unsigned)((n_bins + 63) / 64), (unsigned)B);
+  pixel_gemm_kernel<1><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
+  int rc = check_launch();
+  if (rc) return rc;
+  scale_bias_kernel<<<(n_bins + 255) / 256, 256, 0, st>>>(bias, biasf, n_bins, LOG2E);
   return check_launch();
 }
 

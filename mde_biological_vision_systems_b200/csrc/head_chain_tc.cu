@@ -6,7 +6,8 @@
 // One persistent, warp-specialised kernel (1 CTA / SM, 224 threads):
 //   warp 0      TMA producer for the activation tiles  x[b, k, p0:p0+128]  (NCHW, so the pixel axis is contiguous:
 //               the A operand is MN-major).  A tile is 128 pixels x 128 channels fp32 = 64 KB, streamed as four
-//               32-channel stages of 16 KB (four 32-pixel x 32-channel SWIZZLE_128B boxes each) through an NS-deep ring.
+//               32-channel stages of 16 KB (four 32-pixel x 32-channel SWIZZLE_128B_ATOM_32B boxes each) through an
+//               NS-deep ring.
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M = 128 pixels, N = NB, K = 8 per instruction,
 //               16 instructions per tile), accumulating in TMEM; two TMEM accumulator buffers so the epilogue of tile
 //               i overlaps the MMAs of tile i+1.
@@ -38,7 +39,7 @@ enum { EPI_STORE = 0, EPI_SOFTMAX = 1 };
 struct DebugCfg {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, version;
 };
-static DebugCfg g_dbg = {4096, 1024, 16, 1024, 1};
+static DebugCfg g_dbg = {4096, 512, 16, 1024, 1};
 
 template <int NB>
 struct SmemPlan {
@@ -172,8 +173,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const uint32_t b_base = s_w + kc * (NB * 128);
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {
-            // A (MN-major, SW128): one 8-channel K-atom = 8 rows x 128 B = 1024 B; 32-pixel MN-atoms 4096 B apart
-            const uint64_t adesc = make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B, dbg.version);
+            // A (MN-major fp32/TF32 => "128B swizzle, 32B atom" layout, descriptor type 1): rows = channels (128 B =
+            // 32 pixels each), K-atom = 4 rows = 512 B (SBO), 32-pixel MN-atoms 4096 B apart (LBO); one MMA eats K = 8
+            // channels = 1024 B.  (Plain SWIZZLE_128B with an MN-major 32-bit operand silently yields zeros.)
+            const uint64_t adesc = make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B_32B, dbg.version);
             // B (K-major, SW128): 8 tf32 = 32 B along the 128-B swizzle row; 8-row atoms 1024 B apart
             const uint64_t bdesc = make_smem_desc(b_base + j * 32, dbg.b_lbo, dbg.b_sbo, SWZ_128B, dbg.version);
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
@@ -289,7 +292,7 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
     const uint64_t dims[3] = {(uint64_t)P, (uint64_t)KDIM, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)P * 4, (uint64_t)P * KDIM * 4};
     const uint32_t box[3] = {32, KC, 1};
-    if (!encode_f32(&mx, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+    if (!encode_f32(&mx, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return MDE_ERR_DRIVER;
   }
   {
     const uint64_t dims[3] = {(uint64_t)KDIM, (uint64_t)NB, (uint64_t)B};

@@ -119,8 +119,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 // ---- descriptors ---------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
-//   [46,48) version = 1 (sm_100) | [49,52) base offset | [52] LBO mode | [61,64) swizzle: 0 none, 2 128B, 4 64B, 6 32B
-constexpr uint32_t SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6;
+//   [46,48) version = 1 (sm_100) | [49,52) base offset | [52] LBO mode | [61,64) swizzle: 0 none, 1 128B/32B-atom, 2 128B, 4 64B, 6 32B
+// Measured on B200 (tools/tc_selftest.cu): K-major no-swizzle: LBO = k-core stride, SBO = 8-row-group stride;
+// K-major SW128: SBO = 1024 (8 rows x 128 B), start address += 32 B per K = 8 step; MN-major TF32 needs type 1.
+constexpr uint32_t SWZ_NONE = 0, SWZ_128B_32B = 1 /* 128B span, 32B atom: MN-major 32-bit operands */, SWZ_128B = 2,
+                   SWZ_64B = 4, SWZ_32B = 6;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swz,
                                                    uint32_t version = 1) {
   uint64_t d = 0;

@@ -1,0 +1,228 @@
+// K1b -- PatchTransformerEncoder layers (post-LN nn.TransformerEncoderLayer, d_model 128, 4 heads, FF 1024, ReLU).
+//
+// Reference: models/layers.py:8-9,23 (nn.TransformerEncoder of 4 default nn.TransformerEncoderLayer), eval semantics
+// (dropout is the identity).  Token layout is the reference's [S, N, E]: row index = s * N + n.
+// The sequence is short (S = 13*17 = 221 tokens/image) and the whole encoder is 0.68 GFLOP/image (3 % of the head),
+// so these are exact-fp32 SIMT kernels (the queries feed a softmax downstream, see DESIGN.md "precision"):
+//   linear_kernel      C = act(A W^T + b)            64x64x16 shared-memory tiles, 4x4 register blocking
+//   attention_kernel   softmax(Q K^T / sqrt(hd)) V   one CTA per (image, head), K and V resident in shared memory,
+//                                                    one warp per query row, lane == head-dim channel (hd = 32)
+//   add_layernorm_kernel  LN(x + y) * g + b          one warp per token row (E = 128 -> float4 per lane)
+#include "common.cuh"
+
+namespace mde {
+
+// C[m, n] = act( sum_k A[m*lda + k] * W[n*ldw + k] + bias[n] )
+template <int ACT>  // 0 none, 1 relu
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                                                     int ldw, const float* __restrict__ bias, float* __restrict__ C,
+                                                     int ldc, int M, int N, int K) {
+  __shared__ float sa[16][64 + 4];
+  __shared__ float sw[16][64 + 4];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each 4 (m) x 4 (n)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = threadIdx.x >> 2;        // 0..63 tile row
+  const int lk = (threadIdx.x & 3) * 4;   // 0,4,8,12
+  const bool vec = (K % 4 == 0) && (lda % 4 == 0) && (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float va[4] = {0.f, 0.f, 0.f, 0.f}, vw[4] = {0.f, 0.f, 0.f, 0.f};
+    const int gm = m0 + lr, gn = n0 + lr, gk = k0 + lk;
+    if (gm < M) {
+      if (vec && gk + 3 < K) {
+        const float4 t = *reinterpret_cast<const float4*>(A + (long long)gm * lda + gk);
+        va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (gk + i < K) va[i] = A[(long long)gm * lda + gk + i];
+      }
+    }
+    if (gn < N) {
+      if (vec && gk + 3 < K) {
+        const float4 t = *reinterpret_cast<const float4*>(W + (long long)gn * ldw + gk);
+        vw[0] = t.x; vw[1] = t.y; vw[2] = t.z; vw[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (gk + i < K) vw[i] = W[(long long)gn * ldw + gk + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sa[lk + i][lr] = va[i];
+      sw[lk + i][lr] = vw[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&sa[kk][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&sw[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (ACT == 1) v = fmaxf(v, 0.f);
+      C[(long long)m * ldc + n] = v;
+    }
+  }
+}
+
+// qkv [S*NB, 3E] (row = s*NB + n); out [S*NB, E].  grid (NB*heads, ceil(S/ROWS_PER_CTA)); dynamic smem: K,V [S][HD+1]
+template <int HD>
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int S,
+                                                        int NB, int E, int heads, float scale) {
+  extern __shared__ float smem_att[];
+  float* sk = smem_att;                      // [S][HD+1]
+  float* sv = sk + (size_t)S * (HD + 1);     // [S][HD+1]
+  float* sp = sv + (size_t)S * (HD + 1);     // [warps][S] probabilities
+  const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int ld = 3 * E;
+  for (int i = threadIdx.x; i < S * HD; i += blockDim.x) {
+    const int s = i / HD, d = i % HD;
+    const float* row = qkv + ((long long)s * NB + n) * ld + hh * HD + d;
+    sk[s * (HD + 1) + d] = row[E];
+    sv[s * (HD + 1) + d] = row[2 * E];
+  }
+  __syncthreads();
+  float* myp = sp + (size_t)warp * S;
+  const int rows_per_cta = (S + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
+  for (int i = r0 + warp; i < r1; i += nwarps) {
+    // every lane holds the whole (pre-scaled, as torch does: q / sqrt(hd)) query row
+    const float qd = qkv[((long long)i * NB + n) * ld + hh * HD + lane] * scale;
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = __shfl_sync(0xffffffffu, qd, d);
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) a = fmaf(q[d], sk[j * (HD + 1) + d], a);
+      myp[j] = a;
+      mx = fmaxf(mx, a);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float e = expf(myp[j] - mx);
+      myp[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o = 0.f;
+    for (int j = 0; j < S; ++j) o = fmaf(myp[j], sv[j * (HD + 1) + lane], o);
+    out[((long long)i * NB + n) * E + hh * HD + lane] = o / sum;
+    __syncwarp();
+  }
+}
+
+// out[m,:] = LayerNorm(x[m,:] + y[m,:]) * g + b ;  E == 128 (one float4 per lane)
+__global__ void __launch_bounds__(256) add_layernorm128_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                               const float* __restrict__ g, const float* __restrict__ b,
+                                                               float* __restrict__ out, int M, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4 a = reinterpret_cast<const float4*>(x + (long long)row * 128)[lane];
+  const float4 c = reinterpret_cast<const float4*>(y + (long long)row * 128)[lane];
+  float v[4] = {a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w};
+  float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / 128.f);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] -= mean;
+    var = fmaf(v[i], v[i], var);
+  }
+  var = warp_sum(var) * (1.f / 128.f);
+  const float rstd = rsqrtf(var + eps);
+  const float4 gg = reinterpret_cast<const float4*>(g)[lane];
+  const float4 bb = reinterpret_cast<const float4*>(b)[lane];
+  float4 o;
+  o.x = v[0] * rstd * gg.x + bb.x;
+  o.y = v[1] * rstd * gg.y + bb.y;
+  o.z = v[2] * rstd * gg.z + bb.z;
+  o.w = v[3] * rstd * gg.w + bb.w;
+  reinterpret_cast<float4*>(out + (long long)row * 128)[lane] = o;
+}
+
+static int launch_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
+                         int N, int K, int act, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (act == 1) linear_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
+  else linear_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
+  return check_launch();
+}
+
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+int64_t mde_encoder_layer_ws_floats(int S, int NB, int E, int FF) {
+  const int64_t M = (int64_t)S * NB;
+  return M * (3 * E + E + E + FF);
+}
+
+int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const float* in_b, const float* out_w,
+                          const float* out_b, const float* ln1_w, const float* ln1_b, const float* l1_w, const float* l1_b,
+                          const float* l2_w, const float* l2_b, const float* ln2_w, const float* ln2_b, float* ws, int S,
+                          int NB, int E, int heads, int FF, float eps, mde_stream_t stream) {
+  if (!x || !y || !in_w || !in_b || !out_w || !out_b || !ln1_w || !ln1_b || !l1_w || !l1_b || !l2_w || !l2_b || !ln2_w ||
+      !ln2_b || !ws)
+    return MDE_ERR_BAD_POINTER;
+  if (S <= 0 || NB <= 0 || E != 128 || heads <= 0 || E % heads != 0 || E / heads != 32 || FF <= 0) return MDE_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = S * NB;
+  float* qkv = ws;
+  float* att = qkv + (size_t)M * 3 * E;
+  float* tmp = att + (size_t)M * E;
+  float* ff = tmp + (size_t)M * E;
+  int rc;
+  if ((rc = launch_linear(x, E, in_w, E, in_b, qkv, 3 * E, M, 3 * E, E, 0, st))) return rc;
+  {
+    const int hd = E / heads;
+    const size_t sm = sizeof(float) * ((size_t)2 * S * (hd + 1) + (size_t)8 * S);
+    if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    int ysplit = (2 * MDE_NUM_SMS + NB * heads - 1) / (NB * heads);
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > (S + 7) / 8) ysplit = (S + 7) / 8;
+    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att, S, NB, E, heads, 1.0f / sqrtf((float)hd));
+    if ((rc = check_launch())) return rc;
+  }
+  if ((rc = launch_linear(att, E, out_w, E, out_b, tmp, E, M, E, E, 0, st))) return rc;
+  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, tmp, ln1_w, ln1_b, att, M, eps);  // att := LN1(x + sa)
+  if ((rc = check_launch())) return rc;
+  if ((rc = launch_linear(att, E, l1_w, E, l1_b, ff, FF, M, FF, E, 1, st))) return rc;
+  if ((rc = launch_linear(ff, FF, l2_w, FF, l2_b, tmp, E, M, E, FF, 0, st))) return rc;
+  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(att, tmp, ln2_w, ln2_b, y, M, eps);
+  return check_launch();
+}
+
+}  // extern "C"

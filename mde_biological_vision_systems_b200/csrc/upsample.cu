@@ -1,0 +1,137 @@
+// "Next" row (f)1 -- DecoderBN's up-sampling step: bilinear (align_corners=True) resize of x to the skip tensor's size
+// fused with the channel concatenation, forward and backward.
+//
+// Reference: UpSampleBN.forward (models/unet_adaptive_bins.py:51-54):
+//   up_x = F.interpolate(x, size=skip.shape[-2:], mode='bilinear', align_corners=True);  f = cat([up_x, skip], 1)
+// ATen's upsample_bilinear2d kernel takes 16.9 ms per step for the four decoder stages of config 2 (ncu launch list,
+// profiles/r1_launches_step.txt) -- half of the whole forward step; this kernel writes the concatenated tensor once at
+// HBM speed (one float4 store per 4 output pixels, the low-resolution source stays in L1/L2).
+#include "common.cuh"
+
+namespace mde {
+
+__device__ __forceinline__ void up_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  const float s = scale * (float)dst;  // ATen area_pixel_compute_source_index, align_corners=True
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+// grid: (ceil(H*W / (VEC*256)), C1 + C2, B)
+template <int VEC>
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                              float* __restrict__ out, int C1, int C2, int h, int w,
+                                                              int H, int W, float sy, float sx) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const long long HW = (long long)H * W;
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (p >= HW) return;
+  float* o = out + ((long long)b * (C1 + C2) + c) * HW + p;
+  if (c >= C1) {
+    const float* s = skip + ((long long)b * C2 + (c - C1)) * HW + p;
+    if (VEC == 4) stg_stream(reinterpret_cast<float4*>(o), ldg_stream(reinterpret_cast<const float4*>(s)));
+    else o[0] = s[0];
+    return;
+  }
+  const float* src = x + ((long long)b * C1 + c) * h * w;
+  const int y = (int)(p / W), x0p = (int)(p % W);
+  int y0, y1;
+  float ly0, ly1;
+  up_src(y, sy, h, y0, y1, ly0, ly1);
+  const float* r0 = src + y0 * w;
+  const float* r1 = src + y1 * w;
+  float v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    int xa, xb;
+    float lx0, lx1;
+    up_src(x0p + i, sx, w, xa, xb, lx0, lx1);
+    v[i] = ly0 * (lx0 * __ldg(r0 + xa) + lx1 * __ldg(r0 + xb)) + ly1 * (lx0 * __ldg(r1 + xa) + lx1 * __ldg(r1 + xb));
+  }
+  if (VEC == 4) stg_stream(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+  else o[0] = v[0];
+}
+
+// Backward of the resize part, gather form (deterministic, no atomics): one thread per low-res pixel sums the
+// contributions of the (<= ~3x3 for a 2x up-scale) high-res pixels whose bilinear taps include it.
+// gout: [B, C1 + C2, H, W] (only the first C1 channels are read); gx: [B, C1, h, w]
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int C1,
+                                                           int Ctot, int h, int w, int H, int W, float sy, float sx,
+                                                           float inv_sy, float inv_sx) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= h * w) return;
+  const int i = q / w, j = q % w;
+  const float* g = gout + ((long long)b * Ctot + c) * H * W;
+  // candidate output rows: those with source index in (i-1, i+1)
+  int Y0 = (int)floorf((float)(i - 1) * inv_sy) - 1, Y1 = (int)ceilf((float)(i + 1) * inv_sy) + 1;
+  int X0 = (int)floorf((float)(j - 1) * inv_sx) - 1, X1 = (int)ceilf((float)(j + 1) * inv_sx) + 1;
+  if (sy == 0.f) { Y0 = 0; Y1 = H - 1; }
+  if (sx == 0.f) { X0 = 0; X1 = W - 1; }
+  Y0 = max(Y0, 0); Y1 = min(Y1, H - 1); X0 = max(X0, 0); X1 = min(X1, W - 1);
+  float acc = 0.f;
+  for (int Y = Y0; Y <= Y1; ++Y) {
+    int y0, y1;
+    float ly0, ly1;
+    up_src(Y, sy, h, y0, y1, ly0, ly1);
+    float wy = 0.f;
+    if (y0 == i) wy += ly0;
+    if (y1 == i) wy += ly1;
+    if (wy == 0.f) continue;
+    float racc = 0.f;
+    for (int X = X0; X <= X1; ++X) {
+      int xa, xb;
+      float lx0, lx1;
+      up_src(X, sx, w, xa, xb, lx0, lx1);
+      float wx = 0.f;
+      if (xa == j) wx += lx0;
+      if (xb == j) wx += lx1;
+      if (wx != 0.f) racc = fmaf(wx, g[(long long)Y * W + X], racc);
+    }
+    acc = fmaf(wy, racc, acc);
+  }
+  gx[((long long)b * C1 + c) * h * w + q] = acc;
+}
+
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+static inline float up_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B, int C1, int C2, int h, int w, int H,
+                            int W, mde_stream_t stream) {
+  if (!x || !out || (C2 > 0 && !skip)) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C1 < 0 || C2 < 0 || C1 + C2 <= 0 || C1 + C2 > 65535 || B > 65535 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+    return MDE_ERR_BAD_SHAPE;
+  const float sy = up_scale(h, H), sx = up_scale(w, W);
+  const long long HW = (long long)H * W;
+  const bool vec = (W % 4 == 0) && aligned(out, 16) && (C2 == 0 || aligned(skip, 16));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    dim3 grid((unsigned)((HW / 4 + 255) / 256), (unsigned)(C1 + C2), (unsigned)B);
+    upsample_concat_kernel<4><<<grid, 256, 0, st>>>(x, skip, out, C1, C2, h, w, H, W, sy, sx);
+  } else {
+    dim3 grid((unsigned)((HW + 255) / 256), (unsigned)(C1 + C2), (unsigned)B);
+    upsample_concat_kernel<1><<<grid, 256, 0, st>>>(x, skip, out, C1, C2, h, w, H, W, sy, sx);
+  }
+  return check_launch();
+}
+
+int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
+                     mde_stream_t stream) {
+  if (!gout || !gx) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C1 <= 0 || C1 > Ctot || C1 > 65535 || B > 65535 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+    return MDE_ERR_BAD_SHAPE;
+  const float sy = up_scale(h, H), sx = up_scale(w, W);
+  dim3 grid((unsigned)((h * w + 255) / 256), (unsigned)C1, (unsigned)B);
+  upsample_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, C1, Ctot, h, w, H, W, sy, sx,
+                                                              sy > 0.f ? 1.f / sy : 0.f, sx > 0.f ? 1.f / sx : 0.f);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -23,10 +23,21 @@ class PatchTransformerEncoder(nn.Module):
                                            padding=0)
         self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
 
+    def _needs_autograd(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def forward(self, x):
         emb = self.embedding_convPxP(x).flatten(2)  # [N, E, S]
         emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
-        return self.transformer_encoder(emb.permute(2, 0, 1))  # [S, N, E]
+        tokens = emb.permute(2, 0, 1)  # [S, N, E]
+        if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0):
+            # training: dropout and the backward pass run through the stock torch layers (DESIGN.md "training")
+            return self.transformer_encoder(tokens)
+        ws = None
+        tokens = tokens.contiguous()
+        for layer in self.transformer_encoder.layers:
+            tokens, ws = ops.encoder_layer(tokens, layer, ws)
+        return tokens
 
 
 class PixelWiseDotProduct(nn.Module):

@@ -21,7 +21,8 @@ class mViT(nn.Module):
     # -- pieces shared by the reference-shaped forward() and the fused path of UnetAdaptiveBins ------------------
     def tokens_and_features(self, x):
         """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w])"""
-        tgt = self.patch_transformer(x.clone())
+        # the reference clones x first (miniViT.py:25); nothing below writes to x, so the 29 MB/img copy is skipped
+        tgt = self.patch_transformer(x)
         return tgt, self.conv3x3(x)
 
     def bin_widths(self, tgt, min_val=None, max_val=None):

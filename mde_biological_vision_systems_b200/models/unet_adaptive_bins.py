@@ -39,6 +39,8 @@ class UpSampleBN(nn.Module):
         self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
 
     def forward(self, x, concat_with):
+        if x.is_cuda:  # fused resize + concat kernel (ATen's align_corners bilinear kernel dominates the step otherwise)
+            return self._net(ops.upsample_concat(x, concat_with))
         x = F.interpolate(x, size=concat_with.shape[-2:], mode='bilinear', align_corners=True)
         return self._net(torch.cat((x, concat_with), dim=1))
 

@@ -95,6 +95,8 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
         rows, d = table.shape
     if out is None:
         out = torch.empty((b, d, h, w), dtype=table.dtype, device=labels.device)
+    if labels.numel() == 0:
+        return out
     flag = None
     if background is None:
         flag = torch.zeros(1, dtype=torch.int32, device=labels.device)
@@ -220,6 +222,32 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# transformer encoder layer
+# ------------------------------------------------------------------------------------------------------------
+def encoder_layer(x, layer, ws=None):
+    """One nn.TransformerEncoderLayer (post-LN, ReLU, eval semantics) on tokens x [S, N, E]; ``layer`` is the torch
+    module holding the parameters.  Returns a new [S, N, E] tensor."""
+    lib = _lib.load()
+    _need_cuda(x)
+    x = x.contiguous()
+    s, n, e = x.shape
+    a = layer.self_attn
+    ff = layer.linear1.out_features
+    need = int(lib.mde_encoder_layer_ws_floats(s, n, e, ff))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    with timing("encoder_layer"):
+        rc = lib.mde_encoder_layer_fwd(
+            _p(x), _p(y), _p(a.in_proj_weight), _p(a.in_proj_bias), _p(a.out_proj.weight), _p(a.out_proj.bias),
+            _p(layer.norm1.weight), _p(layer.norm1.bias), _p(layer.linear1.weight), _p(layer.linear1.bias),
+            _p(layer.linear2.weight), _p(layer.linear2.bias), _p(layer.norm2.weight), _p(layer.norm2.bias), _p(ws),
+            s, n, e, a.num_heads, ff, float(layer.norm1.eps), _s())
+    _lib.check(rc, "mde_encoder_layer_fwd")
+    return y, ws
+
+
+# ------------------------------------------------------------------------------------------------------------
 # range attention / conv_out / bins
 # ------------------------------------------------------------------------------------------------------------
 def round_tf32(x, scale=1.0):
@@ -282,8 +310,7 @@ def fold_queries(w_out, bias, queries, operand_scale=TF32_TRUNC_COMP):
     lib = _lib.load()
     wt = w_out.reshape(w_out.shape[0], -1).contiguous()
     n_bins, n = wt.shape
-    if queries.stride(2) != 1 or queries.stride(1) != queries.shape[2]:
-        queries = queries.contiguous()
+    queries = queries.contiguous()
     b, _, k = queries.shape
     wf = torch.empty((b, n_bins, k), dtype=torch.float32, device=queries.device)
     biasf = torch.empty((n_bins,), dtype=torch.float32, device=queries.device)
@@ -307,6 +334,35 @@ def head_chain(x, wf, biasf, centers):
 
 def head_chain_supported(x, n_bins):
     return x.shape[1] == 128 and n_bins == 256 and (x.shape[2] * x.shape[3]) % 128 == 0
+
+
+class _UpsampleConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip):
+        lib = _lib.load()
+        b, c1, h, w = x.shape
+        _, c2, hh, ww = skip.shape
+        out = torch.empty((b, c1 + c2, hh, ww), dtype=torch.float32, device=x.device)
+        with timing("upsample_concat"):
+            rc = lib.mde_upsample_concat_fwd(_p(x), _p(skip), _p(out), b, c1, c2, h, w, hh, ww, _s())
+        _lib.check(rc, "mde_upsample_concat_fwd")
+        ctx.shape = (b, c1, c2, h, w, hh, ww)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        b, c1, c2, h, w, hh, ww = ctx.shape
+        gout = gout.contiguous()
+        gx = torch.empty((b, c1, h, w), dtype=torch.float32, device=gout.device)
+        _lib.check(lib.mde_upsample_bwd(_p(gout), _p(gx), b, c1, c1 + c2, h, w, hh, ww, _s()), "mde_upsample_bwd")
+        return gx, gout[:, c1:]
+
+
+def upsample_concat(x, skip):
+    """cat((bilinear_align_corners(x -> skip's size), skip), dim=1) in one pass (DecoderBN's UpSampleBN input)."""
+    _need_cuda(x, skip)
+    return _UpsampleConcat.apply(x.contiguous().float(), skip.contiguous().float())
 
 
 def relu_eps(x, eps=1e-4):

@@ -45,8 +45,8 @@ def label_maps(b, h, w, seed=2, lo=-1, hi=100, inject=(-7, 101, 255, 1000), n_re
     for i in range(b):
         n = int(rng.integers(n_rect[0], n_rect[1] + 1))
         for r in range(1, n + 1):
-            hh = int(rng.integers(max(2, h // 20), max(3, h // 3)))
-            ww = int(rng.integers(max(2, w // 20), max(3, w // 3)))
+            hh = min(h, int(rng.integers(max(2, h // 20), max(3, h // 3))))
+            ww = min(w, int(rng.integers(max(2, w // 20), max(3, w // 3))))
             y0 = int(rng.integers(0, h - hh + 1))
             x0 = int(rng.integers(0, w - ww + 1))
             if inject and rng.random() < 0.1:

@@ -79,9 +79,9 @@ def test_instance_loader_golden(mode, golden_digests):
 
 
 def test_gather_full_size_and_ragged():
-    """Config 2 shape (B=16, 416x544) against the oracle, plus ragged sizes that take the scalar path."""
+    """Config 2 image size (416x544, 4 images to keep the CPU oracle quick) against the oracle, plus ragged sizes that take the scalar path."""
     table64 = load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy")
-    for (b, h, w) in [(16, 416, 544), (3, 37, 53), (1, 1, 1), (2, 5, 4)]:
+    for (b, h, w) in [(4, 416, 544), (3, 37, 53), (1, 1, 1), (2, 5, 4)]:
         lab, _ = synthetic.label_maps(b, h, w, seed=100 + h, n_rect=(1, 6) if h < 40 else (20, 60))
         raw_ref, ref = oracle.semantics_loader("glove-25d-ade20k-places", lab.numpy(), table64)
         labd = lab.to(DEV)
@@ -174,6 +174,16 @@ def test_input_insertion_golden(name, golden):
 def _head_state():
     m = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None)
     return m, {k: v for k, v in m.state_dict().items()}
+
+
+def test_patch_transformer_golden(golden):
+    """patch-embed + 4 encoder layers (our fp32 kernels) vs the reference module's tokens [S, N, E]."""
+    m, _ = _head_state()
+    m.to(DEV)
+    x = synthetic.decoder_features(2, 128, 176, 192, seed=21).to(DEV)
+    with torch.no_grad():
+        tgt = m.adaptive_bins_layer.patch_transformer(x.clone())
+    np.testing.assert_allclose(tgt.cpu().numpy(), golden["head/tgt"], rtol=1e-3, atol=2e-4)
 
 
 def test_regressor_bins(golden):
@@ -275,6 +285,25 @@ def test_full_model_golden(golden):
     with torch.no_grad():
         _, pred = m(x)
     assert_depth_close(pred.cpu(), golden["full/pred"], tf32=False)
+
+
+@pytest.mark.parametrize("shape", [((2, 5, 15, 19), (2, 3, 26, 34)), ((1, 4, 13, 17), (1, 2, 27, 35)), ((2, 3, 8, 8), (2, 1, 8, 8))])
+def test_upsample_concat_forward_backward(shape):
+    """DecoderBN up-sampling step vs F.interpolate(bilinear, align_corners=True) + cat, values and gradients."""
+    rng = np.random.default_rng(31)
+    xs, ss = shape
+    x = torch.from_numpy(rng.standard_normal(xs).astype(np.float32)).requires_grad_(True)
+    skip = torch.from_numpy(rng.standard_normal(ss).astype(np.float32)).requires_grad_(True)
+    ref = torch.cat((torch.nn.functional.interpolate(x, size=ss[-2:], mode="bilinear", align_corners=True), skip), 1)
+    g = torch.from_numpy(rng.standard_normal(ref.shape).astype(np.float32))
+    ref.backward(g)
+    xd = x.detach().to(DEV).requires_grad_(True)
+    sd = skip.detach().to(DEV).requires_grad_(True)
+    out = ops.upsample_concat(xd, sd)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+    out.backward(g.to(DEV))
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), x.grad.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(sd.grad.cpu().numpy(), skip.grad.numpy(), rtol=0, atol=0)
 
 
 def test_noadabins_epilogue():
