@@ -88,6 +88,15 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
                            int norm_mode, float min_val, float max_val, float* y_raw, float* widths_normed,
                            float* edges, float* centers, mde_stream_t stream);
 
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  fp32 SIMT, row-major with leading
+ * dimensions lda/ldw/ldc (the nn.Linear building block of the regressor and the encoder layers). */
+int mde_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                   int K, int act, mde_stream_t stream);
+/* normalisation + widths + cumsum edges + centres from a ready regressor output y_raw [B,n_bins]
+ * (the tail of mde_regressor_bins_fwd; miniViT.py:36-44, unet_adaptive_bins.py:292-296) */
+int mde_bins_finalize_fwd(float* y_raw, int B, int n_bins, int norm_mode, float min_val, float max_val,
+                          float* widths_normed, float* edges, float* centers, mde_stream_t stream);
+
 /* ---- K1b: one post-LN transformer encoder layer (models/layers.py:8-9,23: nn.TransformerEncoderLayer(128, 4, 1024),
  * ReLU, eps 1e-5, eval semantics).  Tokens x, y are [S, NB, E] row-major (row = s*NB + n), E = 128, E/heads = 32.
  * Parameter tensors keep torch's layouts: in_w [3E,E], out_w [E,E], l1_w [FF,E], l2_w [E,FF].
@@ -115,18 +124,21 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
 
 /* ---- K1d+K1e+K2 fused: range attention -> conv_out -> softmax -> centre-weighted sum, nothing but pred is
  * written (miniViT.py:33 + unet_adaptive_bins.py:286-300).  TMA-fed tcgen05 (TF32), accumulators in TMEM.
- *   x [B,128,P] float32 (conv3x3 output, NCHW), wf [B,n_bins,128] float32 = (conv_out.weight @ queries[b]) * log2(e)
- *   rounded to TF32 (mde_fold_queries produces it), biasf [n_bins] = bias*log2(e), centers [B,n_bins], pred [B,P].
- * Requires P % 128 == 0, n_bins == 256. */
-int mde_head_chain_fwd(const float* x, const float* wf, const float* biasf, const float* centers, float* pred, int B,
-                       int n_bins, int64_t P, mde_stream_t stream);
-/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale ),  biasf = bias * log2e   (fp32 FMA).
+ *   x        activations (the conv3x3 output), float32: [B,128,P] (NCHW, x_channels_last = 0) or [B,P,128] (NHWC, = 1)
+ *   wf       [B,n_bins,128] float32 = (conv_out.weight @ queries[b]) * log2(e), TF32-rounded   (mde_fold_queries)
+ *   biasf    [B,n_bins]     float32 = log2(e) * (conv_out.bias + wf-fold of the producer's bias)  (mde_fold_queries)
+ *   centers  [B,n_bins], pred [B,P].   Requires P % 128 == 0, n_bins == 256. */
+int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
+                       float* pred, int B, int n_bins, int64_t P, mde_stream_t stream);
+/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale )          (fp32 FMA, tiled)
+ * biasf[b,j] = log2e * ( bias[j] + sum_k (w_out @ q[b])[j,k] * feat_bias[k] )            (feat_bias may be NULL)
  * operand_scale = MDE_TF32_TRUNC_COMP compensates the mean mantissa loss of the OTHER operand, which the tensor
- * core truncates (not rounds) to TF32 when it reads raw fp32 from shared memory; 1.0f disables it. */
+ * core truncates (not rounds) to TF32 when it reads raw fp32 from shared memory; 1.0f disables it.
+ * q[b] must be a dense [N,K] block (q_batch_stride == N*K). */
 #define MDE_TF32_TRUNC_COMP 1.000352f
-int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride, float* wf,
-                     float* biasf, int B, int n_bins, int N, int K, float operand_scale, mde_stream_t stream);
-
+int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride,
+                     const float* feat_bias, float* wf, float* biasf, int B, int n_bins, int N, int K,
+                     float operand_scale, mde_stream_t stream);
 /* out[i] = round-to-nearest TF32 of in[i]*scale (so the tensor cores' operand truncation is exact for this tensor) */
 int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stream_t stream);
 /* bring-up knobs for the UMMA shared-memory descriptors (bytes) and the last barrier-timeout code (0 = none;

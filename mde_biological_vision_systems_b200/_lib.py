@@ -27,13 +27,15 @@ SIGNATURES = {
                                _f32, _p]),
     "mde_regressor_bins_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32,
                                       _p, _p, _p, _p, _p]),
+    "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),
     "mde_encoder_layer_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),
     "mde_encoder_layer_fwd": (_i32, [_p] * 15 + [_i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_range_attention": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),
-    "mde_head_chain_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
-    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_head_chain_fwd": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_round_tf32": (_i32, [_p, _p, _i64, _f32, _p]),
     "mde_tc_debug_config": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "mde_tc_last_error": (_i32, []),

@@ -43,12 +43,17 @@ __global__ void __launch_bounds__(256) regressor_bins_kernel(const float* __rest
   float* h2 = h1 + H;
   float* y = h2 + H;
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < E; i += blockDim.x) sin[i] = t0[(long long)b * t0_stride + i];
-  __syncthreads();
-  dense_layer(w1, b1, sin, h1, H, E, true);
-  dense_layer(w2, b2, h1, h2, H, H, true);
-  dense_layer(w3, b3, h2, y, n_bins, H, false);
-  for (int i = threadIdx.x; i < n_bins; i += blockDim.x) y_raw[(long long)b * n_bins + i] = y[i];
+  if (w1 != nullptr) {
+    for (int i = threadIdx.x; i < E; i += blockDim.x) sin[i] = t0[(long long)b * t0_stride + i];
+    __syncthreads();
+    dense_layer(w1, b1, sin, h1, H, E, true);
+    dense_layer(w2, b2, h1, h2, H, H, true);
+    dense_layer(w3, b3, h2, y, n_bins, H, false);
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) y_raw[(long long)b * n_bins + i] = y[i];
+  } else {  // finalize-only mode: the regressor output was produced by mde_linear_fwd
+    for (int i = threadIdx.x; i < n_bins; i += blockDim.x) y[i] = y_raw[(long long)b * n_bins + i];
+    __syncthreads();
+  }
   // normalisation (miniViT.py:36-44)
   __shared__ float red[8];
   __shared__ float bcast;
@@ -293,9 +298,24 @@ __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict
 // fold_queries: wf[b,j,k] = tf32_rna( log2e * scale * sum_n w_out[j,n] * q[b,n,k] ) is pixel_gemm<1> with x := q[b]
 // viewed as [n][k] ("pixels" = k); biasf[j] = log2e * bias[j]
 // ------------------------------------------------------------------------------------------------------------
-__global__ void scale_bias_kernel(const float* __restrict__ bias, float* __restrict__ biasf, int n, float s) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) biasf[i] = bias[i] * s;
+// biasf[b,j] = log2e * bias[j] + (1/operand_scale) * sum_k wf[b,j,k] * feat_bias[k]
+// (wf already carries log2e * operand_scale).  feat_bias is the bias of the conv that produced the activations: it is a
+// per-channel constant at every pixel, so it moves through the contraction into a per-image, per-bin bias and the
+// producer can run bias-free (saves a full read+write pass over the 29 MB/img feature map).
+__global__ void __launch_bounds__(256) chain_bias_kernel(const float* __restrict__ bias, const float* __restrict__ wf,
+                                                         const float* __restrict__ feat_bias, float* __restrict__ biasf,
+                                                         int n_bins, int K, float log2e, float inv_scale) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n_bins) return;
+  float a = 0.f;
+  if (feat_bias) {
+    const float* row = wf + ((long long)b * n_bins + j) * K;
+    for (int k = lane; k < K; k += 32) a = fmaf(row[k], feat_bias[k], a);
+    a = warp_sum(a);
+  }
+  if (lane == 0) biasf[(long long)b * n_bins + j] = fmaf(a, inv_scale, bias[j] * log2e);
 }
 
 }  // namespace mde
@@ -316,6 +336,18 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
   regressor_bins_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(t0, t0_stride, w1, b1, w2, b2, w3, b3, E, H, n_bins,
                                                               norm_mode, min_val, max_val, y_raw, widths_normed, edges,
                                                               centers);
+  return check_launch();
+}
+
+int mde_bins_finalize_fwd(float* y_raw, int B, int n_bins, int norm_mode, float min_val, float max_val,
+                          float* widths_normed, float* edges, float* centers, mde_stream_t stream) {
+  if (!y_raw || !widths_normed || !edges || !centers) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || n_bins <= 0 || n_bins > 4096) return MDE_ERR_BAD_SHAPE;
+  if (norm_mode < 0 || norm_mode > 2) return MDE_ERR_UNSUPPORTED;
+  const size_t sm = sizeof(float) * (size_t)(n_bins) + sizeof(double) * (size_t)(n_bins + 2);
+  regressor_bins_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr, 0, 0, n_bins, norm_mode, min_val, max_val, y_raw,
+                                                              widths_normed, edges, centers);
   return check_launch();
 }
 
@@ -361,8 +393,9 @@ int mde_range_attention(const float* x, const float* q, float* y, int B, int K, 
   return MDE_ERR_UNSUPPORTED;
 }
 
-int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride, float* wf,
-                     float* biasf, int B, int n_bins, int N, int K, float operand_scale, mde_stream_t stream) {
+int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride,
+                     const float* feat_bias, float* wf, float* biasf, int B, int n_bins, int N, int K,
+                     float operand_scale, mde_stream_t stream) {
   if (!w_out || !bias || !q || !wf || !biasf) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || B > 65535 || n_bins <= 0 || N <= 0 || K <= 0) return MDE_ERR_BAD_SHAPE;
   if (q_batch_stride != (int64_t)N * K) return MDE_ERR_BAD_SHAPE;  // q[b] must be a dense [N,K] block
@@ -372,7 +405,8 @@ int mde_fold_queries(const float* w_out, const float* bias, const float* q, int6
   pixel_gemm_kernel<1><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
   int rc = check_launch();
   if (rc) return rc;
-  scale_bias_kernel<<<(n_bins + 255) / 256, 256, 0, st>>>(bias, biasf, n_bins, LOG2E);
+  chain_bias_kernel<<<dim3((unsigned)((n_bins + 7) / 8), (unsigned)B), 256, 0, st>>>(bias, wf, feat_bias, biasf, n_bins, K,
+                                                                                       LOG2E, 1.f / operand_scale);
   return check_launch();
 }
 

@@ -3,7 +3,7 @@
 // Reference: PixelWiseDotProduct (models/layers.py:31-36), conv_out + Softmax(dim=1)
 // (models/unet_adaptive_bins.py:190-191,286) and the centre-weighted sum (:298-300).
 //
-// One persistent, warp-specialised kernel (1 CTA / SM, 224 threads):
+// One persistent, warp-specialised kernel (1 CTA / SM, 352 threads):
 //   warp 0      TMA producer for the activation tiles  x[b, k, p0:p0+128]  (NCHW, so the pixel axis is contiguous:
 //               the A operand is MN-major).  A tile is 128 pixels x 128 channels fp32 = 64 KB, streamed as four
 //               32-channel stages of 16 KB (four 32-pixel x 32-channel SWIZZLE_128B_ATOM_32B boxes each) through an
@@ -13,7 +13,8 @@
 //               i overlaps the MMAs of tile i+1.
 //   warp 2      per-image weight loader (B operand, K-major, SWIZZLE_128B; re-loaded when the CTA crosses an image
 //               boundary) + TMEM allocation / release.
-//   warps 3-6   epilogue: tcgen05.ld 32 columns at a time (thread = pixel row), then either
+//   warps 3-10  two 4-warp epilogue groups (group g drains TMEM buffer g): tcgen05.ld 32 columns at a time (thread =
+//               pixel row), then either
 //                 EPI_STORE   : write y[b, n, p]                      (stand-alone range attention, N = 128)
 //                 EPI_SOFTMAX : online softmax over the NB = 256 logits and centre-weighted sum -> pred[b, p]
 //               so in the fused form neither the range-attention maps (29 MB/img) nor the logits / softmax
@@ -32,8 +33,9 @@ constexpr int KDIM = 128;                        // contraction length (channels
 constexpr int KC = 32;                           // channels per stage = one 128-byte swizzle row per channel
 constexpr int STAGE_BYTES = TILE_M * KC * 4;     // 16384
 constexpr int BOX_BYTES = 32 * KC * 4;           // one 32-pixel x 32-channel box
-constexpr int NUM_THREADS = 224;
-constexpr int EPI_WARP0 = 3;
+constexpr int EPI_WARP0 = 3;                     // warps 0..2: TMA producer, MMA issuer, weight loader / TMEM allocator
+constexpr int EPI_GROUPS = 2;                    // two 4-warp epilogue groups: group g drains TMEM buffer g (tiles it%2==g)
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + 4 * EPI_GROUPS);  // 352
 enum { EPI_STORE = 0, EPI_SOFTMAX = 1 };
 
 struct DebugCfg {
@@ -46,12 +48,14 @@ struct SmemPlan {
   static constexpr int W_BYTES = NB * KDIM * 4;  // per-image B operand: 4 K-chunks x [NB rows][128 B]
   static constexpr int NS = (NB == 256) ? 5 : 8;
   static constexpr int RING_BYTES = NS * STAGE_BYTES;
-  static constexpr int CONST_BYTES = 2 * NB * 4;  // exp2(bias) and exp2(bias)*centre per bin
+  static constexpr int CONST_BYTES = EPI_GROUPS * 2 * NB * 4;  // per group: exp2(bias) and exp2(bias)*centre per bin
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = W_BYTES + RING_BYTES + CONST_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-template <int NB, int EPI>
+// A_KMAJOR = false: activations NCHW (pixel axis contiguous, MN-major A, four 32-pixel boxes per stage)
+// A_KMAJOR = true : activations NHWC / channels_last (channel axis contiguous, K-major A, one 128-row box per stage)
+template <int NB, int EPI, bool A_KMAJOR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     head_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ biasf, const float* __restrict__ centers, float* __restrict__ out,
@@ -63,8 +67,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
   const uint32_t s_w = base;
   const uint32_t s_ring = s_w + Plan::W_BYTES;
-  float* c_fac = reinterpret_cast<float*>(gbase + Plan::W_BYTES + Plan::RING_BYTES);  // [NB] exp2(bias)
-  float* c_cen = c_fac + NB;                                                            // [NB] exp2(bias)*centre
+  float* c_all = reinterpret_cast<float*>(gbase + Plan::W_BYTES + Plan::RING_BYTES);  // [group][2][NB]
   const uint32_t s_bar = s_ring + Plan::RING_BYTES + Plan::CONST_BYTES;
   // barrier slots (8 B each)
   const uint32_t bar_full = s_bar;                 // [NS]
@@ -120,9 +123,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
           mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
           const uint32_t dst = s_ring + stage * STAGE_BYTES;
+          if (A_KMAJOR) {
+            tma_load_2d(dst, &map_x, bar_full + 8 * stage, kc * KC, (int)((long long)img * P + p0));
+          } else {
 #pragma unroll
-          for (int m = 0; m < 4; ++m)
-            tma_load_3d(dst + m * BOX_BYTES, &map_x, bar_full + 8 * stage, p0 + 32 * m, kc * KC, img);
+            for (int m = 0; m < 4; ++m)
+              tma_load_3d(dst + m * BOX_BYTES, &map_x, bar_full + 8 * stage, p0 + 32 * m, kc * KC, img);
+          }
           if (++stage == NS) {
             stage = 0;
             phase ^= 1;
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_TF32, TILE_M, NB, /*A MN-major*/ 1, /*B K-major*/ 0);
+      constexpr uint32_t idesc = make_idesc(FMT_TF32, TILE_M, NB, /*A MN-major?*/ A_KMAJOR ? 0 : 1, /*B K-major*/ 0);
       uint32_t stage = 0, phase = 0, wphase = 0;
       int cur = -1;
       int it = 0;
@@ -176,7 +183,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             // A (MN-major fp32/TF32 => "128B swizzle, 32B atom" layout, descriptor type 1): rows = channels (128 B =
             // 32 pixels each), K-atom = 4 rows = 512 B (SBO), 32-pixel MN-atoms 4096 B apart (LBO); one MMA eats K = 8
             // channels = 1024 B.  (Plain SWIZZLE_128B with an MN-major 32-bit operand silently yields zeros.)
-            const uint64_t adesc = make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B_32B, dbg.version);
+            const uint64_t adesc = A_KMAJOR
+                                       ? make_smem_desc(a_base + j * 32, dbg.b_lbo, dbg.b_sbo, SWZ_128B, dbg.version)
+                                       : make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B_32B, dbg.version);
             // B (K-major, SW128): 8 tf32 = 32 B along the 128-B swizzle row; 8-row atoms 1024 B apart
             const uint64_t bdesc = make_smem_desc(b_base + j * 32, dbg.b_lbo, dbg.b_sbo, SWZ_128B, dbg.version);
             umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
@@ -191,31 +200,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
     }
   } else {
-    // ================= epilogue warps (3..6) =================
+    // ================= epilogue warps: group 0 = warps 3..6, group 1 = warps 7..10 =================
+    // Two groups so that every SM sub-partition hosts two independent epilogue warps (one per in-flight tile): a
+    // single warp per sub-partition is latency-bound on its own dependent max / ex2 / fma chains.
+    const int group = (warp - EPI_WARP0) >> 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
-    const int epi_tid = threadIdx.x - EPI_WARP0 * 32;
+    const int gtid = (threadIdx.x - EPI_WARP0 * 32) & 127;
+    float* c_fac = c_all + group * 2 * NB;  // [NB] exp2(bias)
+    float* c_cen = c_fac + NB;              // [NB] exp2(bias)*centre
+    const uint32_t buf = group;
     int cur = -1;
-    int it = 0;
-    for (int t = t_begin; t < t_end; ++t, ++it) {
+    for (int it = group; t_begin + it < t_end; it += EPI_GROUPS) {
+      const int t = t_begin + it;
       const int img = t / tiles_per_img;
       const int p0 = (t - img * tiles_per_img) * TILE_M;
       if (EPI == EPI_SOFTMAX && img != cur) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading the old constants
-        for (int j = epi_tid; j < NB; j += 128) {
-          const float f = exp2f(biasf[j]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");  // the group finished reading the old constants
+        for (int j = gtid; j < NB; j += 128) {
+          const float f = exp2f(biasf[(long long)img * NB + j]);
           c_fac[j] = f;
           c_cen[j] = f * centers[(long long)img * NB + j];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
       }
       cur = img;
-      const uint32_t buf = it & 1;
       mbar_wait(bar_accfull + 8 * buf, (it >> 1) & 1, 6);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * NB + ((uint32_t)(quarter * 32) << 16);
       const long long pix = (long long)p0 + quarter * 32 + lane;
       if (EPI == EPI_SOFTMAX) {
-        float m = -INFINITY, s = 0.f, ws = 0.f;
+        float m = -INFINITY;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < NB; c0 += 32) {
           uint32_t r[32];
@@ -226,13 +241,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
           }
-          float cm = __uint_as_float(r[0]);
+          // chunk maximum as a tree (5 dependent levels instead of 31)
+          float t8[8];
 #pragma unroll
-          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
+          for (int i = 0; i < 8; ++i)
+            t8[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+          const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
           if (cm > m) {
             const float sc = ex2_approx(m - cm);  // 0 on the first chunk (m = -inf)
-            s *= sc;
-            ws *= sc;
+            s0 *= sc; s1 *= sc; s2 *= sc; s3 *= sc;
+            w0 *= sc; w1 *= sc; w2 *= sc; w3 *= sc;
             m = cm;
           }
 #pragma unroll
@@ -243,17 +262,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const float e1 = ex2_approx(__uint_as_float(r[i + 1]) - m);
             const float e2 = ex2_approx(__uint_as_float(r[i + 2]) - m);
             const float e3 = ex2_approx(__uint_as_float(r[i + 3]) - m);
-            s = fmaf(e0, f.x, s);
-            ws = fmaf(e0, g.x, ws);
-            s = fmaf(e1, f.y, s);
-            ws = fmaf(e1, g.y, ws);
-            s = fmaf(e2, f.z, s);
-            ws = fmaf(e2, g.z, ws);
-            s = fmaf(e3, f.w, s);
-            ws = fmaf(e3, g.w, ws);
+            s0 = fmaf(e0, f.x, s0); w0 = fmaf(e0, g.x, w0);   // four independent accumulator pairs
+            s1 = fmaf(e1, f.y, s1); w1 = fmaf(e1, g.y, w1);
+            s2 = fmaf(e2, f.z, s2); w2 = fmaf(e2, g.z, w2);
+            s3 = fmaf(e3, f.w, s3); w3 = fmaf(e3, g.w, w3);
           }
         }
-        out[(long long)img * P + pix] = ws / s;
+        out[(long long)img * P + pix] = ((w0 + w1) + (w2 + w3)) / ((s0 + s1) + (s2 + s3));
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < NB; c0 += 32) {
@@ -281,14 +296,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
 }
 
-template <int NB, int EPI>
+template <int NB, int EPI, bool A_KMAJOR>
 static int launch_chain(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
                         long long P, cudaStream_t st) {
   using Plan = SmemPlan<NB>;
   if (P % TILE_M != 0) return MDE_ERR_BAD_SHAPE;
   if (!aligned(x, 16) || !aligned(w, 16)) return MDE_ERR_BAD_POINTER;
   CUtensorMap mx, mw;
-  {
+  if (A_KMAJOR) {
+    if ((long long)B * P > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
+    const uint64_t dims[2] = {(uint64_t)KDIM, (uint64_t)B * (uint64_t)P};
+    const uint64_t strides[1] = {(uint64_t)KDIM * 4};
+    const uint32_t box[2] = {KC, TILE_M};
+    if (!encode_f32(&mx, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+  } else {
     const uint64_t dims[3] = {(uint64_t)P, (uint64_t)KDIM, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)P * 4, (uint64_t)P * KDIM * 4};
     const uint32_t box[3] = {32, KC, 1};
@@ -306,12 +327,12 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
   const int grid = (int)(total < MDE_NUM_SMS ? total : MDE_NUM_SMS);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL) !=
+    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI, A_KMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL) !=
         cudaSuccess)
       return MDE_ERR_LAUNCH;
     attr_set = true;
   }
-  head_chain_kernel<NB, EPI><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
+  head_chain_kernel<NB, EPI, A_KMAJOR><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
                                                                       (int)total, P, g_dbg);
   return check_launch();
 }
@@ -331,18 +352,20 @@ using namespace mde;
 
 extern "C" {
 
-int mde_head_chain_fwd(const float* x, const float* wf, const float* biasf, const float* centers, float* pred, int B,
-                       int n_bins, int64_t P, mde_stream_t stream) {
+int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
+                       float* pred, int B, int n_bins, int64_t P, mde_stream_t stream) {
   if (!x || !wf || !biasf || !centers || !pred) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
   if (n_bins != 256) return MDE_ERR_UNSUPPORTED;
-  return tc::launch_chain<256, tc::EPI_SOFTMAX>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
+  if (x_channels_last)
+    return tc::launch_chain<256, tc::EPI_SOFTMAX, true>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
+  return tc::launch_chain<256, tc::EPI_SOFTMAX, false>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
 }
 
 // stand-alone range attention on tensor cores (called by mde_range_attention(impl = 1)); q should be TF32-rounded
 int mde_range_attention_tc(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, cudaStream_t st) {
   if (K != 128 || N != 128) return MDE_ERR_UNSUPPORTED;
-  return tc::launch_chain<128, tc::EPI_STORE>(x, q, nullptr, nullptr, y, B, P, st);
+  return tc::launch_chain<128, tc::EPI_STORE, false>(x, q, nullptr, nullptr, y, B, P, st);
 }
 
 int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stream_t stream) {

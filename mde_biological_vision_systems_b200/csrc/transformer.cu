@@ -13,7 +13,7 @@
 namespace mde {
 
 // C[m, n] = act( sum_k A[m*lda + k] * W[n*ldw + k] + bias[n] )
-template <int ACT>  // 0 none, 1 relu
+template <int ACT>  // 0 none, 1 relu, 2 leaky relu (slope 0.01)
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                      int ldw, const float* __restrict__ bias, float* __restrict__ C,
                                                      int ldc, int M, int N, int K) {
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
       if (n >= N) continue;
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
       if (ACT == 1) v = fmaxf(v, 0.f);
+      if (ACT == 2) v = v > 0.f ? v : 0.01f * v;
       C[(long long)m * ldc + n] = v;
     }
   }
@@ -170,6 +171,7 @@ static int launch_linear(const float* A, int lda, const float* W, int ldw, const
                          int N, int K, int act, cudaStream_t st) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   if (act == 1) linear_kernel<1><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
+  else if (act == 2) linear_kernel<2><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
   else linear_kernel<0><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K);
   return check_launch();
 }
@@ -179,6 +181,13 @@ static int launch_linear(const float* A, int lda, const float* W, int ldw, const
 using namespace mde;
 
 extern "C" {
+
+int mde_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                   int K, int act, mde_stream_t stream) {
+  if (!A || !W || !C) return MDE_ERR_BAD_POINTER;
+  if (M <= 0 || N <= 0 || K <= 0 || lda < K || ldw < K || ldc < N || act < 0 || act > 2) return MDE_ERR_BAD_SHAPE;
+  return launch_linear(A, lda, W, ldw, bias, C, ldc, M, N, K, act, (cudaStream_t)stream);
+}
 
 int64_t mde_encoder_layer_ws_floats(int S, int NB, int E, int FF) {
   const int64_t M = (int64_t)S * NB;

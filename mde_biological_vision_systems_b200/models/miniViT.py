@@ -19,17 +19,38 @@ class mViT(nn.Module):
                                        nn.LeakyReLU(), nn.Linear(256, dim_out))
 
     # -- pieces shared by the reference-shaped forward() and the fused path of UnetAdaptiveBins ------------------
-    def tokens_and_features(self, x):
-        """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w])"""
+    def tokens_and_features(self, x, bias_free=False):
+        """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w]).  With ``bias_free`` the 3x3 conv runs without its bias (the caller
+        folds it into the fused chain, ops.fold_queries(feat_bias=...)), which saves a full pass over the feature map."""
         # the reference clones x first (miniViT.py:25); nothing below writes to x, so the 29 MB/img copy is skipped
         tgt = self.patch_transformer(x)
+        if bias_free:
+            c = self.conv3x3
+            return tgt, torch.nn.functional.conv2d(x, c.weight, None, c.stride, c.padding)
         return tgt, self.conv3x3(x)
 
     def bin_widths(self, tgt, min_val=None, max_val=None):
-        """regressor + normalisation on token 0 (miniViT.py:35-45); with min/max also edges and centres."""
+        """regressor + normalisation on token 0 (miniViT.py:35-45); with min/max also edges and centres.
+        -> (widths_normed, edges, centers, y_raw)"""
         r = self.regressor
+        lo = 0.0 if min_val is None else min_val
+        hi = 1.0 if max_val is None else max_val
+        if torch.is_grad_enabled() and (tgt.requires_grad or r[0].weight.requires_grad):
+            # training: this [B,256]-sized piece goes through autograd (same arithmetic as the kernel)
+            y = self.regressor(tgt[0])
+            if self.norm == 'linear':
+                wn = torch.relu(y) + 0.1
+                wn = wn / wn.sum(dim=1, keepdim=True)
+            elif self.norm == 'softmax':
+                wn = torch.softmax(y, dim=1)
+            else:
+                wn = torch.sigmoid(y)
+                wn = wn / wn.sum(dim=1, keepdim=True)
+            widths = torch.nn.functional.pad((hi - lo) * wn, (1, 0), mode='constant', value=lo)
+            edges = torch.cumsum(widths, dim=1)
+            return wn, edges, 0.5 * (edges[:, :-1] + edges[:, 1:]), y
         return ops.regressor_bins(tgt[0], r[0].weight, r[0].bias, r[2].weight, r[2].bias, r[4].weight, r[4].bias,
-                                  self.norm, 0.0 if min_val is None else min_val, 1.0 if max_val is None else max_val)
+                                  self.norm, lo, hi)
 
     def forward(self, x):
         """-> (bin_widths_normed [N, dim_out], range_attention_maps [N, n_query, h, w]) as the reference."""

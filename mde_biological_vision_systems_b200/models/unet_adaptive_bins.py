@@ -182,12 +182,27 @@ class UnetAdaptiveBins(nn.Module):
     def _head(self, unet_out):
         head = self.adaptive_bins_layer
         conv = self.conv_out[0]
+        fusable = self.fused_head and unet_out.is_cuda and self.num_classes == 256 \
+            and (unet_out.shape[2] * unet_out.shape[3]) % 128 == 0 and head.conv3x3.out_channels == 128 \
+            and head.n_query_channels == 128
+        needs_grad = torch.is_grad_enabled() and (unet_out.requires_grad or conv.weight.requires_grad)
+        if needs_grad and not fusable:
+            raise RuntimeError("training needs the fused head (n_bins = 256, 128 query channels, h*w % 128 == 0)")
+        if fusable and not needs_grad:
+            # inference fast path: the head's two cuDNN convs read a channels_last copy of unet_out (cuDNN converts to
+            # NHWC internally anyway), the 3x3 conv runs bias-free and leaves its output in NHWC, which the tcgen05
+            # chain consumes in place as a K-major operand; the conv bias is folded into the chain's per-image bias.
+            x_cl = unet_out.contiguous(memory_format=torch.channels_last)
+            tgt, feat = head.tokens_and_features(x_cl, bias_free=True)
+            _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
+            queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)
+            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries, feat_bias=head.conv3x3.bias)
+            return bin_edges, ops.head_chain(feat, wf, biasf, centers)
         tgt, feat = head.tokens_and_features(unet_out)
         _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
         queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)  # [N, 128, E] view
-        if self.fused_head and ops.head_chain_supported(feat, self.num_classes):
-            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries)
-            pred = ops.head_chain(feat, wf, biasf, centers)
+        if needs_grad:
+            pred = ops.head_chain_autograd(feat, queries, conv.weight, conv.bias, centers)
         else:
             ram = ops.range_attention(feat, queries)
             pred = ops.bins_pred(ops.conv1x1(ram, conv.weight, conv.bias), centers)

@@ -200,8 +200,24 @@ def aux_mlp(x, w0, b0, w1, b1, in_div=1.0, out=None):
 _NORM = {"linear": 0, "softmax": 1, "sigmoid": 2}
 
 
-def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val):
-    """t0 [B,E] (rows may be strided) -> (widths_normed [B,n], edges [B,n+1], centers [B,n], y_raw [B,n])."""
+def linear(x, weight, bias, act=0):
+    """act(x @ weight.T + bias) for a 2-D x whose rows may be strided (fp32 SIMT kernel); act 0/1/2 = none/ReLU/LeakyReLU."""
+    lib = _lib.load()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    m, k = x.shape
+    n = weight.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    rc = lib.mde_linear_fwd(_p(x), x.stride(0), _p(weight.contiguous()), k, _p(bias.contiguous()) if bias is not None else None,
+                            _p(out), n, m, n, k, int(act), _s())
+    _lib.check(rc, "mde_linear_fwd")
+    return out
+
+
+def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=True):
+    """t0 [B,E] (rows may be strided) -> (widths_normed [B,n], edges [B,n+1], centers [B,n], y_raw [B,n]).
+    split=True runs the three dense layers as separate wide launches and a small finalise kernel (the single-CTA-per-
+    image variant is latency bound: 105 us at B = 16); split=False keeps everything in one launch."""
     lib = _lib.load()
     _need_cuda(t0, w1, w2, w3)
     if t0.stride(1) != 1:
@@ -209,10 +225,17 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val):
     b, e = t0.shape
     hdim, n = w1.shape[0], w3.shape[0]
     dev = t0.device
-    y_raw = torch.empty((b, n), dtype=torch.float32, device=dev)
     wn = torch.empty((b, n), dtype=torch.float32, device=dev)
     edges = torch.empty((b, n + 1), dtype=torch.float32, device=dev)
     centers = torch.empty((b, n), dtype=torch.float32, device=dev)
+    if split:
+        with timing("regressor_bins"):
+            y_raw = linear(linear(linear(t0, w1, b1, 2), w2, b2, 2), w3, b3, 0)
+            rc = lib.mde_bins_finalize_fwd(_p(y_raw), b, n, _NORM.get(norm, 2), float(min_val), float(max_val), _p(wn),
+                                           _p(edges), _p(centers), _s())
+        _lib.check(rc, "mde_bins_finalize_fwd")
+        return wn, edges, centers, y_raw
+    y_raw = torch.empty((b, n), dtype=torch.float32, device=dev)
     rc = lib.mde_regressor_bins_fwd(_p(t0), t0.stride(0), _p(w1.contiguous()), _p(b1.contiguous()), _p(w2.contiguous()),
                                     _p(b2.contiguous()), _p(w3.contiguous()), _p(b3.contiguous()), b, e, hdim, n,
                                     _NORM.get(norm, 2), float(min_val), float(max_val), _p(y_raw), _p(wn), _p(edges),
@@ -305,31 +328,91 @@ def bins_pred(logits, centers):
     return pred
 
 
-def fold_queries(w_out, bias, queries, operand_scale=TF32_TRUNC_COMP):
-    """wf[b] = tf32(log2e * w_out @ queries[b]) [B,n_bins,K];  biasf = log2e * bias.  queries [B,N,K] (strided ok)."""
+def fold_queries(w_out, bias, queries, feat_bias=None, operand_scale=TF32_TRUNC_COMP):
+    """wf[b] = tf32(log2e * w_out @ queries[b]) [B,n_bins,K];  biasf [B,n_bins] = log2e * (bias + (w_out @ q[b]) @
+    feat_bias).  ``feat_bias`` is the bias of the conv that produced the chain's activations (folded in so that the
+    producer can run bias-free)."""
     lib = _lib.load()
     wt = w_out.reshape(w_out.shape[0], -1).contiguous()
     n_bins, n = wt.shape
     queries = queries.contiguous()
     b, _, k = queries.shape
     wf = torch.empty((b, n_bins, k), dtype=torch.float32, device=queries.device)
-    biasf = torch.empty((n_bins,), dtype=torch.float32, device=queries.device)
-    rc = lib.mde_fold_queries(_p(wt), _p(bias.contiguous()), _p(queries), queries.stride(0), _p(wf), _p(biasf), b, n_bins,
-                              n, k, float(operand_scale), _s())
+    biasf = torch.empty((b, n_bins), dtype=torch.float32, device=queries.device)
+    with timing("fold_queries"):
+        rc = lib.mde_fold_queries(_p(wt), _p(bias.contiguous()), _p(queries), n * k,
+                                  _p(feat_bias.contiguous()) if feat_bias is not None else None, _p(wf), _p(biasf), b,
+                                  n_bins, n, k, float(operand_scale), _s())
     _lib.check(rc, "mde_fold_queries")
     return wf, biasf
 
 
 def head_chain(x, wf, biasf, centers):
-    """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x [B,128,h,w] -> [B,1,h,w]."""
+    """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x [B,128,h,w], either
+    contiguous NCHW or channels_last (NHWC strides; consumed in place, no copy) -> pred [B,1,h,w]."""
     lib = _lib.load()
-    x = x.contiguous()
     b, k, h, w = x.shape
+    nhwc = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+    if not nhwc:
+        x = x.contiguous()
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
     with timing("head_chain"):
-        rc = lib.mde_head_chain_fwd(_p(x), _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b, wf.shape[1], h * w, _s())
+        rc = lib.mde_head_chain_fwd(_p(x), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b,
+                                    wf.shape[1], h * w, _s())
     _lib.check(rc, "mde_head_chain_fwd")
     return pred
+
+
+class _HeadChainFn(torch.autograd.Function):
+    """Training wrapper of the fused chain: forward = fold_queries + head_chain (our kernels, nothing but pred is
+    written); backward re-computes the range-attention maps / softmax per image group with cuBLAS + ATen and
+    back-propagates to the features, the queries, conv_out and the centres (a hand-written fused backward is the
+    next step)."""
+
+    @staticmethod
+    def forward(ctx, feat, queries, w_out, b_out, centers):
+        wf, biasf = fold_queries(w_out, b_out, queries)
+        pred = head_chain(feat, wf, biasf, centers)
+        ctx.save_for_backward(feat, queries, w_out, b_out, centers, pred)
+        return pred
+
+    @staticmethod
+    def backward(ctx, gpred):
+        feat, queries, w_out, b_out, centers, pred = ctx.saved_tensors
+        b, k, h, w = feat.shape
+        p = h * w
+        wo = w_out.reshape(w_out.shape[0], -1)
+        gfeat = torch.empty_like(feat)
+        gq = torch.empty_like(queries)
+        gw = torch.zeros_like(wo)
+        gb = torch.zeros_like(b_out)
+        gc = torch.empty_like(centers)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            step = 4
+            for i in range(0, b, step):
+                sl = slice(i, min(b, i + step))
+                x = feat[sl].reshape(-1, k, p)
+                q = queries[sl]
+                r = torch.bmm(q, x)                                         # [n,128,P]
+                logits = torch.matmul(wo, r) + b_out.view(1, -1, 1)         # [n,256,P]
+                sm = torch.softmax(logits, dim=1)
+                g = gpred[sl].reshape(-1, 1, p)
+                gc[sl] = (sm * g).sum(dim=2)
+                gl = sm * (centers[sl].unsqueeze(2) - pred[sl].reshape(-1, 1, p)) * g
+                gw += torch.einsum("njp,nkp->jk", gl, r)
+                gb += gl.sum(dim=(0, 2))
+                gr = torch.matmul(wo.t(), gl)                               # [n,128,P]
+                gq[sl] = torch.bmm(gr, x.transpose(1, 2))
+                gfeat[sl] = torch.bmm(q.transpose(1, 2), gr).reshape(-1, k, h, w)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return gfeat, gq, gw.view_as(w_out), gb, gc
+
+
+def head_chain_autograd(feat, queries, w_out, b_out, centers):
+    return _HeadChainFn.apply(feat.contiguous(), queries.contiguous(), w_out, b_out, centers.contiguous())
 
 
 def head_chain_supported(x, n_bins):

@@ -1,0 +1,61 @@
+"""One training iteration with the reference's semantics (train.py:338-455), on the B200 kernels.
+
+    zero_grad -> loaders (GPU gather) -> model -> mask = depth > min_depth -> SILog + w_chamfer * chamfer ->
+    backward -> [gradient mean all-reduce over ranks] -> clip_grad_norm_(0.1) -> AdamW.step -> OneCycleLR.step
+
+Loss is computed per rank on the local shard (train.py:414-426); only gradients (and SyncBatchNorm statistics when
+``sync_bn`` is on, train.py:296) cross GPUs.  This is the harness bench.py times for "train imgs/s"; it is host logic,
+not a re-implementation of train.py's logging / validation / checkpoint code (out of scope).
+"""
+import torch
+import torch.nn as nn
+
+from .loss import BinsChamferLoss, SILogLoss
+from .parallel import GradientAverager
+
+
+class TrainStep:
+    def __init__(self, model, semantics_loader=None, instance_loader=None, lr=0.000357, wd=0.1, w_chamfer=0.1,
+                 min_depth=1e-3, total_steps=1000, div_factor=25, final_div_factor=100, same_lr=False, bucket_mb=25.0):
+        self.model = model
+        self.semantics_loader = semantics_loader
+        self.instance_loader = instance_loader
+        self.w_chamfer = w_chamfer
+        self.min_depth = min_depth
+        self.criterion_ueff = SILogLoss()
+        self.criterion_bins = BinsChamferLoss() if w_chamfer > 0 else None
+        if same_lr:
+            params = model.parameters()
+        else:  # train.py:351-352
+            params = [{"params": model.get_1x_lr_params(), "lr": lr / 10}, {"params": model.get_10x_lr_params(), "lr": lr}]
+        self.optimizer = torch.optim.AdamW(params, weight_decay=wd, lr=lr)
+        max_lr = [g["lr"] for g in self.optimizer.param_groups]
+        self.scheduler = torch.optim.lr_scheduler.OneCycleLR(
+            self.optimizer, max_lr, total_steps=total_steps, cycle_momentum=True, base_momentum=0.85, max_momentum=0.95,
+            div_factor=div_factor, final_div_factor=final_div_factor)
+        self.averager = GradientAverager(model.parameters(), bucket_mb=bucket_mb)
+
+    def __call__(self, batch, device):
+        self.optimizer.zero_grad(set_to_none=True)
+        img = batch["image"].to(device, non_blocking=True)
+        depth = batch["depth"].to(device, non_blocking=True)
+        kwargs = {}
+        if self.semantics_loader is not None:
+            _, sem = self.semantics_loader.get_semantics(batch)
+            if sem is not None:
+                kwargs["semantics"] = sem
+        if self.instance_loader is not None:
+            _, emb, areas = self.instance_loader.get_instance_segmentation(batch)
+            if emb is not None:
+                kwargs.update(instance_labels=emb, instance_areas=areas)
+        bin_edges, pred = self.model(img, **kwargs)
+        mask = depth > self.min_depth
+        loss = self.criterion_ueff(pred, depth, mask=mask.to(torch.bool), interpolate=True)
+        if self.criterion_bins is not None and bin_edges is not None:
+            loss = loss + self.w_chamfer * self.criterion_bins(bin_edges, depth)
+        loss.backward()
+        self.averager.reduce()
+        nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
+        self.optimizer.step()
+        self.scheduler.step()
+        return loss.detach()

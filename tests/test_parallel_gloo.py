@@ -1,0 +1,70 @@
+"""CPU, world_size 2, gloo: the host logic of the N > 1 path (sharding, gradient mean all-reduce, max-over-ranks)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mde_biological_vision_systems_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 1))
+        data = torch.randn(10, 8)
+        target = torch.randn(10, 1)
+        idx = parallel.shard_indices(10, rank, world)
+        loss = torch.nn.functional.mse_loss(model(data[idx]), target[idx])
+        loss.backward()
+        n = parallel.GradientAverager(model.parameters(), bucket_mb=0.0001).reduce()
+        assert n == sum(p.numel() for p in model.parameters())
+        torch.save([p.grad.clone() for p in model.parameters()], os.path.join(tmp, f"g{rank}.pt"))
+        t = parallel.max_over_ranks(10.0 + rank)
+        assert t == 10.0 + world - 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_indices():
+    for n, world in [(10, 2), (7, 2), (16, 8), (3, 4)]:
+        shards = [parallel.shard_indices(n, r, world) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1
+        assert set(sum(shards, [])) == set(range(n))
+        nopad = [parallel.shard_indices(n, r, world, pad=False) for r in range(world)]
+        assert sorted(sum(nopad, [])) == list(range(n))
+    assert parallel.per_rank_batch(16, 8) == 2 and parallel.per_rank_batch(16, 8, use_new_batching=True) == 16
+
+
+def test_gradient_mean_allreduce_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g0 = torch.load(os.path.join(tmp_path, "g0.pt"))
+    g1 = torch.load(os.path.join(tmp_path, "g1.pt"))
+    # reference: mean over ranks of the per-rank gradients, computed serially
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 1))
+    data = torch.randn(10, 8)
+    target = torch.randn(10, 1)
+    grads = []
+    for r in range(world):
+        model.zero_grad()
+        idx = parallel.shard_indices(10, r, world)
+        torch.nn.functional.mse_loss(model(data[idx]), target[idx]).backward()
+        grads.append([p.grad.clone() for p in model.parameters()])
+    for a, b, x, y in zip(g0, g1, grads[0], grads[1]):
+        torch.testing.assert_close(a, b)
+        torch.testing.assert_close(a, (x + y) / 2)
