@@ -157,6 +157,9 @@ int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B
 int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
                      mde_stream_t stream);
 
+/* NCHW [B,C,P] -> NHWC [B,P,C] transpose (feeds the head's cuDNN convs and the K-major chain operand) */
+int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream);
+
 /* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
  * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is
  * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (zeroed by the call; holds

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mde_tc_last_error": (_i32, []),
     "mde_upsample_concat_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_upsample_bwd": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_nchw_to_nhwc": (_i32, [_p, _p, _i32, _i32, _i64, _p]),
     "mde_relu_eps_fwd": (_i32, [_p, _p, _i64, _f32, _p]),
     "mde_silog_ws_bytes": (_i64, []),
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),

@@ -135,3 +135,41 @@ int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCHW -> NHWC (channels_last) transpose through shared memory: reads are coalesced along pixels, writes along
+// channels.  ATen's strided copy does this at ~1.8 TB/s (527 us for the 464 MB feature map of config 2); this tile
+// kernel is a plain HBM stream.  grid (ceil(P/64), ceil(C/64), B), block 256.
+namespace mde {
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                           long long P) {
+  __shared__ float tile[64][65];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const float* src = in + (long long)b * C * P;
+  float* dst = out + (long long)b * C * P;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + ty + i * 4;
+    const long long p = p0 + tx;
+    tile[ty + i * 4][tx] = (c < C && p < P) ? src[(long long)c * P + p] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const long long p = p0 + ty + i * 4;
+    const int c = c0 + tx;
+    if (p < P && c < C) dst[p * C + c] = tile[tx][ty + i * 4];
+  }
+}
+}  // namespace mde
+
+extern "C" int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C <= 0 || P <= 0 || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
+  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P);
+  return mde::check_launch();
+}

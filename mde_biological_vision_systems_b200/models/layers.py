@@ -27,7 +27,13 @@ class PatchTransformerEncoder(nn.Module):
         return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
 
     def forward(self, x):
-        emb = self.embedding_convPxP(x).flatten(2)  # [N, E, S]
+        conv = self.embedding_convPxP
+        if x.is_cuda and not self._needs_autograd(x) and x.is_contiguous(memory_format=torch.channels_last) \
+                and not x.is_contiguous():
+            from .miniViT import _channels_last_weight  # NHWC input: hand cuDNN a cached NHWC filter as well
+            emb = torch.nn.functional.conv2d(x, _channels_last_weight(conv), conv.bias, conv.stride).flatten(2)
+        else:
+            emb = conv(x).flatten(2)  # [N, E, S]
         emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
         tokens = emb.permute(2, 0, 1)  # [S, N, E]
         if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0):

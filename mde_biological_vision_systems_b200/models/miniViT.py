@@ -6,6 +6,17 @@ from .. import ops
 from .layers import PatchTransformerEncoder, PixelWiseDotProduct
 
 
+def _channels_last_weight(conv):
+    """NHWC copy of a conv weight, cached per parameter version (cuDNN otherwise re-lays-out the weights every call:
+    2 x 126 us for the 16.8 MB patch-embedding filter)."""
+    w = conv.weight
+    cached = getattr(conv, "_mde_w_cl", None)
+    if cached is None or cached[0] != w._version or cached[1].device != w.device:
+        cached = (w._version, w.detach().contiguous(memory_format=torch.channels_last))
+        conv._mde_w_cl = cached
+    return cached[1]
+
+
 class mViT(nn.Module):
     def __init__(self, in_channels, n_query_channels=128, patch_size=16, dim_out=256, embedding_dim=128, num_heads=4,
                  norm='linear'):
@@ -26,7 +37,7 @@ class mViT(nn.Module):
         tgt = self.patch_transformer(x)
         if bias_free:
             c = self.conv3x3
-            return tgt, torch.nn.functional.conv2d(x, c.weight, None, c.stride, c.padding)
+            return tgt, torch.nn.functional.conv2d(x, _channels_last_weight(c), None, c.stride, c.padding)
         return tgt, self.conv3x3(x)
 
     def bin_widths(self, tgt, min_val=None, max_val=None):

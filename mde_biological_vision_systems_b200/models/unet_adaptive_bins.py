@@ -192,7 +192,7 @@ class UnetAdaptiveBins(nn.Module):
             # inference fast path: the head's two cuDNN convs read a channels_last copy of unet_out (cuDNN converts to
             # NHWC internally anyway), the 3x3 conv runs bias-free and leaves its output in NHWC, which the tcgen05
             # chain consumes in place as a K-major operand; the conv bias is folded into the chain's per-image bias.
-            x_cl = unet_out.contiguous(memory_format=torch.channels_last)
+            x_cl = ops.to_channels_last(unet_out)
             tgt, feat = head.tokens_and_features(x_cl, bias_free=True)
             _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
             queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)

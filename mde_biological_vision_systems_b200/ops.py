@@ -448,6 +448,21 @@ def upsample_concat(x, skip):
     return _UpsampleConcat.apply(x.contiguous().float(), skip.contiguous().float())
 
 
+def to_channels_last(x):
+    """NCHW-contiguous fp32 [B,C,H,W] -> the same logical tensor with channels_last strides (tiled transpose kernel)."""
+    lib = _lib.load()
+    _need_cuda(x)
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    x = x.contiguous()
+    b, c, h, w = x.shape
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    with timing("nchw_to_nhwc"):
+        rc = lib.mde_nchw_to_nhwc(_p(x), _p(out), b, c, h * w, _s())
+    _lib.check(rc, "mde_nchw_to_nhwc")
+    return out
+
+
 def relu_eps(x, eps=1e-4):
     lib = _lib.load()
     x = x.contiguous()

@@ -308,6 +308,14 @@ def test_upsample_concat_forward_backward(shape):
     np.testing.assert_allclose(sd.grad.cpu().numpy(), skip.grad.numpy(), rtol=0, atol=0)
 
 
+def test_nchw_to_nhwc():
+    rng = np.random.default_rng(33)
+    for shape in [(2, 128, 16, 24), (1, 70, 5, 7), (3, 3, 9, 2)]:
+        x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(DEV)
+        y = ops.to_channels_last(x)
+        assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, x)
+
+
 def test_noadabins_epilogue():
     x = torch.from_numpy(np.random.default_rng(3).standard_normal((2, 1, 24, 32)).astype(np.float32))
     assert np.array_equal(ops.relu_eps(x.to(DEV)).cpu().numpy(), oracle.noadabins_epilogue(x).numpy())
