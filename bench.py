@@ -131,7 +131,7 @@ def run_reference(args):
     }))
 
 
-def run_train(args, dev, world, rank, host, loader):
+def run_train(args, dev, world, rank, host, loader, sync_bn=True):
     """Training iteration with the reference's semantics (train.py:387-455): forward + SILog + 0.1 chamfer + backward +
     gradient mean all-reduce over ranks (NCCL) + clip 0.1 + AdamW + OneCycle, batch 16 per GPU (weak scaling,
     --use_new_batching), SyncBatchNorm when N > 1 (train.py:296).  Inputs come from pinned host memory every step."""
@@ -145,7 +145,7 @@ def run_train(args, dev, world, rank, host, loader):
     model = UnetAdaptiveBins.build(n_bins=N_BINS, min_val=1e-3, max_val=10.0, norm="linear", encoder_name="efficientnet-b1",
                                    semantics_mode=SEM_MODE, instance_segmentation_mode=None, insertion_point="input",
                                    image="rgb").to(dev)
-    if world > 1:
+    if world > 1 and sync_bn:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model.train()
     stepper = TrainStep(model, semantics_loader=loader, total_steps=1000)
@@ -170,7 +170,7 @@ def run_train(args, dev, world, rank, host, loader):
     B = args.batch
     return {"metric": "train imgs/s (fwd + SILog + 0.1*chamfer + bwd + grad all-reduce + clip + AdamW/OneCycle)",
             "value": world * B / (ms_step * 1e-3), "unit": "imgs/s", "ms_per_step": ms_step, "steps": steps,
-            "batch_per_gpu": B, "sync_bn": world > 1, "loss": float(loss.item()),
+            "batch_per_gpu": B, "sync_bn": world > 1 and sync_bn, "loss": float(loss.item()),
             "gpu_launches_per_step": (ops.launch_count() - l0) / steps,
             "note": "head backward re-computes through cuBLAS/ATen; encoder layers run the stock torch modules in train mode"}
 
@@ -274,6 +274,8 @@ def run_ours(args):
     train = None
     if not args.no_train:
         train = run_train(args, dev, world, rank, host, loader)
+        if world > 1:  # the same step with per-rank BatchNorm statistics: isolates the cost of stock SyncBatchNorm
+            train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -284,11 +286,19 @@ def run_ours(args):
         chain_ms = ktimes.get("head_chain")
         alg_bytes = B * (128 * P * 4 + P * 4)  # read conv3x3 features once, write pred
         roof = None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)["head_chain_kernel"]
+            if tr["batch"] == B:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         if chain_ms:
             ach = alg_bytes / (chain_ms * 1e-3) / 1e9
             flops = B * 2.0 * P * N_BINS * 128
             roof = {"kernel": "head_chain_kernel<256,softmax> (range-attention x conv_out fold + softmax + bins)",
-                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                     "peak_source": src, "ms_per_launch": chain_ms,
                     "tensor": {"achieved_tflops": flops / (chain_ms * 1e-3) / 1e12, "peak_tf32_tflops": bf16 / 2,
                                "frac": flops / (chain_ms * 1e-3) / 1e12 / (bf16 / 2), "note": "TF32 peak taken as measured bf16/2"}}

@@ -145,6 +145,8 @@ int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stre
  * synchronises the device).  Test/debug only. */
 int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version);
 int mde_tc_last_error(void);
+/* tuning aid: device buffer [148][8] int64 of per-role wait cycles filled by the following chain launches (NULL = off) */
+int mde_tc_debug_profile(long long* buf);
 
 /* ---- A8': noAdaBins epilogue relu(x) + 1e-4 (unet_adaptive_bins.py:240-242) */
 int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_t stream);

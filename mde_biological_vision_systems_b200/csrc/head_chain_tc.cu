@@ -13,8 +13,8 @@
 //               i overlaps the MMAs of tile i+1.
 //   warp 2      per-image weight loader (B operand, K-major, SWIZZLE_128B; re-loaded when the CTA crosses an image
 //               boundary) + TMEM allocation / release.
-//   warps 3-10  two 4-warp epilogue groups (group g drains TMEM buffer g): tcgen05.ld 32 columns at a time (thread =
-//               pixel row), then either
+//   warps 3-10  epilogue, 8 warps per tile (4 TMEM lane quarters x 2 column halves): tcgen05.ld 32 columns at a time
+//               (thread = pixel row; the next chunk is prefetched while the current one is reduced), then either
 //                 EPI_STORE   : write y[b, n, p]                      (stand-alone range attention, N = 128)
 //                 EPI_SOFTMAX : online softmax over the NB = 256 logits and centre-weighted sum -> pred[b, p]
 //               so in the fused form neither the range-attention maps (29 MB/img) nor the logits / softmax
@@ -34,21 +34,30 @@ constexpr int KC = 32;                           // channels per stage = one 128
 constexpr int STAGE_BYTES = TILE_M * KC * 4;     // 16384
 constexpr int BOX_BYTES = 32 * KC * 4;           // one 32-pixel x 32-channel box
 constexpr int EPI_WARP0 = 3;                     // warps 0..2: TMA producer, MMA issuer, weight loader / TMEM allocator
-constexpr int EPI_GROUPS = 2;                    // two 4-warp epilogue groups: group g drains TMEM buffer g (tiles it%2==g)
-constexpr int NUM_THREADS = 32 * (EPI_WARP0 + 4 * EPI_GROUPS);  // 352
+constexpr int EPI_SPLIT = 2;                     // 8 epilogue warps per tile: 4 lane quarters x 2 column halves
+constexpr int EPI_THREADS = 128 * EPI_SPLIT;
+constexpr int NUM_THREADS = 32 * EPI_WARP0 + EPI_THREADS;  // 352
 enum { EPI_STORE = 0, EPI_SOFTMAX = 1 };
 
 struct DebugCfg {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, version;
+  long long* prof;  // optional [grid][8] cycle counters: where each role waits (bring-up / tuning only)
 };
-static DebugCfg g_dbg = {4096, 512, 16, 1024, 1};
+static DebugCfg g_dbg = {4096, 512, 16, 1024, 1, nullptr};
+
+#define MDE_TIMED_WAIT(acc, ...)        \
+  {                                     \
+    const long long t__ = clock64();    \
+    __VA_ARGS__;                        \
+    acc += clock64() - t__;             \
+  }
 
 template <int NB>
 struct SmemPlan {
   static constexpr int W_BYTES = NB * KDIM * 4;  // per-image B operand: 4 K-chunks x [NB rows][128 B]
   static constexpr int NS = (NB == 256) ? 5 : 8;
   static constexpr int RING_BYTES = NS * STAGE_BYTES;
-  static constexpr int CONST_BYTES = EPI_GROUPS * 2 * NB * 4;  // per group: exp2(bias) and exp2(bias)*centre per bin
+  static constexpr int CONST_BYTES = 2 * NB * 4 + 128 * 4 * 4;  // exp2(bias), exp2(bias)*centre per bin; merge slots
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = W_BYTES + RING_BYTES + CONST_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     mbar_init(bar_wempty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, 4);  // one arrive per epilogue warp
+      mbar_init(bar_accempty + 8 * i, 4 * EPI_SPLIT);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -115,12 +124,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 0) {
     // ================= activation producer =================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
+      // Optional L2 prefetch PF_DIST tiles ahead (cp.async.bulk.prefetch.tensor).  Measured on B200 (scripts/
+      // chain_waits.py): the MMA thread waits only ~490 of ~3800 cycles/tile for activations and the prefetch did not
+      // reduce that (116 vs 109 us), so it is off; the kernel is bound by the SS-mode tensor pipe reading 12 KB of
+      // shared memory per 128x256x8 TF32 MMA (~190 instead of 128 cycles each) -- the fix is cta_group::2.
+      constexpr int PF_DIST = 0;
+      auto prefetch_tile = [&](int t) {
         const int img = t / tiles_per_img;
         const int p0 = (t - img * tiles_per_img) * TILE_M;
         for (int kc = 0; kc < KDIM / KC; ++kc) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+          if (A_KMAJOR) {
+            tma_prefetch_l2_2d(&map_x, kc * KC, (int)((long long)img * P + p0));
+          } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) tma_prefetch_l2_3d(&map_x, p0 + 32 * m, kc * KC, img);
+          }
+        }
+      };
+      if (PF_DIST > 0)
+        for (int d = 1; d < PF_DIST && t_begin + d < t_end; ++d) prefetch_tile(t_begin + d);
+      uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int t = t_begin; t < t_end; ++t) {
+        const int img = t / tiles_per_img;
+        const int p0 = (t - img * tiles_per_img) * TILE_M;
+        if (PF_DIST > 0 && t + PF_DIST < t_end) prefetch_tile(t + PF_DIST);
+        for (int kc = 0; kc < KDIM / KC; ++kc) {
+          MDE_TIMED_WAIT(w_empty, mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1))
           mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
           const uint32_t dst = s_ring + stage * STAGE_BYTES;
           if (A_KMAJOR) {
@@ -135,6 +166,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             phase ^= 1;
           }
         }
+      }
+      if (dbg.prof) {
+        dbg.prof[blockIdx.x * 8 + 0] = w_empty;
+        dbg.prof[blockIdx.x * 8 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == 2) {
@@ -161,20 +196,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       uint32_t stage = 0, phase = 0, wphase = 0;
       int cur = -1;
       int it = 0;
+      long long w_full = 0, w_acc = 0, w_w = 0;
+      const long long t_start = clock64();
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int img = t / tiles_per_img;
         if (img != cur) {
           if (cur >= 0) umma_commit(bar_wempty);  // fires when every MMA that read the old weights is done
-          mbar_wait(bar_wfull, wphase, 3);
+          MDE_TIMED_WAIT(w_w, mbar_wait(bar_wfull, wphase, 3))
           wphase ^= 1;
           cur = img;
         }
         const uint32_t buf = it & 1;
-        mbar_wait(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4);
+        MDE_TIMED_WAIT(w_acc, mbar_wait(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4))
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * NB;
         for (int kc = 0; kc < KDIM / KC; ++kc) {
-          mbar_wait(bar_full + 8 * stage, phase, 5);
+          MDE_TIMED_WAIT(w_full, mbar_wait(bar_full + 8 * stage, phase, 5))
           tc_fence_after();
           const uint32_t a_base = s_ring + stage * STAGE_BYTES;
           const uint32_t b_base = s_w + kc * (NB * 128);
@@ -198,93 +235,126 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         umma_commit(bar_accfull + 8 * buf);
       }
+      if (dbg.prof) {
+        dbg.prof[blockIdx.x * 8 + 2] = w_full;
+        dbg.prof[blockIdx.x * 8 + 3] = w_acc;
+        dbg.prof[blockIdx.x * 8 + 4] = w_w;
+        dbg.prof[blockIdx.x * 8 + 5] = clock64() - t_start;
+      }
     }
   } else {
-    // ================= epilogue warps: group 0 = warps 3..6, group 1 = warps 7..10 =================
-    // Two groups so that every SM sub-partition hosts two independent epilogue warps (one per in-flight tile): a
-    // single warp per sub-partition is latency-bound on its own dependent max / ex2 / fma chains.
-    const int group = (warp - EPI_WARP0) >> 2;
+    // ================= epilogue: warps 3..10, all on the same tile =================
+    // warp -> (lane quarter = warp & 3, column half = (warp - 3) / 4).  Splitting the 256 accumulator columns over two
+    // warps per lane quarter halves the time a TMEM buffer is held, so the MMAs of tile i+1 (other buffer) fully
+    // overlap the epilogue of tile i; the two partial softmax states are merged through shared memory.
+    const int half = (warp - EPI_WARP0) >> 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
-    const int gtid = (threadIdx.x - EPI_WARP0 * 32) & 127;
-    float* c_fac = c_all + group * 2 * NB;  // [NB] exp2(bias)
-    float* c_cen = c_fac + NB;              // [NB] exp2(bias)*centre
-    const uint32_t buf = group;
+    const int etid = threadIdx.x - EPI_WARP0 * 32;
+    float* c_fac = c_all;           // [NB] exp2(bias)
+    float* c_cen = c_all + NB;      // [NB] exp2(bias)*centre
+    float4* merge = reinterpret_cast<float4*>(c_all + 2 * NB);  // [128] (m, s, ws, -) of the upper column half
+    constexpr int COLS = NB / EPI_SPLIT;  // columns per warp
     int cur = -1;
-    for (int it = group; t_begin + it < t_end; it += EPI_GROUPS) {
-      const int t = t_begin + it;
+    int it = 0;
+    long long w_accfull = 0;
+    const long long t_start = clock64();
+    for (int t = t_begin; t < t_end; ++t, ++it) {
       const int img = t / tiles_per_img;
       const int p0 = (t - img * tiles_per_img) * TILE_M;
       if (EPI == EPI_SOFTMAX && img != cur) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");  // the group finished reading the old constants
-        for (int j = gtid; j < NB; j += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // everyone finished reading the old constants
+        for (int j = etid; j < NB; j += EPI_THREADS) {
           const float f = exp2f(biasf[(long long)img * NB + j]);
           c_fac[j] = f;
           c_cen[j] = f * centers[(long long)img * NB + j];
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       }
       cur = img;
-      mbar_wait(bar_accfull + 8 * buf, (it >> 1) & 1, 6);
+      const uint32_t buf = it & 1;
+      MDE_TIMED_WAIT(w_accfull, mbar_wait(bar_accfull + 8 * buf, (it >> 1) & 1, 6))
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * NB + ((uint32_t)(quarter * 32) << 16);
-      const long long pix = (long long)p0 + quarter * 32 + lane;
-      if (EPI == EPI_SOFTMAX) {
+      const uint32_t taddr = tmem_base + buf * NB + half * COLS + ((uint32_t)(quarter * 32) << 16);
+      const int row = quarter * 32 + lane;
+      const long long pix = (long long)p0 + row;
+      if constexpr (EPI == EPI_SOFTMAX) {
         float m = -INFINITY;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < NB; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c0, r);
-          tmem_ld_wait();
-          if (c0 + 32 == NB) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
-          }
-          // chunk maximum as a tree (5 dependent levels instead of 31)
-          float t8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            t8[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
-                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
-          const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
-          if (cm > m) {
-            const float sc = ex2_approx(m - cm);  // 0 on the first chunk (m = -inf)
-            s0 *= sc; s1 *= sc; s2 *= sc; s3 *= sc;
-            w0 *= sc; w1 *= sc; w2 *= sc; w3 *= sc;
-            m = cm;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 f = *reinterpret_cast<const float4*>(c_fac + c0 + i);
-            const float4 g = *reinterpret_cast<const float4*>(c_cen + c0 + i);
-            const float e0 = ex2_approx(__uint_as_float(r[i + 0]) - m);
-            const float e1 = ex2_approx(__uint_as_float(r[i + 1]) - m);
-            const float e2 = ex2_approx(__uint_as_float(r[i + 2]) - m);
-            const float e3 = ex2_approx(__uint_as_float(r[i + 3]) - m);
-            s0 = fmaf(e0, f.x, s0); w0 = fmaf(e0, g.x, w0);   // four independent accumulator pairs
-            s1 = fmaf(e1, f.y, s1); w1 = fmaf(e1, g.y, w1);
-            s2 = fmaf(e2, f.z, s2); w2 = fmaf(e2, g.z, w2);
-            s3 = fmaf(e3, f.w, s3); w3 = fmaf(e3, g.w, w3);
-          }
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(taddr, ra);
+        // one 32-column chunk: r = registers of this chunk, nxt = registers to prefetch the next chunk into
+#define MDE_CHUNK(r, nxt, c0, last)                                                                                    \
+  {                                                                                                                    \
+    tmem_ld_wait();                                                                                                    \
+    if (last) { /* accumulator fully read: hand the TMEM buffer back to the MMA warp */                                \
+      tc_fence_before();                                                                                               \
+      __syncwarp();                                                                                                    \
+      if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);                                                              \
+    } else {                                                                                                           \
+      tmem_ld_32x32(taddr + (c0) + 32, nxt); /* prefetch: overlaps the math below */                                   \
+    }                                                                                                                  \
+    float t8[8];                                                                                                       \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) t8[i] =                                                              \
+        fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),                                         \
+              fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));                                    \
+    const float cm =                                                                                                   \
+        fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));       \
+    if (cm > m) {                                                                                                      \
+      const float sc = ex2_approx(m - cm); /* 0 on the first chunk (m = -inf) */                                       \
+      s0 *= sc; s1 *= sc; s2 *= sc; s3 *= sc;                                                                          \
+      w0 *= sc; w1 *= sc; w2 *= sc; w3 *= sc;                                                                          \
+      m = cm;                                                                                                          \
+    }                                                                                                                  \
+    _Pragma("unroll") for (int i = 0; i < 32; i += 4) {                                                                \
+      const float4 f = *reinterpret_cast<const float4*>(c_fac + half * COLS + (c0) + i);                               \
+      const float4 g = *reinterpret_cast<const float4*>(c_cen + half * COLS + (c0) + i);                               \
+      const float e0 = ex2_approx(__uint_as_float(r[i + 0]) - m);                                                      \
+      const float e1 = ex2_approx(__uint_as_float(r[i + 1]) - m);                                                      \
+      const float e2 = ex2_approx(__uint_as_float(r[i + 2]) - m);                                                      \
+      const float e3 = ex2_approx(__uint_as_float(r[i + 3]) - m);                                                      \
+      s0 = fmaf(e0, f.x, s0); w0 = fmaf(e0, g.x, w0);                                                                  \
+      s1 = fmaf(e1, f.y, s1); w1 = fmaf(e1, g.y, w1);                                                                  \
+      s2 = fmaf(e2, f.z, s2); w2 = fmaf(e2, g.z, w2);                                                                  \
+      s3 = fmaf(e3, f.w, s3); w3 = fmaf(e3, g.w, w3);                                                                  \
+    }                                                                                                                  \
+  }
+        static_assert(COLS == 128, "the unrolled epilogue below covers 4 chunks of 32 columns per warp");
+        MDE_CHUNK(ra, rb, 0, false)
+        MDE_CHUNK(rb, ra, 32, false)
+        MDE_CHUNK(ra, rb, 64, false)
+        MDE_CHUNK(rb, ra, 96, true)
+#undef MDE_CHUNK
+        const float s = (s0 + s1) + (s2 + s3), ws = (w0 + w1) + (w2 + w3);
+        // merge the two column halves of each pixel row
+        if (half == 1) merge[row] = make_float4(m, s, ws, 0.f);
+        asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (half == 0) {
+          const float4 o = merge[row];
+          const float mm = fmaxf(m, o.x);
+          const float a = ex2_approx(m - mm), bsc = ex2_approx(o.x - mm);
+          out[(long long)img * P + pix] = (ws * a + o.z * bsc) / (s * a + o.y * bsc);
         }
-        out[(long long)img * P + pix] = ((w0 + w1) + (w2 + w3)) / ((s0 + s1) + (s2 + s3));
+        asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // merge slots free for the next tile
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < NB; c0 += 32) {
+        for (int c0 = 0; c0 < COLS; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c0, r);
           tmem_ld_wait();
-          if (c0 + 32 == NB) {
+          if (c0 + 32 == COLS) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
           }
-          float* dst = out + ((long long)img * NB + c0) * P + pix;
+          float* dst = out + ((long long)img * NB + half * COLS + c0) * P + pix;
 #pragma unroll
           for (int i = 0; i < 32; ++i) dst[(long long)i * P] = __uint_as_float(r[i]);  // 128 B per warp per row
         }
       }
+    }
+    if (dbg.prof && etid == 0) {
+      dbg.prof[blockIdx.x * 8 + 6] = w_accfull;
+      dbg.prof[blockIdx.x * 8 + 7] = clock64() - t_start;
     }
   }
   // ---- teardown ----
@@ -384,6 +454,14 @@ int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version)
   tc::g_dbg.b_lbo = (uint32_t)b_lbo;
   tc::g_dbg.b_sbo = (uint32_t)b_sbo;
   tc::g_dbg.version = (uint32_t)version;
+  return MDE_OK;
+}
+
+// device buffer of [grid][8] int64 cycle counters filled by the next chain launches (NULL disables): per CTA
+// {producer wait-empty, producer total, mma wait-full, mma wait-acc-empty, mma wait-weights, mma total,
+//  epilogue wait-acc-full, epilogue total}
+int mde_tc_debug_profile(long long* buf) {
+  tc::g_dbg.prof = buf;
   return MDE_OK;
 }
 
