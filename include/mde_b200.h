@@ -88,6 +88,15 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
                            int norm_mode, float min_val, float max_val, float* y_raw, float* widths_normed,
                            float* edges, float* centers, mde_stream_t stream);
 
+/* ---- K1a: patch-embedding conv (kernel = stride = patch) + positional rows (models/layers.py:11-12,17-19) as a
+ * TMA-fed tcgen05 split-K GEMM (TF32).  x_nhwc: channels_last activations [B,h,w,C]; w_nhwc: the conv filter in
+ * channels_last order [E,patch,patch,C], TF32-rounded (and scaled by MDE_TF32_TRUNC_COMP) by the caller;
+ * bias [E]; pos [>=S, E] (positional_encodings); tokens [S,B,E] with S = (h/patch)*(w/patch); E must be 128.
+ * ws: mde_patch_embed_ws_floats(...) floats of scratch (split-K partials). */
+int64_t mde_patch_embed_ws_floats(int B, int h, int w, int patch, int C);
+int mde_patch_embed_fwd(const float* x_nhwc, const float* w_nhwc, const float* bias, const float* pos, float* tokens,
+                        float* ws, int B, int h, int w, int C, int patch, int E, mde_stream_t stream);
+
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  fp32 SIMT, row-major with leading
  * dimensions lda/ldw/ldc (the nn.Linear building block of the regressor and the encoder layers). */
 int mde_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

@@ -22,25 +22,35 @@ class PatchTransformerEncoder(nn.Module):
         self.embedding_convPxP = nn.Conv2d(in_channels, embedding_dim, kernel_size=patch_size, stride=patch_size,
                                            padding=0)
         self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
+        self.use_tc_patch_embed = True  # False: cuDNN conv for the patch embedding (the transformer stays on our kernels)
 
     def _needs_autograd(self, x):
         return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
 
+    def _prepared_weight(self):
+        """TF32-rounded NHWC filter for the tcgen05 patch GEMM, cached per parameter version."""
+        w = self.embedding_convPxP.weight
+        cached = getattr(self, "_mde_w_prep", None)
+        if cached is None or cached[0] != w._version or cached[1].device != w.device:
+            cached = (w._version, ops.prepare_patch_weight(w))
+            self._mde_w_prep = cached
+        return cached[1]
+
     def forward(self, x):
         conv = self.embedding_convPxP
-        if x.is_cuda and not self._needs_autograd(x) and x.is_contiguous(memory_format=torch.channels_last) \
-                and not x.is_contiguous():
-            from .miniViT import _channels_last_weight  # NHWC input: hand cuDNN a cached NHWC filter as well
-            emb = torch.nn.functional.conv2d(x, _channels_last_weight(conv), conv.bias, conv.stride).flatten(2)
-        else:
+        if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0) or not x.is_cuda:
+            # training: dropout and the backward pass run through the stock torch layers (DESIGN.md section 6)
             emb = conv(x).flatten(2)  # [N, E, S]
-        emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
-        tokens = emb.permute(2, 0, 1)  # [S, N, E]
-        if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0):
-            # training: dropout and the backward pass run through the stock torch layers (DESIGN.md "training")
-            return self.transformer_encoder(tokens)
+            emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
+            return self.transformer_encoder(emb.permute(2, 0, 1))
+        if self.use_tc_patch_embed and ops.patch_embed_supported(x, conv):
+            # channels_last input: TMA + tcgen05 split-K GEMM writes the [S, N, E] tokens (bias and positional rows added)
+            tokens = ops.patch_embed(x, self._prepared_weight(), conv.bias, self.positional_encodings, conv.kernel_size[0])
+        else:
+            emb = conv(x).flatten(2)
+            emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
+            tokens = emb.permute(2, 0, 1).contiguous()
         ws = None
-        tokens = tokens.contiguous()
         for layer in self.transformer_encoder.layers:
             tokens, ws = ops.encoder_layer(tokens, layer, ws)
         return tokens

@@ -245,6 +245,40 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=Tru
 
 
 # ------------------------------------------------------------------------------------------------------------
+# patch embedding
+# ------------------------------------------------------------------------------------------------------------
+def prepare_patch_weight(weight):
+    """Conv filter [E,C,p,p] -> channels_last order [E,p,p,C], scaled by TF32_TRUNC_COMP and rounded to TF32 (the B
+    operand of the patch-embedding GEMM as it lies in memory)."""
+    w = weight.detach().permute(0, 2, 3, 1).contiguous()
+    return round_tf32(w, TF32_TRUNC_COMP)
+
+
+def patch_embed_supported(x, conv):
+    k = conv.kernel_size
+    return (x.is_cuda and x.dtype == torch.float32 and conv.out_channels == 128 and k[0] == k[1] and conv.stride == k
+            and conv.padding == (0, 0) and (k[0] * x.shape[1]) % 32 == 0 and x.shape[3] // k[0] <= 128
+            and -(-(x.shape[2] // k[0]) // (128 // (x.shape[3] // k[0]))) <= 4
+            and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+
+
+def patch_embed(x_cl, w_prepared, bias, pos, patch):
+    """tokens [S,B,E] = conv(k = s = patch)(x).flatten(2).permute(2,0,1) + pos[:S] on the tcgen05 split-K GEMM;
+    x_cl must be channels_last."""
+    lib = _lib.load()
+    b, c, h, w = x_cl.shape
+    e = w_prepared.shape[0]
+    s = (h // patch) * (w // patch)
+    tokens = torch.empty((s, b, e), dtype=torch.float32, device=x_cl.device)
+    ws = torch.empty(int(lib.mde_patch_embed_ws_floats(b, h, w, patch, c)), dtype=torch.float32, device=x_cl.device)
+    with timing("patch_embed"):
+        rc = lib.mde_patch_embed_fwd(_p(x_cl), _p(w_prepared), _p(bias.contiguous()), _p(pos.contiguous()), _p(tokens),
+                                     _p(ws), b, h, w, c, patch, e, _s())
+    _lib.check(rc, "mde_patch_embed_fwd")
+    return tokens
+
+
+# ------------------------------------------------------------------------------------------------------------
 # transformer encoder layer
 # ------------------------------------------------------------------------------------------------------------
 def encoder_layer(x, layer, ws=None):
