@@ -306,6 +306,15 @@ def run_ours(args):
         if ktimes.get("gather_embed"):
             gb = B * H * W * (8 + 8 + 25 * 4) / 1e9  # label read + clamped write-back + 25 fp32 planes
             others["gather_embed"] = {"ms": ktimes["gather_embed"], "GBps": gb / (ktimes["gather_embed"] * 1e-3), "frac_hbm": gb / (ktimes["gather_embed"] * 1e-3) / hbm}
+        if ktimes.get("conv3x3"):
+            fl = B * 2.0 * P * 128 * 128 * 9
+            t = ktimes["conv3x3"] * 1e-3
+            others["conv3x3_tc"] = {"ms": ktimes["conv3x3"], "tflops": fl / t / 1e12, "frac_tf32_peak": fl / t / 1e12 / (bf16 / 2),
+                                    "GBps_algorithmic": B * 2 * 128 * P * 4 / t / 1e9}
+        if ktimes.get("patch_embed"):
+            t = ktimes["patch_embed"] * 1e-3
+            others["patch_embed_tc"] = {"ms": ktimes["patch_embed"], "GBps": B * 128 * P * 4 / t / 1e9,
+                                        "frac_hbm": B * 128 * P * 4 / t / 1e9 / hbm}
         if ktimes.get("silog_fwd"):
             gb = B * (H * W * 5 + P * 4) / 1e9
             others["silog_fwd"] = {"ms": ktimes["silog_fwd"], "GBps": gb / (ktimes["silog_fwd"] * 1e-3), "frac_hbm": gb / (ktimes["silog_fwd"] * 1e-3) / hbm}

@@ -97,6 +97,20 @@ int64_t mde_patch_embed_ws_floats(int B, int h, int w, int patch, int C);
 int mde_patch_embed_fwd(const float* x_nhwc, const float* w_nhwc, const float* bias, const float* pos, float* tokens,
                         float* ws, int B, int h, int w, int C, int patch, int E, mde_stream_t stream);
 
+/* ---- K1c: 3x3 / stride 1 / pad 1 convolution on channels_last activations as a TMA-fed tcgen05 implicit GEMM (TF32
+ * inputs, fp32 accumulation) with a fused per-channel affine + LeakyReLU epilogue: mViT.conv3x3 (models/miniViT.py:16,27)
+ * and the DecoderBN blocks Conv3x3 -> BatchNorm(eval) -> LeakyReLU / conv3 (models/unet_adaptive_bins.py:39-49,73).
+ *   x_nhwc [B,H,W,C] float32; y_nhwc [B,H,W,Cout] float32 = lrelu(conv(x) * scale[co] + shift[co]); scale / shift may be
+ *   NULL (1 / 0; pass the conv bias as shift); lrelu_slope 1.0f = no activation; round_tf32 != 0 rounds the outputs to
+ *   TF32 (exact operands for a following tensor-core contraction).
+ *   w_prep: the filter re-laid-out as [dx][dy][Cout][C] and TF32-rounded by mde_conv3x3_prep_weight (operand_scale =
+ *   MDE_TF32_TRUNC_COMP when x is raw fp32, 1.0f when x is already TF32-rounded).
+ * Requires C % 4 == 0 and Cout either <= 256 and a multiple of 16, or divisible by a multiple of 32 that is <= 256. */
+int mde_conv3x3_prep_weight(const float* w_oihw, float* w_prep, int Cout, int C, float operand_scale,
+                            mde_stream_t stream);
+int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* scale, const float* shift, float* y_nhwc,
+                         int B, int H, int W, int C, int Cout, float lrelu_slope, int round_tf32, mde_stream_t stream);
+
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  fp32 SIMT, row-major with leading
  * dimensions lda/ldw/ldc (the nn.Linear building block of the regressor and the encoder layers). */
 int mde_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,

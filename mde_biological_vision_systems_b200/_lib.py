@@ -29,6 +29,8 @@ SIGNATURES = {
                                       _p, _p, _p, _p, _p]),
     "mde_patch_embed_ws_floats": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "mde_patch_embed_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_conv3x3_prep_weight": (_i32, [_p, _p, _i32, _i32, _f32, _p]),
+    "mde_conv3x3_nhwc_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
     "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),
     "mde_encoder_layer_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),

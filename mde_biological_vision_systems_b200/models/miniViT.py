@@ -28,6 +28,25 @@ class mViT(nn.Module):
         self.conv3x3 = nn.Conv2d(in_channels, embedding_dim, kernel_size=3, stride=1, padding=1)
         self.regressor = nn.Sequential(nn.Linear(embedding_dim, 256), nn.LeakyReLU(), nn.Linear(256, 256),
                                        nn.LeakyReLU(), nn.Linear(256, dim_out))
+        # 3x3 conv of the inference fast path: "tc" = tcgen05 implicit GEMM (TF32 inputs), "cudnn" = library conv,
+        # "auto" = "tc" when torch.backends.cudnn.allow_tf32 (PyTorch's default, i.e. the precision the reference's own
+        # conv runs at on a GPU) and the exact-fp32 library conv otherwise
+        self.conv3x3_impl = "auto"
+
+    def _conv3x3_uses_tc(self, x):
+        impl = self.conv3x3_impl
+        if impl == "auto":
+            impl = "tc" if torch.backends.cudnn.allow_tf32 else "cudnn"
+        return impl == "tc" and ops.conv3x3_supported(x, self.conv3x3.out_channels)
+
+    def _prepared_conv3x3(self):
+        """[dx][dy][Cout][C] TF32 filter for the tcgen05 conv, cached per parameter version."""
+        w = self.conv3x3.weight
+        cached = getattr(self, "_mde_w3_prep", None)
+        if cached is None or cached[0] != w._version or cached[1].device != w.device:
+            cached = (w._version, ops.prepare_conv3x3_weight(w))
+            self._mde_w3_prep = cached
+        return cached[1]
 
     # -- pieces shared by the reference-shaped forward() and the fused path of UnetAdaptiveBins ------------------
     def tokens_and_features(self, x, bias_free=False):
@@ -35,6 +54,9 @@ class mViT(nn.Module):
         folds it into the fused chain, ops.fold_queries(feat_bias=...)), which saves a full pass over the feature map."""
         # the reference clones x first (miniViT.py:25); nothing below writes to x, so the 29 MB/img copy is skipped
         tgt = self.patch_transformer(x)
+        if bias_free and self._conv3x3_uses_tc(x):
+            # tcgen05 implicit GEMM; the outputs are rounded to TF32 so that the chain's tensor-core read is exact
+            return tgt, ops.conv3x3_nhwc(x, self._prepared_conv3x3(), round_tf32=True)
         if bias_free:
             c = self.conv3x3
             return tgt, torch.nn.functional.conv2d(x, _channels_last_weight(c), None, c.stride, c.padding)

@@ -196,7 +196,9 @@ class UnetAdaptiveBins(nn.Module):
             tgt, feat = head.tokens_and_features(x_cl, bias_free=True)
             _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
             queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)
-            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries, feat_bias=head.conv3x3.bias)
+            # features that come TF32-rounded from our conv need no truncation compensation on the folded operand
+            comp = 1.0 if head._conv3x3_uses_tc(x_cl) else ops.TF32_TRUNC_COMP
+            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries, feat_bias=head.conv3x3.bias, operand_scale=comp)
             return bin_edges, ops.head_chain(feat, wf, biasf, centers)
         tgt, feat = head.tokens_and_features(unet_out)
         _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)

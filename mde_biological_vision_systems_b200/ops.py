@@ -279,6 +279,44 @@ def patch_embed(x_cl, w_prepared, bias, pos, patch):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# 3x3 convolution (tcgen05 implicit GEMM, NHWC)
+# ------------------------------------------------------------------------------------------------------------
+def prepare_conv3x3_weight(weight, operand_scale=TF32_TRUNC_COMP):
+    """Conv filter [Cout,C,3,3] -> [dx][dy][Cout][C], scaled and rounded to TF32 (the B operand tiles as TMA reads them)."""
+    lib = _lib.load()
+    _need_cuda(weight)
+    w = weight.detach().contiguous().float()
+    cout, c = w.shape[0], w.shape[1]
+    out = torch.empty((3, 3, cout, c), dtype=torch.float32, device=w.device)
+    _lib.check(lib.mde_conv3x3_prep_weight(_p(w), _p(out), cout, c, float(operand_scale), _s()), "mde_conv3x3_prep_weight")
+    return out
+
+
+def conv3x3_supported(x, cout):
+    n_ok = (cout <= 256 and cout % 16 == 0) or any(cout % c == 0 for c in range(32, 257, 32))
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and n_ok
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv3x3_nhwc(x_cl, w_prep, scale=None, shift=None, slope=1.0, round_tf32=False, out=None):
+    """y = lrelu(conv3x3(x, pad 1) * scale + shift) on the tcgen05 implicit GEMM.  x_cl: channels_last [B,C,H,W];
+    w_prep from prepare_conv3x3_weight; returns a channels_last [B,Cout,H,W] tensor."""
+    lib = _lib.load()
+    _need_cuda(x_cl, w_prep)
+    b, c, h, w = x_cl.shape
+    if not x_cl.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("conv3x3_nhwc expects a channels_last tensor")
+    cout = w_prep.shape[2]
+    if out is None:
+        out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    with timing("conv3x3"):
+        rc = lib.mde_conv3x3_nhwc_fwd(_p(x_cl), _p(w_prep), _p(scale), _p(shift), _p(out), b, h, w, c, cout, float(slope),
+                                      1 if round_tf32 else 0, _s())
+    _lib.check(rc, "mde_conv3x3_nhwc_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # transformer encoder layer
 # ------------------------------------------------------------------------------------------------------------
 def encoder_layer(x, layer, ws=None):

@@ -206,6 +206,43 @@ def test_patch_embed_tc(shape):
     assert err < 1e-3, err
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 128, 48, 64), cout=128),                       # head conv3x3: NT = 2, 16-px patches, exact tiling
+    dict(shape=(1, 128, 26, 34), cout=128),                       # ragged: edge tiles zero-filled / clipped by TMA
+    dict(shape=(2, 176, 40, 24), cout=80, affine=True, slope=0.01),   # decoder up4-like: N tile 80, C % 32 != 0
+    dict(shape=(1, 344, 13, 17), cout=160, affine=True, slope=0.01),  # up3-like: N tile 160 (one patch per CTA)
+    dict(shape=(1, 680, 9, 11), cout=320, affine=True, slope=0.01),   # up2-like: two N tiles of 160
+    dict(shape=(1, 96, 7, 5), cout=640, affine=True, slope=0.01),     # five N tiles of 128
+    dict(shape=(1, 80, 16, 16), cout=128, round_tf32=True),
+])
+def test_conv3x3_tc(cfg):
+    """tcgen05 implicit-GEMM 3x3 conv (NHWC, TF32) vs an fp64 conv of the reference's Conv2d(+BN eval affine+LeakyReLU)."""
+    rng = np.random.default_rng(91)
+    b, c, h, w = cfg["shape"]
+    cout = cfg["cout"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), None, padding=1)
+    if cfg.get("affine"):
+        scale = torch.from_numpy((0.5 + rng.random(cout)).astype(np.float32))
+        ref = ref * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    else:
+        scale = None
+        ref = ref + bias.double().view(1, -1, 1, 1)
+    slope = cfg.get("slope", 1.0)
+    ref = torch.where(ref > 0, ref, ref * slope)
+    x_cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert ops.conv3x3_supported(x_cl, cout)
+    out = ops.conv3x3_nhwc(x_cl, ops.prepare_conv3x3_weight(wt.to(DEV)), None if scale is None else scale.to(DEV),
+                           bias.to(DEV), slope=slope, round_tf32=cfg.get("round_tf32", False))
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 1e-3, err
+    if cfg.get("round_tf32"):
+        assert torch.equal(out, ops.round_tf32(out.contiguous()).contiguous(memory_format=torch.channels_last))
+
+
 def test_regressor_bins(golden):
     m, sd = _head_state()
     tgt = torch.from_numpy(golden["head/tgt"])
@@ -279,6 +316,21 @@ def test_head_golden(fused, golden):
         edges, pred = m._head(x)
     assert rel_err(edges.cpu(), golden["head/edges"]) < REL_DEPTH
     assert_depth_close(pred.cpu(), golden["head/pred"], tf32=fused)
+
+
+def test_head_golden_tf32_conv(golden):
+    """Same as test_head_golden(fused) with the 3x3 conv on the tcgen05 implicit GEMM (TF32 inputs -- what the reference's
+    cuDNN conv does under PyTorch's default allow_tf32) in front of the TF32 chain."""
+    m, _ = _head_state()
+    m.to(DEV)
+    m.adaptive_bins_layer.conv3x3_impl = "tc"
+    x = synthetic.decoder_features(2, 128, 176, 192, seed=21).to(DEV)
+    with torch.no_grad():
+        edges, pred = m._head(x)
+    assert rel_err(edges.cpu(), golden["head/edges"]) < REL_DEPTH
+    mx, p999 = rel_stats(pred.cpu(), golden["head/pred"])
+    print("tf32 conv + chain: max %.3e p99.9 %.3e" % (mx, p999))
+    assert_depth_close(pred.cpu(), golden["head/pred"], tf32=True)
 
 
 def test_mvit_forward_surface(golden):
