@@ -309,7 +309,10 @@ def run_ours(args):
         if ktimes.get("conv3x3"):
             fl = B * 2.0 * P * 128 * 128 * 9
             t = ktimes["conv3x3"] * 1e-3
-            others["conv3x3_tc"] = {"ms": ktimes["conv3x3"], "tflops": fl / t / 1e12, "frac_tf32_peak": fl / t / 1e12 / (bf16 / 2),
+            others["conv3x3_tc"] = {"ms": ktimes["conv3x3"], "tflops": fl / t / 1e12,
+                                    "frac_tf32_nominal": fl / t / 1e12 / 1125.0, "frac_of_measured_bf16_half": fl / t / 1e12 / (bf16 / 2),
+                                    "note": "head conv3x3 launch only; TF32 dense nominal 1125 TFLOP/s (B200_PROFILING.md); "
+                                            "SS-MMA at N=128 is shared-memory-bandwidth bound (8 KB operand reads per 64-clk MMA)",
                                     "GBps_algorithmic": B * 2 * 128 * P * 4 / t / 1e9}
         if ktimes.get("patch_embed"):
             t = ktimes["patch_embed"] * 1e-3

@@ -182,6 +182,11 @@ int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B
 int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
                      mde_stream_t stream);
 
+/* channels_last variant feeding mde_conv3x3_nhwc_fwd: x_nhwc [B,h,w,C1]; skip [B,H,W,C2] (skip_channels_last != 0) or
+ * [B,C2,H,W]; out_nhwc [B,H,W,C1+C2].  C1 % 4 == 0 and C2 % 4 == 0. */
+int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last, float* out_nhwc, int B,
+                                 int C1, int C2, int h, int w, int H, int W, mde_stream_t stream);
+
 /* NCHW [B,C,P] -> NHWC [B,P,C] transpose (feeds the head's cuDNN convs and the K-major chain operand) */
 int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream);
 

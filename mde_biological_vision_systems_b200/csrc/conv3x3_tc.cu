@@ -16,6 +16,11 @@
 //     the tensor pipe, is what bounds an fp32-operand implicit GEMM.
 //   * B: one box {32 ch, N tile, 3 (dy), 1 (dx)} of the filter pre-laid-out as [dx][dy][C_out][C] (TF32-rounded, scaled
 //     by MDE_TF32_TRUNC_COMP): three K-major 128B-swizzled operand tiles shared by all NT patches.
+// Measured (B200, head conv 128 -> 128 at B = 16, 208 x 272): 0.327 ms = 816 TFLOP/s = 72 % of the 1.125 PFLOP/s TF32
+// peak (cuDNN: 0.73 ms).  The ceiling is shared-memory bandwidth: an M = 128, N = 128, K = 8 TF32 SS-MMA reads 4 KB of A and
+// 4 KB of B per 64 tensor clocks (128 B/clk, all the SM has) while TMA writes the next stage; a variant with 3-4 stacked
+// patches, separate A/B rings and single-buffered accumulators (fewer operand bytes from L2) was slower (0.36-0.42 ms), so
+// the next step for this kernel is cta_group::2 (each CTA reads only half of B).
 // Accumulators: NT x N-tile fp32 columns per buffer, two buffers in TMEM, so the epilogue of one super tile overlaps the
 // MMAs of the next.  Epilogue: tcgen05.ld -> affine / LeakyReLU / optional TF32 rounding -> swizzled shared staging ->
 // TMA tensor store (edge tiles are clipped by the hardware; no predicates anywhere).  Persistent, 1 CTA / SM,

@@ -142,13 +142,13 @@ int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int 
 // kernel is a plain HBM stream.  grid (ceil(P/64), ceil(C/64), B), block 256.
 namespace mde {
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                                           long long P) {
+                                                           long long P, int pitch) {
   __shared__ float tile[64][65];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
   const float* src = in + (long long)b * C * P;
-  float* dst = out + (long long)b * C * P;
+  float* dst = out + (long long)b * pitch * P;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   for (int i = 0; i < 16; ++i) {
     const long long p = p0 + ty + i * 4;
     const int c = c0 + tx;
-    if (p < P && c < C) dst[p * C + c] = tile[tx][ty + i * 4];
+    if (p < P && c < C) dst[p * pitch + c] = tile[tx][ty + i * 4];
   }
 }
 }  // namespace mde
@@ -170,6 +170,77 @@ extern "C" int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64
   if (!in || !out) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || C <= 0 || P <= 0 || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
   dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P);
+  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, C);
   return mde::check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// channels_last variant of the DecoderBN up-sampling step (feeds the tcgen05 conv3x3): x [B,h,w,C1] NHWC is resized
+// (bilinear, align_corners=True) into channels [0,C1) of out [B,H,W,C1+C2]; the skip tensor (NHWC or NCHW) is copied /
+// transposed into channels [C1, C1+C2).  One thread = 4 channels of one output pixel: float4 loads of the four taps,
+// one float4 store; consecutive threads walk the channel axis, so every access is a full 128-byte line.
+namespace mde {
+__global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int C1,
+                                                            int Ctot, int h, int w, int H, int W, float sy, float sx,
+                                                            long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = C1 >> 2;
+  const int cg = (int)(idx % c4);
+  long long p = idx / c4;
+  const int X = (int)(p % W);
+  p /= W;
+  const int Y = (int)(p % H);
+  const int b = (int)(p / H);
+  int y0, y1, xa, xb;
+  float ly0, ly1, lx0, lx1;
+  up_src(Y, sy, h, y0, y1, ly0, ly1);
+  up_src(X, sx, w, xa, xb, lx0, lx1);
+  const float4* src = reinterpret_cast<const float4*>(x + (long long)b * h * w * C1) + cg;
+  const float4 v00 = __ldg(src + ((long long)y0 * w + xa) * c4), v01 = __ldg(src + ((long long)y0 * w + xb) * c4);
+  const float4 v10 = __ldg(src + ((long long)y1 * w + xa) * c4), v11 = __ldg(src + ((long long)y1 * w + xb) * c4);
+  float4 o;  // same association as ATen: ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * c + lx1 * d)
+  o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+  o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+  o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+  o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  stg_stream(reinterpret_cast<float4*>(out + (((long long)b * H + Y) * W + X) * Ctot) + cg, o);
+}
+
+__global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __restrict__ skip, float* __restrict__ out,
+                                                                 int C2, int Ctot, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = C2 >> 2;
+  const int cg = (int)(idx % c4);
+  const long long p = idx / c4;
+  stg_stream(reinterpret_cast<float4*>(out + p * Ctot) + cg, ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg));
+}
+}  // namespace mde
+
+extern "C" int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last,
+                                            float* out_nhwc, int B, int C1, int C2, int h, int w, int H, int W,
+                                            mde_stream_t stream) {
+  using namespace mde;
+  if (!x_nhwc || !out_nhwc || (C2 > 0 && !skip)) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C1 <= 0 || C2 < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return MDE_ERR_BAD_SHAPE;
+  if (C1 % 4 != 0 || C2 % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(out_nhwc, 16) || (C2 > 0 && !aligned(skip, 16)))
+    return MDE_ERR_UNSUPPORTED;
+  const int Ctot = C1 + C2;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * H * W * (C1 / 4);
+  upsample_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out_nhwc, C1, Ctot, h, w, H, W, sy, sx,
+                                                                        total);
+  int rc = check_launch();
+  if (rc || C2 == 0) return rc;
+  const long long P = (long long)H * W;
+  if (skip_channels_last) {
+    const long long t2 = (long long)B * P * (C2 / 4);
+    copy_channels_nhwc_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out_nhwc + C1, C2, Ctot, t2);
+  } else {
+    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(skip, out_nhwc + C1, C2, P, Ctot);
+  }
+  return check_launch();
 }

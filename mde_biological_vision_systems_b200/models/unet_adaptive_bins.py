@@ -38,6 +38,38 @@ class UpSampleBN(nn.Module):
         super().__init__()
         self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
 
+    def _folded(self):
+        """Per conv block: ([dx][dy][Cout][C] TF32 filter, scale, shift) with the eval-mode BatchNorm folded into a
+        per-channel affine (scale = gamma / sqrt(var + eps), shift = beta + (conv bias - mean) * scale); cached per
+        parameter / running-statistics version."""
+        tensors = []
+        for i in (0, 3):
+            conv, bn = self._net[i], self._net[i + 1]
+            tensors += [conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = tuple(t._version for t in tensors) + (tensors[0].device,)
+        cached = getattr(self, "_mde_folded", None)
+        if cached is None or cached[0] != key:
+            blocks = []
+            with torch.no_grad():
+                for i in (0, 3):
+                    conv, bn = self._net[i], self._net[i + 1]
+                    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+                    shift = bn.bias + (conv.bias - bn.running_mean) * scale
+                    # block 2 reads block 1's TF32-rounded output: its filter needs no truncation compensation
+                    w = ops.prepare_conv3x3_weight(conv.weight, ops.TF32_TRUNC_COMP if i == 0 else 1.0)
+                    blocks.append((w, scale.contiguous(), shift.contiguous(), self._net[i + 2].negative_slope))
+            cached = (key, blocks)
+            self._mde_folded = cached
+        return cached[1]
+
+    def forward_tc(self, x_cl, concat_with, round_out=False):
+        """Inference path on our kernels, channels_last throughout: resize + concat (one streaming pass) -> 2 x tcgen05
+        conv3x3 with BatchNorm(eval) + LeakyReLU in the epilogue."""
+        (w1, s1, b1, a1), (w2, s2, b2, a2) = self._folded()
+        y = ops.upsample_concat_nhwc(x_cl, concat_with)
+        y = ops.conv3x3_nhwc(y, w1, s1, b1, slope=a1, round_tf32=True)
+        return ops.conv3x3_nhwc(y, w2, s2, b2, slope=a2, round_tf32=round_out)
+
     def forward(self, x, concat_with):
         if x.is_cuda:  # fused resize + concat kernel (ATen's align_corners bilinear kernel dominates the step otherwise)
             return self._net(ops.upsample_concat(x, concat_with))
@@ -60,8 +92,33 @@ class DecoderBN(nn.Module):
         self.mode = mode
         self.conv3 = nn.Conv2d(f // 16, num_classes if mode == "AdaBins" else 1, kernel_size=3, stride=1, padding=1)
 
+        self.conv_impl = "auto"  # "tc": tcgen05 conv3x3 path; "cudnn": stock modules; "auto": tc iff cudnn.allow_tf32
+
+    def _use_tc(self, bottleneck):
+        impl = self.conv_impl
+        if impl == "auto":
+            impl = "tc" if torch.backends.cudnn.allow_tf32 else "cudnn"
+        return (impl == "tc" and bottleneck.is_cuda and not self.training and not torch.is_grad_enabled()
+                and bottleneck.dtype == torch.float32)
+
+    def _prepared_conv3(self):
+        w = self.conv3.weight
+        cached = getattr(self, "_mde_w3_prep", None)
+        if cached is None or cached[0] != w._version or cached[1].device != w.device:
+            cached = (w._version, ops.prepare_conv3x3_weight(w, 1.0))
+            self._mde_w3_prep = cached
+        return cached[1]
+
     def forward(self, features):
         s0, s1, s2, s3, bottleneck = features[4], features[5], features[6], features[8], features[11]
+        if self._use_tc(bottleneck):
+            # (f)1: the whole decoder on our kernels, channels_last; conv2 (1x1, padding 1) is a plain library GEMM
+            y = self.conv2(bottleneck.contiguous(memory_format=torch.channels_last))
+            y = y.contiguous(memory_format=torch.channels_last)
+            ups = ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0))
+            for i, (up, skip) in enumerate(ups):
+                y = up.forward_tc(y, skip, round_out=(i == 3))
+            return ops.conv3x3_nhwc(y, self._prepared_conv3(), None, self.conv3.bias)
         y = self.conv2(bottleneck)
         for up, skip in ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0)):
             y = up(y, skip)

@@ -520,6 +520,25 @@ def upsample_concat(x, skip):
     return _UpsampleConcat.apply(x.contiguous().float(), skip.contiguous().float())
 
 
+def upsample_concat_nhwc(x_cl, skip):
+    """channels_last DecoderBN up-sampling step: bilinear(align_corners=True) resize of x_cl [B,C1,h,w] (channels_last)
+    to skip's size, concatenated with skip (either memory format) -> channels_last [B,C1+C2,H,W]; inference only."""
+    lib = _lib.load()
+    _need_cuda(x_cl, skip)
+    if not x_cl.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("upsample_concat_nhwc expects a channels_last x")
+    b, c1, h, w = x_cl.shape
+    _, c2, hh, ww = skip.shape
+    skip_cl = skip.is_contiguous(memory_format=torch.channels_last)
+    if not skip_cl:
+        skip = skip.contiguous()
+    out = torch.empty((b, c1 + c2, hh, ww), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    with timing("upsample_concat_nhwc"):
+        rc = lib.mde_upsample_concat_nhwc_fwd(_p(x_cl), _p(skip), 1 if skip_cl else 0, _p(out), b, c1, c2, h, w, hh, ww, _s())
+    _lib.check(rc, "mde_upsample_concat_nhwc_fwd")
+    return out
+
+
 def to_channels_last(x):
     """NCHW-contiguous fp32 [B,C,H,W] -> the same logical tensor with channels_last strides (tiled transpose kernel)."""
     lib = _lib.load()

@@ -378,6 +378,38 @@ def test_upsample_concat_forward_backward(shape):
     np.testing.assert_allclose(sd.grad.cpu().numpy(), skip.grad.numpy(), rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("skip_cl", [False, True])
+def test_upsample_concat_nhwc(skip_cl):
+    """channels_last resize + concat (feeds the tcgen05 decoder convs) vs F.interpolate(align_corners=True) + cat."""
+    rng = np.random.default_rng(35)
+    for xs, ss in [((2, 8, 15, 19), (2, 12, 26, 34)), ((1, 64, 13, 17), (1, 4, 27, 35)), ((2, 4, 8, 8), (2, 8, 8, 8))]:
+        x = torch.from_numpy(rng.standard_normal(xs).astype(np.float32))
+        skip = torch.from_numpy(rng.standard_normal(ss).astype(np.float32))
+        ref = torch.cat((torch.nn.functional.interpolate(x, size=ss[-2:], mode="bilinear", align_corners=True), skip), 1)
+        sd = skip.to(DEV)
+        if skip_cl:
+            sd = sd.contiguous(memory_format=torch.channels_last)
+        out = ops.upsample_concat_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), sd)
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_decoder_tc_vs_stock():
+    """(f)1 DecoderBN on our kernels (channels_last, tcgen05 conv3x3 with BatchNorm(eval)+LeakyReLU folded into the
+    epilogue) vs the stock torch modules in strict fp32 on the same encoder features."""
+    m = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None).to(DEV)
+    x = synthetic.image(2, 160, 192, seed=37).to(DEV)
+    with torch.no_grad():
+        feats = m.encoder(x)
+        m.decoder.conv_impl = "cudnn"
+        ref = m.decoder(feats)
+        m.decoder.conv_impl = "tc"
+        out = m.decoder(feats)
+    assert out.shape == ref.shape
+    err = float((out - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-3, err
+
+
 def test_nchw_to_nhwc():
     rng = np.random.default_rng(33)
     for shape in [(2, 128, 16, 24), (1, 70, 5, 7), (3, 3, 9, 2)]:
