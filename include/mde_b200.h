@@ -31,6 +31,7 @@ enum {
 };
 
 enum { MDE_F32 = 0, MDE_F64 = 1 };
+enum { MDE_I64 = 0, MDE_I32 = 1, MDE_U8 = 2 }; /* label element types */
 enum { MDE_NORM_LINEAR = 0, MDE_NORM_SOFTMAX = 1, MDE_NORM_SIGMOID = 2 };
 
 int mde_version(void);
@@ -54,6 +55,14 @@ int64_t mde_launch_count(void);
 int mde_gather_embed(const int64_t* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
                      int rows, int D, int background, int out_dtype, int64_t table_image_stride,
                      int32_t* oob_flag, mde_stream_t stream);
+
+/* Same gather on the labels' wire formats ("next" row (f)3): label_dtype MDE_I64 (batch tensors, dataloader.py:200-205),
+ * MDE_I32 (the .npz instance label / area maps, dataloader.py:136-150) or MDE_U8 (semantic maps after
+ * astype(np.ubyte), dataloader.py:121-133 -- a -1 "no prediction" label arrives as 255 and is clamped like any other
+ * out-of-range value).  labels_out (optional) receives the clamped labels as int64. */
+int mde_gather_embed_labels(const void* labels, int label_dtype, int64_t* labels_out, const void* table, void* out, int B,
+                            int64_t HW, int rows, int D, int background, int out_dtype, int64_t table_image_stride,
+                            int32_t* oob_flag, mde_stream_t stream);
 
 /* Per-image class histogram -> per-image table of area fractions count/HW (float64), the gather table of
  * SemanticsLoader.get_semantics_inst_areas (SemanticsLoader.py:88-99).
@@ -210,6 +219,21 @@ int mde_chamfer_fwd(const float* edges, const float* target, int B, int n_bins, 
                     void* ws, float* loss, mde_stream_t stream);
 int mde_chamfer_bwd(const float* edges, int B, int n_bins, const void* ws, const float* grad_loss,
                     float* grad_edges, mde_stream_t stream);
+
+/* ---- "next" row (f)2: evaluation epilogue + metrics (evaluate.py:50-71,128-152; train.py:543-568; utils.py:119-139).
+ * pred [B,1,h,w] (bilinearly up-sampled to HxW with align_corners=True inside the kernel when h,w != H,W), gt [B,1,H,W];
+ * pred is clipped to [min_depth_eval, max_depth_eval] (nan -> min, inf -> max); valid = gt in (min, max) inside the crop
+ * box rows [crop_y0, crop_y1) x cols [crop_x0, crop_x1) (pass 0,H,0,W for no crop).  out [B,10] float32 per image:
+ * a1 a2 a3 abs_rel rmse log_10 rmse_log silog sq_rel n_valid (NaN metrics when n_valid == 0, like numpy's empty mean).
+ * ws: mde_eval_metrics_ws_bytes(B) bytes of scratch (zeroed by the call). */
+int64_t mde_eval_metrics_ws_bytes(int B);
+int mde_eval_metrics_fwd(const float* pred, const float* gt, int B, int h, int w, int H, int W, float min_depth_eval,
+                         float max_depth_eval, int crop_y0, int crop_y1, int crop_x0, int crop_x1, void* ws, float* out,
+                         mde_stream_t stream);
+/* mirror test-time augmentation of infer.py:108-118: out = 0.5 * (clip(a, lo, hi) + clip(flip_w(b_flipped), lo, hi));
+ * a, b_flipped, out are [rows, w] float32 (rows = B*h). */
+int mde_flip_average(const float* a, const float* b_flipped, float* out, int64_t rows, int w, float lo, float hi,
+                     mde_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,8 +71,13 @@ class InstanceSegmentationLoader():
         areas_raw = batch['instance_areas'].to(self.device, non_blocking=True)
         bg = self.background_class_num
         # the embedding stays float64 in the reference (no .float() at :107-109)
-        emb = ops.gather_embed(raw, self._table("emb", self.word_embeddings_semantics, torch.float64), background=bg,
-                               write_back=True)
+        table = self._table("emb", self.word_embeddings_semantics, torch.float64)
+        if raw.dtype == torch.int64:
+            emb = ops.gather_embed(raw, table, background=bg, write_back=True)
+        else:  # int32 instance maps as stored on disk (.npz 'arr_0', dataloader.py:136-150): 4 B/px over the bus
+            raw64 = torch.empty(raw.shape, dtype=torch.int64, device=raw.device)
+            emb = ops.gather_embed(raw, table, background=bg, labels_out=raw64)
+            raw = raw64
         areas = ops.cast_i64_f32(areas_raw) if areas_raw.dtype == torch.int64 else areas_raw.float()
         if self.human_sizes is not None:
             sizes = ops.gather_embed(raw, self._table("sizes", self.human_sizes, torch.float32), background=None)

@@ -73,7 +73,15 @@ class SemanticsLoader():
                 "ade20k_classes_abs_sizes_shuffled.npy" if "shuffled" in mode else "ade20k_classes_abs_sizes.npy")
 
     def load_word_embeddings(self):
-        if self.embeddings_path is not None:
+        mode = self.args.use_semantics
+        if mode is not None and "one-hot" in mode:
+            # "next" row (f)4: the reference ships params/..._sem_one-hot-ade20k-places_... but has no code for the mode
+            # (SemanticsLoader.py:44-55, unet_adaptive_bins.py:377-378); implemented here as the same gather with a
+            # 101 x 101 identity table (an extension: the reference has no implementation to compare with)
+            if "ade20k-places" not in mode:
+                sys.exit("Error: one-hot semantics are only defined for the ade20k-places label set.")
+            self.word_embeddings_semantics = torch.eye(101, dtype=torch.float64)
+        elif self.embeddings_path is not None:
             self.word_embeddings_semantics = torch.from_numpy(np.load(self.embeddings_path))
 
     def load_human_sizes(self):
@@ -101,7 +109,16 @@ class SemanticsLoader():
         host_raw = batch['semantics']
         raw = host_raw.to(self.device, non_blocking=True).contiguous()
         places = "ade20k-places" in mode
-        if "raw" in mode:
+        compact = raw.dtype in (torch.int32, torch.uint8)  # on-disk label formats travel as 4 / 1 byte per pixel
+        if compact and "raw" in mode:
+            raw, compact = raw.long(), False
+        if compact:
+            dtype = torch.float32 if places else torch.float64
+            table = self._table("emb", self.word_embeddings_semantics, dtype)
+            raw64 = torch.empty(raw.shape, dtype=torch.int64, device=raw.device)
+            semantics = ops.gather_embed(raw, table, background=100 if places else None, labels_out=raw64)
+            raw = raw64
+        elif "raw" in mode:
             if places:  # clamp only, no gather
                 raw = raw.clamp_(max=100)
                 raw[raw < 0] = 100

@@ -20,6 +20,7 @@ SIGNATURES = {
     "mde_check_device": (_i32, []),
     "mde_launch_count": (_i64, []),
     "mde_gather_embed": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
+    "mde_gather_embed_labels": (_i32, [_p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     "mde_class_area_table": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p]),
     "mde_cast_i64_f32": (_i32, [_p, _p, _i64, _p]),
     "mde_aux_mlp_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i64, _f32, _p]),
@@ -49,6 +50,9 @@ SIGNATURES = {
     "mde_upsample_bwd": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_nchw_to_nhwc": (_i32, [_p, _p, _i32, _i32, _i64, _p]),
     "mde_relu_eps_fwd": (_i32, [_p, _p, _i64, _f32, _p]),
+    "mde_eval_metrics_ws_bytes": (_i64, [_i32]),
+    "mde_eval_metrics_fwd": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "mde_flip_average": (_i32, [_p, _p, _p, _i64, _i32, _f32, _f32, _p]),
     "mde_silog_ws_bytes": (_i64, []),
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_silog_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -37,9 +37,24 @@ __device__ __forceinline__ int clamp_label(long long l, int rows, int background
   return (int)l;
 }
 
+// four consecutive labels of the on-disk / wire label types: int64 (the reference's batch tensors), int32 (the .npz
+// instance maps, dataloader.py:136-150) and uint8 (semantic maps after astype(np.ubyte), dataloader.py:121-133)
+__device__ __forceinline__ void load4(const long long* p, long long (&v)[4]) {
+  const longlong2 a = *reinterpret_cast<const longlong2*>(p), c = *reinterpret_cast<const longlong2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y;
+}
+__device__ __forceinline__ void load4(const int* p, long long (&v)[4]) {
+  const int4 a = *reinterpret_cast<const int4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const unsigned char* p, long long (&v)[4]) {
+  const uchar4 a = *reinterpret_cast<const uchar4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+
 // VEC = 4: HW % 4 == 0 and 16/32-byte aligned pointers; VEC = 1: generic scalar path.
-template <typename T, int VEC, bool SMEM>
-__global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __restrict__ labels,
+template <typename T, typename L, int VEC, bool SMEM>
+__global__ void __launch_bounds__(256) gather_embed_kernel(const L* __restrict__ labels,
                                                             long long* labels_out, const T* __restrict__ table,
                                                             T* __restrict__ out, long long HW, int rows, int D,
                                                             int background, long long table_image_stride,
@@ -53,7 +68,7 @@ __global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __re
     __syncthreads();
     tab = stab;
   }
-  const long long* lab = labels + (long long)b * HW;
+  const L* lab = labels + (long long)b * HW;
   long long* lab_out = labels_out ? labels_out + (long long)b * HW : nullptr;
   T* o = out + (long long)b * D * HW;
   const long long groups = HW / VEC;
@@ -62,13 +77,13 @@ __global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __re
        g += (long long)gridDim.x * blockDim.x) {
     const long long p = g * VEC;
     if (VEC == 4) {
-      const longlong2 a = *reinterpret_cast<const longlong2*>(lab + p);
-      const longlong2 c = *reinterpret_cast<const longlong2*>(lab + p + 2);
-      const int l0 = clamp_label(a.x, rows, background, oob), l1 = clamp_label(a.y, rows, background, oob);
-      const int l2 = clamp_label(c.x, rows, background, oob), l3 = clamp_label(c.y, rows, background, oob);
+      long long v[4];
+      load4(lab + p, v);
+      const int l0 = clamp_label(v[0], rows, background, oob), l1 = clamp_label(v[1], rows, background, oob);
+      const int l2 = clamp_label(v[2], rows, background, oob), l3 = clamp_label(v[3], rows, background, oob);
       if (lab_out) {
-        *reinterpret_cast<longlong2*>(lab_out + p) = make_longlong2(l0 < 0 ? a.x : l0, l1 < 0 ? a.y : l1);
-        *reinterpret_cast<longlong2*>(lab_out + p + 2) = make_longlong2(l2 < 0 ? c.x : l2, l3 < 0 ? c.y : l3);
+        *reinterpret_cast<longlong2*>(lab_out + p) = make_longlong2(l0 < 0 ? v[0] : l0, l1 < 0 ? v[1] : l1);
+        *reinterpret_cast<longlong2*>(lab_out + p + 2) = make_longlong2(l2 < 0 ? v[2] : l2, l3 < 0 ? v[3] : l3);
       }
       const T* r0 = tab + (l0 < 0 ? 0 : l0) * D;
       const T* r1 = tab + (l1 < 0 ? 0 : l1) * D;
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __re
                        l3 < 0 ? z : r3[d]);
       }
     } else {
-      const long long raw = lab[p];
+      const long long raw = (long long)lab[p];
       const int l = clamp_label(raw, rows, background, oob);
       if (lab_out) lab_out[p] = l < 0 ? raw : l;
       const T* r = tab + (l < 0 ? 0 : l) * D;
@@ -91,24 +106,25 @@ __global__ void __launch_bounds__(256) gather_embed_kernel(const long long* __re
   if (oob && oob_flag) atomicExch(oob_flag, 1);
 }
 
-template <typename T>
-static int launch_gather(const int64_t* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
+template <typename T, typename L>
+static int launch_gather(const void* labels, int64_t* labels_out, const void* table, void* out, int B, int64_t HW,
                          int rows, int D, int background, int64_t tis, int32_t* oob_flag, cudaStream_t st) {
   const size_t tab_bytes = (size_t)rows * D * sizeof(T);
   const bool smem = tab_bytes <= 48 * 1024;
-  const bool vec = (HW % 4 == 0) && aligned(labels, 16) && aligned(out, 16) && (!labels_out || aligned(labels_out, 16));
+  const bool vec = (HW % 4 == 0) && aligned(labels, 4 * sizeof(L) > 16 ? 16 : 4 * sizeof(L)) && aligned(out, 16) &&
+                   (!labels_out || aligned(labels_out, 16));
   const long long groups = vec ? HW / 4 : HW;
   long long gx = (groups + 256 * 4 - 1) / (256 * 4);
   if (gx < 1) gx = 1;
   if (gx > 65535) gx = 65535;
   dim3 grid((unsigned)gx, (unsigned)B);
   const size_t sm = smem ? tab_bytes : 0;
-  const long long* L = reinterpret_cast<const long long*>(labels);
+  const L* Lp = reinterpret_cast<const L*>(labels);
   long long* LO = reinterpret_cast<long long*>(labels_out);
   const T* Tb = reinterpret_cast<const T*>(table);
   T* O = reinterpret_cast<T*>(out);
 #define MDE_GATHER_LAUNCH(V, S) \
-  gather_embed_kernel<T, V, S><<<grid, 256, sm, st>>>(L, LO, Tb, O, HW, rows, D, background, tis, oob_flag)
+  gather_embed_kernel<T, L, V, S><<<grid, 256, sm, st>>>(Lp, LO, Tb, O, HW, rows, D, background, tis, oob_flag)
   if (vec && smem) MDE_GATHER_LAUNCH(4, true);
   else if (vec) MDE_GATHER_LAUNCH(4, false);
   else if (smem) MDE_GATHER_LAUNCH(1, true);
@@ -186,11 +202,30 @@ int mde_gather_embed(const int64_t* labels, int64_t* labels_out, const void* tab
   if (!labels || !table || !out) return MDE_ERR_BAD_POINTER;
   if (B < 0 || HW < 0 || rows <= 0 || D <= 0 || background >= rows || B > 65535) return MDE_ERR_BAD_SHAPE;
   if (B == 0 || HW == 0) return MDE_OK;
+  return mde_gather_embed_labels(labels, MDE_I64, labels_out, table, out, B, HW, rows, D, background, out_dtype,
+                                 table_image_stride, oob_flag, stream);
+}
+
+int mde_gather_embed_labels(const void* labels, int label_dtype, int64_t* labels_out, const void* table, void* out, int B,
+                            int64_t HW, int rows, int D, int background, int out_dtype, int64_t table_image_stride,
+                            int32_t* oob_flag, mde_stream_t stream) {
+  if (!labels || !table || !out) return MDE_ERR_BAD_POINTER;
+  if (B < 0 || HW < 0 || rows <= 0 || D <= 0 || background >= rows || B > 65535) return MDE_ERR_BAD_SHAPE;
+  if (B == 0 || HW == 0) return MDE_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == MDE_F32)
-    return launch_gather<float>(labels, labels_out, table, out, B, HW, rows, D, background, table_image_stride, oob_flag, st);
-  if (out_dtype == MDE_F64)
-    return launch_gather<double>(labels, labels_out, table, out, B, HW, rows, D, background, table_image_stride, oob_flag, st);
+#define MDE_GATHER_DISPATCH(T)                                                                                          \
+  switch (label_dtype) {                                                                                                \
+    case MDE_I64: return launch_gather<T, long long>(labels, labels_out, table, out, B, HW, rows, D, background,       \
+                                                     table_image_stride, oob_flag, st);                                \
+    case MDE_I32: return launch_gather<T, int>(labels, labels_out, table, out, B, HW, rows, D, background,             \
+                                               table_image_stride, oob_flag, st);                                      \
+    case MDE_U8: return launch_gather<T, unsigned char>(labels, labels_out, table, out, B, HW, rows, D, background,    \
+                                                        table_image_stride, oob_flag, st);                             \
+    default: return MDE_ERR_UNSUPPORTED;                                                                                \
+  }
+  if (out_dtype == MDE_F32) MDE_GATHER_DISPATCH(float)
+  if (out_dtype == MDE_F64) MDE_GATHER_DISPATCH(double)
+#undef MDE_GATHER_DISPATCH
   return MDE_ERR_UNSUPPORTED;
 }
 

@@ -344,6 +344,8 @@ class UnetAdaptiveBins(nn.Module):
                 n += 300
             elif "glove-25d" in semantics_mode:
                 n += 25
+            elif "one-hot" in semantics_mode:
+                n += 101  # (f)4 extension: one plane per ADE20K-places class (no reference implementation exists)
             else:
                 sys.exit("Error [models/unet_adaptive_bins.py]: semantics mode not recognised")
             n += 10 * (("inst-areas" in semantics_mode) + ("human-sizes" in semantics_mode))

@@ -77,17 +77,29 @@ def kernel_times_ms():
 # ------------------------------------------------------------------------------------------------------------
 # K3: gathers
 # ------------------------------------------------------------------------------------------------------------
-def gather_embed(labels, table, background=None, write_back=False, out=None, table_image_stride=0):
-    """labels int64 [B,1,H,W]; table [rows,D] (f32/f64, CUDA) -> [B,D,H,W] of table.dtype.
+_LABEL_DTYPES = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}
+
+
+def gather_embed(labels, table, background=None, write_back=False, out=None, table_image_stride=0, labels_out=None):
+    """labels [B,1,H,W] int64 (the reference's batch tensors) or int32 / uint8 (the on-disk label formats, "next" row
+    (f)3); table [rows,D] (f32/f64, CUDA) -> [B,D,H,W] of table.dtype.
     background: clamp target for labels outside [0,rows-1] (None = no clamp; out-of-range raises IndexError like
-    the reference's index_select).  write_back=True stores the clamped labels into ``labels`` (the reference clamps
-    the batch tensor in place: SemanticsLoader.py:115-118)."""
+    the reference's index_select).  write_back=True stores the clamped labels into ``labels`` (int64 only; the
+    reference clamps the batch tensor in place: SemanticsLoader.py:115-118); ``labels_out`` (int64 [B,1,H,W]) receives
+    them for any label dtype."""
     lib = _lib.load()
     _need_cuda(labels, table)
-    if labels.dtype != torch.int64 or labels.dim() != 4 or labels.shape[1] != 1 or not labels.is_contiguous():
-        raise ValueError("labels must be a contiguous int64 [B,1,H,W] tensor")
+    if labels.dtype not in _LABEL_DTYPES or labels.dim() != 4 or labels.shape[1] != 1 or not labels.is_contiguous():
+        raise ValueError("labels must be a contiguous int64 / int32 / uint8 [B,1,H,W] tensor")
     if table.dtype not in (torch.float32, torch.float64) or not table.is_contiguous():
         raise ValueError("table must be contiguous float32/float64")
+    if write_back:
+        if labels.dtype != torch.int64:
+            raise ValueError("write_back needs int64 labels (pass labels_out for compact label types)")
+        labels_out = labels
+    if labels_out is not None and (labels_out.dtype != torch.int64 or labels_out.shape != labels.shape
+                                   or not labels_out.is_contiguous()):
+        raise ValueError("labels_out must be a contiguous int64 tensor of the labels' shape")
     b, _, h, w = labels.shape
     if table_image_stride:
         rows, d = table.shape[1], table.shape[2]
@@ -101,10 +113,10 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
     if background is None:
         flag = torch.zeros(1, dtype=torch.int32, device=labels.device)
     with timing("gather_embed"):
-        rc = lib.mde_gather_embed(_p(labels), _p(labels) if write_back else None, _p(table), _p(out), b, h * w, rows, d,
-                                  -1 if background is None else int(background),
-                                  0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
-    _lib.check(rc, "mde_gather_embed")
+        rc = lib.mde_gather_embed_labels(_p(labels), _LABEL_DTYPES[labels.dtype], _p(labels_out), _p(table), _p(out), b,
+                                         h * w, rows, d, -1 if background is None else int(background),
+                                         0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
+    _lib.check(rc, "mde_gather_embed_labels")
     if flag is not None and int(flag.item()) != 0:
         raise IndexError("index out of range in label gather (table has %d rows)" % rows)
     return out
@@ -637,3 +649,41 @@ def bins_chamfer(edges, target_depth_maps, min_target=1e-3):
     if edges.dim() != 2 or target_depth_maps.shape[0] != edges.shape[0]:
         raise ValueError("bins_chamfer expects edges [B,n_bins+1] and targets [B,...]")
     return _Chamfer.apply(edges.contiguous().float(), target_depth_maps.contiguous().float(), min_target)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# "next" row (f)2: evaluation epilogue + metrics
+# ------------------------------------------------------------------------------------------------------------
+METRIC_KEYS = ("a1", "a2", "a3", "abs_rel", "rmse", "log_10", "rmse_log", "silog", "sq_rel")
+
+
+def eval_metrics(pred, gt, min_depth_eval, max_depth_eval, crop_box=None):
+    """pred [B,1,h,w], gt [B,1,H,W] (CUDA float32) -> [B,10] float32: the reference's nine metrics per image
+    (METRIC_KEYS order) + the number of valid pixels.  The bilinear up-sampling, the clipping of the prediction and the
+    validity / crop mask of evaluate.py:59-71,128-150 are fused into the reduction.  crop_box = (y0, y1, x0, x1)."""
+    lib = _lib.load()
+    _need_cuda(pred, gt)
+    if pred.dim() != 4 or gt.dim() != 4 or pred.shape[1] != 1 or gt.shape[1] != 1 or pred.shape[0] != gt.shape[0]:
+        raise ValueError("eval_metrics expects pred [B,1,h,w] and gt [B,1,H,W]")
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    b, _, h, w = pred.shape
+    hh, ww = gt.shape[-2:]
+    y0, y1, x0, x1 = (0, hh, 0, ww) if crop_box is None else crop_box
+    ws = torch.empty(int(lib.mde_eval_metrics_ws_bytes(b)), dtype=torch.uint8, device=pred.device)
+    out = torch.empty((b, 10), dtype=torch.float32, device=pred.device)
+    with timing("eval_metrics"):
+        rc = lib.mde_eval_metrics_fwd(_p(pred), _p(gt), b, h, w, hh, ww, float(min_depth_eval), float(max_depth_eval),
+                                      int(y0), int(y1), int(x0), int(x1), _p(ws), _p(out), _s())
+    _lib.check(rc, "mde_eval_metrics_fwd")
+    return out
+
+
+def flip_average(pred, pred_of_flipped, lo, hi):
+    """0.5 * (clip(pred) + clip(flip_w(pred_of_flipped)))  -- the mirror test-time augmentation of infer.py:108-118."""
+    lib = _lib.load()
+    _need_cuda(pred, pred_of_flipped)
+    a, bf = pred.contiguous().float(), pred_of_flipped.contiguous().float()
+    out = torch.empty_like(a)
+    w = a.shape[-1]
+    _lib.check(lib.mde_flip_average(_p(a), _p(bf), _p(out), a.numel() // w, w, float(lo), float(hi), _s()), "mde_flip_average")
+    return out

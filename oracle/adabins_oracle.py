@@ -311,6 +311,49 @@ def compute_errors(gt, pred):
         sq_rel=np.mean(((gt - pred) ** 2) / gt))
 
 
+def eval_crop_box(h, w, garg_crop=False, eigen_crop=False, dataset="nyu"):
+    """(y0, y1, x0, x1) of evaluate.py:136-148 / train.py:552-564; the full frame without a crop flag."""
+    if garg_crop:
+        return int(0.40810811 * h), int(0.99189189 * h), int(0.03594771 * w), int(0.96405229 * w)
+    if eigen_crop:
+        if dataset == "kitti":
+            return int(0.3324324 * h), int(0.91351351 * h), int(0.0359477 * w), int(0.96405229 * w)
+        return 45, 471, 41, 601
+    return 0, h, 0, w
+
+
+def eval_epilogue(pred, gt, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False, dataset="nyu"):
+    """evaluate.py:59-71 + :128-150 for ONE image: pred [1,1,h,w] tensor, gt [1,1,H,W] tensor ->
+    (gt[valid], pred[valid]) float32 vectors ready for compute_errors.  (When a crop flag is set the reference ANDs the
+    validity mask with the crop box; without one it would AND with an undefined eval_mask -- the full frame is used.)"""
+    p = torch.nn.functional.interpolate(pred, gt.shape[-2:], mode="bilinear", align_corners=True)
+    return eval_mask_and_clip(p, gt, min_depth_eval, max_depth_eval, garg_crop, eigen_crop, dataset)
+
+
+def eval_mask_and_clip(p, gt, min_depth_eval, max_depth_eval, garg_crop=False, eigen_crop=False, dataset="nyu"):
+    """The part of eval_epilogue after the up-sampling (p already has gt's size)."""
+    p = p.squeeze().cpu().numpy().copy()
+    p[p < min_depth_eval] = min_depth_eval
+    p[p > max_depth_eval] = max_depth_eval
+    p[np.isinf(p)] = max_depth_eval
+    p[np.isnan(p)] = min_depth_eval
+    g = gt.squeeze().cpu().numpy()
+    valid = np.logical_and(g > min_depth_eval, g < max_depth_eval)
+    y0, y1, x0, x1 = eval_crop_box(g.shape[0], g.shape[1], garg_crop, eigen_crop, dataset)
+    box = np.zeros(valid.shape, dtype=bool)
+    box[y0:y1, x0:x1] = True
+    valid = np.logical_and(valid, box)
+    return g[valid], p[valid]
+
+
+def flip_tta(model_fn, image, min_depth, max_depth):
+    """infer.py:108-118: average of the clipped prediction and the clipped, un-mirrored prediction of the mirrored image
+    (both at the model's output resolution)."""
+    pred = np.clip(model_fn(image).cpu().numpy(), min_depth, max_depth)
+    pred_lr = np.clip(model_fn(torch.flip(image, dims=[-1])).cpu().numpy()[..., ::-1], min_depth, max_depth)
+    return 0.5 * (pred + pred_lr)
+
+
 # ----------------------------------------------------------------------------------------------
 # Whole-path helper used by the CPU baseline: forward + SILog + chamfer given a backbone callable
 # ----------------------------------------------------------------------------------------------

@@ -521,3 +521,112 @@ def test_full_size_properties():
     assert rel_err(e1.cpu(), e2.cpu()) < REL_DEPTH  # the fused path embeds patches in TF32, the other in fp32
     assert_depth_close(p1.cpu(), p2.cpu(), tf32=True)
     assert float(p1.min()) >= 1e-3 and float(p1.max()) <= 10.0  # a convex combination of the bin centres
+
+
+# ------------------------------------------------------------------------------------------------------------
+# "next" rows (f)2-(f)4
+# ------------------------------------------------------------------------------------------------------------
+def test_eval_metrics_golden():
+    """Fused evaluation epilogue + metrics vs the reference's utils.compute_errors (tests/golden/make_golden_eval.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_eval as mg
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_eval.npz"))
+    from mde_biological_vision_systems_b200 import evaluation
+    for name, (b, h, w, H, W, lo, hi, garg, eigen, ds) in mg.CASES.items():
+        pred, gt = mg.case_inputs(name)
+        box = evaluation.crop_box(H, W, garg, eigen, ds)
+        assert box == oracle.eval_crop_box(H, W, garg, eigen, ds)
+        out = ops.eval_metrics(pred.to(DEV), gt.to(DEV), lo, hi, box).cpu().numpy().astype(np.float64)
+        ref = gold[name]
+        assert np.array_equal(out[:, 9], ref[:, 9]), name          # valid-pixel counts: exact
+        np.testing.assert_allclose(out[:, :3], ref[:, :3], rtol=0, atol=1.5 / ref[:, 9].min())  # threshold counts
+        np.testing.assert_allclose(out[:, 3:9], ref[:, 3:9], rtol=1e-4, err_msg=name)
+    # non-finite predictions: reference = ATen's CUDA bilinear kernel (where the reference runs it) + the numpy epilogue
+    pred, gt = mg.case_inputs("nyu_eigen")
+    pred[0, 0, 100, 200] = float("nan")
+    pred[1, 0, 50, 60] = float("inf")
+    pred[1, 0, 70, 90] = float("-inf")
+    up = torch.nn.functional.interpolate(pred.to(DEV), gt.shape[-2:], mode="bilinear", align_corners=True).cpu()
+    out = ops.eval_metrics(pred.to(DEV), gt.to(DEV), 1e-3, 10.0, (45, 471, 41, 601)).cpu().numpy().astype(np.float64)
+    for i in range(2):
+        g, p = oracle.eval_mask_and_clip(up[i:i + 1], gt[i:i + 1], 1e-3, 10.0, False, True, "nyu")
+        m = oracle.compute_errors(g, p)
+        np.testing.assert_allclose(out[i, :9], [m[k] for k in mg.KEYS], rtol=2e-4, atol=2e-5)
+        assert out[i, 9] == g.size
+    # an image without any valid pixel -> NaN like numpy's mean of an empty array
+    gt = torch.zeros(1, 1, 8, 8, device=DEV)
+    assert torch.isnan(ops.eval_metrics(torch.ones(1, 1, 4, 4, device=DEV), gt, 1e-3, 10.0)[0, 0])
+
+
+def test_flip_average():
+    rng = np.random.default_rng(71)
+    a = torch.from_numpy((12 * rng.random((2, 1, 9, 14)) - 1).astype(np.float32))
+    b = torch.from_numpy((12 * rng.random((2, 1, 9, 14)) - 1).astype(np.float32))
+    ref = 0.5 * (np.clip(a.numpy(), 1e-3, 10) + np.clip(b.numpy()[..., ::-1], 1e-3, 10))
+    assert np.array_equal(ops.flip_average(a.to(DEV), b.to(DEV), 1e-3, 10).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.uint8])
+def test_gather_compact_label_formats(dtype, golden_digests):
+    """(f)3: int32 / uint8 label maps (the on-disk formats) gather to the same bits as the int64 batch tensors."""
+    mode = "glove-25d-ade20k-places"
+    lab, _ = sem_labels(mode)
+    wire = lab.to(torch.uint8) if dtype == torch.uint8 else lab.to(torch.int32)  # -1 -> 255 like astype(np.ubyte)
+    raw, sem = SemanticsLoader(Args(use_semantics=mode)).get_semantics({"semantics": wire})
+    ref_raw, ref = oracle.semantics_loader(mode, wire.long().numpy(), load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy"))
+    assert raw.dtype == torch.int64 and np.array_equal(raw.cpu().numpy(), ref_raw)
+    assert np.array_equal(sem.cpu().numpy(), ref)
+    if dtype == torch.int32:  # int32 keeps the sign, so the result is the golden int64 one
+        assert digest(sem.cpu().numpy()) == golden_digests[f"sem/{mode}/out"]
+        ilab, iar = inst_labels("ade20k_swin")
+        out = InstanceSegmentationLoader(Args(use_instance_segmentation="ade20k_swin")).get_instance_segmentation(
+            {"instance_labels": ilab.to(torch.int32), "instance_areas": iar.to(torch.int32)})
+        assert digest(out[0].cpu().numpy()) == golden_digests["inst/ade20k_swin/raw"]
+        assert digest(out[1].cpu().numpy()) == golden_digests["inst/ade20k_swin/emb"]
+        assert digest(out[2].cpu().numpy()) == golden_digests["inst/ade20k_swin/areas"]
+
+
+def test_one_hot_semantics():
+    """(f)4: one-hot-ade20k-places = the K3 gather with a 101 x 101 identity table (no reference implementation)."""
+    mode = "one-hot-ade20k-places"
+    lab, _ = sem_labels(mode)
+    raw, sem = SemanticsLoader(Args(use_semantics=mode)).get_semantics({"semantics": lab.clone()})
+    assert sem.shape == (lab.shape[0], 101, lab.shape[2], lab.shape[3]) and sem.dtype == torch.float32
+    clamped = lab.clone()
+    clamped[(clamped > 100) | (clamped < 0)] = 100
+    ref = torch.nn.functional.one_hot(clamped[:, 0], 101).permute(0, 3, 1, 2).float()
+    assert torch.equal(sem.cpu(), ref) and torch.equal(raw.cpu(), clamped)
+    from mde_biological_vision_systems_b200.models import UnetAdaptiveBins as U
+    assert U.get_num_channels_to_add("efficientnet-b1", mode, None, "rgb") == 101
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5 as parity cases
+# ------------------------------------------------------------------------------------------------------------
+def test_config4_b5_head_vs_oracle():
+    """EfficientNet-B5 AdaBins (original, before-attn without extras): decoder width 2048, head on our kernels."""
+    m = make_model(encoder_name="efficientnet-b5", insertion_point="before-attn", semantics_mode=None,
+                   instance_segmentation_mode=None).to(DEV)
+    x = synthetic.image(1, 352, 384, seed=81).to(DEV)
+    with torch.no_grad():
+        unet_out = m.decoder(m.encoder(x))
+        edges, pred = m(x)
+    assert unet_out.shape == (1, 128, 176, 192) and pred.shape == (1, 1, 176, 192) and edges.shape == (1, 257)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    e_ref, p_ref = oracle.head(unet_out.cpu().contiguous(), sd, 1e-3, 10.0)
+    assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
+    assert_depth_close(pred.cpu(), p_ref, tf32=True)
+
+
+def test_config5_noadabins_480x640():
+    """noAdaBins EfficientNet-B1 at 480x640: (None, relu(unet_out) + 1e-4), one channel at half resolution."""
+    m = make_model(encoder_name="efficientnet-b1-noAdaBins", insertion_point="input", semantics_mode=None,
+                   instance_segmentation_mode=None).to(DEV)
+    x = synthetic.image(2, 480, 640, seed=82).to(DEV)
+    with torch.no_grad():
+        unet_out = m.decoder(m.encoder(x))
+        edges, pred = m(x)
+    assert edges is None and pred.shape == (2, 1, 240, 320)
+    assert np.array_equal(pred.cpu().numpy(), oracle.noadabins_epilogue(unet_out.cpu()).numpy())

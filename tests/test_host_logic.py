@@ -41,8 +41,10 @@ def test_num_channels_to_add():
     assert f("efficientnet-b1", "glove", None, "rgb") == 300
     assert f("efficientnet-b1", "raw", None, "rgb") == 1
     assert f("efficientnet-b1", None, None, "rgb") == 0
+    # (f)4 extension: the reference has a params file for this mode but exits on it (unet_adaptive_bins.py:377-378)
+    assert f("efficientnet-b1", "one-hot-ade20k-places", None, "rgb") == 101
     with pytest.raises(SystemExit):
-        f("efficientnet-b1", "one-hot-ade20k-places", None, "rgb")
+        f("efficientnet-b1", "not-a-mode", None, "rgb")
 
 
 def test_build_surface():

@@ -117,3 +117,20 @@ def test_chamfer_edge_cases(golden):
     # an image with no valid target gives NaN (0/0), as the reference's mean over an empty cloud
     depth[0] = 0.0
     assert torch.isnan(oracle.bins_chamfer(edges, depth))
+
+
+def test_eval_metrics_oracle_vs_reference_golden():
+    """(f)2: oracle.compute_errors (float64 restatement) and oracle.eval_epilogue vs the reference's own
+    utils.compute_errors outputs recorded by tests/golden/make_golden_eval.py."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_eval as mg
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_eval.npz"))
+    for name, (b, h, w, H, W, lo, hi, garg, eigen, ds) in mg.CASES.items():
+        pred, gt = mg.case_inputs(name)
+        for i in range(b):
+            g, p = oracle.eval_epilogue(pred[i:i + 1], gt[i:i + 1], lo, hi, garg, eigen, ds)
+            m = oracle.compute_errors(g, p)
+            row = np.array([m[k] for k in mg.KEYS] + [g.size], dtype=np.float64)
+            np.testing.assert_allclose(row, gold[name][i], rtol=2e-5, atol=2e-5)
