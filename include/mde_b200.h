@@ -187,9 +187,12 @@ int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_
  * resize of x [B,C1,h,w] to HxW fused with torch.cat((up_x, skip [B,C2,H,W]), 1) -> out [B,C1+C2,H,W]. */
 int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B, int C1, int C2, int h, int w, int H,
                             int W, mde_stream_t stream);
-/* gradient of the resize part: gout [B,Ctot,H,W] (first C1 channels read) -> gx [B,C1,h,w]; deterministic gather */
-int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
-                     mde_stream_t stream);
+/* gradient of the resize part, deterministic gather: gout [B,Ctot,H,W] -> gx [B,C1,h,w] (channels_last == 0) or
+ * gout [B,H,W,Ctot] -> gx [B,h,w,C1] (channels_last != 0); only the first C1 channels of gout are read.
+ * ws: mde_upsample_bwd_ws_bytes(h, w) bytes of scratch (per-axis inverse tap tables, rebuilt by every call). */
+int64_t mde_upsample_bwd_ws_bytes(int h, int w);
+int mde_upsample_bwd(const float* gout, float* gx, int channels_last, int B, int C1, int Ctot, int h, int w, int H, int W,
+                     void* ws, mde_stream_t stream);
 
 /* channels_last variant feeding mde_conv3x3_nhwc_fwd: x_nhwc [B,h,w,C1]; skip [B,H,W,C2] (skip_channels_last != 0) or
  * [B,C2,H,W]; out_nhwc [B,H,W,C1+C2].  C1 % 4 == 0 and C2 % 4 == 0. */

@@ -54,45 +54,101 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
   else o[0] = v[0];
 }
 
-// Backward of the resize part, gather form (deterministic, no atomics): one thread per low-res pixel sums the
-// contributions of the (<= ~3x3 for a 2x up-scale) high-res pixels whose bilinear taps include it.
-// gout: [B, C1 + C2, H, W] (only the first C1 channels are read); gx: [B, C1, h, w]
+// Backward of the resize part, gather form (deterministic, no atomics).  A prologue kernel inverts the 1-D bilinear
+// maps once per call: for every low-res index the (<= UP_TAPS) high-res indices whose taps touch it and their weights;
+// the main kernels then sum wy * wx * gout over that small stencil.
+constexpr int UP_TAPS = 8;
+struct UpTap {
+  int idx[UP_TAPS];   // high-res index, -1 = unused
+  float wt[UP_TAPS];
+};
+
+__global__ void upsample_taps_kernel(UpTap* __restrict__ taps, int in_size, int out_size, float scale, float inv_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in_size) return;
+  int lo = (int)floorf((float)(i - 1) * inv_scale) - 1, hi = (int)ceilf((float)(i + 1) * inv_scale) + 1;
+  if (scale == 0.f) { lo = 0; hi = out_size - 1; }
+  lo = max(lo, 0);
+  hi = min(hi, out_size - 1);
+  UpTap t;
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < UP_TAPS; ++k) { t.idx[k] = -1; t.wt[k] = 0.f; }
+  for (int Y = lo; Y <= hi; ++Y) {
+    int a, b;
+    float la, lb;
+    up_src(Y, scale, in_size, a, b, la, lb);
+    float wv = 0.f;
+    if (a == i) wv += la;
+    if (b == i) wv += lb;
+    if (wv != 0.f && n < UP_TAPS) {
+      t.idx[n] = Y;
+      t.wt[n] = wv;
+      ++n;
+    }
+  }
+  taps[i] = t;
+}
+
+// gout: [B, Ctot, H, W] (only the first C1 channels are read); gx: [B, C1, h, w]
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gx, int C1,
-                                                           int Ctot, int h, int w, int H, int W, float sy, float sx,
-                                                           float inv_sy, float inv_sx) {
+                                                           int Ctot, int h, int w, int H, int W,
+                                                           const UpTap* __restrict__ ty, const UpTap* __restrict__ tx) {
   const int c = blockIdx.y, b = blockIdx.z;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= h * w) return;
-  const int i = q / w, j = q % w;
+  const int i = q / w, j = q - i * w;
   const float* g = gout + ((long long)b * Ctot + c) * H * W;
-  // candidate output rows: those with source index in (i-1, i+1)
-  int Y0 = (int)floorf((float)(i - 1) * inv_sy) - 1, Y1 = (int)ceilf((float)(i + 1) * inv_sy) + 1;
-  int X0 = (int)floorf((float)(j - 1) * inv_sx) - 1, X1 = (int)ceilf((float)(j + 1) * inv_sx) + 1;
-  if (sy == 0.f) { Y0 = 0; Y1 = H - 1; }
-  if (sx == 0.f) { X0 = 0; X1 = W - 1; }
-  Y0 = max(Y0, 0); Y1 = min(Y1, H - 1); X0 = max(X0, 0); X1 = min(X1, W - 1);
+  const UpTap a = ty[i], bt = tx[j];
   float acc = 0.f;
-  for (int Y = Y0; Y <= Y1; ++Y) {
-    int y0, y1;
-    float ly0, ly1;
-    up_src(Y, sy, h, y0, y1, ly0, ly1);
-    float wy = 0.f;
-    if (y0 == i) wy += ly0;
-    if (y1 == i) wy += ly1;
-    if (wy == 0.f) continue;
+#pragma unroll
+  for (int u = 0; u < UP_TAPS; ++u) {
+    if (a.idx[u] < 0) break;
+    const float* row = g + (long long)a.idx[u] * W;
     float racc = 0.f;
-    for (int X = X0; X <= X1; ++X) {
-      int xa, xb;
-      float lx0, lx1;
-      up_src(X, sx, w, xa, xb, lx0, lx1);
-      float wx = 0.f;
-      if (xa == j) wx += lx0;
-      if (xb == j) wx += lx1;
-      if (wx != 0.f) racc = fmaf(wx, g[(long long)Y * W + X], racc);
+#pragma unroll
+    for (int v = 0; v < UP_TAPS; ++v) {
+      if (bt.idx[v] < 0) break;
+      racc = fmaf(bt.wt[v], __ldg(row + bt.idx[v]), racc);
     }
-    acc = fmaf(wy, racc, acc);
+    acc = fmaf(a.wt[u], racc, acc);
   }
   gx[((long long)b * C1 + c) * h * w + q] = acc;
+}
+
+// channels_last: gout [B, H, W, Ctot] (channels [0, C1) read), gx [B, h, w, C1]; one thread = 4 channels of one pixel
+__global__ void __launch_bounds__(256) upsample_bwd_nhwc_kernel(const float* __restrict__ gout, float* __restrict__ gx,
+                                                                int C1, int Ctot, int h, int w, int H, int W,
+                                                                const UpTap* __restrict__ ty, const UpTap* __restrict__ tx,
+                                                                long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = C1 >> 2;
+  const int cg = (int)(idx % c4);
+  long long p = idx / c4;
+  const int j = (int)(p % w);
+  p /= w;
+  const int i = (int)(p % h);
+  const int b = (int)(p / h);
+  const UpTap a = ty[i], bt = tx[j];
+  const float* g = gout + (long long)b * H * W * Ctot + cg * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < UP_TAPS; ++u) {
+    if (a.idx[u] < 0) break;
+    const float* row = g + (long long)a.idx[u] * W * Ctot;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < UP_TAPS; ++v) {
+      if (bt.idx[v] < 0) break;
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(row + (long long)bt.idx[v] * Ctot));
+      r.x = fmaf(bt.wt[v], gv.x, r.x); r.y = fmaf(bt.wt[v], gv.y, r.y);
+      r.z = fmaf(bt.wt[v], gv.z, r.z); r.w = fmaf(bt.wt[v], gv.w, r.w);
+    }
+    acc.x = fmaf(a.wt[u], r.x, acc.x); acc.y = fmaf(a.wt[u], r.y, acc.y);
+    acc.z = fmaf(a.wt[u], r.z, acc.z); acc.w = fmaf(a.wt[u], r.w, acc.w);
+  }
+  reinterpret_cast<float4*>(gx + (((long long)b * h + i) * w + j) * C1)[cg] = acc;
 }
 
 }  // namespace mde
@@ -122,15 +178,38 @@ int mde_upsample_concat_fwd(const float* x, const float* skip, float* out, int B
   return check_launch();
 }
 
-int mde_upsample_bwd(const float* gout, float* gx, int B, int C1, int Ctot, int h, int w, int H, int W,
-                     mde_stream_t stream) {
-  if (!gout || !gx) return MDE_ERR_BAD_POINTER;
+int64_t mde_upsample_bwd_ws_bytes(int h, int w) { return (int64_t)sizeof(UpTap) * ((int64_t)h + w); }
+
+static int launch_taps(void* ws, int h, int w, int H, int W, cudaStream_t st) {
+  const float sy = up_scale(h, H), sx = up_scale(w, W);
+  UpTap* ty = reinterpret_cast<UpTap*>(ws);
+  upsample_taps_kernel<<<(h + 127) / 128, 128, 0, st>>>(ty, h, H, sy, sy > 0.f ? 1.f / sy : 0.f);
+  int rc = check_launch();
+  if (rc) return rc;
+  upsample_taps_kernel<<<(w + 127) / 128, 128, 0, st>>>(ty + h, w, W, sx, sx > 0.f ? 1.f / sx : 0.f);
+  return check_launch();
+}
+
+int mde_upsample_bwd(const float* gout, float* gx, int channels_last, int B, int C1, int Ctot, int h, int w, int H, int W,
+                     void* ws, mde_stream_t stream) {
+  if (!gout || !gx || !ws) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || C1 <= 0 || C1 > Ctot || C1 > 65535 || B > 65535 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
     return MDE_ERR_BAD_SHAPE;
-  const float sy = up_scale(h, H), sx = up_scale(w, W);
-  dim3 grid((unsigned)((h * w + 255) / 256), (unsigned)C1, (unsigned)B);
-  upsample_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, gx, C1, Ctot, h, w, H, W, sy, sx,
-                                                              sy > 0.f ? 1.f / sy : 0.f, sx > 0.f ? 1.f / sx : 0.f);
+  // a low-res index is touched by at most 2 * (H / h) + 1 high-res indices; the tap tables hold UP_TAPS
+  if (2LL * H > (long long)(UP_TAPS - 1) * h || 2LL * W > (long long)(UP_TAPS - 1) * w) return MDE_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_taps(ws, h, w, H, W, st);
+  if (rc) return rc;
+  const UpTap* ty = reinterpret_cast<const UpTap*>(ws);
+  if (channels_last) {
+    if (C1 % 4 != 0 || Ctot % 4 != 0 || !aligned(gout, 16) || !aligned(gx, 16)) return MDE_ERR_UNSUPPORTED;
+    const long long total = (long long)B * h * w * (C1 / 4);
+    upsample_bwd_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gout, gx, C1, Ctot, h, w, H, W, ty, ty + h,
+                                                                             total);
+  } else {
+    dim3 grid((unsigned)((h * w + 255) / 256), (unsigned)C1, (unsigned)B);
+    upsample_bwd_kernel<<<grid, 256, 0, st>>>(gout, gx, C1, Ctot, h, w, H, W, ty, ty + h);
+  }
   return check_launch();
 }
 

@@ -522,7 +522,10 @@ class _UpsampleConcat(torch.autograd.Function):
         b, c1, c2, h, w, hh, ww = ctx.shape
         gout = gout.contiguous()
         gx = torch.empty((b, c1, h, w), dtype=torch.float32, device=gout.device)
-        _lib.check(lib.mde_upsample_bwd(_p(gout), _p(gx), b, c1, c1 + c2, h, w, hh, ww, _s()), "mde_upsample_bwd")
+        ws = torch.empty(int(lib.mde_upsample_bwd_ws_bytes(h, w)), dtype=torch.uint8, device=gout.device)
+        with timing("upsample_bwd"):
+            rc = lib.mde_upsample_bwd(_p(gout), _p(gx), 0, b, c1, c1 + c2, h, w, hh, ww, _p(ws), _s())
+        _lib.check(rc, "mde_upsample_bwd")
         return gx, gout[:, c1:]
 
 
@@ -532,11 +535,38 @@ def upsample_concat(x, skip):
     return _UpsampleConcat.apply(x.contiguous().float(), skip.contiguous().float())
 
 
+class _UpsampleConcatNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_cl, skip):
+        out = _upsample_concat_nhwc_fwd(x_cl, skip)
+        ctx.shape = (x_cl.shape[0], x_cl.shape[1], skip.shape[1], x_cl.shape[2], x_cl.shape[3], skip.shape[2], skip.shape[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        b, c1, c2, h, w, hh, ww = ctx.shape
+        if not gout.is_contiguous(memory_format=torch.channels_last):
+            gout = gout.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty((b, c1, h, w), dtype=torch.float32, device=gout.device, memory_format=torch.channels_last)
+        ws = torch.empty(int(lib.mde_upsample_bwd_ws_bytes(h, w)), dtype=torch.uint8, device=gout.device)
+        with timing("upsample_bwd"):
+            rc = lib.mde_upsample_bwd(_p(gout), _p(gx), 1, b, c1, c1 + c2, h, w, hh, ww, _p(ws), _s())
+        _lib.check(rc, "mde_upsample_bwd")
+        return gx, gout[:, c1:]
+
+
 def upsample_concat_nhwc(x_cl, skip):
     """channels_last DecoderBN up-sampling step: bilinear(align_corners=True) resize of x_cl [B,C1,h,w] (channels_last)
-    to skip's size, concatenated with skip (either memory format) -> channels_last [B,C1+C2,H,W]; inference only."""
-    lib = _lib.load()
+    to skip's size, concatenated with skip (either memory format) -> channels_last [B,C1+C2,H,W]; differentiable."""
     _need_cuda(x_cl, skip)
+    if torch.is_grad_enabled() and (x_cl.requires_grad or skip.requires_grad):
+        return _UpsampleConcatNHWC.apply(x_cl, skip)
+    return _upsample_concat_nhwc_fwd(x_cl, skip)
+
+
+def _upsample_concat_nhwc_fwd(x_cl, skip):
+    lib = _lib.load()
     if not x_cl.is_contiguous(memory_format=torch.channels_last):
         raise ValueError("upsample_concat_nhwc expects a channels_last x")
     b, c1, h, w = x_cl.shape

@@ -57,6 +57,18 @@ if what in ("infer", "both"):
 
 if what in ("train", "both"):
     model.train()
+    if os.environ.get("MDE_EXPERIMENT_CL") == "1":
+        # experiment: whole model in channels_last with the stock resize + cat (how much do cuDNN's NHWC kernels buy?)
+        import torch.nn.functional as F
+        from mde_biological_vision_systems_b200.models import unet_adaptive_bins as uab
+
+        def stock_forward(self, x, concat_with):
+            x = F.interpolate(x, size=concat_with.shape[-2:], mode='bilinear', align_corners=True)
+            return self._net(torch.cat((x, concat_with), dim=1))
+
+        uab.UpSampleBN.forward = stock_forward
+        model = model.to(memory_format=torch.channels_last)
+        batch["image"] = batch["image"].contiguous(memory_format=torch.channels_last)
     stepper = TrainStep(model, semantics_loader=loader, total_steps=1000)
     for _ in range(3):
         stepper(batch, dev)
