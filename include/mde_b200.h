@@ -120,6 +120,15 @@ int mde_conv3x3_prep_weight(const float* w_oihw, float* w_prep, int Cout, int C,
 int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* scale, const float* shift, float* y_nhwc,
                          int B, int H, int W, int C, int Cout, float lrelu_slope, int round_tf32, mde_stream_t stream);
 
+/* Batched NT GEMM on tcgen05 (TF32 inputs, fp32 accumulate):  C[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k].
+ * A [batch][M][K] with row pitch lda and batch stride a_batch (floats; multiples of 4), B [batch][N][K] likewise,
+ * C [batch][M][N] with row pitch ldc / batch stride c_batch.  splits > 1 splits the K range over CTAs and accumulates
+ * into C with atomicAdd (the caller zeroes C).  The building block of the head's backward pass (autograd of
+ * models/layers.py:31-36 + unet_adaptive_bins.py:286): d feat = W'^T gl, d W' = gl^T feat. */
+int mde_gemm_nt_tf32(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch, float* C,
+                     int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                     mde_stream_t stream);
+
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  fp32 SIMT, row-major with leading
  * dimensions lda/ldw/ldc (the nn.Linear building block of the regressor and the encoder layers). */
 int mde_linear_fwd(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
@@ -162,6 +171,18 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
  *   centers  [B,n_bins], pred [B,P].   Requires P % 128 == 0, n_bins == 256. */
 int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
                        float* pred, int B, int n_bins, int64_t P, mde_stream_t stream);
+/* Training forms of the fused chain (autograd of layers.py:31-36 + unet_adaptive_bins.py:286-300 in hand-written form):
+ *  - mde_head_chain_fwd_train: the forward, additionally storing the per-pixel softmax state stats [B,P,2]
+ *    (max logit in log2 units, sum_j 2^(z_j - max));
+ *  - mde_head_chain_bwd_logits: recomputes the logits on the tensor cores and writes d loss / d logit (natural-log
+ *    units, TF32-rounded) as gl [B,P,n_bins] and glT [B,n_bins,P], plus gc [B,n_bins] = d loss / d centres and
+ *    gb [B,n_bins] = sum_p gl (both zeroed by the call).  gpred [B,P] is the upstream gradient of pred.
+ *  The remaining products (d feat = gl W', d W' = gl^T feat) are mde_gemm_nt_tf32 calls. */
+int mde_head_chain_fwd_train(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
+                             float* pred, float* stats, int B, int n_bins, int64_t P, mde_stream_t stream);
+int mde_head_chain_bwd_logits(const float* x, int x_channels_last, const float* wf, const float* biasf,
+                              const float* centers, const float* pred, const float* stats, const float* gpred, float* gl,
+                              float* glT, float* gc, float* gb, int B, int n_bins, int64_t P, mde_stream_t stream);
 /* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale )          (fp32 FMA, tiled)
  * biasf[b,j] = log2e * ( bias[j] + sum_k (w_out @ q[b])[j,k] * feat_bias[k] )            (feat_bias may be NULL)
  * operand_scale = MDE_TF32_TRUNC_COMP compensates the mean mantissa loss of the OTHER operand, which the tensor

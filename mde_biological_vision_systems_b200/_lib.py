@@ -32,6 +32,7 @@ SIGNATURES = {
     "mde_patch_embed_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_conv3x3_prep_weight": (_i32, [_p, _p, _i32, _i32, _f32, _p]),
     "mde_conv3x3_nhwc_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
+    "mde_gemm_nt_tf32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),
     "mde_encoder_layer_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),
@@ -40,6 +41,8 @@ SIGNATURES = {
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),
     "mde_head_chain_fwd": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_head_chain_fwd_train": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_head_chain_bwd_logits": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_round_tf32": (_i32, [_p, _p, _i64, _f32, _p]),
     "mde_tc_debug_config": (_i32, [_i32, _i32, _i32, _i32, _i32]),

@@ -37,7 +37,36 @@ constexpr int EPI_WARP0 = 3;                     // warps 0..2: TMA producer, MM
 constexpr int EPI_SPLIT = 2;                     // 8 epilogue warps per tile: 4 lane quarters x 2 column halves
 constexpr int EPI_THREADS = 128 * EPI_SPLIT;
 constexpr int NUM_THREADS = 32 * EPI_WARP0 + EPI_THREADS;  // 352
-enum { EPI_STORE = 0, EPI_SOFTMAX = 1 };
+enum { EPI_STORE = 0, EPI_SOFTMAX = 1, EPI_BWD = 2 };
+
+// extra pointers of the training forms (all may be null for inference):
+//   EPI_SOFTMAX: stats [B,P,2] receives the per-pixel softmax state (max logit in log2 units, sum of 2^(z - max) * 2^bias)
+//   EPI_BWD    : reads stats, pred (the forward output) and gpred [B,P]; writes gl [B,P,NB], glT [B,NB,P] (TF32-rounded
+//                d loss / d logit) and accumulates gc [B,NB] (d loss / d centre) and gb [B,NB] (sum over pixels of gl)
+struct ChainTrain {
+  float* stats;
+  const float* pred;
+  const float* gpred;
+  float* gl;
+  float* glT;
+  float* gc;
+  float* gb;
+};
+
+// column sums over the 32 lanes of a warp of v[32] (lane = row): afterwards v[0] of lane l holds sum_rows v[l]
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 struct DebugCfg {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, version;
@@ -68,7 +97,7 @@ template <int NB, int EPI, bool A_KMAJOR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     head_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ biasf, const float* __restrict__ centers, float* __restrict__ out,
-                      int tiles_per_img, int total_tiles, long long P, DebugCfg dbg) {
+                      int tiles_per_img, int total_tiles, long long P, DebugCfg dbg, ChainTrain tr) {
   using Plan = SmemPlan<NB>;
   constexpr int NS = Plan::NS;
   extern __shared__ unsigned char smem_dyn[];
@@ -254,6 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     float* c_cen = c_all + NB;      // [NB] exp2(bias)*centre
     float4* merge = reinterpret_cast<float4*>(c_all + 2 * NB);  // [128] (m, s, ws, -) of the upper column half
     constexpr int COLS = NB / EPI_SPLIT;  // columns per warp
+    float acc_gb[4] = {0.f, 0.f, 0.f, 0.f}, acc_gc[4] = {0.f, 0.f, 0.f, 0.f};  // EPI_BWD: per-lane bin sums
     int cur = -1;
     int it = 0;
     long long w_accfull = 0;
@@ -261,7 +291,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int img = t / tiles_per_img;
       const int p0 = (t - img * tiles_per_img) * TILE_M;
-      if (EPI == EPI_SOFTMAX && img != cur) {
+      if (EPI == EPI_BWD && img != cur && cur >= 0) {
+        // per-bin sums of the image just finished: lane l of this warp owns bin half*COLS + 32*chunk + l
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          atomicAdd(tr.gb + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gb[c]);
+          atomicAdd(tr.gc + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gc[c]);
+          acc_gb[c] = 0.f;
+          acc_gc[c] = 0.f;
+        }
+      }
+      if (EPI != EPI_STORE && img != cur) {
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // everyone finished reading the old constants
         for (int j = etid; j < NB; j += EPI_THREADS) {
           const float f = exp2f(biasf[(long long)img * NB + j]);
@@ -332,9 +372,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const float4 o = merge[row];
           const float mm = fmaxf(m, o.x);
           const float a = ex2_approx(m - mm), bsc = ex2_approx(o.x - mm);
-          out[(long long)img * P + pix] = (ws * a + o.z * bsc) / (s * a + o.y * bsc);
+          const float stot = s * a + o.y * bsc;
+          out[(long long)img * P + pix] = (ws * a + o.z * bsc) / stot;
+          if (tr.stats) *reinterpret_cast<float2*>(tr.stats + 2 * ((long long)img * P + pix)) = make_float2(mm, stot);
         }
         asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // merge slots free for the next tile
+      } else if constexpr (EPI == EPI_BWD) {
+        // single pass given the forward's softmax state: p_j = 2^(z_j - m) f_j / S;  u_j = p_j g;  gl_j = u_j (c_j - pred)
+        static_assert(COLS == 128, "4 chunks of 32 columns per warp");
+        const long long gp = (long long)img * P + pix;
+        const float2 st = *reinterpret_cast<const float2*>(tr.stats + 2 * gp);
+        const float predv = tr.pred[gp];
+        const float inv = tr.gpred[gp] / st.y;
+        float* gl_row = tr.gl + gp * NB + half * COLS;
+        float* glt_col = tr.glT + ((long long)img * NB + half * COLS) * P + pix;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + 32 * c, r);
+          tmem_ld_wait();
+          if (c == 3) {  // accumulator fully read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+          }
+          float e[32], gv[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(c_fac + half * COLS + 32 * c + i);
+            const float4 cc = *reinterpret_cast<const float4*>(c_cen + half * COLS + 32 * c + i);
+            const float fa[4] = {f.x, f.y, f.z, f.w}, ca[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float ev = ex2_approx(__uint_as_float(r[i + q]) - st.x) * inv;
+              gv[i + q] = tf32_round(ev * (ca[q] - fa[q] * predv));
+              e[i + q] = ev * fa[q];  // u_j
+            }
+            *reinterpret_cast<float4*>(gl_row + 32 * c + i) = make_float4(gv[i], gv[i + 1], gv[i + 2], gv[i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) glt_col[(long long)(32 * c + i) * P] = gv[i];  // 128 B per warp per bin row
+          acc_gb[c] += warp_transpose_sum(gv, lane);
+          acc_gc[c] += warp_transpose_sum(e, lane);
+        }
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS; c0 += 32) {
@@ -350,6 +430,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) dst[(long long)i * P] = __uint_as_float(r[i]);  // 128 B per warp per row
         }
+      }
+    }
+    if (EPI == EPI_BWD && cur >= 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(tr.gb + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gb[c]);
+        atomicAdd(tr.gc + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gc[c]);
       }
     }
     if (dbg.prof && etid == 0) {
@@ -368,7 +455,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
 template <int NB, int EPI, bool A_KMAJOR>
 static int launch_chain(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
-                        long long P, cudaStream_t st) {
+                        long long P, cudaStream_t st, ChainTrain tr = ChainTrain{}) {
   using Plan = SmemPlan<NB>;
   if (P % TILE_M != 0) return MDE_ERR_BAD_SHAPE;
   if (!aligned(x, 16) || !aligned(w, 16)) return MDE_ERR_BAD_POINTER;
@@ -403,7 +490,7 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
     attr_set = true;
   }
   head_chain_kernel<NB, EPI, A_KMAJOR><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
-                                                                      (int)total, P, g_dbg);
+                                                                      (int)total, P, g_dbg, tr);
   return check_launch();
 }
 
@@ -430,6 +517,42 @@ int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, con
   if (x_channels_last)
     return tc::launch_chain<256, tc::EPI_SOFTMAX, true>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
   return tc::launch_chain<256, tc::EPI_SOFTMAX, false>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream);
+}
+
+// training forward: as mde_head_chain_fwd, also recording the per-pixel softmax state stats [B,P,2] for the backward
+int mde_head_chain_fwd_train(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
+                             float* pred, float* stats, int B, int n_bins, int64_t P, mde_stream_t stream) {
+  if (!x || !wf || !biasf || !centers || !pred || !stats) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
+  if (n_bins != 256) return MDE_ERR_UNSUPPORTED;
+  tc::ChainTrain tr{};
+  tr.stats = stats;
+  if (x_channels_last)
+    return tc::launch_chain<256, tc::EPI_SOFTMAX, true>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream, tr);
+  return tc::launch_chain<256, tc::EPI_SOFTMAX, false>(x, wf, biasf, centers, pred, B, P, (cudaStream_t)stream, tr);
+}
+
+// backward, step 1: recompute the logits on the tensor cores and emit d loss / d logit in both layouts + per-bin sums
+int mde_head_chain_bwd_logits(const float* x, int x_channels_last, const float* wf, const float* biasf,
+                              const float* centers, const float* pred, const float* stats, const float* gpred, float* gl,
+                              float* glT, float* gc, float* gb, int B, int n_bins, int64_t P, mde_stream_t stream) {
+  if (!x || !wf || !biasf || !centers || !pred || !stats || !gpred || !gl || !glT || !gc || !gb) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
+  if (n_bins != 256) return MDE_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(gc, 0, sizeof(float) * (size_t)B * n_bins, st);
+  cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)B * n_bins, st);
+  tc::ChainTrain tr{};
+  tr.stats = const_cast<float*>(stats);
+  tr.pred = pred;
+  tr.gpred = gpred;
+  tr.gl = gl;
+  tr.glT = glT;
+  tr.gc = gc;
+  tr.gb = gb;
+  if (x_channels_last)
+    return tc::launch_chain<256, tc::EPI_BWD, true>(x, wf, biasf, centers, nullptr, B, P, st, tr);
+  return tc::launch_chain<256, tc::EPI_BWD, false>(x, wf, biasf, centers, nullptr, B, P, st, tr);
 }
 
 // stand-alone range attention on tensor cores (called by mde_range_attention(impl = 1)); q should be TF32-rounded

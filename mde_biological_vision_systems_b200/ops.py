@@ -291,6 +291,36 @@ def patch_embed(x_cl, w_prepared, bias, pos, patch):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# batched NT GEMM (tcgen05, TF32)
+# ------------------------------------------------------------------------------------------------------------
+def gemm_nt(a, b, out=None, splits=1, alpha=1.0):
+    """out[..., m, n] (+)= alpha * sum_k a[..., m, k] * b[..., n, k] on the tcgen05 GEMM (TF32 inputs).  a [batch,M,K] or
+    [M,K], b [batch,N,K] or [N,K]; rows must be dense along k (stride 1), row / batch pitches multiples of 4 floats.
+    splits > 1: split-K with atomic accumulation into ``out`` (zeroed here unless the caller passes it)."""
+    lib = _lib.load()
+    _need_cuda(a, b)
+    squeeze = a.dim() == 2
+    if squeeze:
+        a, b = a.unsqueeze(0), b.unsqueeze(0)
+    if a.stride(2) != 1:
+        a = a.contiguous()
+    if b.stride(2) != 1:
+        b = b.contiguous()
+    batch, m, k = a.shape
+    n = b.shape[1]
+    if out is None:
+        out = (torch.zeros if splits > 1 else torch.empty)((batch, m, n), dtype=torch.float32, device=a.device)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    if o3.stride(2) != 1:
+        raise ValueError("gemm_nt: out must be dense along its last dimension")
+    with timing("gemm_nt"):
+        rc = lib.mde_gemm_nt_tf32(_p(a), a.stride(1), a.stride(0), _p(b), b.stride(1), b.stride(0), _p(o3), o3.stride(1),
+                                  o3.stride(0), batch, m, n, k, int(splits), float(alpha), _s())
+    _lib.check(rc, "mde_gemm_nt_tf32")
+    return out[0] if (squeeze and out.dim() == 3) else out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # 3x3 convolution (tcgen05 implicit GEMM, NHWC)
 # ------------------------------------------------------------------------------------------------------------
 def prepare_conv3x3_weight(weight, operand_scale=TF32_TRUNC_COMP):
@@ -447,56 +477,87 @@ def head_chain(x, wf, biasf, centers):
     return pred
 
 
+def _is_nhwc(x):
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+
+
+def nhwc_to_nchw(x_cl):
+    """channels_last [B,C,H,W] -> contiguous NCHW copy (the same tiled-transpose kernel, roles of C and P swapped)."""
+    lib = _lib.load()
+    b, c, h, w = x_cl.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=x_cl.device)
+    _lib.check(lib.mde_nchw_to_nhwc(_p(x_cl), _p(out), b, h * w, c, _s()), "mde_nchw_to_nhwc")
+    return out
+
+
 class _HeadChainFn(torch.autograd.Function):
-    """Training wrapper of the fused chain: forward = fold_queries + head_chain (our kernels, nothing but pred is
-    written); backward re-computes the range-attention maps / softmax per image group with cuBLAS + ATen and
-    back-propagates to the features, the queries, conv_out and the centres (a hand-written fused backward is the
-    next step)."""
+    """Training wrapper of the fused chain, forward and backward on the hand-written kernels:
+    forward  = fold_queries + head_chain (training form: also stores the per-pixel softmax state, 8 B/px);
+    backward = (1) the chain re-run with the backward epilogue: logits recomputed on the tensor cores, d loss / d logit
+               written once in both layouts, d centres and the bias sums reduced in the epilogue;
+               (2) d feat = gl W'  and (3) d W' = gl^T feat (split-K) on the tcgen05 NT GEMM;
+               (4) the 256x128x128-sized products that unfold W' = W_out Q_b (a few MFLOP) in torch."""
 
     @staticmethod
     def forward(ctx, feat, queries, w_out, b_out, centers):
+        lib = _lib.load()
+        nhwc = _is_nhwc(feat)
+        if not nhwc:
+            feat = feat.contiguous()
+        b, k, h, w = feat.shape
         wf, biasf = fold_queries(w_out, b_out, queries)
-        pred = head_chain(feat, wf, biasf, centers)
-        ctx.save_for_backward(feat, queries, w_out, b_out, centers, pred)
+        pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=feat.device)
+        stats = torch.empty((b, h * w, 2), dtype=torch.float32, device=feat.device)
+        with timing("head_chain"):
+            rc = lib.mde_head_chain_fwd_train(_p(feat), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers), _p(pred),
+                                              _p(stats), b, wf.shape[1], h * w, _s())
+        _lib.check(rc, "mde_head_chain_fwd_train")
+        ctx.save_for_backward(feat, queries, w_out, b_out, centers, pred, stats, wf, biasf)
+        ctx.nhwc = nhwc
         return pred
 
     @staticmethod
     def backward(ctx, gpred):
-        feat, queries, w_out, b_out, centers, pred = ctx.saved_tensors
+        lib = _lib.load()
+        feat, queries, w_out, b_out, centers, pred, stats, wf, biasf = ctx.saved_tensors
+        nhwc = ctx.nhwc
         b, k, h, w = feat.shape
         p = h * w
+        nb = wf.shape[1]
+        dev = feat.device
+        gpred = gpred.contiguous().float()
+        gl = torch.empty((b, p, nb), dtype=torch.float32, device=dev)
+        glT = torch.empty((b, nb, p), dtype=torch.float32, device=dev)
+        gc = torch.empty((b, nb), dtype=torch.float32, device=dev)
+        gb_img = torch.empty((b, nb), dtype=torch.float32, device=dev)
+        with timing("head_chain_bwd"):
+            rc = lib.mde_head_chain_bwd_logits(_p(feat), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers), _p(pred),
+                                               _p(stats), _p(gpred), _p(gl), _p(glT), _p(gc), _p(gb_img), b, nb, p, _s())
+        _lib.check(rc, "mde_head_chain_bwd_logits")
+        # W' = W_out Q_b without the log2(e) scale, TF32-rounded; its transpose is the K-major operand of d feat
+        wplain, _ = fold_queries(w_out, b_out, queries, operand_scale=1.0 / LOG2E)
+        wpt = wplain.transpose(1, 2).contiguous()                       # [B,128,256]
+        if nhwc:
+            gfeat = torch.empty((b, k, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+            gemm_nt(gl, wpt, out=gfeat.permute(0, 2, 3, 1).reshape(b, p, k))   # [B,P,128] = gl [B,P,256] . W'^T
+            feat_t = nhwc_to_nchw(feat).reshape(b, k, p)
+        else:
+            gfeat = torch.empty((b, k, h, w), dtype=torch.float32, device=dev)
+            gemm_nt(wpt, gl, out=gfeat.reshape(b, k, p))                        # [B,128,P] = W'^T . gl^T
+            feat_t = feat.reshape(b, k, p)
+        # d W'[j,k] = sum_p gl[p,j] feat[p,k]: K = P pixels, split over CTAs (the raw-fp32 operand is truncated by the
+        # tensor core, hence the compensation factor)
+        gwp = gemm_nt(glT, feat_t, splits=max(1, min(64, (2 * 148) // max(1, 2 * b) * 2)), alpha=TF32_TRUNC_COMP)
         wo = w_out.reshape(w_out.shape[0], -1)
-        gfeat = torch.empty_like(feat)
-        gq = torch.empty_like(queries)
-        gw = torch.zeros_like(wo)
-        gb = torch.zeros_like(b_out)
-        gc = torch.empty_like(centers)
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            step = 4
-            for i in range(0, b, step):
-                sl = slice(i, min(b, i + step))
-                x = feat[sl].reshape(-1, k, p)
-                q = queries[sl]
-                r = torch.bmm(q, x)                                         # [n,128,P]
-                logits = torch.matmul(wo, r) + b_out.view(1, -1, 1)         # [n,256,P]
-                sm = torch.softmax(logits, dim=1)
-                g = gpred[sl].reshape(-1, 1, p)
-                gc[sl] = (sm * g).sum(dim=2)
-                gl = sm * (centers[sl].unsqueeze(2) - pred[sl].reshape(-1, 1, p)) * g
-                gw += torch.einsum("njp,nkp->jk", gl, r)
-                gb += gl.sum(dim=(0, 2))
-                gr = torch.matmul(wo.t(), gl)                               # [n,128,P]
-                gq[sl] = torch.bmm(gr, x.transpose(1, 2))
-                gfeat[sl] = torch.bmm(q.transpose(1, 2), gr).reshape(-1, k, h, w)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-        return gfeat, gq, gw.view_as(w_out), gb, gc
+        gw = torch.einsum("bjk,bnk->jn", gwp, queries)                   # d W_out
+        gq = torch.matmul(wo.t().unsqueeze(0), gwp)                      # d Q_b = W_out^T d W'_b
+        return gfeat, gq, gw.view_as(w_out), gb_img.sum(dim=0), gc
 
 
 def head_chain_autograd(feat, queries, w_out, b_out, centers):
-    return _HeadChainFn.apply(feat.contiguous(), queries.contiguous(), w_out, b_out, centers.contiguous())
+    """pred = fused chain(feat, queries, conv_out, centres) with gradients to all five inputs; feat may be NCHW or
+    channels_last (consumed in place either way)."""
+    return _HeadChainFn.apply(feat, queries.contiguous(), w_out, b_out, centers.contiguous())
 
 
 def head_chain_supported(x, n_bins):

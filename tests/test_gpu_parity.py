@@ -243,6 +243,22 @@ def test_conv3x3_tc(cfg):
         assert torch.equal(out, ops.round_tf32(out.contiguous()).contiguous(memory_format=torch.channels_last))
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(batch=2, m=128, n=512, k=256, splits=1),     # d feat^T = W'^T gl shape family
+    dict(batch=3, m=256, n=128, k=4096, splits=8),    # d W' = gl^T feat (split-K, atomic accumulation)
+    dict(batch=1, m=200, n=72, k=100, splits=1),      # ragged M / N / K: TMA zero fill + guarded stores
+    dict(batch=2, m=64, n=300, k=40, splits=3),
+])
+def test_gemm_nt_tc(cfg):
+    rng = np.random.default_rng(93)
+    a = torch.from_numpy(rng.standard_normal((cfg["batch"], cfg["m"], cfg["k"])).astype(np.float32))
+    b = torch.from_numpy(rng.standard_normal((cfg["batch"], cfg["n"], cfg["k"])).astype(np.float32))
+    ref = torch.matmul(a.double(), b.double().transpose(1, 2))
+    out = ops.gemm_nt(a.to(DEV), b.to(DEV), splits=cfg["splits"], alpha=0.5).cpu().double()
+    err = float((out - 0.5 * ref).abs().max()) / float(ref.abs().max())
+    assert err < 1e-3, err
+
+
 def test_regressor_bins(golden):
     m, sd = _head_state()
     tgt = torch.from_numpy(golden["head/tgt"])
@@ -331,6 +347,38 @@ def test_head_golden_tf32_conv(golden):
     mx, p999 = rel_stats(pred.cpu(), golden["head/pred"])
     print("tf32 conv + chain: max %.3e p99.9 %.3e" % (mx, p999))
     assert_depth_close(pred.cpu(), golden["head/pred"], tf32=True)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_head_chain_backward(layout):
+    """Hand-written backward of the fused chain (backward-epilogue chain + two tcgen05 GEMMs) vs float64 autograd through
+    the reference formulation: PixelWiseDotProduct -> conv_out -> Softmax(dim=1) -> sum(out * centres)."""
+    rng = np.random.default_rng(95)
+    b, k, h, w, nb = 2, 128, 48, 64, 256
+    feat = torch.from_numpy(rng.standard_normal((b, k, h, w)).astype(np.float32))
+    q = torch.from_numpy((rng.standard_normal((b, 128, k)) * 0.3).astype(np.float32))
+    w_out = torch.from_numpy((rng.standard_normal((nb, 128, 1, 1)) * 0.2).astype(np.float32))
+    b_out = torch.from_numpy(rng.standard_normal(nb).astype(np.float32))
+    widths = torch.from_numpy(rng.random((b, nb)).astype(np.float32) + 0.1)
+    centers = torch.cumsum(widths / widths.sum(1, keepdim=True) * 10, dim=1)
+    g = torch.from_numpy(rng.standard_normal((b, 1, h, w)).astype(np.float32))
+    ref_in = [t.double().requires_grad_(True) for t in (feat, q, w_out, b_out, centers)]
+    ram = oracle.pixelwise_dot(ref_in[0], ref_in[1])
+    sm = torch.softmax(torch.nn.functional.conv2d(ram, ref_in[2], ref_in[3]), dim=1)
+    pred_ref = (sm * ref_in[4].view(b, nb, 1, 1)).sum(1, keepdim=True)
+    (pred_ref * g.double()).sum().backward()
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (feat, q, w_out, b_out, centers)]
+    x = dev_in[0]
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    pred = ops.head_chain_autograd(x, dev_in[1], dev_in[2], dev_in[3], dev_in[4])
+    # random operands give logits of std ~8 here (the trained-shape golden case is ~3): TF32 forward error scales with it
+    assert rel_err(pred.detach().cpu(), pred_ref.detach().float()) < 1e-2
+    (pred * g.to(DEV)).sum().backward()
+    for name, a, r in zip(("feat", "queries", "w_out", "b_out", "centers"), dev_in, ref_in):
+        ga, gr = a.grad.cpu().double(), r.grad
+        err = float((ga - gr).abs().max()) / float(gr.abs().max())
+        assert err < 5e-3, (name, err)
 
 
 def test_mvit_forward_surface(golden):
@@ -427,9 +475,12 @@ def test_channels_last_model_matches_nchw():
     grads = []
     for m in (m1, m2):
         m.train()
-        for mod in m.modules():
+        for mod in m.modules():  # no randomness: nn.Dropout modules and the attention-weight dropout of nn.MultiheadAttention
             if isinstance(mod, torch.nn.Dropout):
                 mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+        torch.manual_seed(0)
         m.zero_grad(set_to_none=True)
         e, p = m(x)
         loss = SILogLoss()(p, depth, mask=depth > 1e-3) + 0.1 * BinsChamferLoss()(e, depth)
@@ -438,9 +489,9 @@ def test_channels_last_model_matches_nchw():
                       m.encoder.original_model.conv_stem.weight.grad.detach().cpu().clone()))
     assert abs(grads[0][0] - grads[1][0]) <= 1e-3 * abs(grads[0][0])
     # train-mode BatchNorm at batch 2 makes these gradients ill-conditioned: against an fp64 evaluation BOTH layouts sit at
-    # 0.2-2 % of the largest entry (scripts/debug_cl.py, measured on B200), so the two fp32 paths are compared at 8 %
+    # 0.2-2 % of the largest entry (scripts/debug_cl.py, measured on B200), so the two fp32 paths are compared at 5 %
     for a, b in zip(grads[0][1:], grads[1][1:]):
-        assert float((a - b).abs().max()) <= 8e-2 * float(a.abs().max()) + 1e-7
+        assert float((a - b).abs().max()) <= 5e-2 * float(a.abs().max()) + 1e-7
 
 
 def test_decoder_tc_vs_stock():
