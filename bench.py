@@ -244,6 +244,37 @@ def run_ours(args):
     ms_total = timed(resident, False, args.steps)
     launches = ops.launch_count() - launches0
     ms_e2e = timed(host, True, args.steps)
+
+    # the same end-to-end loop with the package's DevicePrefetcher: the H2D copies of step i+1 run on a side stream under
+    # the kernels of step i (every copy and every loss read-back is still inside the timed region)
+    def timed_prefetch(hbatch, steps):
+        from mde_biological_vision_systems_b200.prefetch import DevicePrefetcher
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        pending = None
+        for batch in DevicePrefetcher((hbatch for _ in range(steps)), dev):
+            loss = step(batch, False)
+            if pending is not None:
+                float(pending.item())  # read the previous step's loss while this step runs
+            pending = loss
+        float(pending.item())
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    timed_prefetch(host, 2)
+    ms_e2e_pf = timed_prefetch(host, args.steps)
+    host_u8 = dict(host, semantics=host["semantics"].clamp(-1, 254).to(torch.uint8).pin_memory())  # on-disk label format
+    timed_prefetch(host_u8, 2)
+    ms_e2e_u8 = timed_prefetch(host_u8, args.steps)
+    h2d_u8 = sum(v.numel() * v.element_size() for v in host_u8.values())
     # per-kernel durations, measured live with CUDA events on the launching stream (a separate pass so the event
     # records do not perturb the headline number)
     ops.enable_kernel_timing(True)
@@ -288,7 +319,7 @@ def run_ours(args):
         roof = None
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
                 tr = json.load(f)["head_chain_kernel"]
             if tr["batch"] == B:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
@@ -331,8 +362,16 @@ def run_ours(args):
             "config": {"workload": "BASELINE config 2: EfficientNet-B1 AdaBins + GloVe-25d ADE20K-places @input, batch 16/GPU, 416x544, n_bins 256, random init",
                        "batch_per_gpu": B, "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "backbone": "encoder/decoder are PyTorch-cuDNN passthrough (not hot path)"},
-            "e2e": {"value": pix / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": pix / (ms_e2e_pf / args.steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_pf / args.steps,
+                    "how": "host batch in pinned memory (int64 labels, the reference's batch contract) -> DevicePrefetcher "
+                           "(H2D on a side stream, overlapped with the previous step) -> loaders + model + losses -> "
+                           "loss.item(); every copy and read-back inside the timed region",
+                    "serial_copies": {"value": pix / (ms_e2e / args.steps * 1e-3) / 1e6, "ms_per_step": ms_e2e / args.steps,
+                                      "note": "same loop with blocking in-step copies, no overlap"},
+                    "uint8_labels": {"value": pix / (ms_e2e_u8 / args.steps * 1e-3) / 1e6, "ms_per_step": ms_e2e_u8 / args.steps,
+                                     "h2d_bytes_per_step": h2d_u8,
+                                     "note": "labels travel in their on-disk uint8 format (label_io, section 8(f)3)"}},
             "gpu_launches": int(launches),
             "hot_path": {"what": "gather + mViT head + bins + SILog + chamfer on a fixed unet_out", "ms_per_step": hot_ms,
                          "value": B * H * W / (hot_ms * 1e-3) / 1e6, "unit": "Mpix/s per GPU", "share_of_step": hot_ms / ms_step},
