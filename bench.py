@@ -131,7 +131,7 @@ def run_reference(args):
     }))
 
 
-def run_train(args, dev, world, rank, host, loader, sync_bn=True):
+def run_train(args, dev, world, rank, host, loader, sync_bn="kernels"):
     """Training iteration with the reference's semantics (train.py:387-455): forward + SILog + 0.1 chamfer + backward +
     gradient mean all-reduce over ranks (NCCL) + clip 0.1 + AdamW + OneCycle, batch 16 per GPU (weak scaling,
     --use_new_batching), SyncBatchNorm when N > 1 (train.py:296).  Inputs come from pinned host memory every step."""
@@ -145,8 +145,11 @@ def run_train(args, dev, world, rank, host, loader, sync_bn=True):
     model = UnetAdaptiveBins.build(n_bins=N_BINS, min_val=1e-3, max_val=10.0, norm="linear", encoder_name="efficientnet-b1",
                                    semantics_mode=SEM_MODE, instance_segmentation_mode=None, insertion_point="input",
                                    image="rgb").to(dev)
-    if world > 1 and sync_bn:
+    if world > 1 and sync_bn == "stock":
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    elif world > 1 and sync_bn:
+        from mde_biological_vision_systems_b200 import parallel
+        model = parallel.convert_sync_batchnorm(model)  # global-batch statistics on the B200 kernels (csrc/bn_sync.cu)
     model.train()
     stepper = TrainStep(model, semantics_loader=loader, total_steps=1000)
     steps = max(2, min(args.steps, 5))
@@ -170,7 +173,7 @@ def run_train(args, dev, world, rank, host, loader, sync_bn=True):
     B = args.batch
     return {"metric": "train imgs/s (fwd + SILog + 0.1*chamfer + bwd + grad all-reduce + clip + AdamW/OneCycle)",
             "value": world * B / (ms_step * 1e-3), "unit": "imgs/s", "ms_per_step": ms_step, "steps": steps,
-            "batch_per_gpu": B, "sync_bn": world > 1 and sync_bn, "loss": float(loss.item()),
+            "batch_per_gpu": B, "sync_bn": (sync_bn if world > 1 else False), "loss": float(loss.item()),
             "gpu_launches_per_step": (ops.launch_count() - l0) / steps,
             "note": "model in channels_last; head chain forward+backward on the tcgen05 kernels; the 4 transformer encoder layers (dropout) and the EfficientNet/decoder bodies run stock torch/cuDNN modules in train mode"}
 
@@ -304,8 +307,9 @@ def run_ours(args):
         hot_ms = s.elapsed_time(e) / args.steps
     train = None
     if not args.no_train:
-        train = run_train(args, dev, world, rank, host, loader)
-        if world > 1:  # the same step with per-rank BatchNorm statistics: isolates the cost of stock SyncBatchNorm
+        train = run_train(args, dev, world, rank, host, loader, sync_bn="kernels")
+        if world > 1:  # the same step with torch's own SyncBatchNorm and with per-rank statistics, for comparison
+            train["stock_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="stock")
             train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
     clocks = sampler.stop() if sampler else None
 

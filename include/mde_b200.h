@@ -259,6 +259,25 @@ int mde_eval_metrics_fwd(const float* pred, const float* gt, int B, int h, int w
 int mde_flip_average(const float* a, const float* b_flipped, float* out, int64_t rows, int w, float lo, float hi,
                      mde_stream_t stream);
 
+/* ---- section 8(e): SyncBatchNorm building blocks (train.py:296, nn.SyncBatchNorm semantics: statistics over the global
+ * batch) on channels_last activations x [N pixels, C] (C % 4 == 0).  A layer is
+ *   forward : mde_bn_stats_nhwc -> all-reduce(SUM) of stats (+ the pixel count) over ranks -> mde_bn_apply_nhwc
+ *   backward: mde_bn_bwd_reduce_nhwc -> all-reduce(SUM) of sums -> mde_bn_bwd_apply_nhwc
+ * stats / sums: float64 [2C] = per-channel (sum x, sum x^2) / (sum dy, sum dy*xhat).  zero_next == NULL: the producing
+ * call zeroes stats / sums itself (memset); zero_next != NULL: stats / sums must already be zero and the kernel zeroes
+ * zero_next [2C] for the NEXT call (double buffering: no memset launches in the training loop);
+ * count = global number of pixels per channel; save_mean / save_invstd [C] are written by apply and read by the backward;
+ * running_mean / running_var (may be NULL) get torch's momentum update with the unbiased variance.
+ * The local (pre-all-reduce) sums are d bias and d weight. */
+int mde_bn_stats_nhwc(const float* x, int64_t N, int C, double* stats, double* zero_next, mde_stream_t stream);
+int mde_bn_apply_nhwc(const float* x, float* y, int64_t N, int C, const double* stats, double count, const float* weight,
+                      const float* bias, float eps, float* save_mean, float* save_invstd, float* running_mean,
+                      float* running_var, float momentum, mde_stream_t stream);
+int mde_bn_bwd_reduce_nhwc(const float* x, const float* dy, int64_t N, int C, const float* mean, const float* invstd,
+                           double* sums, double* zero_next, mde_stream_t stream);
+int mde_bn_bwd_apply_nhwc(const float* x, const float* dy, float* dx, int64_t N, int C, const float* mean,
+                          const float* invstd, const float* weight, const double* sums, double count, mde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,10 @@ SIGNATURES = {
     "mde_eval_metrics_ws_bytes": (_i64, [_i32]),
     "mde_eval_metrics_fwd": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_flip_average": (_i32, [_p, _p, _p, _i64, _i32, _f32, _f32, _p]),
+    "mde_bn_stats_nhwc": (_i32, [_p, _i64, _i32, _p, _p, _p]),
+    "mde_bn_apply_nhwc": (_i32, [_p, _p, _i64, _i32, _p, ctypes.c_double, _p, _p, _f32, _p, _p, _p, _p, _f32, _p]),
+    "mde_bn_bwd_reduce_nhwc": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "mde_bn_bwd_apply_nhwc": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, ctypes.c_double, _p]),
     "mde_silog_ws_bytes": (_i64, []),
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_silog_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -86,3 +86,147 @@ class GradientAverager:
                 off += n
             total += off
         return total  # elements exchanged
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SyncBatchNorm on the B200 kernels (csrc/bn_sync.cu)
+# ---------------------------------------------------------------------------------------------------------------
+class _SyncBatchNormFn(torch.autograd.Function):
+    """Training-mode batch norm with statistics over the global batch: two streaming kernels and ONE all-reduce of the raw
+    per-channel moments per direction (nn.SyncBatchNorm: three kernels + an all_gather forward, two + an all_reduce
+    backward, plus bookkeeping copies).  x must be a channels_last CUDA tensor with C % 4 == 0."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, bufs):
+        from . import _lib, ops
+        lib = _lib.load()
+        b, c, h, w = x.shape
+        n = b * h * w
+        # bufs: the module's two pairs of float64 [2C+1] scratch rows (forward / backward), used alternately: the kernel
+        # of call k zeroes the row of call k+1, so the loop issues no memsets
+        stats, nxt = bufs.next_forward(c, x.device)
+        _lib.check(lib.mde_bn_stats_nhwc(ops._p(x), n, c, ops._p(stats), ops._p(nxt), ops._s()), "mde_bn_stats_nhwc")
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            if _COUNT_FROM_ALLREDUCE:
+                stats[2 * c] = float(n)
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+            count = float(stats[2 * c].item()) if _COUNT_FROM_ALLREDUCE else float(n * world)
+        else:
+            count = float(n)
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        rc = lib.mde_bn_apply_nhwc(ops._p(x), ops._p(y), n, c, ops._p(stats), count, ops._p(weight), ops._p(bias), float(eps),
+                                   ops._p(save_mean), ops._p(save_invstd), ops._p(running_mean), ops._p(running_var),
+                                   float(momentum), ops._s())
+        _lib.check(rc, "mde_bn_apply_nhwc")
+        ctx.save_for_backward(x, weight, save_mean, save_invstd)
+        ctx.count, ctx.group, ctx.world, ctx.bufs = count, group, world, bufs
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _lib, ops
+        lib = _lib.load()
+        x, weight, mean, invstd = ctx.saved_tensors
+        b, c, h, w = x.shape
+        n = b * h * w
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        sums, nxt = ctx.bufs.next_backward(c, x.device)
+        rc = lib.mde_bn_bwd_reduce_nhwc(ops._p(x), ops._p(dy), n, c, ops._p(mean), ops._p(invstd), ops._p(sums), ops._p(nxt),
+                                        ops._s())
+        _lib.check(rc, "mde_bn_bwd_reduce_nhwc")
+        local = sums[:2 * c].float()  # d bias, d weight are the LOCAL sums (DDP averages parameter gradients afterwards)
+        if ctx.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        rc = lib.mde_bn_bwd_apply_nhwc(ops._p(x), ops._p(dy), ops._p(dx), n, c, ops._p(mean), ops._p(invstd), ops._p(weight),
+                                       ops._p(sums), ctx.count, ops._s())
+        _lib.check(rc, "mde_bn_bwd_apply_nhwc")
+        gw = local[c:] if weight is not None else None
+        gb = local[:c] if weight is not None else None
+        return dx, gw, gb, None, None, None, None, None, None
+
+
+class _BnScratch:
+    """Per-module float64 scratch rows for the raw moments: [2][2C+1] for the forward and for the backward, allocated
+    zeroed once; each kernel zeroes the row the next call will accumulate into."""
+
+    def __init__(self):
+        self.fwd = self.bwd = None
+        self.fi = self.bi = 0
+
+    def _rows(self, cur, c, device):
+        if cur is None or cur.shape[1] != 2 * c + 1 or cur.device != device:
+            cur = torch.zeros((2, 2 * c + 1), dtype=torch.float64, device=device)
+        return cur
+
+    def next_forward(self, c, device):
+        self.fwd = self._rows(self.fwd, c, device)
+        self.fi ^= 1
+        return self.fwd[self.fi], self.fwd[self.fi ^ 1]
+
+    def next_backward(self, c, device):
+        self.bwd = self._rows(self.bwd, c, device)
+        self.bi ^= 1
+        return self.bwd[self.bi], self.bwd[self.bi ^ 1]
+
+
+# every rank of this path holds the same per-GPU batch (weak scaling, train.py:286-287), so the global pixel count is
+# n * world and needs no device->host read; set True for ragged last batches
+_COUNT_FROM_ALLREDUCE = False
+
+
+class SyncBatchNorm2d(torch.nn.BatchNorm2d):
+    """Drop-in for nn.SyncBatchNorm on 4-D inputs (same parameters, buffers and state_dict keys).  Training mode with a
+    process group of more than one rank -- or ``force_kernels`` -- runs the B200 kernels; eval mode is plain batch norm
+    with the running statistics, exactly as nn.SyncBatchNorm does."""
+
+    def __init__(self, *args, process_group=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.process_group = process_group
+        self.force_kernels = False
+        self._scratch = _BnScratch()
+
+    def forward(self, x):
+        world = dist.get_world_size(self.process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        use = self.training and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 \
+            and self.track_running_stats and (world > 1 or self.force_kernels)
+        if not use:
+            if self.training and world > 1:
+                raise RuntimeError("SyncBatchNorm2d: unsupported input for the synchronised kernels "
+                                   f"(shape {tuple(x.shape)}, dtype {x.dtype}, cuda {x.is_cuda})")
+            return super().forward(x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        momentum = self.momentum
+        if self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(self.num_batches_tracked)
+        return _SyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                      0.0 if momentum is None else momentum, self.process_group, self._scratch)
+
+
+def convert_sync_batchnorm(module, process_group=None):
+    """train.py:296 counterpart: replace every nn.BatchNorm2d by SyncBatchNorm2d sharing its parameters and buffers
+    (state_dict keys unchanged); other batch-norm flavours fall back to torch's own SyncBatchNorm conversion."""
+    out = module
+    if isinstance(module, torch.nn.BatchNorm2d) and not isinstance(module, SyncBatchNorm2d):
+        if module.num_features % 4 == 0 and module.track_running_stats:
+            out = SyncBatchNorm2d(module.num_features, module.eps, module.momentum, module.affine,
+                                  module.track_running_stats, process_group=process_group)
+            if module.affine:
+                out.weight, out.bias = module.weight, module.bias
+            out.running_mean, out.running_var = module.running_mean, module.running_var
+            out.num_batches_tracked = module.num_batches_tracked
+            out.training = module.training
+        else:
+            return torch.nn.SyncBatchNorm.convert_sync_batchnorm(module, process_group)
+    for name, child in module.named_children():
+        new = convert_sync_batchnorm(child, process_group)
+        if new is not child:
+            out.add_module(name, new)
+    return out

@@ -730,3 +730,36 @@ def test_config5_noadabins_480x640():
         edges, pred = m(x)
     assert edges is None and pred.shape == (2, 1, 240, 320)
     assert np.array_equal(pred.cpu().numpy(), oracle.noadabins_epilogue(unet_out.cpu()).numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# section 8(e): SyncBatchNorm kernels (world size 1 == plain training-mode batch norm, the all-reduce is the identity)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4, 16, 33, 47), (2, 96, 20, 24), (3, 1280, 5, 7), (2, 40, 64, 80)])
+def test_sync_batchnorm_kernels_vs_torch(shape):
+    from mde_biological_vision_systems_b200.parallel import SyncBatchNorm2d
+    rng = np.random.default_rng(97)
+    b, c, h, w = shape
+    x = torch.from_numpy((rng.standard_normal(shape) * 2 + 3).astype(np.float32))
+    g = torch.from_numpy(rng.standard_normal(shape).astype(np.float32))
+    ref = torch.nn.BatchNorm2d(c).double()
+    with torch.no_grad():
+        ref.weight.copy_(torch.from_numpy(1 + 0.3 * rng.standard_normal(c)))
+        ref.bias.copy_(torch.from_numpy(0.2 * rng.standard_normal(c)))
+    ours = SyncBatchNorm2d(c).to(DEV)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ours.force_kernels = True
+    ref.train(), ours.train()
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(g.double())
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yd = ours(xd)
+    yd.backward(g.to(DEV))
+    np.testing.assert_allclose(yd.detach().cpu().numpy(), yr.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-3, atol=1e-4 * float(xr.grad.abs().max()) + 1e-6)
+    np.testing.assert_allclose(ours.weight.grad.cpu().numpy(), ref.weight.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(ours.bias.grad.cpu().numpy(), ref.bias.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(ours.running_mean.cpu().numpy(), ref.running_mean.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ours.running_var.cpu().numpy(), ref.running_var.numpy(), rtol=1e-4, atol=1e-6)
+    assert int(ours.num_batches_tracked) == 1

@@ -68,3 +68,22 @@ def test_gradient_mean_allreduce_world2(tmp_path):
     for a, b, x, y in zip(g0, g1, grads[0], grads[1]):
         torch.testing.assert_close(a, b)
         torch.testing.assert_close(a, (x + y) / 2)
+
+
+def test_convert_sync_batchnorm_keeps_state_dict():
+    """parallel.convert_sync_batchnorm swaps BatchNorm2d modules for the kernel-backed SyncBatchNorm2d without touching
+    parameter identity or state_dict keys (train.py:296 semantics); eval mode on CPU is plain batch norm."""
+    import torch
+    from mde_biological_vision_systems_b200 import parallel
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Sequential(torch.nn.Conv2d(8, 6, 1), torch.nn.BatchNorm2d(6)))
+    keys = list(net.state_dict().keys())
+    w = net[1].weight
+    conv = parallel.convert_sync_batchnorm(net)
+    assert list(conv.state_dict().keys()) == keys
+    assert isinstance(conv[1], parallel.SyncBatchNorm2d) and conv[1].weight is w
+    assert isinstance(conv[3][1], torch.nn.SyncBatchNorm)  # 6 channels: not a multiple of 4 -> torch's module
+    conv.eval()
+    x = torch.randn(2, 3, 9, 9)
+    ref = torch.nn.functional.batch_norm(net[0](x), w.new_zeros(8), w.new_ones(8), w, net[1].bias, False, 0.1, 1e-5)
+    assert torch.allclose(conv[1](net[0](x)), ref, atol=1e-6)
