@@ -24,6 +24,12 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _f32(t):
+    """The kernels are fp32: tensors produced under autocast (bf16 / fp16 activations of the stock torch modules) are
+    widened here -- handing their storage to a kernel as-is would be read as garbage."""
+    return t if t.dtype == torch.float32 else t.float()
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -215,6 +221,7 @@ _NORM = {"linear": 0, "softmax": 1, "sigmoid": 2}
 def linear(x, weight, bias, act=0):
     """act(x @ weight.T + bias) for a 2-D x whose rows may be strided (fp32 SIMT kernel); act 0/1/2 = none/ReLU/LeakyReLU."""
     lib = _lib.load()
+    x, weight = _f32(x), _f32(weight)
     if x.stride(1) != 1:
         x = x.contiguous()
     m, k = x.shape
@@ -232,6 +239,7 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=Tru
     image variant is latency bound: 105 us at B = 16); split=False keeps everything in one launch."""
     lib = _lib.load()
     _need_cuda(t0, w1, w2, w3)
+    t0 = _f32(t0)
     if t0.stride(1) != 1:
         t0 = t0.contiguous()
     b, e = t0.shape
@@ -346,8 +354,8 @@ def conv3x3_nhwc(x_cl, w_prep, scale=None, shift=None, slope=1.0, round_tf32=Fal
     lib = _lib.load()
     _need_cuda(x_cl, w_prep)
     b, c, h, w = x_cl.shape
-    if not x_cl.is_contiguous(memory_format=torch.channels_last):
-        raise ValueError("conv3x3_nhwc expects a channels_last tensor")
+    if x_cl.dtype != torch.float32 or not x_cl.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("conv3x3_nhwc expects a float32 channels_last tensor")
     cout = w_prep.shape[2]
     if out is None:
         out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
@@ -366,7 +374,7 @@ def encoder_layer(x, layer, ws=None):
     module holding the parameters.  Returns a new [S, N, E] tensor."""
     lib = _lib.load()
     _need_cuda(x)
-    x = x.contiguous()
+    x = _f32(x).contiguous()
     s, n, e = x.shape
     a = layer.self_attn
     ff = layer.linear1.out_features
@@ -420,7 +428,7 @@ def range_attention(x, queries, impl="auto"):
 def conv1x1(ram, weight, bias):
     """logits[b,j,h,w] = bias[j] + sum_n weight[j,n] ram[b,n,h,w]   (conv_out's Conv2d(128,n_bins,1), SIMT fp32)."""
     lib = _lib.load()
-    ram = ram.contiguous()
+    ram = _f32(ram).contiguous()
     b, k, h, w = ram.shape
     wt = weight.reshape(weight.shape[0], -1).contiguous()
     out = torch.empty((b, wt.shape[0], h, w), dtype=torch.float32, device=ram.device)
@@ -433,7 +441,7 @@ def conv1x1(ram, weight, bias):
 def bins_pred(logits, centers):
     """pred[b,0,h,w] = sum_j softmax_j(logits[b,:,h,w]) * centers[b,j]  (streaming K2 kernel)."""
     lib = _lib.load()
-    logits = logits.contiguous()
+    logits = _f32(logits).contiguous()
     b, n, h, w = logits.shape
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=logits.device)
     with timing("bins_pred"):
@@ -447,9 +455,10 @@ def fold_queries(w_out, bias, queries, feat_bias=None, operand_scale=TF32_TRUNC_
     feat_bias).  ``feat_bias`` is the bias of the conv that produced the chain's activations (folded in so that the
     producer can run bias-free)."""
     lib = _lib.load()
-    wt = w_out.reshape(w_out.shape[0], -1).contiguous()
+    wt = _f32(w_out).reshape(w_out.shape[0], -1).contiguous()
     n_bins, n = wt.shape
-    queries = queries.contiguous()
+    queries = _f32(queries).contiguous()
+    bias = _f32(bias)
     b, _, k = queries.shape
     wf = torch.empty((b, n_bins, k), dtype=torch.float32, device=queries.device)
     biasf = torch.empty((b, n_bins), dtype=torch.float32, device=queries.device)
@@ -465,6 +474,7 @@ def head_chain(x, wf, biasf, centers):
     """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x [B,128,h,w], either
     contiguous NCHW or channels_last (NHWC strides; consumed in place, no copy) -> pred [B,1,h,w]."""
     lib = _lib.load()
+    x, wf, biasf, centers = _f32(x), _f32(wf), _f32(biasf), _f32(centers)
     b, k, h, w = x.shape
     nhwc = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
     if not nhwc:
@@ -557,7 +567,7 @@ class _HeadChainFn(torch.autograd.Function):
 def head_chain_autograd(feat, queries, w_out, b_out, centers):
     """pred = fused chain(feat, queries, conv_out, centres) with gradients to all five inputs; feat may be NCHW or
     channels_last (consumed in place either way)."""
-    return _HeadChainFn.apply(feat, queries.contiguous(), w_out, b_out, centers.contiguous())
+    return _HeadChainFn.apply(_f32(feat), _f32(queries).contiguous(), _f32(w_out), _f32(b_out), _f32(centers).contiguous())
 
 
 def head_chain_supported(x, n_bins):
@@ -581,7 +591,7 @@ class _UpsampleConcat(torch.autograd.Function):
     def backward(ctx, gout):
         lib = _lib.load()
         b, c1, c2, h, w, hh, ww = ctx.shape
-        gout = gout.contiguous()
+        gout = _f32(gout).contiguous()
         gx = torch.empty((b, c1, h, w), dtype=torch.float32, device=gout.device)
         ws = torch.empty(int(lib.mde_upsample_bwd_ws_bytes(h, w)), dtype=torch.uint8, device=gout.device)
         with timing("upsample_bwd"):
@@ -607,6 +617,7 @@ class _UpsampleConcatNHWC(torch.autograd.Function):
     def backward(ctx, gout):
         lib = _lib.load()
         b, c1, c2, h, w, hh, ww = ctx.shape
+        gout = _f32(gout)
         if not gout.is_contiguous(memory_format=torch.channels_last):
             gout = gout.contiguous(memory_format=torch.channels_last)
         gx = torch.empty((b, c1, h, w), dtype=torch.float32, device=gout.device, memory_format=torch.channels_last)
@@ -621,6 +632,7 @@ def upsample_concat_nhwc(x_cl, skip):
     """channels_last DecoderBN up-sampling step: bilinear(align_corners=True) resize of x_cl [B,C1,h,w] (channels_last)
     to skip's size, concatenated with skip (either memory format) -> channels_last [B,C1+C2,H,W]; differentiable."""
     _need_cuda(x_cl, skip)
+    x_cl, skip = _f32(x_cl), _f32(skip)
     if torch.is_grad_enabled() and (x_cl.requires_grad or skip.requires_grad):
         return _UpsampleConcatNHWC.apply(x_cl, skip)
     return _upsample_concat_nhwc_fwd(x_cl, skip)
@@ -646,6 +658,7 @@ def to_channels_last(x):
     """NCHW-contiguous fp32 [B,C,H,W] -> the same logical tensor with channels_last strides (tiled transpose kernel)."""
     lib = _lib.load()
     _need_cuda(x)
+    x = _f32(x)
     if x.is_contiguous(memory_format=torch.channels_last):
         return x
     x = x.contiguous()
@@ -659,7 +672,7 @@ def to_channels_last(x):
 
 def relu_eps(x, eps=1e-4):
     lib = _lib.load()
-    x = x.contiguous()
+    x = _f32(x).contiguous()
     y = torch.empty_like(x)
     _lib.check(lib.mde_relu_eps_fwd(_p(x), _p(y), x.numel(), float(eps), _s()), "mde_relu_eps_fwd")
     return y

@@ -192,6 +192,8 @@ class SyncBatchNorm2d(torch.nn.BatchNorm2d):
 
     def forward(self, x):
         world = dist.get_world_size(self.process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.training and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and (world > 1 or self.force_kernels):
+            x = x.float()  # autocast activations: statistics and normalisation run in fp32, like torch's batch norm
         use = self.training and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] % 4 == 0 \
             and self.track_running_stats and (world > 1 or self.force_kernels)
         if not use:

@@ -763,3 +763,28 @@ def test_sync_batchnorm_kernels_vs_torch(shape):
     np.testing.assert_allclose(ours.running_mean.cpu().numpy(), ref.running_mean.numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ours.running_var.cpu().numpy(), ref.running_var.numpy(), rtol=1e-4, atol=1e-6)
     assert int(ours.num_batches_tracked) == 1
+
+
+def test_autocast_bf16_training_step():
+    """BASELINE config 4 runs DDP training under bf16 autocast: the stock torch bodies then produce bf16 activations, the
+    hand-written kernels stay fp32 (inputs are widened at the operator boundary).  north_star tolerance for bf16: 2e-2."""
+    kw = dict(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None)
+    m = make_model(**kw).to(DEV).channels_last_()
+    x = synthetic.image(2, 352, 384, seed=83).to(DEV)
+    depth = synthetic.depth(2, 352, 384, seed=84).to(DEV)
+    with torch.no_grad():
+        e32, p32 = m(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            e16, p16 = m(x)
+    assert p16.dtype == torch.float32 and e16.dtype == torch.float32
+    rel = ((p16 - p32).abs() / p32.abs()).flatten()
+    assert float(rel.mean()) < 2e-2 and float(rel.kthvalue(int(rel.numel() * 0.99)).values) < 1e-1, (float(rel.mean()), float(rel.max()))
+    assert rel_err(e16.cpu(), e32.cpu()) < 5e-2
+    m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        e, p = m(x)
+        loss = SILogLoss()(p, depth, mask=depth > 1e-3) + 0.1 * BinsChamferLoss()(e, depth)
+    loss.backward()
+    assert torch.isfinite(loss)
+    g = m.decoder.up4._net[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
