@@ -128,6 +128,17 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
 int mde_gemm_nt_tf32(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch, float* C,
                      int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
                      mde_stream_t stream);
+/* Same with an nn.Linear-style epilogue: + bias[N] (added once), act 0 none / 1 ReLU, and split_out != 0 writing each
+ * output row as [v | v - trunc_tf32(v) | v] (ldc >= 3N) -- the A operand of a following 3xTF32 product
+ * (A' = [a | a_lo | a] against B' = [b_hi | b_hi | b_lo] along K gives fp32-grade accuracy on the TF32 tensor cores). */
+int mde_gemm_nt_tf32_ex(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch, float* C,
+                        int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                        const float* bias, int act, int split_out, mde_stream_t stream);
+/* Deterministic split-K: plane_stride > 0 makes K split s store its partial product at C + s * plane_stride floats (the
+ * consumer sums the planes; the actual number of planes is min(splits, ceil(K / 32))). */
+int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
+                            float* C, int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                            const float* bias, int act, int split_out, int64_t plane_stride, mde_stream_t stream);
 
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.01).  fp32 SIMT, row-major with leading
  * dimensions lda/ldw/ldc (the nn.Linear building block of the regressor and the encoder layers). */
@@ -147,6 +158,19 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
                           const float* out_b, const float* ln1_w, const float* ln1_b, const float* l1_w, const float* l1_b,
                           const float* l2_w, const float* l2_b, const float* ln2_w, const float* ln2_b, float* ws, int S,
                           int NB, int E, int heads, int FF, float eps, mde_stream_t stream);
+
+/* Tensor-core form of the same layer: the four nn.Linear products run on mde_gemm_nt_tf32_ex in 3xTF32.  x3: tokens in
+ * split form [S*NB][3E] = [v | v - trunc_tf32(v) | v] (mde_split3_tf32 makes it from plain rows); the *_w3 weights are
+ * [w_hi | w_hi | w_lo] along K (w_hi = round_tf32(w), w_lo = round_tf32(w - w_hi)): in_w3 [3E][3E], out_w3 [E][3E],
+ * l1_w3 [FF][3E], l2_w3 [E][3FF].  y: next layer's split-form input (y_split != 0, [S*NB][3E]) or plain [S,NB,E].
+ * ws: mde_encoder_layer_tc_ws_floats(S,NB,E,FF) floats. */
+int64_t mde_encoder_layer_tc_ws_floats(int S, int NB, int E, int FF);
+int mde_split3_tf32(const float* in, float* out, int64_t rows, int E, mde_stream_t stream);
+int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float* in_w3, const float* in_b,
+                             const float* out_w3, const float* out_b, const float* ln1_w, const float* ln1_b,
+                             const float* l1_w3, const float* l1_b, const float* l2_w3, const float* l2_b, const float* ln2_w,
+                             const float* ln2_b, float* ws, int S, int NB, int E, int heads, int FF, float eps,
+                             mde_stream_t stream);
 
 /* ---- K1d: range-attention contraction  y[b,n,p] = sum_k x[b,k,p] * q[b,n,k]  (layers.py:31-36) ----------
  * x [B,K,P] float32 (NCHW with P = h*w), q [B,N,K] float32, y [B,N,P] float32.

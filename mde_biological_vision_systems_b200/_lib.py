@@ -33,10 +33,15 @@ SIGNATURES = {
     "mde_conv3x3_prep_weight": (_i32, [_p, _p, _i32, _i32, _f32, _p]),
     "mde_conv3x3_nhwc_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
     "mde_gemm_nt_tf32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_gemm_nt_tf32_ex": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _p]),
+    "mde_gemm_nt_tf32_planes": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _i64, _p]),
     "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),
     "mde_encoder_layer_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),
     "mde_encoder_layer_fwd": (_i32, [_p] * 15 + [_i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_encoder_layer_tc_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),
+    "mde_split3_tf32": (_i32, [_p, _p, _i64, _i32, _p]),
+    "mde_encoder_layer_tc_fwd": (_i32, [_p, _p, _i32] + [_p] * 13 + [_i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_range_attention": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),

@@ -8,6 +8,8 @@
 // One CTA = one 128 x TN output tile of one batch entry and one K split: warp 0 TMA producer (A box {32, 128}, B box
 // {32, TN}, SWIZZLE_128B, out-of-range rows / k zero-filled by the TMA), warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 3-6 epilogue (tcgen05.ld -> plain store, or atomicAdd when the K range is split).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -28,7 +30,13 @@ struct GemmGeom {
   int tmem_cols;
   int atomic;              // accumulate with atomicAdd (split-K)
   float alpha;
+  const float* bias;       // [N] added once (by K split 0), may be null
+  int act;                 // 0 none, 1 ReLU (not with split-K)
+  int split_out;           // 1: write rows as [v | v - trunc_tf32(v) | v] (row pitch >= 3N): the A operand of a 3xTF32 GEMM
+  long long plane_stride;  // > 0: K split s writes its partial product to C + s * plane_stride (no atomics; the consumer sums)
 };
+
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(GM_THREADS, 1)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -42,6 +50,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   const uint32_t s_bar = base + g.nstages * stage_bytes;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * g.nstages, bar_acc = s_bar + 16 * g.nstages;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 16 * g.nstages + 16);
+  float* stg_all = reinterpret_cast<float*>(gbase + (s_bar - base) + 16 * g.nstages + 64);  // [4 warps][32][33] transpose staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x / g.n_tiles, nt = blockIdx.x - mt * g.n_tiles;
   const int split = blockIdx.y, batch = blockIdx.z;
@@ -113,27 +122,62 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
     const int m = m0 + quarter * 32 + lane;
     mbar_wait(bar_acc, 0, 33);
     tc_fence_after();
+    C += (long long)split * g.plane_stride;
     float* crow = C + (long long)batch * g.c_batch + (long long)m * g.ldc + n0;
     const bool row_ok = m < g.M;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < g.tn; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(quarter * 32) << 16), r);
       tmem_ld_wait();
-      if (!row_ok) continue;
       const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));
-      if (g.atomic) {
-        for (int i = 0; i < nvalid; ++i) atomicAdd(crow + c0 + i, g.alpha * __uint_as_float(r[i]));
-      } else if (nvalid == 32 && vec_ok) {
+      float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(crow + c0 + i) =
-              make_float4(g.alpha * __uint_as_float(r[i]), g.alpha * __uint_as_float(r[i + 1]),
-                          g.alpha * __uint_as_float(r[i + 2]), g.alpha * __uint_as_float(r[i + 3]));
-      } else {
-        for (int i = 0; i < nvalid; ++i) crow[c0 + i] = g.alpha * __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) {
+        float t = g.alpha * __uint_as_float(r[i]);
+        if (g.bias != nullptr && split == 0 && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
+        v[i] = g.act == 1 ? fmaxf(t, 0.f) : t;
       }
+      if (g.atomic) {
+        if (row_ok)
+          for (int i = 0; i < nvalid; ++i) atomicAdd(crow + c0 + i, v[i]);
+        continue;
+      }
+      // transpose the warp's 32 rows x 32 columns through shared memory so that 8 lanes write one row's 128 bytes:
+      // every store instruction covers 4 whole lines instead of 32 partial ones
+      float* stg = stg_all + quarter * (32 * 33);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+      __syncwarp();
+      const int cc = (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const int mm = m0 + quarter * 32 + rr;
+        if (mm >= g.M) continue;
+        const float* sp = stg + rr * 33 + cc;
+        const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        float* dst = C + (long long)batch * g.c_batch + (long long)mm * g.ldc + n0 + c0 + cc;
+        if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (!g.split_out || (g.N & 3) == 0)) {
+          *reinterpret_cast<float4*>(dst) = o;
+          if (g.split_out) {
+            *reinterpret_cast<float4*>(dst + g.N) =
+                make_float4(o.x - tf32_trunc(o.x), o.y - tf32_trunc(o.y), o.z - tf32_trunc(o.z), o.w - tf32_trunc(o.w));
+            *reinterpret_cast<float4*>(dst + 2 * g.N) = o;
+          }
+        } else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+          for (int q = 0; q < 4; ++q) {
+            if (cc + q >= nvalid) break;
+            dst[q] = ov[q];
+            if (g.split_out) {
+              dst[g.N + q] = ov[q] - tf32_trunc(ov[q]);
+              dst[2 * g.N + q] = ov[q];
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -154,8 +198,23 @@ extern "C" {
 int mde_gemm_nt_tf32(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch, float* C,
                      int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
                      mde_stream_t stream) {
+  return mde_gemm_nt_tf32_ex(A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, batch, M, N, K, splits, alpha, nullptr, 0, 0,
+                             stream);
+}
+
+int mde_gemm_nt_tf32_ex(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch, float* C,
+                        int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                        const float* bias, int act, int split_out, mde_stream_t stream) {
+  return mde_gemm_nt_tf32_planes(A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, batch, M, N, K, splits, alpha, bias, act,
+                                 split_out, 0, stream);
+}
+
+int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
+                            float* C, int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                            const float* bias, int act, int split_out, int64_t plane_stride, mde_stream_t stream) {
   if (!A || !B || !C) return MDE_ERR_BAD_POINTER;
   if (batch <= 0 || batch > 65535 || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || splits > 65535) return MDE_ERR_BAD_SHAPE;
+  if (act < 0 || act > 1 || (splits > 1 && (act != 0 || split_out)) || (split_out && ldc < 3 * (int64_t)N)) return MDE_ERR_BAD_SHAPE;
   if (lda % 4 != 0 || ldb % 4 != 0 || a_batch % 4 != 0 || b_batch % 4 != 0 || !aligned(A, 16) || !aligned(B, 16))
     return MDE_ERR_UNSUPPORTED;  // TMA: 16-byte global strides
   tc::GemmGeom g;
@@ -163,20 +222,34 @@ int mde_gemm_nt_tf32(const float* A, int64_t lda, int64_t a_batch, const float* 
   g.N = N;
   g.ldc = ldc;
   g.c_batch = c_batch;
-  g.tn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
-  g.n_tiles = (N + g.tn - 1) / g.tn;
   g.total_chunks = (K + tc::GM_KC - 1) / tc::GM_KC;
   if (splits > g.total_chunks) splits = g.total_chunks;
+  // N tile (measured on B200 with scripts/time_gemms.py): 256-wide tiles when they still give >= 2 waves of CTAs (fewer
+  // re-reads of the other operand), otherwise 128 -- narrower tiles did not pay (fixed cost per CTA ~4.5 us)
+  {
+    const long long m_tiles_ = (M + 127) / 128;
+    const int n_cap = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+    int tn = n_cap;
+    if (n_cap == 256 && m_tiles_ * ((N + 255) / 256) * splits * batch < 2 * MDE_NUM_SMS) tn = 128;
+    const char* force = getenv("MDE_GEMM_TN");
+    if (force && atoi(force) >= 16 && atoi(force) <= n_cap) tn = atoi(force) / 16 * 16;
+    g.tn = tn;
+  }
+  g.n_tiles = (N + g.tn - 1) / g.tn;
   g.chunks_per_split = (g.total_chunks + splits - 1) / splits;
   splits = (g.total_chunks + g.chunks_per_split - 1) / g.chunks_per_split;  // no empty split
-  g.atomic = splits > 1 ? 1 : 0;
+  g.plane_stride = plane_stride > 0 ? plane_stride : 0;
+  g.atomic = (splits > 1 && plane_stride <= 0) ? 1 : 0;
   g.alpha = alpha;
+  g.bias = bias;
+  g.act = act;
+  g.split_out = split_out;
   g.tmem_cols = g.tn <= 32 ? 32 : g.tn <= 64 ? 64 : g.tn <= 128 ? 128 : 256;
   const int stage_bytes = 128 * 128 + g.tn * 128;
-  g.nstages = (200 * 1024) / stage_bytes;
+  g.nstages = (184 * 1024) / stage_bytes;
   if (g.nstages > 8) g.nstages = 8;
   if (g.nstages > g.chunks_per_split) g.nstages = g.chunks_per_split;
-  const int smem = g.nstages * stage_bytes + 16 * g.nstages + 64 + 1024;
+  const int smem = g.nstages * stage_bytes + 16 * g.nstages + 64 + 4 * 32 * 33 * 4 + 1024;
   const int m_tiles = (M + 127) / 128;
   if ((long long)m_tiles * g.n_tiles > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
 

@@ -88,9 +88,12 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
 }
 
 // qkv [S*NB, 3E] (row = s*NB + n); out [S*NB, E].  grid (NB*heads, ceil(S/ROWS_PER_CTA)); dynamic smem: K,V [S][HD+1]
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// out rows have pitch out_ld; split3 != 0 writes each row as [v | v - trunc_tf32(v) | v] (the 3xTF32 A operand form)
 template <int HD>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int S,
-                                                        int NB, int E, int heads, float scale) {
+                                                        int NB, int E, int heads, float scale, int out_ld, int split3) {
   extern __shared__ float smem_att[];
   float* sk = smem_att;                      // [S][HD+1]
   float* sv = sk + (size_t)S * (HD + 1);     // [S][HD+1]
@@ -98,11 +101,34 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int ld = 3 * E;
-  for (int i = threadIdx.x; i < S * HD; i += blockDim.x) {
-    const int s = i / HD, d = i % HD;
-    const float* row = qkv + ((long long)s * NB + n) * ld + hh * HD + d;
-    sk[s * (HD + 1) + d] = row[E];
-    sv[s * (HD + 1) + d] = row[2 * E];
+  {
+    // K and V rows of this (image, head): float4 loads, four rows in flight per thread before the dependent smem stores
+    constexpr int V4 = HD / 4;
+    const int total = S * V4;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+      float4 kv[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          const int s = i / V4, d4 = i - s * V4;
+          const float* row = qkv + ((long long)s * NB + n) * ld + hh * HD + d4 * 4;
+          kv[u] = __ldg(reinterpret_cast<const float4*>(row + E));
+          vv[u] = __ldg(reinterpret_cast<const float4*>(row + 2 * E));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          const int s = i / V4, d4 = i - s * V4;
+          float* kd = sk + s * (HD + 1) + d4 * 4;
+          float* vd = sv + s * (HD + 1) + d4 * 4;
+          kd[0] = kv[u].x; kd[1] = kv[u].y; kd[2] = kv[u].z; kd[3] = kv[u].w;
+          vd[0] = vv[u].x; vd[1] = vv[u].y; vd[2] = vv[u].z; vd[3] = vv[u].w;
+        }
+      }
+    }
   }
   __syncthreads();
   float* myp = sp + (size_t)warp * S;
@@ -133,7 +159,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     __syncwarp();
     float o = 0.f;
     for (int j = 0; j < S; ++j) o = fmaf(myp[j], sv[j * (HD + 1) + lane], o);
-    out[((long long)i * NB + n) * E + hh * HD + lane] = o / sum;
+    const float val = o / sum;
+    float* orow = out + ((long long)i * NB + n) * out_ld + hh * HD + lane;
+    orow[0] = val;
+    if (split3) {
+      orow[E] = tf32_lo(val);
+      orow[2 * E] = val;
+    }
     __syncwarp();
   }
 }
@@ -141,12 +173,18 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 // out[m,:] = LayerNorm(x[m,:] + y[m,:]) * g + b ;  E == 128 (one float4 per lane)
 __global__ void __launch_bounds__(256) add_layernorm128_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                const float* __restrict__ g, const float* __restrict__ b,
-                                                               float* __restrict__ out, int M, float eps) {
+                                                               float* __restrict__ out, int M, float eps, int x_ld = 128,
+                                                               int y_ld = 128, int out_ld = 128, int split3 = 0,
+                                                               int y_planes = 1, long long y_plane_stride = 0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float4 a = reinterpret_cast<const float4*>(x + (long long)row * 128)[lane];
-  const float4 c = reinterpret_cast<const float4*>(y + (long long)row * 128)[lane];
+  const float4 a = reinterpret_cast<const float4*>(x + (long long)row * x_ld)[lane];
+  float4 c = reinterpret_cast<const float4*>(y + (long long)row * y_ld)[lane];
+  for (int pl = 1; pl < y_planes; ++pl) {  // split-K partial products of the producing GEMM
+    const float4 t = reinterpret_cast<const float4*>(y + pl * y_plane_stride + (long long)row * y_ld)[lane];
+    c.x += t.x; c.y += t.y; c.z += t.z; c.w += t.w;
+  }
   float v[4] = {a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w};
   float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / 128.f);
   float var = 0.f;
@@ -164,7 +202,26 @@ __global__ void __launch_bounds__(256) add_layernorm128_kernel(const float* __re
   o.y = v[1] * rstd * gg.y + bb.y;
   o.z = v[2] * rstd * gg.z + bb.z;
   o.w = v[3] * rstd * gg.w + bb.w;
-  reinterpret_cast<float4*>(out + (long long)row * 128)[lane] = o;
+  float* orow = out + (long long)row * out_ld;
+  reinterpret_cast<float4*>(orow)[lane] = o;
+  if (split3) {
+    reinterpret_cast<float4*>(orow + 128)[lane] = make_float4(tf32_lo(o.x), tf32_lo(o.y), tf32_lo(o.z), tf32_lo(o.w));
+    reinterpret_cast<float4*>(orow + 256)[lane] = o;
+  }
+}
+
+// [rows][E] -> [rows][3E] = [v | v - trunc_tf32(v) | v]
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
+                                                     int E) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * E) return;
+  const long long r = i / E;
+  const int c = (int)(i - r * E);
+  const float v = in[i];
+  float* o = out + r * 3 * E + c;
+  o[0] = v;
+  o[E] = tf32_lo(v);
+  o[2 * E] = v;
 }
 
 static int launch_linear(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
@@ -222,7 +279,7 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
     int ysplit = (2 * MDE_NUM_SMS + NB * heads - 1) / (NB * heads);
     if (ysplit < 1) ysplit = 1;
     if (ysplit > (S + 7) / 8) ysplit = (S + 7) / 8;
-    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att, S, NB, E, heads, 1.0f / sqrtf((float)hd));
+    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att, S, NB, E, heads, 1.0f / sqrtf((float)hd), E, 0);
     if ((rc = check_launch())) return rc;
   }
   if ((rc = launch_linear(att, E, out_w, E, out_b, tmp, E, M, E, E, 0, st))) return rc;
@@ -231,6 +288,78 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
   if ((rc = launch_linear(att, E, l1_w, E, l1_b, ff, FF, M, FF, E, 1, st))) return rc;
   if ((rc = launch_linear(ff, FF, l2_w, FF, l2_b, tmp, E, M, E, FF, 0, st))) return rc;
   add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(att, tmp, ln2_w, ln2_b, y, M, eps);
+  return check_launch();
+}
+
+// ---- tensor-core variant: the four nn.Linear products on the tcgen05 NT GEMM in 3xTF32 --------------------------------
+// Token matrices travel in "split form" rows [v | v_lo | v] (pitch 3E, v_lo = v - trunc_tf32(v)) and the weights as
+// [w_hi | w_hi | w_lo] along K (prepared once by the caller), so ONE K' = 3K TF32 GEMM evaluates v_hi*w_hi + v_lo*w_hi +
+// v_hi*w_lo: fp32-grade accuracy (the queries feed a softmax downstream) at tensor-core speed.
+int64_t mde_encoder_layer_tc_ws_floats(int S, int NB, int E, int FF) {
+  const int64_t M = (int64_t)S * NB;
+  return M * (3 * E /*qkv*/ + 3 * E /*att3*/ + 4 * E /*tmp: up to 4 split-K planes*/ + 3 * E /*x1_3*/ + 3 * (int64_t)FF /*h3*/);
+}
+
+int mde_split3_tf32(const float* in, float* out, int64_t rows, int E, mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (rows <= 0 || E <= 0) return MDE_ERR_BAD_SHAPE;
+  const long long n = rows * E;
+  split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, E);
+  return check_launch();
+}
+
+int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float* in_w3, const float* in_b,
+                             const float* out_w3, const float* out_b, const float* ln1_w, const float* ln1_b,
+                             const float* l1_w3, const float* l1_b, const float* l2_w3, const float* l2_b, const float* ln2_w,
+                             const float* ln2_b, float* ws, int S, int NB, int E, int heads, int FF, float eps,
+                             mde_stream_t stream) {
+  if (!x3 || !y || !in_w3 || !in_b || !out_w3 || !out_b || !ln1_w || !ln1_b || !l1_w3 || !l1_b || !l2_w3 || !l2_b || !ln2_w ||
+      !ln2_b || !ws)
+    return MDE_ERR_BAD_POINTER;
+  if (S <= 0 || NB <= 0 || E != 128 || heads <= 0 || E % heads != 0 || E / heads != 32 || FF <= 0 || FF % 4 != 0)
+    return MDE_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = S * NB, E3 = 3 * E;
+  float* qkv = ws;                        // [M][3E] plain q | k | v
+  float* att3 = qkv + (size_t)M * E3;     // [M][3E] split form
+  float* tmp = att3 + (size_t)M * E3;     // [M][E]
+  float* x13 = tmp + (size_t)4 * M * E;   // [M][3E] split form of LN1 output
+  float* h3 = x13 + (size_t)M * E3;       // [M][3FF] split form of relu(linear1)
+  int rc;
+  // qkv = x W_in^T + b_in
+  if ((rc = mde_gemm_nt_tf32_ex(x3, E3, 0, in_w3, E3, 0, qkv, E3, 0, 1, M, E3, E3, 1, 1.0f, in_b, 0, 0, stream))) return rc;
+  {
+    const int hd = E / heads;
+    const size_t sm = sizeof(float) * ((size_t)2 * S * (hd + 1) + (size_t)8 * S);
+    if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    int ysplit = (2 * MDE_NUM_SMS + NB * heads - 1) / (NB * heads);
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > (S + 7) / 8) ysplit = (S + 7) / 8;
+    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att3, S, NB, E, heads, 1.0f / sqrtf((float)hd), E3, 1);
+    if ((rc = check_launch())) return rc;
+  }
+  // tmp = att W_out^T + b_out ; x1 = LN1(x + tmp)
+  if ((rc = mde_gemm_nt_tf32_ex(att3, E3, 0, out_w3, E3, 0, tmp, E, 0, 1, M, E, E3, 1, 1.0f, out_b, 0, 0, stream))) return rc;
+  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x3, tmp, ln1_w, ln1_b, x13, M, eps, E3, E, E3, 1);
+  if ((rc = check_launch())) return rc;
+  // h = relu(x1 W_1^T + b_1), written in split form; tmp = h W_2^T + b_2: K' = 3 FF is split over 4 CTAs per output
+  // tile, each writing its own partial plane (one CTA per tile: 31.7 us, atomics: 39 us); LN2 sums the planes
+  if ((rc = mde_gemm_nt_tf32_ex(x13, E3, 0, l1_w3, E3, 0, h3, 3 * (int64_t)FF, 0, 1, M, FF, E3, 1, 1.0f, l1_b, 1, 1, stream)))
+    return rc;
+  const int kchunks = (3 * FF + 31) / 32;
+  const int planes = kchunks >= 4 ? 4 : 1;
+  if ((rc = mde_gemm_nt_tf32_planes(h3, 3 * (int64_t)FF, 0, l2_w3, 3 * (int64_t)FF, 0, tmp, E, 0, 1, M, E, 3 * FF, planes, 1.0f,
+                                    l2_b, 0, 0, (int64_t)M * E, stream)))
+    return rc;
+  const int cps = (kchunks + planes - 1) / planes;
+  const int real_planes = (kchunks + cps - 1) / cps;
+  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x13, tmp, ln2_w, ln2_b, y, M, eps, E3, E, y_split ? E3 : E,
+                                                       y_split ? 1 : 0, real_planes, (long long)M * E);
   return check_launch();
 }
 

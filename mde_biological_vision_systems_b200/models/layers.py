@@ -23,6 +23,7 @@ class PatchTransformerEncoder(nn.Module):
                                            padding=0)
         self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
         self.use_tc_patch_embed = True  # False: cuDNN conv for the patch embedding (the transformer stays on our kernels)
+        self.use_tc_layers = True       # False: exact-fp32 SIMT linear kernels instead of the 3xTF32 tcgen05 GEMMs
 
     def _needs_autograd(self, x):
         return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
@@ -50,10 +51,31 @@ class PatchTransformerEncoder(nn.Module):
             emb = conv(x).flatten(2)
             emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
             tokens = emb.permute(2, 0, 1).contiguous()
+        layers = list(self.transformer_encoder.layers)
+        if self.use_tc_layers and self._tc_layers_supported(layers):
+            return ops.encoder_layers_tc(tokens, layers, self._prepared_layers(layers))
         ws = None
-        for layer in self.transformer_encoder.layers:
+        for layer in layers:
             tokens, ws = ops.encoder_layer(tokens, layer, ws)
         return tokens
+
+    @staticmethod
+    def _tc_layers_supported(layers):
+        l0 = layers[0]
+        return (l0.self_attn.embed_dim == 128 and l0.self_attn.num_heads == 4 and l0.linear1.out_features % 4 == 0
+                and not l0.norm_first and l0.self_attn.in_proj_weight is not None)
+
+    def _prepared_layers(self, layers):
+        """[w_hi | w_hi | w_lo] operands of the four linear maps of every layer, cached per parameter version."""
+        params = [p for layer in layers for p in (layer.self_attn.in_proj_weight, layer.self_attn.out_proj.weight,
+                                                  layer.linear1.weight, layer.linear2.weight)]
+        key = tuple(p._version for p in params) + (params[0].device,)
+        cached = getattr(self, "_mde_l3_prep", None)
+        if cached is None or cached[0] != key:
+            prep = [tuple(ops.prepare_linear3(p) for p in params[4 * i: 4 * i + 4]) for i in range(len(layers))]
+            cached = (key, prep)
+            self._mde_l3_prep = cached
+        return cached[1]
 
 
 class PixelWiseDotProduct(nn.Module):

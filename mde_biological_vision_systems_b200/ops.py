@@ -392,6 +392,43 @@ def encoder_layer(x, layer, ws=None):
     return y, ws
 
 
+def prepare_linear3(weight):
+    """nn.Linear weight [N,K] -> [N,3K] = [w_hi | w_hi | w_lo] (w_hi = round_tf32(w), w_lo = round_tf32(w - w_hi)): the B
+    operand of a 3xTF32 product against split-form activations [a | a_lo | a]."""
+    w = _f32(weight.detach()).contiguous()
+    hi = round_tf32(w)
+    lo = round_tf32(w - hi)
+    return torch.cat((hi, hi, lo), dim=1).contiguous()
+
+
+def encoder_layers_tc(tokens, layers, prepared):
+    """Run nn.TransformerEncoderLayer modules (post-LN, ReLU, eval semantics) on tokens [S,N,E] with the four linear
+    products of each layer on the tcgen05 GEMM in 3xTF32 (fp32-grade accuracy).  ``prepared[i]`` = the four
+    prepare_linear3() weights of layer i (in_proj, out_proj, linear1, linear2)."""
+    lib = _lib.load()
+    _need_cuda(tokens)
+    x = _f32(tokens).contiguous()
+    s, n, e = x.shape
+    ff = layers[0].linear1.out_features
+    ws = torch.empty(int(lib.mde_encoder_layer_tc_ws_floats(s, n, e, ff)), dtype=torch.float32, device=x.device)
+    cur = torch.empty((s * n, 3 * e), dtype=torch.float32, device=x.device)
+    nxt = torch.empty_like(cur)
+    out = torch.empty_like(x)
+    with timing("encoder_layers_tc"):
+        _lib.check(lib.mde_split3_tf32(_p(x), _p(cur), s * n, e, _s()), "mde_split3_tf32")
+        for i, (layer, (w_in, w_out, w_1, w_2)) in enumerate(zip(layers, prepared)):
+            last = i == len(layers) - 1
+            a = layer.self_attn
+            rc = lib.mde_encoder_layer_tc_fwd(
+                _p(cur), _p(out if last else nxt), 0 if last else 1, _p(w_in), _p(a.in_proj_bias), _p(w_out),
+                _p(a.out_proj.bias), _p(layer.norm1.weight), _p(layer.norm1.bias), _p(w_1), _p(layer.linear1.bias), _p(w_2),
+                _p(layer.linear2.bias), _p(layer.norm2.weight), _p(layer.norm2.bias), _p(ws), s, n, e, a.num_heads, ff,
+                float(layer.norm1.eps), _s())
+            _lib.check(rc, "mde_encoder_layer_tc_fwd")
+            cur, nxt = nxt, cur
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 # range attention / conv_out / bins
 # ------------------------------------------------------------------------------------------------------------

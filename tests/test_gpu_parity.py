@@ -188,6 +188,27 @@ def test_patch_transformer_golden(golden):
     np.testing.assert_allclose(tgt.cpu().numpy(), golden["head/tgt"], rtol=1e-3, atol=2e-4)
 
 
+def test_encoder_layers_tc_vs_simt_and_fp64(golden):
+    """3xTF32 tcgen05 encoder layers vs the exact-fp32 SIMT kernels and vs a float64 evaluation of the torch layers."""
+    m, _ = _head_state()
+    pt = m.adaptive_bins_layer.patch_transformer.to(DEV)
+    rng = np.random.default_rng(99)
+    for s_len, nb in [(221, 3), (132, 2), (300, 1)]:
+        tok = torch.from_numpy(rng.standard_normal((s_len, nb, 128)).astype(np.float32)).to(DEV)
+        layers = list(pt.transformer_encoder.layers)
+        with torch.no_grad():
+            out_tc = ops.encoder_layers_tc(tok, layers, pt._prepared_layers(layers))
+            cur, ws = tok, None
+            for layer in layers:
+                cur, ws = ops.encoder_layer(cur, layer, ws)
+            ref64 = pt.transformer_encoder.double().eval()(tok.double())
+            pt.transformer_encoder.float()
+        scale = float(ref64.abs().max())
+        e_tc = float((out_tc.double() - ref64).abs().max()) / scale
+        e_simt = float((cur.double() - ref64).abs().max()) / scale
+        assert e_tc < 2e-5 and e_simt < 2e-5, (e_tc, e_simt)
+
+
 @pytest.mark.parametrize("shape", [(2, 128, 176, 192), (1, 128, 208, 272), (3, 128, 240, 320)])
 def test_patch_embed_tc(shape):
     """tcgen05 split-K patch-embedding GEMM (NHWC input) vs the fp32 conv + positional rows of the reference."""
