@@ -87,19 +87,29 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
   }
 }
 
-// qkv [S*NB, 3E] (row = s*NB + n); out [S*NB, E].  grid (NB*heads, ceil(S/ROWS_PER_CTA)); dynamic smem: K,V [S][HD+1]
+// qkv [S*NB, 3E] (row = s*NB + n); out rows have pitch out_ld.  grid (NB*heads, y splits over the query rows).
+// One CTA per (image, head, row range): K and V of the (image, head) resident in shared memory ([S][HD+1], conflict-free);
+// each warp processes FOUR query rows per pass so that every K / V word read from shared memory feeds four FMAs (the
+// one-row-per-warp form was bound by the shared-memory port: 666 warp-wide loads per row, now 222):
+//   scores : lane = key j, q of the four rows broadcast as one float4 per head-dim channel
+//   softmax: probabilities kept interleaved [j][4 rows] in shared memory
+//   P V    : lane = head-dim channel, one float4 broadcast of the four rows' p_j + one V word per key
+// split3 != 0 writes each output row as [v | v - trunc_tf32(v) | v] (the 3xTF32 A operand form).
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// out rows have pitch out_ld; split3 != 0 writes each row as [v | v - trunc_tf32(v) | v] (the 3xTF32 A operand form)
 template <int HD>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int S,
                                                         int NB, int E, int heads, float scale, int out_ld, int split3) {
-  extern __shared__ float smem_att[];
-  float* sk = smem_att;                      // [S][HD+1]
-  float* sv = sk + (size_t)S * (HD + 1);     // [S][HD+1]
-  float* sp = sv + (size_t)S * (HD + 1);     // [warps][S] probabilities
-  const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
+  static_assert(HD == 32, "lane == head-dim channel");
+  extern __shared__ __align__(16) float smem_att[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* sk = smem_att;                               // [S][HD+1]
+  float* sv = sk + (size_t)S * (HD + 1);              // [S][HD+1]
+  size_t off = (size_t)2 * S * (HD + 1);
+  off = (off + 3) & ~(size_t)3;                       // float4 alignment of the per-warp areas
+  float* sq = smem_att + off + (size_t)warp * (4 * HD + 4 * S);  // [HD][4]  q of the four rows, channel-major
+  float* sp = sq + 4 * HD;                                       // [S][4]   scores / probabilities of the four rows
+  const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
   const int ld = 3 * E;
   {
     // K and V rows of this (image, head): float4 loads, four rows in flight per thread before the dependent smem stores
@@ -131,40 +141,71 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     }
   }
   __syncthreads();
-  float* myp = sp + (size_t)warp * S;
   const int rows_per_cta = (S + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
-  for (int i = r0 + warp; i < r1; i += nwarps) {
-    // every lane holds the whole (pre-scaled, as torch does: q / sqrt(hd)) query row
-    const float qd = qkv[((long long)i * NB + n) * ld + hh * HD + lane] * scale;
-    float q[HD];
+  for (int i0 = r0 + 4 * warp; i0 < r1; i0 += 4 * nwarps) {
+    // (1) the four (pre-scaled, as torch does: q / sqrt(hd)) query rows -> sq[d][r]
+    float4 qv;
+    {
+      float t[4];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = __shfl_sync(0xffffffffu, qd, d);
-    float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) {
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) a = fmaf(q[d], sk[j * (HD + 1) + d], a);
-      myp[j] = a;
-      mx = fmaxf(mx, a);
+      for (int r = 0; r < 4; ++r) {
+        const int i = min(i0 + r, S - 1);
+        t[r] = qkv[((long long)i * NB + n) * ld + hh * HD + lane] * scale;
+      }
+      qv = make_float4(t[0], t[1], t[2], t[3]);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < S; j += 32) {
-      const float e = expf(myp[j] - mx);
-      myp[j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
+    reinterpret_cast<float4*>(sq)[lane] = qv;
     __syncwarp();
-    float o = 0.f;
-    for (int j = 0; j < S; ++j) o = fmaf(myp[j], sv[j * (HD + 1) + lane], o);
-    const float val = o / sum;
-    float* orow = out + ((long long)i * NB + n) * out_ld + hh * HD + lane;
-    orow[0] = val;
-    if (split3) {
-      orow[E] = tf32_lo(val);
-      orow[2 * E] = val;
+    // (2) scores, lane = key
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int j0 = 0; j0 < S; j0 += 32) {
+      const int j = j0 + lane;
+      const float* kr = sk + (size_t)min(j, S - 1) * (HD + 1);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        const float4 q4 = reinterpret_cast<const float4*>(sq)[d];
+        const float kd = kr[d];
+        a0 = fmaf(q4.x, kd, a0); a1 = fmaf(q4.y, kd, a1); a2 = fmaf(q4.z, kd, a2); a3 = fmaf(q4.w, kd, a3);
+      }
+      if (j < S) {
+        reinterpret_cast<float4*>(sp)[j] = make_float4(a0, a1, a2, a3);
+        mx[0] = fmaxf(mx[0], a0); mx[1] = fmaxf(mx[1], a1); mx[2] = fmaxf(mx[2], a2); mx[3] = fmaxf(mx[3], a3);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mx[r] = warp_max(mx[r]);
+    // (3) exponentials and their sums
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < S; j += 32) {
+      float4 a = reinterpret_cast<float4*>(sp)[j];
+      a.x = expf(a.x - mx[0]); a.y = expf(a.y - mx[1]); a.z = expf(a.z - mx[2]); a.w = expf(a.w - mx[3]);
+      sum[0] += a.x; sum[1] += a.y; sum[2] += a.z; sum[3] += a.w;
+      reinterpret_cast<float4*>(sp)[j] = a;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sum[r] = warp_sum(sum[r]);
+    __syncwarp();
+    // (4) P V, lane = head-dim channel
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float4 p4 = reinterpret_cast<const float4*>(sp)[j];
+      const float vj = sv[(size_t)j * (HD + 1) + lane];
+      o0 = fmaf(p4.x, vj, o0); o1 = fmaf(p4.y, vj, o1); o2 = fmaf(p4.z, vj, o2); o3 = fmaf(p4.w, vj, o3);
+    }
+    const float ov[4] = {o0 / sum[0], o1 / sum[1], o2 / sum[2], o3 / sum[3]};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + r;
+      if (i < r1) {
+        float* orow = out + ((long long)i * NB + n) * out_ld + hh * HD + lane;
+        orow[0] = ov[r];
+        if (split3) {
+          orow[E] = tf32_lo(ov[r]);
+          orow[2 * E] = ov[r];
+        }
+      }
     }
     __syncwarp();
   }
@@ -269,7 +310,7 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
   if ((rc = launch_linear(x, E, in_w, E, in_b, qkv, 3 * E, M, 3 * E, E, 0, st))) return rc;
   {
     const int hd = E / heads;
-    const size_t sm = sizeof(float) * ((size_t)2 * S * (hd + 1) + (size_t)8 * S);
+    const size_t sm = sizeof(float) * ((((size_t)2 * S * (hd + 1) + 3) & ~(size_t)3) + (size_t)8 * (4 * hd + 4 * S));
     if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
     static bool attr = false;
     if (!attr) {
@@ -330,7 +371,7 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
   if ((rc = mde_gemm_nt_tf32_ex(x3, E3, 0, in_w3, E3, 0, qkv, E3, 0, 1, M, E3, E3, 1, 1.0f, in_b, 0, 0, stream))) return rc;
   {
     const int hd = E / heads;
-    const size_t sm = sizeof(float) * ((size_t)2 * S * (hd + 1) + (size_t)8 * S);
+    const size_t sm = sizeof(float) * ((((size_t)2 * S * (hd + 1) + 3) & ~(size_t)3) + (size_t)8 * (4 * hd + 4 * S));
     if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
     static bool attr = false;
     if (!attr) {
