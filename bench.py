@@ -102,7 +102,8 @@ def cpu_forward_losses(batch, steps, warmup):
         with torch.no_grad():
             _, sem = oracle.semantics_loader(SEM_MODE, labels.numpy(), table)
             x = oracle.input_insertion(sd, img, SEM_MODE, None, "rgb", semantics=torch.from_numpy(sem))
-            _, _, l1, l2 = oracle.forward_and_losses(lambda t: model.decoder(model.encoder(t)), sd, x, depth, 1e-3, 10.0)
+            backbone = lambda t: oracle.decoder_bn(oracle.encoder_features(model.encoder.original_model, t), sd)
+            _, _, l1, l2 = oracle.forward_and_losses(backbone, sd, x, depth, 1e-3, 10.0)
             return float(l1) + 0.1 * float(l2)
 
     for _ in range(warmup):

@@ -39,7 +39,9 @@ class PatchTransformerEncoder(nn.Module):
 
     def forward(self, x):
         conv = self.embedding_convPxP
-        if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0) or not x.is_cuda:
+        if not x.is_cuda:
+            raise ops._lib.MdeError("PatchTransformerEncoder runs on the B200 kernels only (no CPU path)")
+        if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0):
             # training: dropout and the backward pass run through the stock torch layers
             emb = conv(x).flatten(2)  # [N, E, S]
             emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)

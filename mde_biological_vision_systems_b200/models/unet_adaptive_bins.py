@@ -76,8 +76,7 @@ class UpSampleBN(nn.Module):
                     and x.shape[1] % 4 == 0 and concat_with.shape[1] % 4 == 0:
                 return self._net(ops.upsample_concat_nhwc(x, concat_with))  # channels_last model: stay in NHWC
             return self._net(ops.upsample_concat(x, concat_with))
-        x = F.interpolate(x, size=concat_with.shape[-2:], mode='bilinear', align_corners=True)
-        return self._net(torch.cat((x, concat_with), dim=1))
+        raise ops._lib.MdeError("UpSampleBN runs on the B200 kernels only (no CPU path)")
 
 
 class DecoderBN(nn.Module):

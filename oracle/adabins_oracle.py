@@ -355,6 +355,42 @@ def flip_tta(model_fn, image, min_depth, max_depth):
 
 
 # ----------------------------------------------------------------------------------------------
+# Encoder walk and DecoderBN (models/unet_adaptive_bins.py:39-116), functional, eval-mode BatchNorm.  The backbone itself
+# is third-party (geffnet): any torch module with the geffnet child order is walked as the reference's Encoder does.
+# ----------------------------------------------------------------------------------------------
+
+
+def encoder_features(backbone, x):
+    """Encoder.forward (:108-116): every child's output (the seven 'blocks' stages individually) appended to a list."""
+    feats = [x]
+    for name, child in backbone._modules.items():
+        stages = child._modules.values() if name == "blocks" else (child,)
+        for stage in stages:
+            feats.append(stage(feats[-1]))
+    return feats
+
+
+def _conv_bn_lrelu(x, sd, p, conv_i, bn_i):
+    x = F.conv2d(x, sd[f"{p}_net.{conv_i}.weight"], sd[f"{p}_net.{conv_i}.bias"], padding=1)
+    x = F.batch_norm(x, sd[f"{p}_net.{bn_i}.running_mean"], sd[f"{p}_net.{bn_i}.running_var"], sd[f"{p}_net.{bn_i}.weight"],
+                     sd[f"{p}_net.{bn_i}.bias"], False, 0.1, 1e-5)
+    return F.leaky_relu(x, 0.01)
+
+
+def decoder_bn(features, sd, p="decoder."):
+    """DecoderBN.forward (:89-100) with UpSampleBN (:51-54): conv2 (1x1, padding 1) -> 4 x [bilinear(align_corners) to
+    the skip's size, cat, 2 x conv3x3-BN-LeakyReLU] -> conv3."""
+    s0, s1, s2, s3, bottleneck = features[4], features[5], features[6], features[8], features[11]
+    y = F.conv2d(bottleneck, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    for name, skip in (("up1.", s3), ("up2.", s2), ("up3.", s1), ("up4.", s0)):
+        y = F.interpolate(y, size=skip.shape[-2:], mode="bilinear", align_corners=True)
+        y = torch.cat([y, skip], dim=1)
+        y = _conv_bn_lrelu(y, sd, p + name, 0, 1)
+        y = _conv_bn_lrelu(y, sd, p + name, 3, 4)
+    return F.conv2d(y, sd[p + "conv3.weight"], sd[p + "conv3.bias"], padding=1)
+
+
+# ----------------------------------------------------------------------------------------------
 # Whole-path helper used by the CPU baseline: forward + SILog + chamfer given a backbone callable
 # ----------------------------------------------------------------------------------------------
 

