@@ -25,6 +25,8 @@
 // MMAs of the next.  Epilogue: tcgen05.ld -> affine / LeakyReLU / optional TF32 rounding -> swizzled shared staging ->
 // TMA tensor store (edge tiles are clipped by the hardware; no predicates anywhere).  Persistent, 1 CTA / SM,
 // warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 3-6 epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -263,7 +265,9 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
   if (C % 4 != 0 || Cout % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(w_prep, 16) || !aligned(y_nhwc, 16))
     return MDE_ERR_UNSUPPORTED;  // TMA: 16-byte global strides
   // N tile: the whole C_out when it fits one instruction (<= 256, multiple of 16), else the largest divisor of C_out
-  // that is a multiple of 32 (so that 32-channel store groups never straddle two N tiles)
+  // that is a multiple of 32 (so that 32-channel store groups never straddle two N tiles).  Measured on B200: choosing
+  // narrower tiles so that two stacked patches share the filter (C_out = 640 as 5 x 128, 320 as 5 x 64) was slower
+  // (up1 + up2: 1.54 vs 1.37 ms) -- the MMA's shared-memory operand reads, not the L2 traffic, set the pace.
   int n_tile = 0;
   if (Cout <= 256 && Cout % 16 == 0) {
     n_tile = Cout;
@@ -273,6 +277,10 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
         n_tile = cand;
         break;
       }
+  }
+  {
+    const char* force = getenv("MDE_CONV_NTILE");  // tuning aid
+    if (force && atoi(force) > 0 && Cout % atoi(force) == 0 && atoi(force) % 32 == 0 && atoi(force) <= 256) n_tile = atoi(force);
   }
   if (n_tile == 0) return MDE_ERR_UNSUPPORTED;
   const int nt = (4 * n_tile <= 512) ? 2 : 1;
