@@ -55,12 +55,45 @@ class SamePadConv2d(nn.Conv2d):
         super().__init__(cin, cout, kernel_size, stride, 0, 1, groups, bias)
 
     def forward(self, x):
+        return self.forward_with(x, self.weight, self.bias)
+
+    def forward_with(self, x, weight, bias):
         kh, kw = self.kernel_size
         ph = _same_pad_amount(x.shape[-2], kh, self.stride[0])
         pw = _same_pad_amount(x.shape[-1], kw, self.stride[1])
         if ph or pw:
             x = F.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
-        return F.conv2d(x, self.weight, self.bias, self.stride, 0, 1, self.groups)
+        return F.conv2d(x, weight, bias, self.stride, 0, 1, self.groups)
+
+
+def _folded_conv_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the preceding convolution: w' = w * gamma / sqrt(var + eps) per output channel,
+    b' = beta + (conv bias - mean) * gamma / sqrt(var + eps); cached on the conv module per parameter / buffer version."""
+    tensors = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple(t._version for t in tensors) + (conv.weight.device, conv.weight.stride())
+    cached = getattr(conv, "_mde_fold", None)
+    if cached is None or cached[0] != key:
+        with torch.no_grad():
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            w = conv.weight * scale.view(-1, 1, 1, 1)
+            b = bn.bias - bn.running_mean * scale
+            if conv.bias is not None:
+                b = b + conv.bias * scale
+        cached = (key, w, b)
+        conv._mde_fold = cached
+    return cached[1], cached[2]
+
+
+def conv_bn(conv, bn, x):
+    """bn(conv(x)); in inference (eval-mode statistics, no autograd) as ONE convolution with the folded filter -- the 69
+    per-block BatchNorm passes of EfficientNet-B1 are 3 ms of a 14 ms step otherwise.  Same values up to fp32 rounding."""
+    if bn.training or torch.is_grad_enabled() or not isinstance(bn, nn.BatchNorm2d) or not bn.track_running_stats \
+            or not bn.affine:
+        return bn(conv(x))
+    w, b = _folded_conv_bn(conv, bn)
+    if isinstance(conv, SamePadConv2d):
+        return conv.forward_with(x, w, b)
+    return conv._conv_forward(x, w, b)
 
 
 def _conv(cin, cout, k, stride=1, groups=1, bias=False):
@@ -95,8 +128,8 @@ class DepthwiseSeparableConv(nn.Module):
         self.act2 = nn.Identity()
 
     def forward(self, x):
-        y = self.act1(self.bn1(self.conv_dw(x)))
-        y = self.bn2(self.conv_pw(self.se(y)))
+        y = self.act1(conv_bn(self.conv_dw, self.bn1, x))
+        y = conv_bn(self.conv_pw, self.bn2, self.se(y))
         return x + y if self.has_residual else y
 
 
@@ -116,9 +149,9 @@ class InvertedResidual(nn.Module):
         self.bn3 = nn.BatchNorm2d(cout, eps=_BN_EPS)
 
     def forward(self, x):
-        y = self.act1(self.bn1(self.conv_pw(x)))
-        y = self.act2(self.bn2(self.conv_dw(y)))
-        y = self.bn3(self.conv_pwl(self.se(y)))
+        y = self.act1(conv_bn(self.conv_pw, self.bn1, x))
+        y = self.act2(conv_bn(self.conv_dw, self.bn2, y))
+        y = conv_bn(self.conv_pwl, self.bn3, self.se(y))
         return x + y if self.has_residual else y
 
 

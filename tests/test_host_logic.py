@@ -79,6 +79,23 @@ def test_backbone_feature_shapes():
         m.decoder(feats)
 
 
+def test_backbone_bn_folding_matches_unfolded():
+    """Inference-time conv+BatchNorm folding inside the EfficientNet blocks gives the unfolded module's values."""
+    from mde_biological_vision_systems_b200.models import efficientnet as E
+    m = make_model(**CASES["b1_plain"])
+    x = torch.randn(1, 3, 64, 96)
+    with torch.no_grad():
+        folded = m.encoder(x)
+    ref = m.encoder(x)  # autograd enabled -> the BatchNorm modules run un-folded
+    for a, b in zip(folded, ref):
+        assert torch.allclose(a, b.detach(), rtol=1e-4, atol=1e-5)
+    blk = m.encoder.original_model.blocks[1][0]
+    w0 = E._folded_conv_bn(blk.conv_pw, blk.bn1)[0]
+    with torch.no_grad():
+        blk.bn1.running_var.mul_(2.0)  # in-place update bumps the version -> the cached fold is rebuilt
+    assert not torch.equal(E._folded_conv_bn(blk.conv_pw, blk.bn1)[0], w0)
+
+
 def test_abi_exports_every_declared_symbol():
     """Every function declared in include/mde_b200.h is exported by the built library and bound in _lib.py."""
     header = open(os.path.join(ROOT, "include", "mde_b200.h")).read()
