@@ -87,6 +87,11 @@ int mde_aux_mlp_bwd(const float* x, int64_t x_batch_stride, const float* w0, con
                     float* gw1, float* gb1, int B, int C_in, int H1, int H2, int64_t HW, float in_scale,
                     mde_stream_t stream);
 
+/* y[p,c] = act(x[p,c] + bias[c]) (+ residual[p,c]) on channels_last activations [pixels, C] (C % 4 == 0); act 0 none,
+ * 1 SiLU; y may alias x.  Epilogue of a convolution whose eval-mode BatchNorm is folded into the filter. */
+int mde_bias_act_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int C, int act,
+                      mde_stream_t stream);
+
 /* ---- K1b/K2 prologue: bin-width regressor + normalisation + cumsum (miniViT.py:17-21,35-45;
  * unet_adaptive_bins.py:292-296).  t0 [B, E] rows at stride t0_stride (token 0 of the transformer output).
  *   w1 [H,E] b1 [H] w2 [H,H] b2 [H] w3 [n_bins,H] b3 [n_bins]   (E = 128, H = 256 in the reference)

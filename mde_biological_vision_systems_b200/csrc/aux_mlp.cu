@@ -213,3 +213,44 @@ int mde_aux_mlp_bwd(const float* x, int64_t xbs, const float* w0, const float* b
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-channel bias (+ SiLU) (+ residual) on channels_last activations, in place or out of place: the epilogue of a
+// convolution whose eval-mode BatchNorm has been folded into its filter (models/efficientnet.py conv_bn).  Without it the
+// folded bias costs one extra elementwise pass per convolution and the activation another.
+// y[p, c] = act(x[p, c] + bias[c]) + (res ? res[p, c] : 0);   act: 0 identity, 1 SiLU
+namespace mde {
+__global__ void __launch_bounds__(256) bias_act_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                            const float* __restrict__ res, float* __restrict__ y,
+                                                            long long total4, int c4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + cg);
+    float o[4] = {v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w};
+    if (act == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
+    }
+    if (res != nullptr) {
+      const float4 r = reinterpret_cast<const float4*>(res)[i];
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace mde
+
+extern "C" int mde_bias_act_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int C,
+                                 int act, mde_stream_t stream) {
+  using namespace mde;
+  if (!x || !bias || !y) return MDE_ERR_BAD_POINTER;
+  if (pixels <= 0 || C <= 0 || act < 0 || act > 1) return MDE_ERR_BAD_SHAPE;
+  if (C % 4 != 0 || !aligned(x, 16) || !aligned(y, 16) || !aligned(bias, 16) || (residual && !aligned(residual, 16)))
+    return MDE_ERR_UNSUPPORTED;
+  const long long total4 = pixels * (C / 4);
+  long long gx = (total4 + 255) / 256;
+  if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;
+  bias_act_nhwc_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, y, total4, C / 4, act);
+  return check_launch();
+}

@@ -212,6 +212,26 @@ def aux_mlp(x, w0, b0, w1, b1, in_div=1.0, out=None):
     return res
 
 
+def bias_act_nhwc_(x_cl, bias, act=0, residual=None):
+    """In place on a channels_last tensor: x = act(x + bias[c]) (+ residual); act 0 none / 1 SiLU."""
+    lib = _lib.load()
+    b, c, h, w = x_cl.shape
+    rc = lib.mde_bias_act_nhwc(_p(x_cl), _p(bias), _p(residual), _p(x_cl), b * h * w, c, int(act), _s())
+    _lib.check(rc, "mde_bias_act_nhwc")
+    return x_cl
+
+
+def bias_act_supported(x, residual=None):
+    ok = (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and _is_nhwc_or_dense_cl(x))
+    if residual is not None:
+        ok = ok and residual.shape == x.shape and residual.dtype == torch.float32 and _is_nhwc_or_dense_cl(residual)
+    return ok
+
+
+def _is_nhwc_or_dense_cl(x):
+    return x.is_contiguous(memory_format=torch.channels_last)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # regressor + bins
 # ------------------------------------------------------------------------------------------------------------
