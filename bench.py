@@ -251,8 +251,9 @@ def run_ours(args):
 
     # the same end-to-end loop with the package's DevicePrefetcher: the H2D copies of step i+1 run on a side stream under
     # the kernels of step i (every copy and every loss read-back is still inside the timed region)
-    def timed_prefetch(hbatch, steps):
+    def timed_prefetch(hbatch, steps, runner=None):
         from mde_biological_vision_systems_b200.prefetch import DevicePrefetcher
+        run = (lambda b: step(b, False)) if runner is None else runner
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -260,10 +261,10 @@ def run_ours(args):
         s.record()
         pending = None
         for batch in DevicePrefetcher((hbatch for _ in range(steps)), dev):
-            loss = step(batch, False)
+            loss = run(batch)
             if pending is not None:
                 float(pending.item())  # read the previous step's loss while this step runs
-            pending = loss
+            pending = loss.clone()     # (a graph replay rewrites its static output tensor)
         float(pending.item())
         e.record()
         torch.cuda.synchronize()
@@ -275,6 +276,38 @@ def run_ours(args):
 
     timed_prefetch(host, 2)
     ms_e2e_pf = timed_prefetch(host, args.steps)
+
+    # the same step replayed as one CUDA graph (mde...graphs.GraphedStep): no host launch gaps
+    graphed = None
+    try:
+        from mde_biological_vision_systems_b200.graphs import GraphedStep
+
+        def graph_fn(image, depth, semantics):
+            return step({"image": image, "depth": depth, "semantics": semantics}, False)
+
+        gstep = GraphedStep(graph_fn, resident)
+        ref_loss = float(step(resident, False))
+        got = float(gstep(**resident))
+        if abs(got - ref_loss) > 1e-4 * abs(ref_loss):
+            raise RuntimeError(f"graph replay loss {got} != eager {ref_loss}")
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(args.steps):
+            gstep(**resident)
+        e_.record()
+        torch.cuda.synchronize()
+        msg = torch.tensor([s_.elapsed_time(e_)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(msg, op=dist.ReduceOp.MAX)
+        graphed = {"ms_per_step": float(msg.item()) / args.steps, "loss_matches_eager": True}
+        timed_prefetch(host, 2, runner=lambda b: gstep(**b))
+        graphed["e2e_ms_per_step"] = timed_prefetch(host, args.steps, runner=lambda b: gstep(**b)) / args.steps
+    except Exception as exc:  # reported, never fatal: the eager numbers stand on their own
+        graphed = {"error": repr(exc)[:300]}
     host_u8 = dict(host, semantics=host["semantics"].clamp(-1, 254).to(torch.uint8).pin_memory())  # on-disk label format
     timed_prefetch(host_u8, 2)
     ms_e2e_u8 = timed_prefetch(host_u8, args.steps)
@@ -318,7 +351,11 @@ def run_ours(args):
         hbm, bf16, src = peaks()
         P = (H // 2) * (W // 2)
         pix = world * B * H * W
-        ms_step = ms_total / args.steps
+        ms_step_eager = ms_total / args.steps
+        ms_e2e_eager = ms_e2e_pf / args.steps
+        use_graph = bool(graphed) and "ms_per_step" in graphed
+        ms_step = graphed["ms_per_step"] if use_graph else ms_step_eager
+        ms_e2e_best = graphed["e2e_ms_per_step"] if use_graph and "e2e_ms_per_step" in graphed else ms_e2e_eager
         chain_ms = ktimes.get("head_chain")
         alg_bytes = B * (128 * P * 4 + P * 4)  # read conv3x3 features once, write pred
         roof = None
@@ -366,12 +403,14 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32 (TF32 tensor-core contraction in the head)", "data": "synthetic",
             "config": {"workload": "BASELINE config 2: EfficientNet-B1 AdaBins + GloVe-25d ADE20K-places @input, batch 16/GPU, 416x544, n_bins 256, random init",
                        "batch_per_gpu": B, "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "backbone": "encoder/decoder are PyTorch-cuDNN passthrough (not hot path)"},
-            "e2e": {"value": pix / (ms_e2e_pf / args.steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_pf / args.steps,
+                       "backbone": "EfficientNet encoder = PyTorch/cuDNN passthrough (channels_last, eval-mode BatchNorm folded); decoder + head + losses + loaders on the hand-written kernels"},
+            "e2e": {"value": pix / (ms_e2e_best * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_best,
                     "how": "host batch in pinned memory (int64 labels, the reference's batch contract) -> DevicePrefetcher "
-                           "(H2D on a side stream, overlapped with the previous step) -> loaders + model + losses -> "
-                           "loss.item(); every copy and read-back inside the timed region",
+                           "(H2D on a side stream, overlapped with the previous step) -> loaders + model + losses "
+                           + ("(one CUDA-graph replay, graphs.GraphedStep) " if use_graph else "(eager launches) ")
+                           + "-> loss.item(); every copy and read-back inside the timed region",
+                    "eager": {"value": pix / (ms_e2e_eager * 1e-3) / 1e6, "ms_per_step": ms_e2e_eager},
                     "serial_copies": {"value": pix / (ms_e2e / args.steps * 1e-3) / 1e6, "ms_per_step": ms_e2e / args.steps,
                                       "note": "same loop with blocking in-step copies, no overlap"},
                     "uint8_labels": {"value": pix / (ms_e2e_u8 / args.steps * 1e-3) / 1e6, "ms_per_step": ms_e2e_u8 / args.steps,
@@ -380,6 +419,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "hot_path": {"what": "gather + mViT head + bins + SILog + chamfer on a fixed unet_out", "ms_per_step": hot_ms,
                          "value": B * H * W / (hot_ms * 1e-3) / 1e6, "unit": "Mpix/s per GPU", "share_of_step": hot_ms / ms_step},
+            "launch": ("cuda_graph_replay (graphs.GraphedStep: the step captured once, replayed per batch; inputs resident, "
+                       "copied into the static capture buffers)" if use_graph else "eager"),
+            "eager": {"value": pix / (ms_step_eager * 1e-3) / 1e6, "ms_per_step": ms_step_eager},
+            "cuda_graph": graphed,
             "roofline": roof, "kernels": others, "clocks": clocks, "train": train,
         }
         if world == 1 and not args.no_cpu:
