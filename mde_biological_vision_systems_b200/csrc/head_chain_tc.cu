@@ -22,6 +22,8 @@
 // In the fused form the two 1x1 contractions are folded by associativity, W'_b = W_out @ Q_b (tiny, exact fp32,
 // mde_fold_queries), pre-scaled by log2(e) and rounded to TF32 once, so the tensor cores run ONE K = 128 contraction
 // per pixel against the per-image 256 x 128 operand; the bias enters the softmax as exp2(b_j) factors.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -81,25 +83,31 @@ static DebugCfg g_dbg = {4096, 512, 16, 1024, 1, nullptr};
     acc += clock64() - t__;             \
   }
 
-template <int NB>
+// CTAS = 2: a CTA pair (cluster of two, tcgen05 cta_group::2) works on two consecutive 128-pixel tiles with ONE M = 256
+// MMA stream issued by the leader: each CTA stages its own tile and only HALF of the per-image B operand (NB/2 bin rows),
+// so the shared-memory operand reads per MMA drop from 12 KB to 8 KB per SM -- the measured ceiling of the 1-CTA form.
+template <int NB, int CTAS = 1>
 struct SmemPlan {
-  static constexpr int W_BYTES = NB * KDIM * 4;  // per-image B operand: 4 K-chunks x [NB rows][128 B]
-  static constexpr int NS = (NB == 256) ? 5 : 8;
+  static constexpr int NBH = NB / CTAS;           // B rows held by one CTA
+  static constexpr int W_BYTES = NBH * KDIM * 4;  // per-image B operand: 4 K-chunks x [NBH rows][128 B]
+  static constexpr int NS = (NB == 256) ? (CTAS == 2 ? 8 : 5) : 8;
   static constexpr int RING_BYTES = NS * STAGE_BYTES;
   static constexpr int CONST_BYTES = 2 * NB * 4 + 128 * 4 * 4;  // exp2(bias), exp2(bias)*centre per bin; merge slots
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = W_BYTES + RING_BYTES + CONST_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 // A_KMAJOR = false: activations NCHW (pixel axis contiguous, MN-major A, four 32-pixel boxes per stage)
 // A_KMAJOR = true : activations NHWC / channels_last (channel axis contiguous, K-major A, one 128-row box per stage)
-template <int NB, int EPI, bool A_KMAJOR>
+template <int NB, int EPI, bool A_KMAJOR, int CTAS = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     head_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ biasf, const float* __restrict__ centers, float* __restrict__ out,
                       int tiles_per_img, int total_tiles, long long P, DebugCfg dbg, ChainTrain tr) {
-  using Plan = SmemPlan<NB>;
+  using Plan = SmemPlan<NB, CTAS>;
   constexpr int NS = Plan::NS;
+  constexpr int NBH = Plan::NBH;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs of the pair)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
@@ -115,12 +123,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const uint32_t bar_accfull = bar_wempty + 8;     // [2]
   const uint32_t bar_accempty = bar_accfull + 16;  // [2]
   const uint32_t s_tmem_slot = bar_accempty + 16;  // uint32
+  const uint32_t bar_peerfull = s_tmem_slot + 8;   // [NS]  leader only: the peer CTA's stage has landed (remote arrive)
+  const uint32_t bar_peerwfull = bar_peerfull + 8 * NS;  // [1]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous tile range of this CTA (so it crosses at most one image boundary)
-  const int t_begin = (int)(((long long)total_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  // contiguous range of tiles (CTAS = 2: tile PAIRS; `tiles_per_img` / `total_tiles` then count pairs) of this CTA /
+  // CTA pair, so that it crosses at most one image boundary
+  const int unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;
+  const int t_begin = (int)(((long long)total_tiles * unit) / nunits);
+  const int t_end = (int)(((long long)total_tiles * (unit + 1)) / nunits);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -131,7 +143,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     mbar_init(bar_wempty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, 4 * EPI_SPLIT);  // one arrive per epilogue warp
+      mbar_init(bar_accempty + 8 * i, 4 * EPI_SPLIT * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
+    }
+    if (CTAS == 2) {
+      for (int i = 0; i < NS; ++i) mbar_init(bar_peerfull + 8 * i, 1);
+      mbar_init(bar_peerwfull, 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -142,11 +158,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
   constexpr uint32_t TMEM_COLS = (2 * NB <= 32) ? 32 : (2 * NB <= 64) ? 64 : (2 * NB <= 128) ? 128 : (2 * NB <= 256) ? 256 : 512;
   if (warp == 2) {
-    tmem_alloc(s_tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc2(s_tmem_slot, TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(s_tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       constexpr int PF_DIST = 0;
       auto prefetch_tile = [&](int t) {
         const int img = t / tiles_per_img;
-        const int p0 = (t - img * tiles_per_img) * TILE_M;
+        const int p0 = ((t - img * tiles_per_img) * CTAS + (int)rank) * TILE_M;
         for (int kc = 0; kc < KDIM / KC; ++kc) {
           if (A_KMAJOR) {
             tma_prefetch_l2_2d(&map_x, kc * KC, (int)((long long)img * P + p0));
@@ -177,7 +199,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const long long t_start = clock64();
       for (int t = t_begin; t < t_end; ++t) {
         const int img = t / tiles_per_img;
-        const int p0 = (t - img * tiles_per_img) * TILE_M;
+        const int p0 = ((t - img * tiles_per_img) * CTAS + (int)rank) * TILE_M;
         if (PF_DIST > 0 && t + PF_DIST < t_end) prefetch_tile(t + PF_DIST);
         for (int kc = 0; kc < KDIM / KC; ++kc) {
           MDE_TIMED_WAIT(w_empty, mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1))
@@ -214,14 +236,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         mbar_expect_tx(bar_wfull, Plan::W_BYTES);
 #pragma unroll
         for (int kc = 0; kc < KDIM / KC; ++kc)
-          tma_load_3d(s_w + kc * (NB * 128), &map_w, bar_wfull, kc * KC, 0, img);
+          tma_load_3d(s_w + kc * (NBH * 128), &map_w, bar_wfull, kc * KC, (int)rank * NBH, img);
         wphase ^= 1;
+      }
+    }
+  } else if (warp == 1 && CTAS == 2 && rank == 1) {
+    // ================= peer CTA: relay "my operands have landed" to the leader's barriers =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, wphase = 0;
+      int cur = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int img = t / tiles_per_img;
+        if (img != cur) {
+          mbar_wait(bar_wfull, wphase, 7);
+          mbar_arrive_remote(bar_peerwfull, 0);
+          wphase ^= 1;
+          cur = img;
+        }
+        for (int kc = 0; kc < KDIM / KC; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase, 8);
+          mbar_arrive_remote(bar_peerfull + 8 * stage, 0);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_TF32, TILE_M, NB, /*A MN-major?*/ A_KMAJOR ? 0 : 1, /*B K-major*/ 0);
+      constexpr uint32_t idesc =
+          make_idesc(FMT_TF32, TILE_M * CTAS, NB, /*A MN-major?*/ A_KMAJOR ? 0 : 1, /*B K-major*/ 0);
       uint32_t stage = 0, phase = 0, wphase = 0;
       int cur = -1;
       int it = 0;
@@ -230,20 +276,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int img = t / tiles_per_img;
         if (img != cur) {
-          if (cur >= 0) umma_commit(bar_wempty);  // fires when every MMA that read the old weights is done
+          if (cur >= 0) {  // fires when every MMA that read the old weights is done
+            if (CTAS == 2) umma2_commit_mc(bar_wempty);
+            else umma_commit(bar_wempty);
+          }
           MDE_TIMED_WAIT(w_w, mbar_wait(bar_wfull, wphase, 3))
+          if (CTAS == 2) mbar_wait_cluster(bar_peerwfull, wphase, 9);
           wphase ^= 1;
           cur = img;
         }
         const uint32_t buf = it & 1;
-        MDE_TIMED_WAIT(w_acc, mbar_wait(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4))
+        if (CTAS == 2) {
+          MDE_TIMED_WAIT(w_acc, mbar_wait_cluster(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4))
+        } else {
+          MDE_TIMED_WAIT(w_acc, mbar_wait(bar_accempty + 8 * buf, ((it >> 1) & 1) ^ 1, 4))
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * NB;
         for (int kc = 0; kc < KDIM / KC; ++kc) {
           MDE_TIMED_WAIT(w_full, mbar_wait(bar_full + 8 * stage, phase, 5))
+          if (CTAS == 2) mbar_wait_cluster(bar_peerfull + 8 * stage, phase, 10);
           tc_fence_after();
           const uint32_t a_base = s_ring + stage * STAGE_BYTES;
-          const uint32_t b_base = s_w + kc * (NB * 128);
+          const uint32_t b_base = s_w + kc * (NBH * 128);
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {
             // A (MN-major fp32/TF32 => "128B swizzle, 32B atom" layout, descriptor type 1): rows = channels (128 B =
@@ -254,15 +309,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                                        : make_smem_desc(a_base + j * 1024, dbg.a_lbo, dbg.a_sbo, SWZ_128B_32B, dbg.version);
             // B (K-major, SW128): 8 tf32 = 32 B along the 128-B swizzle row; 8-row atoms 1024 B apart
             const uint64_t bdesc = make_smem_desc(b_base + j * 32, dbg.b_lbo, dbg.b_sbo, SWZ_128B, dbg.version);
-            umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
+            if (CTAS == 2) umma2_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
+            else umma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kc | j) != 0);
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs complete
+          // frees the stage (in both CTAs of a pair) when these MMAs complete
+          if (CTAS == 2) umma2_commit_mc(bar_empty + 8 * stage);
+          else umma_commit(bar_empty + 8 * stage);
           if (++stage == NS) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(bar_accfull + 8 * buf);
+        if (CTAS == 2) umma2_commit_mc(bar_accfull + 8 * buf);
+        else umma_commit(bar_accfull + 8 * buf);
       }
       if (dbg.prof) {
         dbg.prof[blockIdx.x * 8 + 2] = w_full;
@@ -283,6 +342,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     float* c_cen = c_all + NB;      // [NB] exp2(bias)*centre
     float4* merge = reinterpret_cast<float4*>(c_all + 2 * NB);  // [128] (m, s, ws, -) of the upper column half
     constexpr int COLS = NB / EPI_SPLIT;  // columns per warp
+    // hand an accumulator buffer back to the MMA issuer (the leader CTA's barrier; the peer arrives remotely)
+    auto acc_release = [&](uint32_t bar) {
+      if (CTAS == 2 && rank != 0) mbar_arrive_remote(bar, 0);
+      else mbar_arrive(bar);
+    };
     float acc_gb[4] = {0.f, 0.f, 0.f, 0.f}, acc_gc[4] = {0.f, 0.f, 0.f, 0.f};  // EPI_BWD: per-lane bin sums
     int cur = -1;
     int it = 0;
@@ -290,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const long long t_start = clock64();
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int img = t / tiles_per_img;
-      const int p0 = (t - img * tiles_per_img) * TILE_M;
+      const int p0 = ((t - img * tiles_per_img) * CTAS + (int)rank) * TILE_M;
       if (EPI == EPI_BWD && img != cur && cur >= 0) {
         // per-bin sums of the image just finished: lane l of this warp owns bin half*COLS + 32*chunk + l
 #pragma unroll
@@ -329,7 +393,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (last) { /* accumulator fully read: hand the TMEM buffer back to the MMA warp */                                \
       tc_fence_before();                                                                                               \
       __syncwarp();                                                                                                    \
-      if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);                                                              \
+      if (lane == 0) acc_release(bar_accempty + 8 * buf);                                                              \
     } else {                                                                                                           \
       tmem_ld_32x32(taddr + (c0) + 32, nxt); /* prefetch: overlaps the math below */                                   \
     }                                                                                                                  \
@@ -394,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if (c == 3) {  // accumulator fully read
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+            if (lane == 0) acc_release(bar_accempty + 8 * buf);
           }
           float e[32], gv[32];
 #pragma unroll
@@ -424,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if (c0 + 32 == COLS) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+            if (lane == 0) acc_release(bar_accempty + 8 * buf);
           }
           float* dst = out + ((long long)img * NB + half * COLS + c0) * P + pix;
 #pragma unroll
@@ -446,18 +510,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // neither CTA may exit while the other can still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int NB, int EPI, bool A_KMAJOR>
-static int launch_chain(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
-                        long long P, cudaStream_t st, ChainTrain tr = ChainTrain{}) {
-  using Plan = SmemPlan<NB>;
-  if (P % TILE_M != 0) return MDE_ERR_BAD_SHAPE;
+template <int NB, int EPI, bool A_KMAJOR, int CTAS>
+static int launch_chain_impl(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
+                             long long P, cudaStream_t st, ChainTrain tr) {
+  using Plan = SmemPlan<NB, CTAS>;
+  if (P % (TILE_M * CTAS) != 0) return MDE_ERR_BAD_SHAPE;
   if (!aligned(x, 16) || !aligned(w, 16)) return MDE_ERR_BAD_POINTER;
   CUtensorMap mx, mw;
   if (A_KMAJOR) {
@@ -475,23 +541,58 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
   {
     const uint64_t dims[3] = {(uint64_t)KDIM, (uint64_t)NB, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)KDIM * 4, (uint64_t)NB * KDIM * 4};
-    const uint32_t box[3] = {KC, NB, 1};
+    const uint32_t box[3] = {KC, (uint32_t)(NB / CTAS), 1};  // a CTA of a pair stages its half of the bin rows
     if (!encode_f32(&mw, w, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }
-  const int tiles_per_img = (int)(P / TILE_M);
-  const long long total = (long long)tiles_per_img * B;
+  const int units_per_img = (int)(P / (TILE_M * CTAS));  // tiles (CTAS = 1) or tile pairs (CTAS = 2) per image
+  const long long total = (long long)units_per_img * B;
   if (total > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
-  const int grid = (int)(total < MDE_NUM_SMS ? total : MDE_NUM_SMS);
+  const int max_units = MDE_NUM_SMS / CTAS;
+  const int grid = CTAS * (int)(total < max_units ? total : max_units);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI, A_KMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::TOTAL) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI, A_KMAJOR, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Plan::TOTAL) != cudaSuccess)
       return MDE_ERR_LAUNCH;
     attr_set = true;
   }
-  head_chain_kernel<NB, EPI, A_KMAJOR><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
-                                                                      (int)total, P, g_dbg, tr);
+  if (CTAS == 1) {
+    head_chain_kernel<NB, EPI, A_KMAJOR, CTAS><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out,
+                                                                                      units_per_img, (int)total, P, g_dbg, tr);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Plan::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, head_chain_kernel<NB, EPI, A_KMAJOR, CTAS>, mx, mw, biasf, centers, out, units_per_img,
+                           (int)total, P, g_dbg, tr) != cudaSuccess)
+      return MDE_ERR_LAUNCH;
+  }
   return check_launch();
+}
+
+// MDE_CHAIN_CTAS=2 selects the CTA-pair (cta_group::2) form when the per-image tile count is even.  It is parity-green but
+// NOT the default: measured on B200 at config 2 it runs in 113 us against 107 us for the single-CTA form -- halving the
+// B-operand shared-memory reads does not help because the epilogue (8 warps, 2 per scheduler: 256 warp-wide MUFU.EX2 per
+// tile and scheduler = 2048 clocks of the ~3500 per tile, 28 % of all stall samples) paces the kernel, and the pair adds a
+// relay hop per stage and lock-steps two tiles.
+template <int NB, int EPI, bool A_KMAJOR>
+static int launch_chain(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
+                        long long P, cudaStream_t st, ChainTrain tr = ChainTrain{}) {
+  if constexpr (NB == 256 && EPI != EPI_STORE) {
+    const char* force = getenv("MDE_CHAIN_CTAS");
+    const bool pair = (P % (2 * TILE_M) == 0) && (force && atoi(force) == 2) && g_dbg.prof == nullptr;
+    if (pair) return launch_chain_impl<NB, EPI, A_KMAJOR, 2>(x, w, biasf, centers, out, B, P, st, tr);
+  }
+  return launch_chain_impl<NB, EPI, A_KMAJOR, 1>(x, w, biasf, centers, out, B, P, st, tr);
 }
 
 __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {

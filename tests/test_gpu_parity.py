@@ -402,6 +402,25 @@ def test_head_chain_backward(layout):
         assert err < 5e-3, (name, err)
 
 
+def test_head_chain_cta_pair_matches_single(monkeypatch):
+    """The cta_group::2 form of the chain (two CTAs share one M = 256 MMA stream; opt-in via MDE_CHAIN_CTAS=2) computes
+    the same predictions as the default single-CTA kernel, in both operand layouts."""
+    rng = np.random.default_rng(96)
+    b, h, w = 3, 48, 64
+    feat = torch.from_numpy(rng.standard_normal((b, 128, h, w)).astype(np.float32)).to(DEV)
+    wf = ops.round_tf32(torch.from_numpy((rng.standard_normal((b, 256, 128)) * 0.1).astype(np.float32)).to(DEV))
+    biasf = torch.from_numpy(rng.standard_normal((b, 256)).astype(np.float32)).to(DEV)
+    centers = torch.sort(torch.from_numpy(rng.random((b, 256)).astype(np.float32) * 10), dim=1).values.to(DEV)
+    for x in (feat, feat.contiguous(memory_format=torch.channels_last)):
+        monkeypatch.delenv("MDE_CHAIN_CTAS", raising=False)
+        p1 = ops.head_chain(x, wf, biasf, centers)
+        monkeypatch.setenv("MDE_CHAIN_CTAS", "2")
+        p2 = ops.head_chain(x, wf, biasf, centers)
+        torch.cuda.synchronize()
+        assert float((p1 - p2).abs().max()) <= 1e-5 * float(p1.abs().max())
+    monkeypatch.delenv("MDE_CHAIN_CTAS", raising=False)
+
+
 def test_mvit_forward_surface(golden):
     m, _ = _head_state()
     m.to(DEV)
