@@ -17,10 +17,9 @@
 //   * B: one box {32 ch, N tile, 3 (dy), 1 (dx)} of the filter pre-laid-out as [dx][dy][C_out][C] (TF32-rounded, scaled
 //     by MDE_TF32_TRUNC_COMP): three K-major 128B-swizzled operand tiles shared by all NT patches.
 // Measured (B200, head conv 128 -> 128 at B = 16, 208 x 272): 0.327 ms = 816 TFLOP/s = 72 % of the 1.125 PFLOP/s TF32
-// peak (cuDNN: 0.73 ms).  The ceiling is shared-memory bandwidth: an M = 128, N = 128, K = 8 TF32 SS-MMA reads 4 KB of A and
-// 4 KB of B per 64 tensor clocks (128 B/clk, all the SM has) while TMA writes the next stage; a variant with 3-4 stacked
-// patches, separate A/B rings and single-buffered accumulators (fewer operand bytes from L2) was slower (0.36-0.42 ms), so
-// the next step for this kernel is cta_group::2 (each CTA reads only half of B).
+// nominal peak, tensor pipe 80 % active under ncu (cuDNN: 0.73 ms).  Two attempts to go further were measured and did
+// not pay: a variant with 3-4 stacked patches, separate A/B rings and single-buffered accumulators (fewer operand bytes
+// from L2): 0.36-0.42 ms; CTA pairs (cta_group::2, half the filter rows per CTA, kept below as an opt-in): 0.338 ms.
 // Accumulators: NT x N-tile fp32 columns per buffer, two buffers in TMEM, so the epilogue of one super tile overlaps the
 // MMAs of the next.  Epilogue: tcgen05.ld -> affine / LeakyReLU / optional TF32 rounding -> swizzled shared staging ->
 // TMA tensor store (edge tiles are clipped by the hardware; no predicates anywhere).  Persistent, 1 CTA / SM,
@@ -47,9 +46,14 @@ struct ConvGeom {
   int tmem_cols;
   float slope;                    // LeakyReLU slope (1.0f = identity)
   int round_tf32;
+  int pair_x, pair_y;             // CTA-pair mode: the two CTAs of a pair take adjacent super tiles along x (2,1) or y (1,2)
 };
 
-template <int NT, int TW>
+// CTAS = 2: a CTA pair (cluster of two, tcgen05 cta_group::2) works on two adjacent super tiles with ONE M = 256 MMA stream
+// issued by the leader; each CTA stages its own halo box and only HALF of the filter rows (n_tile / 2 output channels), so
+// the shared-memory operand reads per MMA drop from 8 KB to 6 KB per SM at N = 128 (the measured ceiling of the 1-CTA
+// form) and the filter traffic from L2 halves.  tiles_x / tiles_y then count PAIRS along the paired axis.
+template <int NT, int TW, int CTAS = 1>
 __global__ void __launch_bounds__(CV_THREADS, 1)
     conv3x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_y, const float* __restrict__ scale,
@@ -60,15 +64,20 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
-  const int b_bytes = 3 * g.n_tile * 128;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs of the pair)
+  const int nbh = g.n_tile / CTAS;                            // filter rows staged by this CTA
+  const int b_bytes = 3 * nbh * 128;
   const int stage_bytes = A_BYTES + b_bytes;
   const uint32_t s_stg = base + g.nstages * stage_bytes;  // two staging buffers
   const uint32_t s_bar = s_stg + 2 * CV_STG_BYTES;
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * g.nstages, bar_acc_full = s_bar + 16 * g.nstages,
                  bar_acc_empty = bar_acc_full + 16;
+  const uint32_t bar_peerfull = bar_acc_empty + 16 + 16;  // [nstages] leader only: the peer's stage has landed
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 16 * g.nstages + 32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit0 = blockIdx.x / CTAS, ustep = gridDim.x / CTAS;  // work units = super tiles or super-tile pairs
+  const int rx = (CTAS == 2 && g.pair_x == 2) ? (int)rank : 0, ry = (CTAS == 2 && g.pair_y == 2) ? (int)rank : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.nstages; ++i) {
@@ -77,8 +86,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 128);
+      mbar_init(bar_acc_empty + 8 * i, 4 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
+    if (CTAS == 2)
+      for (int i = 0; i < g.nstages; ++i) mbar_init(bar_peerfull + 8 * i, 1);
     fence_barrier_init();
     fence_proxy_async();
     tma_prefetch_desc(&map_x);
@@ -86,31 +97,37 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
     tma_prefetch_desc(&map_y);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)g.tmem_cols);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc2(smem_u32((const void*)tmem_slot), (uint32_t)g.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)g.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // barrier inits visible to the peer before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < g.total; tile += gridDim.x) {
+      for (int tile = unit0; tile < g.total; tile += ustep) {
         int r = tile;
         const int ni = r % g.tiles_n; r /= g.tiles_n;
         const int txi = r % g.tiles_x; r /= g.tiles_x;
         const int tyi = r % g.tiles_y;
         const int b = r / g.tiles_y;
-        const int x0 = txi * TW, y0 = tyi * SR, n0 = ni * g.n_tile;
+        const int x0 = (txi * g.pair_x + rx) * TW, y0 = (tyi * g.pair_y + ry) * SR, n0 = ni * g.n_tile;
         for (int c = 0; c < g.chunks; ++c) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 21);
             mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
             const uint32_t dst = base + stage * stage_bytes;
             tma_load_4d(dst, &map_x, bar_full + 8 * stage, c * CV_KC, x0 + dx - 1, y0 - 1, b);
-            tma_load_4d(dst + A_BYTES, &map_w, bar_full + 8 * stage, c * CV_KC, n0, 0, dx);
+            tma_load_4d(dst + A_BYTES, &map_w, bar_full + 8 * stage, c * CV_KC, n0 + (int)rank * nbh, 0, dx);
             if (++stage == (uint32_t)g.nstages) {
               stage = 0;
               phase ^= 1;
@@ -119,11 +136,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         }
       }
     }
+  } else if (warp == 1 && CTAS == 2 && rank == 1) {
+    // peer CTA: relay "my operands of this stage have landed" to the leader
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = unit0; tile < g.total; tile += ustep) {
+        for (int c = 0; c < 3 * g.chunks; ++c) {
+          mbar_wait(bar_full + 8 * stage, phase, 28);
+          mbar_arrive_remote(bar_peerfull + 8 * stage, 0);
+          if (++stage == (uint32_t)g.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(FMT_TF32, 128, (uint32_t)g.n_tile, 0, 0);
+      const uint32_t idesc = make_idesc(FMT_TF32, 128 * CTAS, (uint32_t)g.n_tile, 0, 0);
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < g.total; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < g.total; tile += ustep, ++it) {
         const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1, 22);
         tc_fence_after();
@@ -132,6 +164,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         for (int c = 0; c < g.chunks; ++c) {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(bar_full + 8 * stage, phase, 23);
+            if (CTAS == 2) mbar_wait(bar_peerfull + 8 * stage, phase, 29);
             tc_fence_after();
             const uint32_t a0 = base + stage * stage_bytes;
             const uint32_t b0 = a0 + A_BYTES;
@@ -139,23 +172,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
             for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
               for (int j = 0; j < CV_KC / 8; ++j) {
-                const uint64_t bdesc = make_smem_desc(b0 + dy * g.n_tile * 128 + j * 32, 16, 1024, SWZ_128B);
+                const uint64_t bdesc = make_smem_desc(b0 + dy * nbh * 128 + j * 32, 16, 1024, SWZ_128B);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                   const uint64_t adesc = make_smem_desc(a0 + (t * TH + dy) * TW * 128 + j * 32, 16, 1024, SWZ_128B);
-                  umma_tf32_ss(d0 + t * g.n_tile, adesc, bdesc, idesc, first ^ 1);
+                  if (CTAS == 2) umma2_tf32_ss(d0 + t * g.n_tile, adesc, bdesc, idesc, first ^ 1);
+                  else umma_tf32_ss(d0 + t * g.n_tile, adesc, bdesc, idesc, first ^ 1);
                 }
                 first = 0;
               }
             }
-            umma_commit(bar_empty + 8 * stage);
+            if (CTAS == 2) umma2_commit_mc(bar_empty + 8 * stage);
+            else umma_commit(bar_empty + 8 * stage);
             if (++stage == (uint32_t)g.nstages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        umma_commit(bar_acc_full + 8 * buf);
+        if (CTAS == 2) umma2_commit_mc(bar_acc_full + 8 * buf);
+        else umma_commit(bar_acc_full + 8 * buf);
       }
     }
   } else if (warp >= 3) {
@@ -165,13 +201,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int groups = (g.n_tile + 31) / 32;
     uint32_t it = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < g.total; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < g.total; tile += ustep, ++it) {
       int r = tile;
       const int ni = r % g.tiles_n; r /= g.tiles_n;
       const int txi = r % g.tiles_x; r /= g.tiles_x;
       const int tyi = r % g.tiles_y;
       const int b = r / g.tiles_y;
-      const int x0 = txi * TW, y0 = tyi * SR, n0 = ni * g.n_tile;
+      const int x0 = (txi * g.pair_x + rx) * TW, y0 = (tyi * g.pair_y + ry) * SR, n0 = ni * g.n_tile;
       const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(bar_acc_full + 8 * buf, aphase, 24);
       tc_fence_after();
@@ -215,15 +251,21 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) {  // hand the accumulator buffer back to the MMA issuer (the leader's barrier; the peer arrives remotely)
+        if (CTAS == 2 && rank != 0) mbar_arrive_remote(bar_acc_empty + 8 * buf, 0);
+        else mbar_arrive(bar_acc_empty + 8 * buf);
+      }
     }
     if (etid == 0) tma_store_wait<0>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // neither CTA may exit while the other can still signal its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+    if (CTAS == 2) tmem_dealloc2(tmem_base, (uint32_t)g.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
   }
 }
 
@@ -293,10 +335,30 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
   const int tw = padded(16) <= padded(8) ? 16 : 8;
   const int th = 128 / tw, sr = nt * th;
 
+  // CTA pairs (cta_group::2) are opt-in (MDE_CONV_CTAS=2): parity-green, but measured on B200 they do not pay -- head conv
+  // 0.338 ms vs 0.343 ms, whole step 10.99 vs 11.06 ms -- i.e. neither the shared-memory operand reads nor the filter
+  // traffic from L2 is what holds the single-CTA kernel at ~80 % tensor-pipe activity.  The two CTAs of a pair take
+  // adjacent super tiles along the axis that wastes fewer out-of-image tiles.
+  int ctas = 1;
+  {
+    const char* force = getenv("MDE_CONV_CTAS");
+    if (force && atoi(force) == 2 && (n_tile / 2) % 8 == 0) ctas = 2;
+  }
   tc::ConvGeom g;
   g.B = B; g.H = H; g.W = W; g.C = C; g.Cout = Cout;
   g.tiles_x = (W + tw - 1) / tw;
   g.tiles_y = (H + sr - 1) / sr;
+  g.pair_x = g.pair_y = 1;
+  if (ctas == 2) {
+    const int px = (g.tiles_x + 1) / 2, py = (g.tiles_y + 1) / 2;
+    if (2 * px * g.tiles_y <= g.tiles_x * 2 * py) {
+      g.pair_x = 2;
+      g.tiles_x = px;
+    } else {
+      g.pair_y = 2;
+      g.tiles_y = py;
+    }
+  }
   g.tiles_n = Cout / n_tile;
   g.total = g.tiles_x * g.tiles_y * g.tiles_n * B;
   g.chunks = (C + tc::CV_KC - 1) / tc::CV_KC;
@@ -305,12 +367,12 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
   g.round_tf32 = round_tf32;
   int cols = 2 * nt * n_tile + ((n_tile % 32) ? 16 : 0);
   g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  const int a_bytes = (sr + 2) * tw * 128, stage_bytes = a_bytes + 3 * n_tile * 128;
-  const int budget = 222 * 1024 - 2 * tc::CV_STG_BYTES - 1024 - 256;
+  const int a_bytes = (sr + 2) * tw * 128, stage_bytes = a_bytes + 3 * (n_tile / ctas) * 128;
+  const int budget = 222 * 1024 - 2 * tc::CV_STG_BYTES - 1024 - 512;
   g.nstages = budget / stage_bytes;
   if (g.nstages > 6) g.nstages = 6;
   if (g.nstages < 2) return MDE_ERR_UNSUPPORTED;
-  const int smem = g.nstages * stage_bytes + 2 * tc::CV_STG_BYTES + 16 * g.nstages + 64 + 1024;
+  const int smem = g.nstages * stage_bytes + 2 * tc::CV_STG_BYTES + 32 * g.nstages + 128 + 1024;
 
   CUtensorMap mx, mw, my;
   {
@@ -322,7 +384,7 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Cout, 3, 3};
     const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)Cout * C * 4, (uint64_t)3 * Cout * C * 4};
-    const uint32_t box[4] = {(uint32_t)tc::CV_KC, (uint32_t)n_tile, 3, 1};
+    const uint32_t box[4] = {(uint32_t)tc::CV_KC, (uint32_t)(n_tile / ctas), 3, 1};  // a CTA of a pair stages half the rows
     if (!tc::encode_f32(&mw, w_prep, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }
   {
@@ -331,23 +393,47 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
     const uint32_t box[4] = {32, (uint32_t)tw, (uint32_t)th, 1};
     if (!tc::encode_f32(&my, y_nhwc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }
-  const int grid = g.total < MDE_NUM_SMS ? g.total : MDE_NUM_SMS;
+  const int max_units = MDE_NUM_SMS / ctas;
+  const int grid = ctas * (g.total < max_units ? g.total : max_units);
   cudaStream_t st = (cudaStream_t)stream;
-#define MDE_CV_LAUNCH(NT, TW)                                                                                          \
+#define MDE_CV_LAUNCH(NT, TW, CT)                                                                                      \
   {                                                                                                                    \
     static bool attr = false;                                                                                          \
     if (!attr) {                                                                                                       \
-      if (cudaFuncSetAttribute(tc::conv3x3_kernel<NT, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != \
-          cudaSuccess)                                                                                                 \
+      if (cudaFuncSetAttribute(tc::conv3x3_kernel<NT, TW, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                               226 * 1024) != cudaSuccess)                                                             \
         return MDE_ERR_LAUNCH;                                                                                         \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    tc::conv3x3_kernel<NT, TW><<<grid, tc::CV_THREADS, smem, st>>>(mx, mw, my, scale, shift, g);                       \
+    if (CT == 1) {                                                                                                     \
+      tc::conv3x3_kernel<NT, TW, CT><<<grid, tc::CV_THREADS, smem, st>>>(mx, mw, my, scale, shift, g);                 \
+    } else {                                                                                                           \
+      cudaLaunchConfig_t cfg = {};                                                                                     \
+      cfg.gridDim = dim3((unsigned)grid);                                                                              \
+      cfg.blockDim = dim3(tc::CV_THREADS);                                                                             \
+      cfg.dynamicSmemBytes = smem;                                                                                     \
+      cfg.stream = st;                                                                                                 \
+      cudaLaunchAttribute lattr[1];                                                                                    \
+      lattr[0].id = cudaLaunchAttributeClusterDimension;                                                               \
+      lattr[0].val.clusterDim.x = 2;                                                                                   \
+      lattr[0].val.clusterDim.y = 1;                                                                                   \
+      lattr[0].val.clusterDim.z = 1;                                                                                   \
+      cfg.attrs = lattr;                                                                                               \
+      cfg.numAttrs = 1;                                                                                                \
+      if (cudaLaunchKernelEx(&cfg, tc::conv3x3_kernel<NT, TW, CT>, mx, mw, my, scale, shift, g) != cudaSuccess)        \
+        return MDE_ERR_LAUNCH;                                                                                         \
+    }                                                                                                                  \
   }
-  if (nt == 2 && tw == 16) MDE_CV_LAUNCH(2, 16)
-  else if (nt == 2) MDE_CV_LAUNCH(2, 8)
-  else if (tw == 16) MDE_CV_LAUNCH(1, 16)
-  else MDE_CV_LAUNCH(1, 8)
+  switch (ctas * 1000 + nt * 100 + tw) {
+    case 1216: MDE_CV_LAUNCH(2, 16, 1) break;
+    case 1208: MDE_CV_LAUNCH(2, 8, 1) break;
+    case 1116: MDE_CV_LAUNCH(1, 16, 1) break;
+    case 1108: MDE_CV_LAUNCH(1, 8, 1) break;
+    case 2216: MDE_CV_LAUNCH(2, 16, 2) break;
+    case 2208: MDE_CV_LAUNCH(2, 8, 2) break;
+    case 2116: MDE_CV_LAUNCH(1, 16, 2) break;
+    default: MDE_CV_LAUNCH(1, 8, 2) break;
+  }
 #undef MDE_CV_LAUNCH
   return check_launch();
 }

@@ -280,6 +280,23 @@ def test_gemm_nt_tc(cfg):
     assert err < 1e-3, err
 
 
+def test_conv3x3_cta_pair_matches_single(monkeypatch):
+    """The cta_group::2 form of the conv (opt-in via MDE_CONV_CTAS=2; pairs along x or y, odd tile counts) gives the
+    single-CTA kernel's outputs bit for bit (same MMA order per output tile)."""
+    rng = np.random.default_rng(92)
+    for (b, c, h, w, cout) in [(2, 128, 48, 64, 128), (1, 176, 40, 24, 80), (1, 96, 26, 34, 640), (1, 344, 13, 17, 160)]:
+        x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
+        wt = ops.prepare_conv3x3_weight(torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32)).to(DEV))
+        bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(DEV)
+        monkeypatch.delenv("MDE_CONV_CTAS", raising=False)
+        y1 = ops.conv3x3_nhwc(x, wt, None, bias, slope=0.01)
+        monkeypatch.setenv("MDE_CONV_CTAS", "2")
+        y2 = ops.conv3x3_nhwc(x, wt, None, bias, slope=0.01)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y2), (b, c, h, w, cout)
+    monkeypatch.delenv("MDE_CONV_CTAS", raising=False)
+
+
 def test_regressor_bins(golden):
     m, sd = _head_state()
     tgt = torch.from_numpy(golden["head/tgt"])
