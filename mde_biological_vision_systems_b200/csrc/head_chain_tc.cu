@@ -36,9 +36,9 @@ constexpr int KC = 32;                           // channels per stage = one 128
 constexpr int STAGE_BYTES = TILE_M * KC * 4;     // 16384
 constexpr int BOX_BYTES = 32 * KC * 4;           // one 32-pixel x 32-channel box
 constexpr int EPI_WARP0 = 3;                     // warps 0..2: TMA producer, MMA issuer, weight loader / TMEM allocator
-constexpr int EPI_SPLIT = 2;                     // 8 epilogue warps per tile: 4 lane quarters x 2 column halves
-constexpr int EPI_THREADS = 128 * EPI_SPLIT;
-constexpr int NUM_THREADS = 32 * EPI_WARP0 + EPI_THREADS;  // 352
+// epilogue warps per tile = 4 TMEM lane quarters x ES column parts (ES = 2: 8 warps, 128 columns each; ES = 4: 16 warps,
+// 64 columns each -- more warps per scheduler to keep the MUFU busy, at <= 104 registers per thread)
+__host__ __device__ constexpr int chain_threads(int es) { return 32 * EPI_WARP0 + 128 * es; }
 enum { EPI_STORE = 0, EPI_SOFTMAX = 1, EPI_BWD = 2 };
 
 // extra pointers of the training forms (all may be null for inference):
@@ -92,15 +92,15 @@ struct SmemPlan {
   static constexpr int W_BYTES = NBH * KDIM * 4;  // per-image B operand: 4 K-chunks x [NBH rows][128 B]
   static constexpr int NS = (NB == 256) ? (CTAS == 2 ? 8 : 5) : 8;
   static constexpr int RING_BYTES = NS * STAGE_BYTES;
-  static constexpr int CONST_BYTES = 2 * NB * 4 + 128 * 4 * 4;  // exp2(bias), exp2(bias)*centre per bin; merge slots
+  static constexpr int CONST_BYTES = 2 * NB * 4 + 3 * 128 * 4 * 4;  // exp2(bias), exp2(bias)*centre per bin; merge slots
   static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = W_BYTES + RING_BYTES + CONST_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 // A_KMAJOR = false: activations NCHW (pixel axis contiguous, MN-major A, four 32-pixel boxes per stage)
 // A_KMAJOR = true : activations NHWC / channels_last (channel axis contiguous, K-major A, one 128-row box per stage)
-template <int NB, int EPI, bool A_KMAJOR, int CTAS = 1>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int NB, int EPI, bool A_KMAJOR, int CTAS = 1, int ES = 2>
+__global__ void __launch_bounds__(chain_threads(ES), 1)
     head_chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ biasf, const float* __restrict__ centers, float* __restrict__ out,
                       int tiles_per_img, int total_tiles, long long P, DebugCfg dbg, ChainTrain tr) {
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     mbar_init(bar_wempty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, 4 * EPI_SPLIT * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(bar_accempty + 8 * i, 4 * ES * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     if (CTAS == 2) {
       for (int i = 0; i < NS; ++i) mbar_init(bar_peerfull + 8 * i, 1);
@@ -341,7 +341,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     float* c_fac = c_all;           // [NB] exp2(bias)
     float* c_cen = c_all + NB;      // [NB] exp2(bias)*centre
     float4* merge = reinterpret_cast<float4*>(c_all + 2 * NB);  // [128] (m, s, ws, -) of the upper column half
-    constexpr int COLS = NB / EPI_SPLIT;  // columns per warp
+    constexpr int COLS = NB / ES;  // columns per warp
+    constexpr int EPI_THREADS = 128 * ES;
     // hand an accumulator buffer back to the MMA issuer (the leader CTA's barrier; the peer arrives remotely)
     auto acc_release = [&](uint32_t bar) {
       if (CTAS == 2 && rank != 0) mbar_arrive_remote(bar, 0);
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // per-bin sums of the image just finished: lane l of this warp owns bin half*COLS + 32*chunk + l
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          atomicAdd(tr.gb + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gb[c]);
-          atomicAdd(tr.gc + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gc[c]);
+          atomicAdd(tr.gb + (long long)cur * NB + half * (NB / ES) + 32 * c + lane, acc_gb[c]);
+          atomicAdd(tr.gc + (long long)cur * NB + half * (NB / ES) + 32 * c + lane, acc_gc[c]);
           acc_gb[c] = 0.f;
           acc_gc[c] = 0.f;
         }
@@ -422,28 +423,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       s3 = fmaf(e3, f.w, s3); w3 = fmaf(e3, g.w, w3);                                                                  \
     }                                                                                                                  \
   }
-        static_assert(COLS == 128, "the unrolled epilogue below covers 4 chunks of 32 columns per warp");
-        MDE_CHUNK(ra, rb, 0, false)
-        MDE_CHUNK(rb, ra, 32, false)
-        MDE_CHUNK(ra, rb, 64, false)
-        MDE_CHUNK(rb, ra, 96, true)
+        static_assert(COLS == 128 || COLS == 64, "the unrolled epilogue covers 4 or 2 chunks of 32 columns per warp");
+        if constexpr (COLS == 128) {
+          MDE_CHUNK(ra, rb, 0, false)
+          MDE_CHUNK(rb, ra, 32, false)
+          MDE_CHUNK(ra, rb, 64, false)
+          MDE_CHUNK(rb, ra, 96, true)
+        } else {
+          MDE_CHUNK(ra, rb, 0, false)
+          MDE_CHUNK(rb, ra, 32, true)
+        }
 #undef MDE_CHUNK
         const float s = (s0 + s1) + (s2 + s3), ws = (w0 + w1) + (w2 + w3);
-        // merge the two column halves of each pixel row
-        if (half == 1) merge[row] = make_float4(m, s, ws, 0.f);
+        // merge the ES column parts of each pixel row
+        if (half != 0) merge[(half - 1) * 128 + row] = make_float4(m, s, ws, 0.f);
         asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
         if (half == 0) {
-          const float4 o = merge[row];
-          const float mm = fmaxf(m, o.x);
-          const float a = ex2_approx(m - mm), bsc = ex2_approx(o.x - mm);
-          const float stot = s * a + o.y * bsc;
-          out[(long long)img * P + pix] = (ws * a + o.z * bsc) / stot;
+          float mm = m, stot = s, wtot = ws;
+#pragma unroll
+          for (int k = 0; k < ES - 1; ++k) {
+            const float4 o = merge[k * 128 + row];
+            const float nm = fmaxf(mm, o.x);
+            const float a = ex2_approx(mm - nm), bsc = ex2_approx(o.x - nm);
+            stot = stot * a + o.y * bsc;
+            wtot = wtot * a + o.z * bsc;
+            mm = nm;
+          }
+          out[(long long)img * P + pix] = wtot / stot;
           if (tr.stats) *reinterpret_cast<float2*>(tr.stats + 2 * ((long long)img * P + pix)) = make_float2(mm, stot);
         }
         asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // merge slots free for the next tile
       } else if constexpr (EPI == EPI_BWD) {
         // single pass given the forward's softmax state: p_j = 2^(z_j - m) f_j / S;  u_j = p_j g;  gl_j = u_j (c_j - pred)
-        static_assert(COLS == 128, "4 chunks of 32 columns per warp");
+        static_assert(COLS == 128 && ES == 2, "4 chunks of 32 columns per warp");
         const long long gp = (long long)img * P + pix;
         const float2 st = *reinterpret_cast<const float2*>(tr.stats + 2 * gp);
         const float predv = tr.pred[gp];
@@ -499,8 +511,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (EPI == EPI_BWD && cur >= 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        atomicAdd(tr.gb + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gb[c]);
-        atomicAdd(tr.gc + (long long)cur * NB + half * (NB / EPI_SPLIT) + 32 * c + lane, acc_gc[c]);
+        atomicAdd(tr.gb + (long long)cur * NB + half * (NB / ES) + 32 * c + lane, acc_gb[c]);
+        atomicAdd(tr.gc + (long long)cur * NB + half * (NB / ES) + 32 * c + lane, acc_gc[c]);
       }
     }
     if (dbg.prof && etid == 0) {
@@ -519,7 +531,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
 }
 
-template <int NB, int EPI, bool A_KMAJOR, int CTAS>
+template <int NB, int EPI, bool A_KMAJOR, int CTAS, int ES = 2>
 static int launch_chain_impl(const float* x, const float* w, const float* biasf, const float* centers, float* out, int B,
                              long long P, cudaStream_t st, ChainTrain tr) {
   using Plan = SmemPlan<NB, CTAS>;
@@ -551,18 +563,18 @@ static int launch_chain_impl(const float* x, const float* w, const float* biasf,
   const int grid = CTAS * (int)(total < max_units ? total : max_units);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI, A_KMAJOR, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(head_chain_kernel<NB, EPI, A_KMAJOR, CTAS, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Plan::TOTAL) != cudaSuccess)
       return MDE_ERR_LAUNCH;
     attr_set = true;
   }
   if (CTAS == 1) {
-    head_chain_kernel<NB, EPI, A_KMAJOR, CTAS><<<grid, NUM_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out,
-                                                                                      units_per_img, (int)total, P, g_dbg, tr);
+    head_chain_kernel<NB, EPI, A_KMAJOR, CTAS, ES><<<grid, chain_threads(ES), Plan::TOTAL, st>>>(
+        mx, mw, biasf, centers, out, units_per_img, (int)total, P, g_dbg, tr);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(chain_threads(ES));
     cfg.dynamicSmemBytes = Plan::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -572,7 +584,7 @@ static int launch_chain_impl(const float* x, const float* w, const float* biasf,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, head_chain_kernel<NB, EPI, A_KMAJOR, CTAS>, mx, mw, biasf, centers, out, units_per_img,
+    if (cudaLaunchKernelEx(&cfg, head_chain_kernel<NB, EPI, A_KMAJOR, CTAS, ES>, mx, mw, biasf, centers, out, units_per_img,
                            (int)total, P, g_dbg, tr) != cudaSuccess)
       return MDE_ERR_LAUNCH;
   }
@@ -590,6 +602,12 @@ static int launch_chain(const float* x, const float* w, const float* biasf, cons
   if constexpr (NB == 256 && EPI != EPI_STORE) {
     const char* force = getenv("MDE_CHAIN_CTAS");
     const bool pair = (P % (2 * TILE_M) == 0) && (force && atoi(force) == 2) && g_dbg.prof == nullptr;
+    if constexpr (EPI == EPI_SOFTMAX) {
+      const char* es = getenv("MDE_CHAIN_ES");  // tuning aid: 2 = eight 128-column epilogue warps, 4 = sixteen 64-column ones
+      const bool wide = es && atoi(es) == 4;
+      if (pair && wide) return launch_chain_impl<NB, EPI, A_KMAJOR, 2, 4>(x, w, biasf, centers, out, B, P, st, tr);
+      if (wide) return launch_chain_impl<NB, EPI, A_KMAJOR, 1, 4>(x, w, biasf, centers, out, B, P, st, tr);
+    }
     if (pair) return launch_chain_impl<NB, EPI, A_KMAJOR, 2>(x, w, biasf, centers, out, B, P, st, tr);
   }
   return launch_chain_impl<NB, EPI, A_KMAJOR, 1>(x, w, biasf, centers, out, B, P, st, tr);
