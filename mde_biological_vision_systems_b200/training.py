@@ -16,7 +16,12 @@ from .parallel import GradientAverager
 
 class TrainStep:
     def __init__(self, model, semantics_loader=None, instance_loader=None, lr=0.000357, wd=0.1, w_chamfer=0.1,
-                 min_depth=1e-3, total_steps=1000, div_factor=25, final_div_factor=100, same_lr=False, bucket_mb=25.0):
+                 min_depth=1e-3, total_steps=1000, div_factor=25, final_div_factor=100, same_lr=False, bucket_mb=25.0,
+                 cudnn_benchmark=True):
+        # the stock torch bodies (encoder, decoder convolutions in training mode) run fixed shapes every step: let cuDNN
+        # pick its kernels by measurement (64.2 -> 58.4 ms per step on B200; the reference leaves the flag off)
+        if cudnn_benchmark:
+            torch.backends.cudnn.benchmark = True
         self.model = model
         self.semantics_loader = semantics_loader
         self.instance_loader = instance_loader
