@@ -197,6 +197,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    # fixed shapes every step: let cuDNN choose the kernels of the stock torch bodies (the EfficientNet encoder) by measurement
+    torch.backends.cudnn.benchmark = os.environ.get("MDE_CUDNN_BENCHMARK", "0") == "1"  # measured: no effect on inference (11.06 vs 11.04 ms)
 
     torch.manual_seed(0)
     model = UnetAdaptiveBins.build(n_bins=N_BINS, min_val=1e-3, max_val=10.0, norm="linear", encoder_name="efficientnet-b1",
