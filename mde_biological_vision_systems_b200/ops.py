@@ -4,13 +4,13 @@ Every function here launches hand-written sm_100a kernels from libmde_b200.so on
 Inputs must be CUDA tensors; nothing here computes on the CPU or through a PyTorch substitute.
 """
 import ctypes
-import math
 
 import torch
 
 from . import _lib
 
 LOG2E = 1.4426950408889634
+NUM_SMS = 148  # B200
 # mean relative mantissa loss of an fp32 value truncated to TF32 is 2^-11 * E[1/m] = 3.52e-4 (m log-uniform in [1,2));
 # the tensor core truncates the raw-fp32 activation operand, so the pre-rounded weight operand is scaled up by it
 TF32_TRUNC_COMP = 1.000352
@@ -614,7 +614,9 @@ class _HeadChainFn(torch.autograd.Function):
             feat_t = feat.reshape(b, k, p)
         # d W'[j,k] = sum_p gl[p,j] feat[p,k]: K = P pixels, split over CTAs (the raw-fp32 operand is truncated by the
         # tensor core, hence the compensation factor)
-        gwp = gemm_nt(glT, feat_t, splits=max(1, min(64, (2 * 148) // max(1, 2 * b) * 2)), alpha=TF32_TRUNC_COMP)
+        # two 128-row output tiles per image: enough K splits to put about two CTAs on every SM
+        splits = max(1, min(64, (2 * NUM_SMS) // (2 * b)))
+        gwp = gemm_nt(glT, feat_t, splits=splits, alpha=TF32_TRUNC_COMP)
         wo = w_out.reshape(w_out.shape[0], -1)
         gw = torch.einsum("bjk,bnk->jn", gwp, queries)                   # d W_out
         gq = torch.matmul(wo.t().unsqueeze(0), gwp)                      # d Q_b = W_out^T d W'_b
