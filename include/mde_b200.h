@@ -252,6 +252,10 @@ int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int ski
 /* NCHW [B,C,P] -> NHWC [B,P,C] transpose (feeds the head's cuDNN convs and the K-major chain operand) */
 int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream);
 
+/* Same transpose into a channel slice of a wider channels_last tensor (row pitch out_pitch channels; `out` points at the
+ * slice's first channel): concatenates planar sources (image planes, embedding planes) into the NHWC encoder input. */
+int mde_nchw_to_nhwc_slice(const float* in, float* out, int B, int C, int64_t P, int out_pitch, mde_stream_t stream);
+
 /* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
  * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is
  * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (zeroed by the call; holds

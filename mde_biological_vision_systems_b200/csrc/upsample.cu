@@ -297,6 +297,17 @@ __global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __
 }
 }  // namespace mde
 
+// the same transpose into a channel slice of a wider NHWC tensor: out points at the first channel of the slice, rows have
+// out_pitch channels (concatenation of planar NCHW sources into one channels_last tensor without an intermediate copy)
+extern "C" int mde_nchw_to_nhwc_slice(const float* in, float* out, int B, int C, int64_t P, int out_pitch,
+                                      mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C <= 0 || P <= 0 || out_pitch < C || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
+  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, out_pitch);
+  return mde::check_launch();
+}
+
 extern "C" int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last,
                                             float* out_nhwc, int B, int C1, int C2, int h, int w, int H, int W,
                                             mde_stream_t stream) {

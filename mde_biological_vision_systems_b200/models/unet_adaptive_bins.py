@@ -233,6 +233,11 @@ class UnetAdaptiveBins(nn.Module):
         the copy), MLP groups are written in place by the streaming kernel."""
         if not items:
             return x
+        if getattr(self, "_channels_last", False) and x.is_cuda and all(it[0] == "copy" for it in items) \
+                and not (torch.is_grad_enabled() and x.requires_grad):
+            # channels_last model, pass-through groups only (config 2): the planar sources are transposed straight into
+            # their channel slices of the NHWC encoder input (no planar concatenation, no second layout pass)
+            return ops.concat_channels_last([x] + [it[1] for it in items])
         widths = [it[1].shape[1] if it[0] == "copy" else 10 for it in items]
         b, c, h, w = x.shape
         out = torch.empty((b, c + sum(widths), h, w), dtype=torch.float32, device=x.device)

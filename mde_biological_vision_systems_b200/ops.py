@@ -729,6 +729,25 @@ def to_channels_last(x):
     return out
 
 
+def concat_channels_last(sources):
+    """torch.cat(sources, dim=1) of NCHW-contiguous fp32 tensors, produced directly in channels_last memory (one tiled
+    transpose per source into its channel slice; no planar intermediate)."""
+    lib = _lib.load()
+    _need_cuda(*sources)
+    sources = [_f32(t).contiguous() for t in sources]
+    b, _, h, w = sources[0].shape
+    ctot = sum(t.shape[1] for t in sources)
+    out = torch.empty((b, ctot, h, w), dtype=torch.float32, device=sources[0].device, memory_format=torch.channels_last)
+    base = out.data_ptr()
+    ch = 0
+    with timing("nchw_to_nhwc"):
+        for t in sources:
+            rc = lib.mde_nchw_to_nhwc_slice(_p(t), ctypes.c_void_p(base + 4 * ch), b, t.shape[1], h * w, ctot, _s())
+            _lib.check(rc, "mde_nchw_to_nhwc_slice")
+            ch += t.shape[1]
+    return out
+
+
 def relu_eps(x, eps=1e-4):
     lib = _lib.load()
     x = _f32(x).contiguous()

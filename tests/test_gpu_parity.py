@@ -575,6 +575,15 @@ def test_nchw_to_nhwc():
         assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, x)
 
 
+def test_concat_channels_last():
+    rng = np.random.default_rng(34)
+    a = torch.from_numpy(rng.standard_normal((2, 3, 17, 23)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rng.standard_normal((2, 25, 17, 23)).astype(np.float32)).to(DEV)
+    c = torch.from_numpy(rng.standard_normal((2, 70, 17, 23)).astype(np.float32)).to(DEV)
+    out = ops.concat_channels_last([a, b, c])
+    assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, torch.cat((a, b, c), 1))
+
+
 def test_noadabins_epilogue():
     x = torch.from_numpy(np.random.default_rng(3).standard_normal((2, 1, 24, 32)).astype(np.float32))
     assert np.array_equal(ops.relu_eps(x.to(DEV)).cpu().numpy(), oracle.noadabins_epilogue(x).numpy())
