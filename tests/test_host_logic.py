@@ -125,3 +125,49 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} mentions the oracle"
+
+
+def test_label_io_readers_follow_the_dataloader(tmp_path):
+    """(f)3 host side: the on-disk label formats and their 'no prediction' sentinels (dataloader.py:98-161)."""
+    import numpy as np
+    from mde_biological_vision_systems_b200 import label_io
+    hw = (6, 8)
+    rng = np.random.default_rng(0)
+    sem150 = rng.integers(0, 150, hw).astype(np.int64)
+    np.save(tmp_path / "semantic_seg_0.npy", sem150)
+    out = label_io.load_semantic_labels(str(tmp_path / "semantic_seg_0.npy"), "glove-25d", hw)
+    assert out.dtype == np.uint8 and np.array_equal(out, sem150.astype(np.ubyte))
+    inst = rng.integers(-1, 101, hw).astype(np.int32)
+    areas = rng.integers(0, 5000, hw).astype(np.int32)
+    np.savez(tmp_path / "instance_labels_ade20k_swin_0.npz", inst)
+    np.savez(tmp_path / "instance_areas_ade20k_swin_0.npz", areas)
+    np.savez(tmp_path / "instance_labels_ade20k_swin_1.npz", np.array(None, dtype=object))   # detector found nothing
+    np.savez(tmp_path / "instance_areas_ade20k_swin_1.npz", np.array(None, dtype=object))
+    # ade20k-places semantics are read from the Swin label file and cast to ubyte: -1 arrives as 255
+    sem = label_io.load_semantic_labels(str(tmp_path / "instance_labels_ade20k_swin_0.npz"), "glove-25d-ade20k-places", hw)
+    assert sem.dtype == np.uint8 and np.array_equal(sem, inst.astype(np.ubyte)) and (sem[inst == -1] == 255).all()
+    empty = label_io.load_semantic_labels(str(tmp_path / "instance_labels_ade20k_swin_1.npz"), "glove-25d-ade20k-places", hw)
+    assert empty.shape == hw and (empty == 255).all()
+    l0, a0 = label_io.load_instance_maps(str(tmp_path / "instance_labels_ade20k_swin_0.npz"),
+                                         str(tmp_path / "instance_areas_ade20k_swin_0.npz"), "ade20k_swin", hw)
+    assert l0.dtype == np.int32 and np.array_equal(l0, inst) and np.array_equal(a0, areas)
+    l1, a1 = label_io.load_instance_maps(str(tmp_path / "instance_labels_ade20k_swin_1.npz"),
+                                         str(tmp_path / "instance_areas_ade20k_swin_1.npz"), "ade20k_swin_human_sizes", hw)
+    assert (l1 == -1).all() and (a1 == 0).all() and l1.shape == hw
+    batch = label_io.collate([{"semantics": sem, "instance_labels": l0, "instance_areas": a0},
+                              {"semantics": empty, "instance_labels": l1, "instance_areas": a1}], pin=False)
+    assert batch["semantics"].shape == (2, 1, 6, 8) and batch["semantics"].dtype == torch.uint8
+    assert batch["instance_labels"].dtype == torch.int32 and batch["instance_areas"].dtype == torch.int32
+
+
+def test_evaluation_helpers_cpu_side():
+    """crop boxes and the running average of the evaluation module (host logic of (f)2)."""
+    from oracle import adabins_oracle as oracle
+    from mde_biological_vision_systems_b200 import evaluation
+    for (h, w, garg, eigen, ds) in [(480, 640, False, True, "nyu"), (352, 1216, True, False, "kitti"),
+                                    (352, 1216, False, True, "kitti"), (96, 128, False, False, "nyu")]:
+        assert evaluation.crop_box(h, w, garg, eigen, ds) == oracle.eval_crop_box(h, w, garg, eigen, ds)
+    avg = evaluation.RunningAverageDict()
+    avg.update({"a1": 1.0, "rmse": 2.0})
+    avg.update({"a1": 0.0, "rmse": 4.0})
+    assert avg.get_value() == {"a1": 0.5, "rmse": 3.0}
