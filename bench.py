@@ -153,6 +153,8 @@ def run_train(args, dev, world, rank, host, loader, sync_bn="kernels"):
     elif world > 1 and sync_bn:
         from mde_biological_vision_systems_b200 import parallel
         model = parallel.convert_sync_batchnorm(model)  # global-batch statistics on the B200 kernels (csrc/bn_sync.cu)
+        if sync_bn == "p2p":  # statistics exchanged by the kernels themselves over NVLink peer memory (no NCCL in the loop)
+            parallel.enable_p2p_statistics(model)
     model.train()
     stepper = TrainStep(model, semantics_loader=loader, total_steps=1000)
     steps = max(2, min(args.steps, 5))
@@ -349,6 +351,8 @@ def run_ours(args):
         if world > 1:  # the same step with torch's own SyncBatchNorm and with per-rank statistics, for comparison
             train["stock_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="stock")
             train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
+            if os.environ.get("MDE_SYNCBN_P2P") == "1":  # opt-in leg, last: validated at 2 GPUs only so far
+                train["p2p_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="p2p")
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:

@@ -311,6 +311,27 @@ int mde_bn_bwd_reduce_nhwc(const float* x, const float* dy, int64_t N, int C, co
 int mde_bn_bwd_apply_nhwc(const float* x, const float* dy, float* dx, int64_t N, int C, const float* mean,
                           const float* invstd, const float* weight, const double* sums, double count, mde_stream_t stream);
 
+/* Fused statistics exchange over NVLink peer memory instead of an all-reduce call (one process per GPU, <= 8 ranks): every
+ * rank owns a symmetric-memory arena mapped by all peers; peer_bases[r] (HOST array of `world` device addresses) is rank r's
+ * arena in this process.  The *_p2p statistics kernels publish the rank's [2C] float64 partial sums into slot [rank] of every
+ * peer's arena at slot_off (bytes; room for world * 2C doubles) and then raise flag [rank] = epoch at flag_off (world uint64
+ * per arena); the *_p2p consumers spin on the `world` flags of their own arena (my_base) until all reached `epoch`, sum the
+ * partials and continue like the non-p2p kernels.  The caller alternates two (slot_off, flag_off) pairs by epoch parity and
+ * increases epoch by one per call; `local` is the rank's own float64 [2C+1] scratch row (sums + a ticket), zero on entry,
+ * `zero_next` the row of the next call (zeroed by this one). */
+int mde_bn_stats_p2p_nhwc(const float* x, int64_t N, int C, double* local, double* zero_next, const uint64_t* peer_bases,
+                          int world, int rank, int64_t slot_off, int64_t flag_off, uint64_t epoch, mde_stream_t stream);
+int mde_bn_apply_p2p_nhwc(const float* x, float* y, int64_t N, int C, uint64_t my_base, int64_t slot_off, int64_t flag_off,
+                          int world, uint64_t epoch, double count, const float* weight, const float* bias, float eps,
+                          float* save_mean, float* save_invstd, float* running_mean, float* running_var, float momentum,
+                          mde_stream_t stream);
+int mde_bn_bwd_reduce_p2p_nhwc(const float* x, const float* dy, int64_t N, int C, const float* mean, const float* invstd,
+                               double* local, double* zero_next, const uint64_t* peer_bases, int world, int rank,
+                               int64_t slot_off, int64_t flag_off, uint64_t epoch, mde_stream_t stream);
+int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_t N, int C, const float* mean,
+                              const float* invstd, const float* weight, uint64_t my_base, int64_t slot_off, int64_t flag_off,
+                              int world, uint64_t epoch, double count, mde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

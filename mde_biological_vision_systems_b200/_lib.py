@@ -68,6 +68,12 @@ SIGNATURES = {
     "mde_bn_apply_nhwc": (_i32, [_p, _p, _i64, _i32, _p, ctypes.c_double, _p, _p, _f32, _p, _p, _p, _p, _f32, _p]),
     "mde_bn_bwd_reduce_nhwc": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "mde_bn_bwd_apply_nhwc": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, ctypes.c_double, _p]),
+    "mde_bn_stats_p2p_nhwc": (_i32, [_p, _i64, _i32, _p, _p, _p, _i32, _i32, _i64, _i64, ctypes.c_uint64, _p]),
+    "mde_bn_apply_p2p_nhwc": (_i32, [_p, _p, _i64, _i32, ctypes.c_uint64, _i64, _i64, _i32, ctypes.c_uint64, ctypes.c_double,
+                                     _p, _p, _f32, _p, _p, _p, _p, _f32, _p]),
+    "mde_bn_bwd_reduce_p2p_nhwc": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, ctypes.c_uint64, _p]),
+    "mde_bn_bwd_apply_p2p_nhwc": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, ctypes.c_uint64, _i64, _i64, _i32,
+                                         ctypes.c_uint64, ctypes.c_double, _p]),
     "mde_silog_ws_bytes": (_i64, []),
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_silog_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),

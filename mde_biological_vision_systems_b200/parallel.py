@@ -97,7 +97,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
     backward, plus bookkeeping copies).  x must be a channels_last CUDA tensor with C % 4 == 0."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, bufs):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group, bufs, p2p=None):
         from . import _lib, ops
         lib = _lib.load()
         b, c, h, w = x.shape
@@ -105,6 +105,25 @@ class _SyncBatchNormFn(torch.autograd.Function):
         # bufs: the module's two pairs of float64 [2C+1] scratch rows (forward / backward), used alternately: the kernel
         # of call k zeroes the row of call k+1, so the loop issues no memsets
         stats, nxt = bufs.next_forward(c, x.device)
+        if p2p is not None:
+            # fused exchange over NVLink peer memory: the statistics kernel publishes into every peer's arena, the
+            # normalise kernel waits for the world's partial sums -- no collective call between the two kernels
+            arena, epoch, slot_off, flag_off = p2p.next(0)
+            y = torch.empty_like(x, memory_format=torch.channels_last)
+            save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+            save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+            rc = lib.mde_bn_stats_p2p_nhwc(ops._p(x), n, c, ops._p(stats), ops._p(nxt), arena.ptrs, arena.world, arena.rank,
+                                           slot_off, flag_off, epoch, ops._s())
+            _lib.check(rc, "mde_bn_stats_p2p_nhwc")
+            count = float(n * arena.world)
+            rc = lib.mde_bn_apply_p2p_nhwc(ops._p(x), ops._p(y), n, c, arena.my_base, slot_off, flag_off, arena.world, epoch,
+                                           count, ops._p(weight), ops._p(bias), float(eps), ops._p(save_mean),
+                                           ops._p(save_invstd), ops._p(running_mean), ops._p(running_var), float(momentum),
+                                           ops._s())
+            _lib.check(rc, "mde_bn_apply_p2p_nhwc")
+            ctx.save_for_backward(x, weight, save_mean, save_invstd)
+            ctx.count, ctx.group, ctx.world, ctx.bufs, ctx.p2p = count, group, arena.world, bufs, p2p
+            return y
         _lib.check(lib.mde_bn_stats_nhwc(ops._p(x), n, c, ops._p(stats), ops._p(nxt), ops._s()), "mde_bn_stats_nhwc")
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         if world > 1:
@@ -122,7 +141,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
                                    float(momentum), ops._s())
         _lib.check(rc, "mde_bn_apply_nhwc")
         ctx.save_for_backward(x, weight, save_mean, save_invstd)
-        ctx.count, ctx.group, ctx.world, ctx.bufs = count, group, world, bufs
+        ctx.count, ctx.group, ctx.world, ctx.bufs, ctx.p2p = count, group, world, bufs, None
         return y
 
     @staticmethod
@@ -135,6 +154,20 @@ class _SyncBatchNormFn(torch.autograd.Function):
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         sums, nxt = ctx.bufs.next_backward(c, x.device)
+        if ctx.p2p is not None:
+            arena, epoch, slot_off, flag_off = ctx.p2p.next(1)
+            rc = lib.mde_bn_bwd_reduce_p2p_nhwc(ops._p(x), ops._p(dy), n, c, ops._p(mean), ops._p(invstd), ops._p(sums),
+                                                ops._p(nxt), arena.ptrs, arena.world, arena.rank, slot_off, flag_off, epoch,
+                                                ops._s())
+            _lib.check(rc, "mde_bn_bwd_reduce_p2p_nhwc")
+            local = sums[:2 * c].float()
+            dx = torch.empty_like(x, memory_format=torch.channels_last)
+            rc = lib.mde_bn_bwd_apply_p2p_nhwc(ops._p(x), ops._p(dy), ops._p(dx), n, c, ops._p(mean), ops._p(invstd),
+                                               ops._p(weight), arena.my_base, slot_off, flag_off, arena.world, epoch,
+                                               ctx.count, ops._s())
+            _lib.check(rc, "mde_bn_bwd_apply_p2p_nhwc")
+            return dx, (local[c:] if weight is not None else None), (local[:c] if weight is not None else None), \
+                None, None, None, None, None, None, None
         rc = lib.mde_bn_bwd_reduce_nhwc(ops._p(x), ops._p(dy), n, c, ops._p(mean), ops._p(invstd), ops._p(sums), ops._p(nxt),
                                         ops._s())
         _lib.check(rc, "mde_bn_bwd_reduce_nhwc")
@@ -147,7 +180,71 @@ class _SyncBatchNormFn(torch.autograd.Function):
         _lib.check(rc, "mde_bn_bwd_apply_nhwc")
         gw = local[c:] if weight is not None else None
         gb = local[:c] if weight is not None else None
-        return dx, gw, gb, None, None, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None, None, None
+
+
+class P2PArena:
+    """Symmetric-memory arena shared by the ranks of a process group (torch.distributed._symmetric_memory): every rank's
+    buffer is mapped into every process, so kernels exchange data with plain loads / stores over NVLink."""
+
+    def __init__(self, nbytes, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+        if enable is not None:
+            try:
+                enable(group.group_name)
+            except Exception:
+                pass
+        self.buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        if self.world > 8:
+            raise RuntimeError("P2PArena supports at most 8 ranks (one NVSwitch domain)")
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = (ctypes.c_uint64 * 8)(*(ptrs + [0] * (8 - len(ptrs))))
+        self.my_base = ptrs[self.rank]
+        torch.cuda.synchronize()
+        dist.barrier(group=group)  # every arena is zeroed before anyone publishes into it
+
+
+class _P2PRegion:
+    """One SyncBatchNorm2d module's slice of the arena: [direction][epoch parity] x (world slots of 2C doubles) and, behind
+    them, [direction][parity] x world epoch flags."""
+
+    def __init__(self, arena, offset, channels):
+        self.arena, self.c = arena, channels
+        self.slot_bytes = arena.world * 2 * channels * 8
+        self.slots0 = offset
+        self.flags0 = offset + 4 * self.slot_bytes
+        self.epochs = [0, 0]
+
+    @staticmethod
+    def nbytes(world, channels):
+        return (4 * world * 2 * channels * 8 + 4 * world * 8 + 255) // 256 * 256
+
+    def next(self, direction):
+        self.epochs[direction] += 1
+        e = self.epochs[direction]
+        k = 2 * direction + (e & 1)
+        return self.arena, e, self.slots0 + k * self.slot_bytes, self.flags0 + k * self.arena.world * 8
+
+
+def enable_p2p_statistics(module, process_group=None):
+    """Give every SyncBatchNorm2d of ``module`` a region of one symmetric-memory arena: the statistics are then exchanged by
+    the kernels themselves over NVLink peer memory instead of one NCCL all-reduce per layer and direction."""
+    mods = [m for m in module.modules() if isinstance(m, SyncBatchNorm2d)]
+    world = dist.get_world_size(process_group)
+    total, offs = 0, []
+    for m in mods:
+        offs.append(total)
+        total += _P2PRegion.nbytes(world, m.num_features)
+    arena = P2PArena(max(total, 256), process_group)
+    for m, off in zip(mods, offs):
+        m._p2p = _P2PRegion(arena, off, m.num_features)
+    return arena
 
 
 class _BnScratch:
@@ -189,6 +286,7 @@ class SyncBatchNorm2d(torch.nn.BatchNorm2d):
         self.process_group = process_group
         self.force_kernels = False
         self._scratch = _BnScratch()
+        self._p2p = None  # set by enable_p2p_statistics
 
     def forward(self, x):
         world = dist.get_world_size(self.process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -209,7 +307,8 @@ class SyncBatchNorm2d(torch.nn.BatchNorm2d):
             if momentum is None:
                 momentum = 1.0 / float(self.num_batches_tracked)
         return _SyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                      0.0 if momentum is None else momentum, self.process_group, self._scratch)
+                                      0.0 if momentum is None else momentum, self.process_group, self._scratch,
+                                      self._p2p if world > 1 else None)
 
 
 def convert_sync_batchnorm(module, process_group=None):

@@ -25,9 +25,11 @@ model = UnetAdaptiveBins.build(n_bins=256, min_val=1e-3, max_val=10.0, norm="lin
                                semantics_mode=MODE, instance_segmentation_mode=None, insertion_point="input", image="rgb").to(dev)
 if impl == "stock":
     model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-elif impl == "ours":
+elif impl in ("ours", "p2p"):
     from mde_biological_vision_systems_b200 import parallel
     model = parallel.convert_sync_batchnorm(model)
+    if impl == "p2p":
+        parallel.enable_p2p_statistics(model)
 model.train()
 loader = SemanticsLoader(argparse.Namespace(use_semantics=MODE), device=dev)
 batch = {"image": synthetic.image(B, H, W, seed=10 * rank).to(dev), "depth": synthetic.depth(B, H, W, seed=10 * rank + 1).to(dev),
@@ -44,6 +46,13 @@ for _ in range(5):
 e.record()
 torch.cuda.synchronize()
 wall = s.elapsed_time(e) / 5
+if len(sys.argv) > 2 and sys.argv[2] == "quick":
+    wall_all = torch.tensor([wall], device=dev)
+    dist.all_reduce(wall_all, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"== {impl} SyncBN, world {world}: {float(wall_all):.2f} ms/step (max over ranks), {world * B / float(wall_all) * 1e3:.1f} img/s, loss {float(loss):.4f}")
+    dist.destroy_process_group()
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     stepper(batch, dev)
     torch.cuda.synchronize()
