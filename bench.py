@@ -152,9 +152,9 @@ def run_train(args, dev, world, rank, host, loader, sync_bn="kernels"):
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     elif world > 1 and sync_bn:
         from mde_biological_vision_systems_b200 import parallel
-        model = parallel.convert_sync_batchnorm(model)  # global-batch statistics on the B200 kernels (csrc/bn_sync.cu)
-        if sync_bn == "p2p":  # statistics exchanged by the kernels themselves over NVLink peer memory (no NCCL in the loop)
-            parallel.enable_p2p_statistics(model)
+        # global-batch statistics on the B200 kernels (csrc/bn_sync.cu); default: exchanged by the kernels themselves over
+        # NVLink peer memory, "allreduce": one NCCL all-reduce per layer and direction between the two kernels
+        model = parallel.convert_sync_batchnorm(model, p2p=(sync_bn != "allreduce"))
     model.train()
     stepper = TrainStep(model, semantics_loader=loader, total_steps=1000)
     steps = max(2, min(args.steps, 5))
@@ -180,7 +180,7 @@ def run_train(args, dev, world, rank, host, loader, sync_bn="kernels"):
             "value": world * B / (ms_step * 1e-3), "unit": "imgs/s", "ms_per_step": ms_step, "steps": steps,
             "batch_per_gpu": B, "sync_bn": (sync_bn if world > 1 else False), "loss": float(loss.item()),
             "gpu_launches_per_step": (ops.launch_count() - l0) / steps,
-            "note": "model in channels_last; head chain forward+backward on the tcgen05 kernels; the 4 transformer encoder layers (dropout) and the EfficientNet/decoder bodies run stock torch/cuDNN modules in train mode"}
+            "note": "model in channels_last; SyncBatchNorm (N > 1) on our kernels with the statistics exchanged over NVLink peer memory; head chain forward+backward on the tcgen05 kernels; the 4 transformer encoder layers (dropout) and the EfficientNet/decoder bodies run stock torch/cuDNN modules in train mode"}
 
 
 def run_ours(args):
@@ -351,8 +351,8 @@ def run_ours(args):
         if world > 1:  # the same step with torch's own SyncBatchNorm and with per-rank statistics, for comparison
             train["stock_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="stock")
             train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
-            if os.environ.get("MDE_SYNCBN_P2P") == "1":  # opt-in leg, last: validated at 2 GPUs only so far
-                train["p2p_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="p2p")
+            if os.environ.get("MDE_BENCH_ALLREDUCE_BN") == "1":  # our kernels with an NCCL all-reduce instead of peer memory
+                train["allreduce_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="allreduce")
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:

@@ -311,9 +311,28 @@ class SyncBatchNorm2d(torch.nn.BatchNorm2d):
                                       self._p2p if world > 1 else None)
 
 
-def convert_sync_batchnorm(module, process_group=None):
+def convert_sync_batchnorm(module, process_group=None, p2p=True):
     """train.py:296 counterpart: replace every nn.BatchNorm2d by SyncBatchNorm2d sharing its parameters and buffers
-    (state_dict keys unchanged); other batch-norm flavours fall back to torch's own SyncBatchNorm conversion."""
+    (state_dict keys unchanged); other batch-norm flavours fall back to torch's own SyncBatchNorm conversion.
+    With ``p2p`` (default) and an initialised process group of 2..8 ranks on CUDA, the statistics are exchanged by the
+    kernels themselves over NVLink peer memory (enable_p2p_statistics); if the symmetric-memory arena cannot be set up,
+    the modules keep the NCCL all-reduce path."""
+    out = _convert_sync_batchnorm(module, process_group)
+    if p2p and dist.is_available() and dist.is_initialized() and torch.cuda.is_available():
+        world = dist.get_world_size(process_group)
+        if 1 < world <= 8:
+            try:
+                enable_p2p_statistics(out, process_group)
+            except Exception as exc:  # noqa: BLE001 -- any set-up failure leaves the (slower) all-reduce path in place
+                import warnings
+                warnings.warn(f"SyncBatchNorm2d: peer-memory statistics exchange unavailable ({exc!r}); using all-reduce")
+                for m in out.modules():
+                    if isinstance(m, SyncBatchNorm2d):
+                        m._p2p = None
+    return out
+
+
+def _convert_sync_batchnorm(module, process_group=None):
     out = module
     if isinstance(module, torch.nn.BatchNorm2d) and not isinstance(module, SyncBatchNorm2d):
         if module.num_features % 4 == 0 and module.track_running_stats:
@@ -327,7 +346,7 @@ def convert_sync_batchnorm(module, process_group=None):
         else:
             return torch.nn.SyncBatchNorm.convert_sync_batchnorm(module, process_group)
     for name, child in module.named_children():
-        new = convert_sync_batchnorm(child, process_group)
+        new = _convert_sync_batchnorm(child, process_group)
         if new is not child:
             out.add_module(name, new)
     return out

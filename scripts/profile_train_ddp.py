@@ -27,9 +27,7 @@ if impl == "stock":
     model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
 elif impl in ("ours", "p2p"):
     from mde_biological_vision_systems_b200 import parallel
-    model = parallel.convert_sync_batchnorm(model)
-    if impl == "p2p":
-        parallel.enable_p2p_statistics(model)
+    model = parallel.convert_sync_batchnorm(model, p2p=(impl == "p2p"))
 model.train()
 loader = SemanticsLoader(argparse.Namespace(use_semantics=MODE), device=dev)
 batch = {"image": synthetic.image(B, H, W, seed=10 * rank).to(dev), "depth": synthetic.depth(B, H, W, seed=10 * rank + 1).to(dev),

@@ -79,7 +79,7 @@ def test_convert_sync_batchnorm_keeps_state_dict():
                               torch.nn.Sequential(torch.nn.Conv2d(8, 6, 1), torch.nn.BatchNorm2d(6)))
     keys = list(net.state_dict().keys())
     w = net[1].weight
-    conv = parallel.convert_sync_batchnorm(net)
+    conv = parallel.convert_sync_batchnorm(net)  # no process group here: no peer-memory arena is set up
     assert list(conv.state_dict().keys()) == keys
     assert isinstance(conv[1], parallel.SyncBatchNorm2d) and conv[1].weight is w
     assert isinstance(conv[3][1], torch.nn.SyncBatchNorm)  # 6 channels: not a multiple of 4 -> torch's module
