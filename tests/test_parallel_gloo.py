@@ -87,3 +87,31 @@ def test_convert_sync_batchnorm_keeps_state_dict():
     x = torch.randn(2, 3, 9, 9)
     ref = torch.nn.functional.batch_norm(net[0](x), w.new_zeros(8), w.new_ones(8), w, net[1].bias, False, 0.1, 1e-5)
     assert torch.allclose(conv[1](net[0](x)), ref, atol=1e-6)
+
+
+def test_p2p_region_layout_and_epochs():
+    """Bookkeeping of the peer-memory statistics exchange: per module [direction][epoch parity] slot sets and flag rows
+    never overlap, epochs increase per direction, consecutive calls alternate parity (double buffering)."""
+    from mde_biological_vision_systems_b200.parallel import _P2PRegion
+
+    class Arena:
+        world, rank = 4, 1
+
+    c = 96
+    nbytes = _P2PRegion.nbytes(Arena.world, c)
+    assert nbytes % 256 == 0 and nbytes >= 4 * Arena.world * 2 * c * 8 + 4 * Arena.world * 8
+    reg = _P2PRegion(Arena(), 1024, c)
+    seen = {}
+    for direction in (0, 1):
+        for call in range(1, 5):
+            arena, epoch, slot_off, flag_off = reg.next(direction)
+            assert epoch == call
+            seen[(direction, epoch & 1)] = (slot_off, flag_off)
+            assert seen[(direction, epoch & 1)] == (slot_off, flag_off)           # same parity -> same buffers
+            assert 1024 <= slot_off and slot_off + Arena.world * 2 * c * 8 <= 1024 + nbytes
+            assert flag_off + Arena.world * 8 <= 1024 + nbytes
+    slots = sorted(v[0] for v in seen.values())
+    flags = sorted(v[1] for v in seen.values())
+    assert len(set(slots)) == 4 and len(set(flags)) == 4
+    assert all(b - a >= Arena.world * 2 * c * 8 for a, b in zip(slots, slots[1:]))   # slot sets do not overlap
+    assert all(b - a >= Arena.world * 8 for a, b in zip(flags, flags[1:])) and flags[0] >= slots[-1] + Arena.world * 2 * c * 8
