@@ -854,3 +854,24 @@ def test_autocast_bf16_training_step():
     assert torch.isfinite(loss)
     g = m.decoder.up4._net[0].weight.grad
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+def test_before_attn_insertion_vs_oracle():
+    """A3': external info inserted before the attention head (nearest down-sampling of the embedding planes, concatenated
+    onto the decoder output, unet_adaptive_bins.py:244-282): the head then sees 128 + 25 channels."""
+    mode = "glove-25d-ade20k-places"
+    m = make_model(insertion_point="before-attn", semantics_mode=mode, instance_segmentation_mode=None).to(DEV)
+    assert m.num_decoded_channels == 153
+    x = synthetic.image(1, 352, 384, seed=85).to(DEV)
+    lab, _ = sem_labels(mode, 1, 352, 384, seed=86, n_rect=(20, 40))
+    _, sem = SemanticsLoader(Args(use_semantics=mode)).get_semantics({"semantics": lab})
+    with torch.no_grad():
+        edges, pred = m(x, semantics=sem)
+        unet_out = m.decoder(m.encoder(x))
+        small = torch.nn.functional.interpolate(sem, size=unet_out.shape[-2:], mode="nearest").float()
+        cat = torch.cat((unet_out, small), dim=1)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    e_ref, p_ref = oracle.head(cat.cpu().contiguous(), sd, 1e-3, 10.0)
+    assert pred.shape == (1, 1, 176, 192)
+    assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
+    assert_depth_close(pred.cpu(), p_ref, tf32=True)
