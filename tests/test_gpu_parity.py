@@ -875,3 +875,44 @@ def test_before_attn_insertion_vs_oracle():
     assert pred.shape == (1, 1, 176, 192)
     assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
     assert_depth_close(pred.cpu(), p_ref, tf32=True)
+
+
+def test_config3_full_path_vs_oracle_and_training_step():
+    """BASELINE config 3 end to end: GloVe-25d semantics + ADE20K-Swin instance embeddings / areas / human sizes at the input
+    (73 input channels, two trainable 1x1-conv MLPs), channels_last model.  Inference vs the oracle restatement of the
+    whole reference path (loaders -> insertion -> encoder walk -> DecoderBN -> head); then one training step."""
+    smode, imode = "glove-25d", "ade20k_swin_human_sizes"
+    m = make_model(insertion_point="input", semantics_mode=smode, instance_segmentation_mode=imode).to(DEV).channels_last_()
+    b, h, w = 1, 352, 384
+    x = synthetic.image(b, h, w, seed=87)
+    slab, _ = sem_labels(smode, b, h, w, seed=88, n_rect=(20, 40))
+    ilab, iar = inst_labels(imode, b, h, w, seed=89, n_rect=(20, 40))
+    _, sem = SemanticsLoader(Args(use_semantics=smode)).get_semantics({"semantics": slab})
+    _, il, ia = InstanceSegmentationLoader(Args(use_instance_segmentation=imode)).get_instance_segmentation(
+        {"instance_labels": ilab, "instance_areas": iar})
+    with torch.no_grad():
+        edges, pred = m(x.to(DEV), semantics=sem, instance_labels=il, instance_areas=ia)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    _, sem_ref = oracle.semantics_loader(smode, slab.numpy(), load_table("ade20k_150_classes_glove_twitter_27b_25d_embeddings.npy"))
+    _, il_ref, ia_ref = oracle.instance_loader(imode, ilab.numpy(), iar.numpy(),
+                                               load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy"), 100,
+                                               load_table("ade20k_classes_abs_sizes.npy"))
+    cpu = make_model(insertion_point="input", semantics_mode=smode, instance_segmentation_mode=imode)  # same weights, CPU
+    with torch.no_grad():
+        xin = oracle.input_insertion(sd, x, smode, imode, "rgb", semantics=torch.from_numpy(sem_ref),
+                                     instance_labels=torch.from_numpy(il_ref), instance_areas=torch.from_numpy(ia_ref))
+        assert xin.shape[1] == 73
+        unet = oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, xin), sd)
+        e_ref, p_ref = oracle.head(unet, sd, 1e-3, 10.0)
+    assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
+    assert_depth_close(pred.cpu(), p_ref, tf32=True)
+    # one training step: gradients reach the aux MLPs through the channels_last input concatenation
+    depth = synthetic.depth(b, h, w, seed=90).to(DEV)
+    m.train()
+    e, p = m(x.to(DEV), semantics=sem, instance_labels=il, instance_areas=ia)
+    loss = SILogLoss()(p, depth, mask=depth > 1e-3) + 0.1 * BinsChamferLoss()(e, depth)
+    loss.backward()
+    for name in ("instance_areas_fc.0.weight", "instance_absolute_sizes_fc.2.bias", "decoder.conv3.weight",
+                 "adaptive_bins_layer.conv3x3.weight", "conv_out.0.weight"):
+        g = dict(m.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0, name
