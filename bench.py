@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_forward_losses(batch, steps, warmup):
+def cpu_forward_losses(batch, steps, warmup, breakdown=False):
     """The reference path on the host cores: oracle restatement of loaders + head + losses around the same torch
     encoder/decoder modules, torch CPU, all threads.  Returns (seconds per step, cores)."""
     import numpy as np
@@ -113,7 +113,27 @@ def cpu_forward_losses(batch, steps, warmup):
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    return (time.perf_counter() - t0) / max(steps, 1), cores
+    sec = (time.perf_counter() - t0) / max(steps, 1)
+    if not breakdown:
+        return sec, cores
+
+    # the pieces of the path on their own (one run each after the warm full steps above)
+    def once(fn):
+        t = time.perf_counter()
+        out = fn()
+        return out, (time.perf_counter() - t) * 1e3
+
+    parts = {}
+    with torch.no_grad():
+        (_, sem), parts["loader_gather_ms"] = once(lambda: oracle.semantics_loader(SEM_MODE, labels.numpy(), table))
+        x = oracle.input_insertion(sd, img, SEM_MODE, None, "rgb", semantics=torch.from_numpy(sem))
+        unet, parts["encoder_decoder_ms"] = once(
+            lambda: oracle.decoder_bn(oracle.encoder_features(model.encoder.original_model, x), sd))
+        (edges, pred), parts["head_ms"] = once(lambda: oracle.head(unet, sd, 1e-3, 10.0))
+        _, parts["silog_ms"] = once(lambda: oracle.silog(pred, depth, mask=depth > 1e-3, interpolate=True))
+        _, parts["chamfer_ms"] = once(lambda: oracle.bins_chamfer(edges, depth))
+    parts["batch"] = batch
+    return sec, cores, parts
 
 
 def run_reference(args):
@@ -434,9 +454,10 @@ def run_ours(args):
             "roofline": roof, "kernels": others, "clocks": clocks, "train": train,
         }
         if world == 1 and not args.no_cpu:
-            sec, cores = cpu_forward_losses(2, 2, 1)
+            sec, cores, parts = cpu_forward_losses(2, 2, 1, breakdown=True)
             line["cpu_baseline"] = {"value": 2 * H * W / sec / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                    "sample": "batch 2 x 416x544 (config 1), 1 warm-up + 2 timed steps of the oracle port, torch CPU fp32"}
+                                    "sample": "batch 2 x 416x544 (config 1), 1 warm-up + 2 timed steps of the oracle port, torch CPU fp32",
+                                    "breakdown_ms": parts}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
