@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 H, W, N_BINS = 416, 544, 256
 SEM_MODE = "glove-25d-ade20k-places"
-METRIC = "head/loss Mpix/s at 416x544 (gather + UnetAdaptiveBins fwd + SILog + chamfer)"
+METRIC = "head/loss Mpix/s at 416x544 (gather + UnetAdaptiveBins fwd + SILog + chamfer)"  # full-resolution pixels F*B per second
 WORKLOAD = ("BASELINE config 2: EfficientNet-B1 AdaBins + GloVe-25d ADE20K-places @input, batch 16/GPU, 416x544, "
             "n_bins 256, random init")
 
@@ -446,7 +446,8 @@ def run_ours(args):
                                      "note": "labels travel in their on-disk uint8 format (label_io, section 8(f)3)"}},
             "gpu_launches": int(launches),
             "hot_path": {"what": "gather + mViT head + bins + SILog + chamfer on a fixed unet_out", "ms_per_step": hot_ms,
-                         "value": B * H * W / (hot_ms * 1e-3) / 1e6, "unit": "Mpix/s per GPU", "share_of_step": hot_ms / ms_step},
+                         "value": B * H * W / (hot_ms * 1e-3) / 1e6, "unit": "Mpix/s per GPU (full-resolution pixels F*B; the head works on P*B = F*B/4)",
+                         "share_of_step": hot_ms / ms_step_eager},
             "launch": ("cuda_graph_replay (graphs.GraphedStep: the step captured once, replayed per batch; inputs resident, "
                        "copied into the static capture buffers)" if use_graph else "eager"),
             "eager": {"value": pix / (ms_step_eager * 1e-3) / 1e6, "ms_per_step": ms_step_eager},
