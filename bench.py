@@ -367,12 +367,15 @@ def run_ours(args):
         hot_ms = s.elapsed_time(e) / args.steps
     train = None
     if not args.no_train:
-        train = run_train(args, dev, world, rank, host, loader, sync_bn="kernels")
-        if world > 1:  # the same step with torch's own SyncBatchNorm and with per-rank statistics, for comparison
-            train["stock_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="stock")
-            train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
-            if os.environ.get("MDE_BENCH_ALLREDUCE_BN") == "1":  # our kernels with an NCCL all-reduce instead of peer memory
-                train["allreduce_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="allreduce")
+        try:  # the training leg must never cost the inference line above: report its failure instead
+            train = run_train(args, dev, world, rank, host, loader, sync_bn="kernels")
+            if world > 1:  # the same step with torch's own SyncBatchNorm and with per-rank statistics, for comparison
+                train["stock_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="stock")
+                train["local_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn=False)
+                if os.environ.get("MDE_BENCH_ALLREDUCE_BN") == "1":  # our kernels + an NCCL all-reduce instead of peer memory
+                    train["allreduce_sync_bn"] = run_train(args, dev, world, rank, host, loader, sync_bn="allreduce")
+        except Exception as exc:  # noqa: BLE001
+            train = dict(train or {}, error=repr(exc)[:400])
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -461,7 +464,10 @@ def run_ours(args):
                                     "breakdown_ms": parts}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001 -- the JSON line is already out
+            pass
 
 
 def main():
