@@ -92,6 +92,11 @@ int mde_aux_mlp_bwd(const float* x, int64_t x_batch_stride, const float* w0, con
 int mde_bias_act_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int C, int act,
                       mde_stream_t stream);
 
+/* Same epilogue written into a zero-padded tensor y [B, H+pad_top+pad_bottom, W+pad_left+pad_right, C]: folds the F.pad of a
+ * following TensorFlow-"SAME" stride-2 convolution into this pass. */
+int mde_bias_act_pad_nhwc(const float* x, const float* bias, float* y, int B, int H, int W, int C, int pad_top,
+                          int pad_bottom, int pad_left, int pad_right, int act, mde_stream_t stream);
+
 /* ---- K1b/K2 prologue: bin-width regressor + normalisation + cumsum (miniViT.py:17-21,35-45;
  * unet_adaptive_bins.py:292-296).  t0 [B, E] rows at stride t0_stride (token 0 of the transformer output).
  *   w1 [H,E] b1 [H] w2 [H,H] b2 [H] w3 [n_bins,H] b3 [n_bins]   (E = 128, H = 256 in the reference)

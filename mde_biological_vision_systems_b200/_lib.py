@@ -27,6 +27,7 @@ SIGNATURES = {
     "mde_aux_mlp_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64,
                                _f32, _p]),
     "mde_bias_act_nhwc": (_i32, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
+    "mde_bias_act_pad_nhwc": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_regressor_bins_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32,
                                       _p, _p, _p, _p, _p]),
     "mde_patch_embed_ws_floats": (_i64, [_i32, _i32, _i32, _i32, _i32]),

@@ -254,3 +254,51 @@ extern "C" int mde_bias_act_nhwc(const float* x, const float* bias, const float*
   bias_act_nhwc_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(x, bias, residual, y, total4, C / 4, act);
   return check_launch();
 }
+
+// Same epilogue, written into a zero-padded tensor: y [B, H + pt + pb, W + pl + pr, C] = pad(act(x + bias)).  Used when the
+// consumer is a stride-2 TensorFlow-"SAME" convolution (asymmetric padding, models/efficientnet.py SamePadConv2d): the
+// padding copy the reference's F.pad would make is folded into this pass.
+namespace mde {
+__global__ void __launch_bounds__(256) bias_act_pad_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                                float* __restrict__ y, int H, int W, int c4, int pt, int pl,
+                                                                int Ho, int Wo, long long total4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int xo = (int)(p % Wo);
+    p /= Wo;
+    const int yo = (int)(p % Ho);
+    const long long b = p / Ho;
+    const int yi = yo - pt, xi = xo - pl;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+      const float4 v = reinterpret_cast<const float4*>(x)[((b * H + yi) * W + xi) * c4 + cg];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + cg);
+      float t[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
+      if (act == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = t[k] / (1.f + __expf(-t[k]));
+      }
+      o = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+}  // namespace mde
+
+extern "C" int mde_bias_act_pad_nhwc(const float* x, const float* bias, float* y, int B, int H, int W, int C, int pad_top,
+                                     int pad_bottom, int pad_left, int pad_right, int act, mde_stream_t stream) {
+  using namespace mde;
+  if (!x || !bias || !y) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || pad_top < 0 || pad_bottom < 0 || pad_left < 0 || pad_right < 0 || act < 0 ||
+      act > 1)
+    return MDE_ERR_BAD_SHAPE;
+  if (C % 4 != 0 || !aligned(x, 16) || !aligned(y, 16) || !aligned(bias, 16)) return MDE_ERR_UNSUPPORTED;
+  const int Ho = H + pad_top + pad_bottom, Wo = W + pad_left + pad_right;
+  const long long total4 = (long long)B * Ho * Wo * (C / 4);
+  long long gx = (total4 + 255) / 256;
+  if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;
+  bias_act_pad_nhwc_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(x, bias, y, H, W, C / 4, pad_top, pad_left, Ho, Wo,
+                                                                          total4, act);
+  return check_launch();
+}

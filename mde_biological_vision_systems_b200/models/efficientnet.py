@@ -57,12 +57,17 @@ class SamePadConv2d(nn.Conv2d):
     def forward(self, x):
         return self.forward_with(x, self.weight, self.bias)
 
-    def forward_with(self, x, weight, bias):
-        kh, kw = self.kernel_size
-        ph = _same_pad_amount(x.shape[-2], kh, self.stride[0])
-        pw = _same_pad_amount(x.shape[-1], kw, self.stride[1])
-        if ph or pw:
-            x = F.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    def same_pads(self, h, w):
+        """(top, bottom, left, right) zeros TensorFlow's SAME rule adds for an h x w input."""
+        ph = _same_pad_amount(h, self.kernel_size[0], self.stride[0])
+        pw = _same_pad_amount(w, self.kernel_size[1], self.stride[1])
+        return ph // 2, ph - ph // 2, pw // 2, pw - pw // 2
+
+    def forward_with(self, x, weight, bias, prepadded=False):
+        if not prepadded:
+            pt, pb, pl, pr = self.same_pads(x.shape[-2], x.shape[-1])
+            if pt or pb or pl or pr:
+                x = F.pad(x, (pl, pr, pt, pb))
         return F.conv2d(x, weight, bias, self.stride, 0, 1, self.groups)
 
 
@@ -84,11 +89,13 @@ def _folded_conv_bn(conv, bn):
     return cached[1], cached[2]
 
 
-def conv_bn(conv, bn, x, act=None, residual=None):
+def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False):
     """act(bn(conv(x))) (+ residual); in inference (eval-mode statistics, no autograd) as ONE convolution with the folded
     filter -- the 69 per-block BatchNorm passes of EfficientNet-B1 are 3 ms of a 14 ms step otherwise -- followed, on
     channels_last CUDA tensors, by one fused bias + SiLU (+ residual) pass (ops.bias_act_nhwc_) instead of separate bias,
-    activation and add kernels.  Same values up to fp32 rounding."""
+    activation and add kernels.  Same values up to fp32 rounding.
+    ``out_pads`` (top, bottom, left, right): on the fused path the result is written zero-padded (the SAME padding of the
+    stride-2 convolution that consumes it; callers detect it by the grown spatial size and pass ``prepadded`` on)."""
     if bn.training or torch.is_grad_enabled() or not isinstance(bn, nn.BatchNorm2d) or not bn.track_running_stats \
             or not bn.affine:
         y = bn(conv(x))
@@ -97,9 +104,11 @@ def conv_bn(conv, bn, x, act=None, residual=None):
     from .. import ops
     w, b = _folded_conv_bn(conv, bn)
     fused = (act is None or isinstance(act, nn.SiLU)) and x.is_cuda
-    y = conv.forward_with(x, w, None if fused else b) if isinstance(conv, SamePadConv2d) \
+    y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
         else conv._conv_forward(x, w, None if fused else b)
     if fused and ops.bias_act_supported(y, residual):
+        if out_pads is not None and residual is None and any(out_pads):
+            return ops.bias_act_pad_nhwc(y, b, 1 if act is not None else 0, out_pads)
         return ops.bias_act_nhwc_(y, b, 1 if act is not None else 0, residual)
     if fused:
         y = y + b.view(1, -1, 1, 1)
@@ -159,8 +168,10 @@ class InvertedResidual(nn.Module):
         self.bn3 = nn.BatchNorm2d(cout, eps=_BN_EPS)
 
     def forward(self, x):
-        y = conv_bn(self.conv_pw, self.bn1, x, self.act1)
-        y = conv_bn(self.conv_dw, self.bn2, y, self.act2)
+        # a stride-2 SAME depthwise conv follows the 1x1 expansion: let the expansion's epilogue write its output padded
+        pads = self.conv_dw.same_pads(x.shape[-2], x.shape[-1]) if isinstance(self.conv_dw, SamePadConv2d) else None
+        y = conv_bn(self.conv_pw, self.bn1, x, self.act1, out_pads=pads)
+        y = conv_bn(self.conv_dw, self.bn2, y, self.act2, prepadded=(y.shape[-2:] != x.shape[-2:]))
         return conv_bn(self.conv_pwl, self.bn3, self.se(y), None, x if self.has_residual else None)
 
 

@@ -221,6 +221,18 @@ def bias_act_nhwc_(x_cl, bias, act=0, residual=None):
     return x_cl
 
 
+def bias_act_pad_nhwc(x_cl, bias, act, pads):
+    """pad(act(x + bias[c])) into a new channels_last tensor; pads = (top, bottom, left, right) zeros."""
+    lib = _lib.load()
+    b, c, h, w = x_cl.shape
+    pt, pb, pl, pr = (int(v) for v in pads)
+    out = torch.empty((b, c, h + pt + pb, w + pl + pr), dtype=torch.float32, device=x_cl.device,
+                      memory_format=torch.channels_last)
+    rc = lib.mde_bias_act_pad_nhwc(_p(x_cl), _p(bias), _p(out), b, h, w, c, pt, pb, pl, pr, int(act), _s())
+    _lib.check(rc, "mde_bias_act_pad_nhwc")
+    return out
+
+
 def bias_act_supported(x, residual=None):
     ok = (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and _is_nhwc_or_dense_cl(x))
     if residual is not None:
