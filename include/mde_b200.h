@@ -261,6 +261,11 @@ int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_s
  * slice's first channel): concatenates planar sources (image planes, embedding planes) into the NHWC encoder input. */
 int mde_nchw_to_nhwc_slice(const float* in, float* out, int B, int C, int64_t P, int out_pitch, mde_stream_t stream);
 
+/* ... and into a zero-padded channels_last image [B, H+pad_top+pad_bottom, W+pad_left+pad_right, out_pitch]; the border is
+ * not written (the caller zeroes it).  Folds the F.pad of a TensorFlow-"SAME" stem convolution into the concatenation. */
+int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B, int C, int H, int W, int out_pitch, int pad_top,
+                                  int pad_bottom, int pad_left, int pad_right, mde_stream_t stream);
+
 /* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
  * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is
  * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (zeroed by the call; holds

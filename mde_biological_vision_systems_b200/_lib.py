@@ -60,6 +60,7 @@ SIGNATURES = {
     "mde_upsample_bwd_ws_bytes": (_i64, [_i32, _i32]),
     "mde_upsample_bwd": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "mde_nchw_to_nhwc_slice": (_i32, [_p, _p, _i32, _i32, _i64, _i32, _p]),
+    "mde_nchw_to_nhwc_slice_padded": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_nchw_to_nhwc": (_i32, [_p, _p, _i32, _i32, _i64, _p]),
     "mde_relu_eps_fwd": (_i32, [_p, _p, _i64, _f32, _p]),
     "mde_eval_metrics_ws_bytes": (_i64, [_i32]),

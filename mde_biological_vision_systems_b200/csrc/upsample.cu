@@ -220,14 +220,16 @@ int mde_upsample_bwd(const float* gout, float* gx, int channels_last, int B, int
 // channels.  ATen's strided copy does this at ~1.8 TB/s (527 us for the 464 MB feature map of config 2); this tile
 // kernel is a plain HBM stream.  grid (ceil(P/64), ceil(C/64), B), block 256.
 namespace mde {
+// W > 0: the output is a (zero-)padded image of Wo x (Po / Wo) pixels and the source pixel (y, x) lands at (y + pt, x + pl)
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                                           long long P, int pitch) {
+                                                           long long P, int pitch, int W = 0, int Wo = 0, long long Po = 0,
+                                                           int pt = 0, int pl = 0) {
   __shared__ float tile[64][65];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
   const float* src = in + (long long)b * C * P;
-  float* dst = out + (long long)b * pitch * P;
+  float* dst = out + (long long)b * pitch * (W > 0 ? Po : P);
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -240,7 +242,10 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   for (int i = 0; i < 16; ++i) {
     const long long p = p0 + ty + i * 4;
     const int c = c0 + tx;
-    if (p < P && c < C) dst[p * pitch + c] = tile[tx][ty + i * 4];
+    if (p < P && c < C) {
+      const long long po = W > 0 ? ((p / W + pt) * Wo + (p % W + pl)) : p;
+      dst[po * pitch + c] = tile[tx][ty + i * 4];
+    }
   }
 }
 }  // namespace mde
@@ -305,6 +310,22 @@ extern "C" int mde_nchw_to_nhwc_slice(const float* in, float* out, int B, int C,
   if (B <= 0 || C <= 0 || P <= 0 || out_pitch < C || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
   dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
   mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, out_pitch);
+  return mde::check_launch();
+}
+
+// ... and into a padded channels_last image [B, H + pad_top + pad_bottom, W + pad_left + pad_right, out_pitch] (the border
+// is NOT written: the caller zeroes it), so that a following TensorFlow-"SAME" stride-2 convolution needs no F.pad copy
+extern "C" int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B, int C, int H, int W, int out_pitch,
+                                             int pad_top, int pad_bottom, int pad_left, int pad_right, mde_stream_t stream) {
+  if (!in || !out) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || out_pitch < C || B > 65535 || (C + 63) / 64 > 65535 || pad_top < 0 ||
+      pad_bottom < 0 || pad_left < 0 || pad_right < 0)
+    return MDE_ERR_BAD_SHAPE;
+  const long long P = (long long)H * W;
+  const int Wo = W + pad_left + pad_right;
+  const long long Po = (long long)(H + pad_top + pad_bottom) * Wo;
+  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, out_pitch, W, Wo, Po, pad_top, pad_left);
   return mde::check_launch();
 }
 

@@ -134,12 +134,16 @@ class Encoder(nn.Module):
         super().__init__()
         self.original_model = backend
 
-    def forward(self, x):
+    def forward(self, x, stem_prepadded=False):
+        """``stem_prepadded``: x already carries the zero border the TensorFlow-SAME stem convolution would add."""
         feats = [x]
         for name, child in self.original_model._modules.items():
             stages = child._modules.values() if name == 'blocks' else (child,)
             for stage in stages:
-                feats.append(stage(feats[-1]))
+                if name == 'conv_stem' and stem_prepadded and isinstance(stage, SamePadConv2d):
+                    feats.append(stage.forward_with(feats[-1], stage.weight, stage.bias, prepadded=True))
+                else:
+                    feats.append(stage(feats[-1]))
         return feats
 
 
@@ -228,16 +232,17 @@ class UnetAdaptiveBins(nn.Module):
                 items.append(("mlp", self.instance_areas_fc, instance_areas, float(hw)))
         return items
 
-    def _concat_external(self, x, items):
+    def _concat_external(self, x, items, pads=None):
         """One allocation for the widened tensor; pass-through groups are copied (with the .float() cast fused into
-        the copy), MLP groups are written in place by the streaming kernel."""
+        the copy), MLP groups are written in place by the streaming kernel.  ``pads`` (top, bottom, left, right) is honoured
+        only by the channels_last fast path (callers detect it by the grown spatial size)."""
         if not items:
             return x
         if getattr(self, "_channels_last", False) and x.is_cuda and all(it[0] == "copy" for it in items) \
                 and not (torch.is_grad_enabled() and x.requires_grad):
             # channels_last model, pass-through groups only (config 2): the planar sources are transposed straight into
             # their channel slices of the NHWC encoder input (no planar concatenation, no second layout pass)
-            return ops.concat_channels_last([x] + [it[1] for it in items])
+            return ops.concat_channels_last([x] + [it[1] for it in items], pads)
         widths = [it[1].shape[1] if it[0] == "copy" else 10 for it in items]
         b, c, h, w = x.shape
         out = torch.empty((b, c + sum(widths), h, w), dtype=torch.float32, device=x.device)
@@ -285,9 +290,16 @@ class UnetAdaptiveBins(nn.Module):
         return bin_edges, pred
 
     def forward(self, x, semantics=None, instance_labels=None, instance_areas=None, **kwargs):
+        stem_prepadded = False
         if self.insertion_point == "input":
             items = self._external_channels(semantics, instance_labels, instance_areas, x.shape[2] * x.shape[3])
-            x = self._concat_external(x, items)
+            stem = getattr(self.encoder.original_model, "conv_stem", None)
+            pads = None
+            if isinstance(stem, SamePadConv2d) and self.image != "none":
+                pads = stem.same_pads(x.shape[2], x.shape[3])  # written by the concatenation itself instead of an F.pad copy
+            hw = x.shape[-2:]
+            x = self._concat_external(x, items, pads)
+            stem_prepadded = x.shape[-2:] != hw
         if self.image == "none":
             if x.shape[1] <= 3:
                 sys.exit("Error: Add more auxiliary information at input if using no image")
@@ -298,7 +310,7 @@ class UnetAdaptiveBins(nn.Module):
                 x = x.contiguous(memory_format=torch.channels_last)
             else:
                 x = ops.to_channels_last(x)
-        unet_out = self.decoder(self.encoder(x), **kwargs)
+        unet_out = self.decoder(self.encoder(x, stem_prepadded=stem_prepadded), **kwargs)
 
         if "noAdaBins" in self.encoder_name:
             return None, ops.relu_eps(unet_out, 0.0001)

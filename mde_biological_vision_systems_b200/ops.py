@@ -741,22 +741,37 @@ def to_channels_last(x):
     return out
 
 
-def concat_channels_last(sources):
+def concat_channels_last(sources, pads=None):
     """torch.cat(sources, dim=1) of NCHW-contiguous fp32 tensors, produced directly in channels_last memory (one tiled
-    transpose per source into its channel slice; no planar intermediate)."""
+    transpose per source into its channel slice; no planar intermediate).  pads = (top, bottom, left, right): the result is
+    additionally zero-padded spatially (the SAME padding of a stride-2 stem convolution)."""
     lib = _lib.load()
     _need_cuda(*sources)
     sources = [_f32(t).contiguous() for t in sources]
     b, _, h, w = sources[0].shape
     ctot = sum(t.shape[1] for t in sources)
-    out = torch.empty((b, ctot, h, w), dtype=torch.float32, device=sources[0].device, memory_format=torch.channels_last)
+    pt, pb, pl, pr = (0, 0, 0, 0) if pads is None else (int(v) for v in pads)
+    out = torch.empty((b, ctot, h + pt + pb, w + pl + pr), dtype=torch.float32, device=sources[0].device,
+                      memory_format=torch.channels_last)
     base = out.data_ptr()
     ch = 0
     with timing("nchw_to_nhwc"):
         for t in sources:
-            rc = lib.mde_nchw_to_nhwc_slice(_p(t), ctypes.c_void_p(base + 4 * ch), b, t.shape[1], h * w, ctot, _s())
+            dst = ctypes.c_void_p(base + 4 * ch)
+            if pt or pb or pl or pr:
+                rc = lib.mde_nchw_to_nhwc_slice_padded(_p(t), dst, b, t.shape[1], h, w, ctot, pt, pb, pl, pr, _s())
+            else:
+                rc = lib.mde_nchw_to_nhwc_slice(_p(t), dst, b, t.shape[1], h * w, ctot, _s())
             _lib.check(rc, "mde_nchw_to_nhwc_slice")
             ch += t.shape[1]
+    if pt:
+        out[:, :, :pt].zero_()
+    if pb:
+        out[:, :, h + pt:].zero_()
+    if pl:
+        out[:, :, :, :pl].zero_()
+    if pr:
+        out[:, :, :, w + pl:].zero_()
     return out
 
 
