@@ -107,28 +107,50 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
                            int norm_mode, float min_val, float max_val, float* y_raw, float* widths_normed,
                            float* edges, float* centers, mde_stream_t stream);
 
+/* ---- split-bf16 pairs ("bf16x3"): the operand format of the tensor-core kernels below.  An fp32 tensor of n elements
+ * travels as uint16 planes[2][n]: plane 0 = bf16_rn(v), plane 1 = bf16_rn(v - plane 0); products are formed as
+ * hi*hi + mid*hi + hi*mid with fp32 accumulation (~2^-17 relative error per product, against ~2^-13 for TF32): this is what
+ * keeps depth maps within north_star's 1e-3 of the fp32 reference on every pixel.  n % 8 == 0, 16-byte aligned pointers.
+ *   mde_split_bf16       fp32 [n] -> planes [2][n]            mde_merge_bf16   planes -> fp32 (hi + mid)
+ *   mde_split_bf16_nchw  fp32 NCHW [B,C,P] -> planes [2][B,P,C] (NHWC element order; C even) */
+int mde_split_bf16(const float* x, uint16_t* planes, int64_t n, mde_stream_t stream);
+int mde_merge_bf16(const uint16_t* planes, float* out, int64_t n, mde_stream_t stream);
+int mde_split_bf16_nchw(const float* x_nchw, uint16_t* planes_nhwc, int B, int C, int64_t P, mde_stream_t stream);
+
 /* ---- K1a: patch-embedding conv (kernel = stride = patch) + positional rows (models/layers.py:11-12,17-19) as a
- * TMA-fed tcgen05 split-K GEMM (TF32).  x_nhwc: channels_last activations [B,h,w,C]; w_nhwc: the conv filter in
- * channels_last order [E,patch,patch,C], TF32-rounded (and scaled by MDE_TF32_TRUNC_COMP) by the caller;
- * bias [E]; pos [>=S, E] (positional_encodings); tokens [S,B,E] with S = (h/patch)*(w/patch); E must be 128.
- * ws: mde_patch_embed_ws_floats(...) floats of scratch (split-K partials). */
+ * TMA-fed tcgen05 split-K GEMM on split-bf16 pairs (three bf16 products per K step, see below).
+ * x_pair: channels_last activations as a pair, planes[2][B,h,w,C]; w_pair: the conv filter in channels_last order
+ * [E,patch,patch,C] as a pair, planes[2][E*patch*patch*C] (mde_split_bf16 of the permuted filter);
+ * bias [E]; pos [>=S, E] (positional_encodings); tokens [S,B,E] fp32 with S = (h/patch)*(w/patch); E must be 128,
+ * C % 8 == 0, (patch * C) % 64 == 0.  ws: mde_patch_embed_ws_floats(...) floats of scratch (split-K partials). */
 int64_t mde_patch_embed_ws_floats(int B, int h, int w, int patch, int C);
-int mde_patch_embed_fwd(const float* x_nhwc, const float* w_nhwc, const float* bias, const float* pos, float* tokens,
+int mde_patch_embed_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* bias, const float* pos, float* tokens,
                         float* ws, int B, int h, int w, int C, int patch, int E, mde_stream_t stream);
 
-/* ---- K1c: 3x3 / stride 1 / pad 1 convolution on channels_last activations as a TMA-fed tcgen05 implicit GEMM (TF32
- * inputs, fp32 accumulation) with a fused per-channel affine + LeakyReLU epilogue: mViT.conv3x3 (models/miniViT.py:16,27)
+/* ---- K1c: 3x3 / stride 1 / pad 1 convolution on channels_last activations as a TMA-fed tcgen05 implicit GEMM (fp32
+ * accumulation) with a fused per-channel affine + LeakyReLU epilogue: mViT.conv3x3 (models/miniViT.py:16,27)
  * and the DecoderBN blocks Conv3x3 -> BatchNorm(eval) -> LeakyReLU / conv3 (models/unet_adaptive_bins.py:39-49,73).
- *   x_nhwc [B,H,W,C] float32; y_nhwc [B,H,W,Cout] float32 = lrelu(conv(x) * scale[co] + shift[co]); scale / shift may be
- *   NULL (1 / 0; pass the conv bias as shift); lrelu_slope 1.0f = no activation; round_tf32 != 0 rounds the outputs to
- *   TF32 (exact operands for a following tensor-core contraction).
- *   w_prep: the filter re-laid-out as [dx][dy][Cout][C] and TF32-rounded by mde_conv3x3_prep_weight (operand_scale =
- *   MDE_TF32_TRUNC_COMP when x is raw fp32, 1.0f when x is already TF32-rounded).
- * Requires C % 4 == 0 and Cout either <= 256 and a multiple of 16, or divisible by a multiple of 32 that is <= 256. */
+ *   y = lrelu(conv(x) * scale[co] + shift[co]); scale / shift may be NULL (1 / 0; pass the conv bias as shift);
+ *   lrelu_slope 1.0f = no activation.
+ * mde_conv3x3_nhwc_x3_fwd (the model's default): x_pair planes[2][B,H,W,C] and w_pair planes[2][dx][dy][Cout][C]
+ *   (mde_conv3x3_prep_weight_x3) are split-bf16 pairs, three bf16 products per K step; y is fp32 [B,H,W,Cout]
+ *   (y_is_pair == 0) or a pair planes[2][B,H,W,Cout] for the next tensor-core consumer (y_is_pair != 0).
+ *   Requires C % 8 == 0, Cout % 4 == 0 (% 8 for pair output).
+ * mde_conv3x3_nhwc_fwd (single-pass TF32): x_nhwc fp32 whose values are already TF32-representable (rounded by their
+ *   producer -- the tensor core would otherwise truncate them), w_prep = [dx][dy][Cout][C] TF32-rounded
+ *   (mde_conv3x3_prep_weight, operand_scale normally 1.0f); round_tf32 != 0 rounds the outputs to TF32.  C % 4 == 0.
+ * Both: Cout either <= 256 and a multiple of 16, or divisible by a multiple of 32 that is <= 256.
+ * mde_conv3x3_small_nhwc_fwd: exact-fp32 direct kernel for Cout <= 4 (the noAdaBins decoder's conv3, :78-80);
+ *   w_oihw is the torch-layout filter [Cout,C,3,3], bias may be NULL. */
 int mde_conv3x3_prep_weight(const float* w_oihw, float* w_prep, int Cout, int C, float operand_scale,
                             mde_stream_t stream);
+int mde_conv3x3_prep_weight_x3(const float* w_oihw, uint16_t* w_pair, int Cout, int C, mde_stream_t stream);
 int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* scale, const float* shift, float* y_nhwc,
                          int B, int H, int W, int C, int Cout, float lrelu_slope, int round_tf32, mde_stream_t stream);
+int mde_conv3x3_nhwc_x3_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* scale, const float* shift, void* y,
+                            int y_is_pair, int B, int H, int W, int C, int Cout, float lrelu_slope, mde_stream_t stream);
+int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const float* bias, float* y_nhwc, int B, int H, int W,
+                               int C, int Cout, mde_stream_t stream);
 
 /* Batched NT GEMM on tcgen05 (TF32 inputs, fp32 accumulate):  C[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k].
  * A [batch][M][K] with row pitch lda and batch stride a_batch (floats; multiples of 4), B [batch][N][K] likewise,
@@ -184,7 +206,7 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
 
 /* ---- K1d: range-attention contraction  y[b,n,p] = sum_k x[b,k,p] * q[b,n,k]  (layers.py:31-36) ----------
  * x [B,K,P] float32 (NCHW with P = h*w), q [B,N,K] float32, y [B,N,P] float32.
- * impl 0 = SIMT fp32 (exact fp32 FMA), impl 1 = TMA + tcgen05 TF32 (requires P % 128 == 0, K == 128, N % 16 == 0). */
+ * impl 0 = SIMT fp32 (exact fp32 FMA); the tensor-core form is mde_range_attention_tc (split-bf16 pair operands). */
 int mde_range_attention(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, int impl,
                         mde_stream_t stream);
 
@@ -198,13 +220,15 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
                     int64_t P, mde_stream_t stream);
 
 /* ---- K1d+K1e+K2 fused: range attention -> conv_out -> softmax -> centre-weighted sum, nothing but pred is
- * written (miniViT.py:33 + unet_adaptive_bins.py:286-300).  TMA-fed tcgen05 (TF32), accumulators in TMEM.
- *   x        activations (the conv3x3 output), float32: [B,128,P] (NCHW, x_channels_last = 0) or [B,P,128] (NHWC, = 1)
- *   wf       [B,n_bins,128] float32 = (conv_out.weight @ queries[b]) * log2(e), TF32-rounded   (mde_fold_queries)
+ * written (miniViT.py:33 + unet_adaptive_bins.py:286-300).  TMA-fed tcgen05 (three bf16 products per K step on split-bf16
+ * pairs, fp32 accumulators in TMEM).
+ *   x_pair   activations (the conv3x3 output) as a split-bf16 pair, planes[2][B,P,128] (NHWC element order)
+ *   w_pair   planes[2][B,n_bins,128]: the pair of wf = (conv_out.weight @ queries[b]) * log2(e)   (mde_fold_queries
+ *            + mde_split_bf16)
  *   biasf    [B,n_bins]     float32 = log2(e) * (conv_out.bias + wf-fold of the producer's bias)  (mde_fold_queries)
  *   centers  [B,n_bins], pred [B,P].   Requires P % 128 == 0, n_bins == 256. */
-int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
-                       float* pred, int B, int n_bins, int64_t P, mde_stream_t stream);
+int mde_head_chain_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers, float* pred,
+                       int B, int n_bins, int64_t P, mde_stream_t stream);
 /* Training forms of the fused chain (autograd of layers.py:31-36 + unet_adaptive_bins.py:286-300 in hand-written form):
  *  - mde_head_chain_fwd_train: the forward, additionally storing the per-pixel softmax state stats [B,P,2]
  *    (max logit in log2 units, sum_j 2^(z_j - max));
@@ -212,27 +236,28 @@ int mde_head_chain_fwd(const float* x, int x_channels_last, const float* wf, con
  *    units, TF32-rounded) as gl [B,P,n_bins] and glT [B,n_bins,P], plus gc [B,n_bins] = d loss / d centres and
  *    gb [B,n_bins] = sum_p gl (both zeroed by the call).  gpred [B,P] is the upstream gradient of pred.
  *  The remaining products (d feat = gl W', d W' = gl^T feat) are mde_gemm_nt_tf32 calls. */
-int mde_head_chain_fwd_train(const float* x, int x_channels_last, const float* wf, const float* biasf, const float* centers,
+int mde_head_chain_fwd_train(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers,
                              float* pred, float* stats, int B, int n_bins, int64_t P, mde_stream_t stream);
-int mde_head_chain_bwd_logits(const float* x, int x_channels_last, const float* wf, const float* biasf,
-                              const float* centers, const float* pred, const float* stats, const float* gpred, float* gl,
-                              float* glT, float* gc, float* gb, int B, int n_bins, int64_t P, mde_stream_t stream);
-/* wf[b] = round_tf32( (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale )          (fp32 FMA, tiled)
+int mde_head_chain_bwd_logits(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers,
+                              const float* pred, const float* stats, const float* gpred, float* gl, float* glT, float* gc,
+                              float* gb, int B, int n_bins, int64_t P, mde_stream_t stream);
+/* Stand-alone PixelWiseDotProduct (layers.py:31-36) on the same kernel: y[b,n,p] = sum_k x[b,p,k] q[b,n,k] with x_pair
+ * planes[2][B,P,128] and q_pair planes[2][B,128,128]; y fp32 [B,128,P] (NCHW).  K == N == 128, P % 128 == 0. */
+int mde_range_attention_tc(const uint16_t* x_pair, const uint16_t* q_pair, float* y, int B, int K, int N, int64_t P,
+                           mde_stream_t stream);
+/* wf[b] = (w_out [n_bins,N] @ q[b] [N,K]) * log2e * operand_scale   (fp32 FMA, tiled; round_tf32 != 0 additionally rounds
+ *         to TF32, RNA)
  * biasf[b,j] = log2e * ( bias[j] + sum_k (w_out @ q[b])[j,k] * feat_bias[k] )            (feat_bias may be NULL)
- * operand_scale = MDE_TF32_TRUNC_COMP compensates the mean mantissa loss of the OTHER operand, which the tensor
- * core truncates (not rounds) to TF32 when it reads raw fp32 from shared memory; 1.0f disables it.
  * q[b] must be a dense [N,K] block (q_batch_stride == N*K). */
-#define MDE_TF32_TRUNC_COMP 1.000352f
 int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride,
                      const float* feat_bias, float* wf, float* biasf, int B, int n_bins, int N, int K,
-                     float operand_scale, mde_stream_t stream);
+                     float operand_scale, int round_tf32, mde_stream_t stream);
 /* out[i] = round-to-nearest TF32 of in[i]*scale (so the tensor cores' operand truncation is exact for this tensor) */
 int mde_round_tf32(const float* in, float* out, int64_t n, float scale, mde_stream_t stream);
-/* bring-up knobs for the UMMA shared-memory descriptors (bytes) and the last barrier-timeout code (0 = none;
- * synchronises the device).  Test/debug only. */
-int mde_tc_debug_config(int a_lbo, int a_sbo, int b_lbo, int b_sbo, int version);
+/* last barrier-timeout code of the chain kernels (0 = none; synchronises the device).  Test/debug only. */
 int mde_tc_last_error(void);
-/* tuning aid: device buffer [148][8] int64 of per-role wait cycles filled by the following chain launches (NULL = off) */
+/* tuning aid: device buffer [148][8] int64 of per-role wait cycles filled by the following mde_head_chain_fwd launches
+ * (NULL = off; the instrumented kernel is a separate instantiation -- the default one carries no clock reads) */
 int mde_tc_debug_profile(long long* buf);
 
 /* ---- A8': noAdaBins epilogue relu(x) + 1e-4 (unet_adaptive_bins.py:240-242) */
@@ -253,6 +278,10 @@ int mde_upsample_bwd(const float* gout, float* gx, int channels_last, int B, int
  * [B,C2,H,W]; out_nhwc [B,H,W,C1+C2].  C1 % 4 == 0 and C2 % 4 == 0. */
 int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last, float* out_nhwc, int B,
                                  int C1, int C2, int h, int w, int H, int W, mde_stream_t stream);
+/* the same step writing its result as a split-bf16 pair planes[2][B,H,W,C1+C2] (feeds mde_conv3x3_nhwc_x3_fwd);
+ * skip must be NHWC */
+int mde_upsample_concat_nhwc_pair_fwd(const float* x_nhwc, const float* skip_nhwc, uint16_t* out_pair, int B, int C1, int C2,
+                                      int h, int w, int H, int W, mde_stream_t stream);
 
 /* NCHW [B,C,P] -> NHWC [B,P,C] transpose (feeds the head's cuDNN convs and the K-major chain operand) */
 int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream);

@@ -34,6 +34,14 @@ SIGNATURES = {
     "mde_patch_embed_fwd": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_conv3x3_prep_weight": (_i32, [_p, _p, _i32, _i32, _f32, _p]),
     "mde_conv3x3_nhwc_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
+    "mde_conv3x3_prep_weight_x3": (_i32, [_p, _p, _i32, _i32, _p]),
+    "mde_conv3x3_nhwc_x3_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_conv3x3_small_nhwc_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_split_bf16": (_i32, [_p, _p, _i64, _p]),
+    "mde_merge_bf16": (_i32, [_p, _p, _i64, _p]),
+    "mde_split_bf16_nchw": (_i32, [_p, _p, _i32, _i32, _i64, _p]),
+    "mde_range_attention_tc": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _p]),
+    "mde_upsample_concat_nhwc_pair_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_gemm_nt_tf32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_gemm_nt_tf32_ex": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _p]),
     "mde_gemm_nt_tf32_planes": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _i64, _p]),
@@ -47,12 +55,11 @@ SIGNATURES = {
     "mde_range_attention": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _i32, _p]),
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),
-    "mde_head_chain_fwd": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
-    "mde_head_chain_fwd_train": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
-    "mde_head_chain_bwd_logits": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
-    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_head_chain_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_head_chain_fwd_train": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_head_chain_bwd_logits": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
     "mde_round_tf32": (_i32, [_p, _p, _i64, _f32, _p]),
-    "mde_tc_debug_config": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "mde_tc_last_error": (_i32, []),
     "mde_tc_debug_profile": (_i32, [_p]),
     "mde_upsample_concat_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

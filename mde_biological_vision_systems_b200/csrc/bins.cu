@@ -216,7 +216,8 @@ __device__ __forceinline__ float tf32_rna(float v) {
   return __uint_as_float(r);
 }
 
-// EPI 0: y = acc + bias[n];  EPI 1: y = tf32_rna(acc * out_scale)  (operand preparation for the tensor-core chain)
+// EPI 0: y = acc + bias[n];  EPI 1: y = tf32_rna(acc * out_scale);  EPI 2: y = acc * out_scale  (operand preparation
+// for the tensor-core chain)
 template <int EPI>
 __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                          long long wbs, const float* __restrict__ bias,
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict
     float* dst = yb + (long long)n * P + p;
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = EPI == 0 ? acc[i][j] + bv : tf32_rna(acc[i][j] * out_scale);
+    for (int j = 0; j < 4; ++j)
+      o[j] = EPI == 0 ? acc[i][j] + bv : (EPI == 1 ? tf32_rna(acc[i][j] * out_scale) : acc[i][j] * out_scale);
     if (p + 3 < P && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
@@ -382,27 +384,25 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
   return launch_pixel_gemm(ram, w, 0, bias, logits, B, K, n_bins, P, (cudaStream_t)stream);
 }
 
-int mde_range_attention_tc(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, cudaStream_t st);
-
 int mde_range_attention(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, int impl,
                         mde_stream_t stream) {
   if (!x || !q || !y) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || K <= 0 || N <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
   if (impl == 0) return launch_pixel_gemm(x, q, (int64_t)N * K, nullptr, y, B, K, N, P, (cudaStream_t)stream);
-  if (impl == 1) return mde_range_attention_tc(x, q, y, B, K, N, P, (cudaStream_t)stream);
-  return MDE_ERR_UNSUPPORTED;
+  return MDE_ERR_UNSUPPORTED;  // the tensor-core form takes split-bf16 pairs: mde_range_attention_tc
 }
 
 int mde_fold_queries(const float* w_out, const float* bias, const float* q, int64_t q_batch_stride,
                      const float* feat_bias, float* wf, float* biasf, int B, int n_bins, int N, int K,
-                     float operand_scale, mde_stream_t stream) {
+                     float operand_scale, int round_tf32, mde_stream_t stream) {
   if (!w_out || !bias || !q || !wf || !biasf) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || B > 65535 || n_bins <= 0 || N <= 0 || K <= 0) return MDE_ERR_BAD_SHAPE;
   if (q_batch_stride != (int64_t)N * K) return MDE_ERR_BAD_SHAPE;  // q[b] must be a dense [N,K] block
   cudaStream_t st = (cudaStream_t)stream;
   const float LOG2E = 1.4426950408889634f;
   dim3 grid((unsigned)((K + 127) / 128), (unsigned)((n_bins + 63) / 64), (unsigned)B);
-  pixel_gemm_kernel<1><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
+  if (round_tf32) pixel_gemm_kernel<1><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
+  else pixel_gemm_kernel<2><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
   int rc = check_launch();
   if (rc) return rc;
   chain_bias_kernel<<<dim3((unsigned)((n_bins + 7) / 8), (unsigned)B), 256, 0, st>>>(bias, wf, feat_bias, biasf, n_bins, K,

@@ -107,6 +107,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -160,6 +165,16 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t adesc, ui
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], BF16 (or FP16) inputs, FP32 accumulate: K = 16 per instruction, twice the TF32 rate
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -247,6 +262,29 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint
          ((m >> 4) << 24);
 }
 
+// ---- split-bf16 ("bf16x3") operands ------------------------------------------------------------------------------
+// An fp32 value v travels as a PAIR of bf16 planes: hi = bf16_rn(v), mid = bf16_rn(v - hi)  (hi + mid carries 16
+// significant bits).  A product of two such operands on the tensor cores is  hi*hi + mid*hi + hi*mid  (three kind::f16
+// MMAs, fp32 accumulation): relative error ~2^-16.8 per product instead of TF32's ~2^-12.8, at 1.5x the TF32 MMA time.
+__device__ __forceinline__ uint16_t bf16_bits_rn(float v) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& mid) {
+  hi = bf16_bits_rn(v);
+  mid = bf16_bits_rn(v - bf16_bits_to_f32(hi));
+}
+// two values -> packed (lo half = first value) hi and mid words
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& mid) {
+  uint16_t ah, am, bh, bm;
+  split_bf16(a, ah, am);
+  split_bf16(b, bh, bm);
+  hi = (uint32_t)ah | ((uint32_t)bh << 16);
+  mid = (uint32_t)am | ((uint32_t)bm << 16);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -267,6 +305,26 @@ inline EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+// tensor of `dtype`, rank <= 5, dims/strides innermost first (strides in BYTES for dims 1..rank-1)
+inline bool encode_any(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  return fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool encode_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, CUtensorMapSwizzle swz) {
+  return encode_any(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz);
 }
 // fp32 tensor, rank <= 5, dims/strides innermost first (strides in BYTES for dims 1..rank-1)
 inline bool encode_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

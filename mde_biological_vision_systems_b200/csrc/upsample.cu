@@ -7,6 +7,7 @@
 // profiles/r1_launches_step.txt) -- half of the whole forward step; this kernel writes the concatenated tensor once at
 // HBM speed (one float4 store per 4 output pixels, the low-resolution source stays in L1/L2).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mde {
 
@@ -264,9 +265,25 @@ extern "C" int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64
 // transposed into channels [C1, C1+C2).  One thread = 4 channels of one output pixel: float4 loads of the four taps,
 // one float4 store; consecutive threads walk the channel axis, so every access is a full 128-byte line.
 namespace mde {
-__global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int C1,
+// PAIR: the output is a split-bf16 pair (uint16 planes[2][B*H*W*Ctot], tc_common.cuh) for the bf16x3 conv3x3
+template <bool PAIR>
+__device__ __forceinline__ void store4(void* out, long long elem, long long plane_elems, const float4& o) {
+  if constexpr (PAIR) {
+    uint2 hi, mid;
+    tc::split_bf16x2(o.x, o.y, hi.x, mid.x);
+    tc::split_bf16x2(o.z, o.w, hi.y, mid.y);
+    uint16_t* base = reinterpret_cast<uint16_t*>(out);
+    *reinterpret_cast<uint2*>(base + elem) = hi;
+    *reinterpret_cast<uint2*>(base + plane_elems + elem) = mid;
+  } else {
+    stg_stream(reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem), o);
+  }
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ x, void* __restrict__ out, int C1,
                                                             int Ctot, int h, int w, int H, int W, float sy, float sx,
-                                                            long long total) {
+                                                            long long total, long long plane_elems) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = C1 >> 2;
@@ -288,17 +305,19 @@ __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restr
   o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
   o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
   o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
-  stg_stream(reinterpret_cast<float4*>(out + (((long long)b * H + Y) * W + X) * Ctot) + cg, o);
+  store4<PAIR>(out, (((long long)b * H + Y) * W + X) * Ctot + 4 * cg, plane_elems, o);
 }
 
-__global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __restrict__ skip, float* __restrict__ out,
-                                                                 int C2, int Ctot, long long total) {
+template <bool PAIR>
+__global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __restrict__ skip, void* __restrict__ out,
+                                                                 int C1, int C2, int Ctot, long long total,
+                                                                 long long plane_elems) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = C2 >> 2;
   const int cg = (int)(idx % c4);
   const long long p = idx / c4;
-  stg_stream(reinterpret_cast<float4*>(out + p * Ctot) + cg, ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg));
+  store4<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg));
 }
 }  // namespace mde
 
@@ -329,29 +348,47 @@ extern "C" int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B,
   return mde::check_launch();
 }
 
+static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, int skip_channels_last, void* out, bool pair,
+                                       int B, int C1, int C2, int h, int w, int H, int W, cudaStream_t st) {
+  using namespace mde;
+  if (!x_nhwc || !out || (C2 > 0 && !skip)) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || C1 <= 0 || C2 < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return MDE_ERR_BAD_SHAPE;
+  if (C1 % 4 != 0 || C2 % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(out, 16) || (C2 > 0 && !aligned(skip, 16)))
+    return MDE_ERR_UNSUPPORTED;
+  if (pair && C2 > 0 && !skip_channels_last) return MDE_ERR_UNSUPPORTED;  // pair output takes an NHWC skip
+  const int Ctot = C1 + C2;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const long long P = (long long)H * W;
+  const long long plane = (long long)B * P * Ctot;
+  const long long total = (long long)B * P * (C1 / 4);
+  if (pair)
+    upsample_nhwc_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, total, plane);
+  else
+    upsample_nhwc_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, total, plane);
+  int rc = check_launch();
+  if (rc || C2 == 0) return rc;
+  if (skip_channels_last) {
+    const long long t2 = (long long)B * P * (C2 / 4);
+    if (pair)
+      copy_channels_nhwc_kernel<true><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out, C1, C2, Ctot, t2, plane);
+    else
+      copy_channels_nhwc_kernel<false><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out, C1, C2, Ctot, t2, plane);
+  } else {
+    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(skip, reinterpret_cast<float*>(out) + C1, C2, P, Ctot);
+  }
+  return check_launch();
+}
+
 extern "C" int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last,
                                             float* out_nhwc, int B, int C1, int C2, int h, int w, int H, int W,
                                             mde_stream_t stream) {
-  using namespace mde;
-  if (!x_nhwc || !out_nhwc || (C2 > 0 && !skip)) return MDE_ERR_BAD_POINTER;
-  if (B <= 0 || C1 <= 0 || C2 < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return MDE_ERR_BAD_SHAPE;
-  if (C1 % 4 != 0 || C2 % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(out_nhwc, 16) || (C2 > 0 && !aligned(skip, 16)))
-    return MDE_ERR_UNSUPPORTED;
-  const int Ctot = C1 + C2;
-  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)B * H * W * (C1 / 4);
-  upsample_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out_nhwc, C1, Ctot, h, w, H, W, sy, sx,
-                                                                        total);
-  int rc = check_launch();
-  if (rc || C2 == 0) return rc;
-  const long long P = (long long)H * W;
-  if (skip_channels_last) {
-    const long long t2 = (long long)B * P * (C2 / 4);
-    copy_channels_nhwc_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out_nhwc + C1, C2, Ctot, t2);
-  } else {
-    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(skip, out_nhwc + C1, C2, P, Ctot);
-  }
-  return check_launch();
+  return upsample_concat_nhwc_launch(x_nhwc, skip, skip_channels_last, out_nhwc, false, B, C1, C2, h, w, H, W,
+                                     (cudaStream_t)stream);
+}
+
+// the same step writing a split-bf16 pair (planes[2][B,H,W,C1+C2]) for mde_conv3x3_nhwc_x3_fwd; skip must be NHWC
+extern "C" int mde_upsample_concat_nhwc_pair_fwd(const float* x_nhwc, const float* skip_nhwc, uint16_t* out_pair, int B, int C1,
+                                                 int C2, int h, int w, int H, int W, mde_stream_t stream) {
+  return upsample_concat_nhwc_launch(x_nhwc, skip_nhwc, 1, out_pair, true, B, C1, C2, h, w, H, W, (cudaStream_t)stream);
 }

@@ -22,14 +22,14 @@ class PatchTransformerEncoder(nn.Module):
         self.embedding_convPxP = nn.Conv2d(in_channels, embedding_dim, kernel_size=patch_size, stride=patch_size,
                                            padding=0)
         self.positional_encodings = nn.Parameter(torch.rand(500, embedding_dim), requires_grad=True)
-        self.use_tc_patch_embed = True  # False: cuDNN conv for the patch embedding (the transformer stays on our kernels)
+        self.use_tc_patch_embed = True  # False: cuDNN fp32 conv for the patch embedding (the transformer stays on our kernels)
         self.use_tc_layers = True       # False: exact-fp32 SIMT linear kernels instead of the 3xTF32 tcgen05 GEMMs
 
     def _needs_autograd(self, x):
-        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        return torch.is_grad_enabled() and (getattr(x, "requires_grad", False) or any(p.requires_grad for p in self.parameters()))
 
     def _prepared_weight(self):
-        """TF32-rounded NHWC filter for the tcgen05 patch GEMM, cached per parameter version."""
+        """NHWC filter as a split-bf16 pair for the tcgen05 patch GEMM, cached per parameter version."""
         w = self.embedding_convPxP.weight
         cached = getattr(self, "_mde_w_prep", None)
         if cached is None or cached[0] != w._version or cached[1].device != w.device:
@@ -38,19 +38,25 @@ class PatchTransformerEncoder(nn.Module):
         return cached[1]
 
     def forward(self, x):
+        """x: fp32 [N,C,h,w] (either memory format) or the same feature map as an ops.SplitBF16 (inference only)."""
         conv = self.embedding_convPxP
         if not x.is_cuda:
             raise ops._lib.MdeError("PatchTransformerEncoder runs on the B200 kernels only (no CPU path)")
         if self._needs_autograd(x) or (self.training and self.transformer_encoder.layers[0].dropout.p > 0):
             # training: dropout and the backward pass run through the stock torch layers (DESIGN.md section 6)
+            if isinstance(x, ops.SplitBF16):
+                x = x.float()
             emb = conv(x).flatten(2)  # [N, E, S]
             emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
             return self.transformer_encoder(emb.permute(2, 0, 1))
         if self.use_tc_patch_embed and ops.patch_embed_supported(x, conv):
-            # channels_last input: TMA + tcgen05 split-K GEMM writes the [S, N, E] tokens (bias and positional rows added)
+            # TMA + tcgen05 split-K GEMM on split-bf16 pairs writes the [S, N, E] tokens (bias and positional rows added)
             tokens = ops.patch_embed(x, self._prepared_weight(), conv.bias, self.positional_encodings, conv.kernel_size[0])
         else:
-            emb = conv(x).flatten(2)
+            if isinstance(x, ops.SplitBF16):
+                x = x.float()
+            with ops.exact_fp32_library():
+                emb = conv(x).flatten(2)
             emb = emb + self.positional_encodings[: emb.shape[2], :].T.unsqueeze(0)
             tokens = emb.permute(2, 0, 1).contiguous()
         layers = list(self.transformer_encoder.layers)
@@ -81,8 +87,8 @@ class PatchTransformerEncoder(nn.Module):
 
 
 class PixelWiseDotProduct(nn.Module):
-    """y[n, cout, h, w] = sum_c x[n, c, h, w] * K[n, cout, c]  (reference layers.py:27-36) on the tcgen05 /
-    SIMT contraction kernel (ops.range_attention -> mde_range_attention)."""
+    """y[n, cout, h, w] = sum_c x[n, c, h, w] * K[n, cout, c]  (reference layers.py:27-36) on the tcgen05 (three bf16
+    products per K step) / SIMT contraction kernels (ops.range_attention)."""
 
     def __init__(self, impl="auto"):
         super().__init__()

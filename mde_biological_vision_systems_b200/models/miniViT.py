@@ -28,19 +28,15 @@ class mViT(nn.Module):
         self.conv3x3 = nn.Conv2d(in_channels, embedding_dim, kernel_size=3, stride=1, padding=1)
         self.regressor = nn.Sequential(nn.Linear(embedding_dim, 256), nn.LeakyReLU(), nn.Linear(256, 256),
                                        nn.LeakyReLU(), nn.Linear(256, dim_out))
-        # 3x3 conv of the inference fast path: "tc" = tcgen05 implicit GEMM (TF32 inputs), "cudnn" = library conv,
-        # "auto" = "tc" when torch.backends.cudnn.allow_tf32 (PyTorch's default, i.e. the precision the reference's own
-        # conv runs at on a GPU) and the exact-fp32 library conv otherwise
+        # 3x3 conv of the inference path: "tc" = tcgen05 implicit GEMM on split-bf16 pairs (three bf16 products per K step,
+        # fp32-grade), "cudnn" = library conv in true fp32, "auto" = "tc" whenever the shape allows
         self.conv3x3_impl = "auto"
 
-    def _conv3x3_uses_tc(self, x):
-        impl = self.conv3x3_impl
-        if impl == "auto":
-            impl = "tc" if torch.backends.cudnn.allow_tf32 else "cudnn"
-        return impl == "tc" and ops.conv3x3_supported(x, self.conv3x3.out_channels)
+    def _conv3x3_uses_tc(self, x, pair_out=False):
+        return self.conv3x3_impl != "cudnn" and ops.conv3x3_supported(x, self.conv3x3.out_channels, pair_out)
 
     def _prepared_conv3x3(self):
-        """[dx][dy][Cout][C] TF32 filter for the tcgen05 conv, cached per parameter version."""
+        """[dx][dy][Cout][C] split-bf16 filter for the tcgen05 conv, cached per parameter version."""
         w = self.conv3x3.weight
         cached = getattr(self, "_mde_w3_prep", None)
         if cached is None or cached[0] != w._version or cached[1].device != w.device:
@@ -49,18 +45,29 @@ class mViT(nn.Module):
         return cached[1]
 
     # -- pieces shared by the reference-shaped forward() and the fused path of UnetAdaptiveBins ------------------
-    def tokens_and_features(self, x, bias_free=False):
-        """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w]).  With ``bias_free`` the 3x3 conv runs without its bias (the caller
-        folds it into the fused chain, ops.fold_queries(feat_bias=...)), which saves a full pass over the feature map."""
+    def tokens_and_features(self, x, bias_free=False, pair_out=False):
+        """-> (tgt [S,N,E], conv3x3(x) [N,E,h,w]).  x: fp32 tensor or ops.SplitBF16.  With ``bias_free`` the 3x3 conv runs
+        without its bias (the caller folds it into the fused chain, ops.fold_queries(feat_bias=...)), which saves a full pass
+        over the feature map; with ``pair_out`` (inference, tcgen05 conv only) the features come back as an ops.SplitBF16,
+        the operand format of the fused chain."""
         # the reference clones x first (miniViT.py:25); nothing below writes to x, so the 29 MB/img copy is skipped
+        c = self.conv3x3
+        needs_grad = torch.is_grad_enabled() and (getattr(x, "requires_grad", False) or c.weight.requires_grad)
+        if not needs_grad and x.is_cuda and self._conv3x3_uses_tc(x, pair_out):
+            x = ops.split_bf16(x)  # once, for both consumers
+            tgt = self.patch_transformer(x)
+            feat = ops.conv3x3_nhwc(x, self._prepared_conv3x3(), None, None if bias_free else c.bias, pair_out=pair_out,
+                                    name="conv3x3_head")
+            return tgt, feat
         tgt = self.patch_transformer(x)
-        if bias_free and self._conv3x3_uses_tc(x):
-            # tcgen05 implicit GEMM; the outputs are rounded to TF32 so that the chain's tensor-core read is exact
-            return tgt, ops.conv3x3_nhwc(x, self._prepared_conv3x3(), round_tf32=True)
-        if bias_free:
-            c = self.conv3x3
-            return tgt, torch.nn.functional.conv2d(x, _channels_last_weight(c), None, c.stride, c.padding)
-        return tgt, self.conv3x3(x)
+        if isinstance(x, ops.SplitBF16):
+            x = x.float()
+        if needs_grad:
+            return tgt, (torch.nn.functional.conv2d(x, c.weight, None, c.stride, c.padding) if bias_free else c(x))
+        with ops.exact_fp32_library():
+            if bias_free:
+                return tgt, torch.nn.functional.conv2d(x, _channels_last_weight(c), None, c.stride, c.padding)
+            return tgt, c(x)
 
     def bin_widths(self, tgt, min_val=None, max_val=None):
         """regressor + normalisation on token 0 (miniViT.py:35-45); with min/max also edges and centres.

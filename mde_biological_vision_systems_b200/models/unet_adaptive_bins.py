@@ -9,11 +9,18 @@ the head runs on the sm_100a kernels of this package:
 * mViT + conv_out + softmax + bins (:285-302): ops.fold_queries + ops.head_chain (TMA + tcgen05, nothing but
   ``pred`` written) or, when the fused kernel's shape constraints do not hold, range attention -> conv1x1 ->
   ops.bins_pred (streaming);
+* DecoderBN (:39-100) in inference: resize + concat and every 3x3 conv (BatchNorm(eval) + LeakyReLU in
+  the epilogue) on our kernels, activations handed from kernel to kernel as split-bf16 pairs (ops.SplitBF16);
 * noAdaBins epilogue (:240-242): ops.relu_eps.
 
-The EfficientNet encoder and DecoderBN bodies are outside the hot path and stay plain
-PyTorch/cuDNN modules; they only exist so the surface and the checkpoints match.
+Precision: every tensor-core product of the inference path is formed from split-bf16 pairs (three bf16 products, fp32
+accumulation: fp32-grade), and the library passthrough bodies (EfficientNet encoder, decoder conv2) run in true fp32
+(``backbone_tf32 = False``), so `pred` / `bin_edges` stay within 1e-3 of the fp32 reference on every pixel.
+
+The EfficientNet encoder is outside the hot path and stays a plain PyTorch/cuDNN module (as do the
+decoder / head bodies in training mode); it only exists so the surface and the checkpoints match.
 """
+import contextlib
 import sys
 
 import torch
@@ -39,8 +46,8 @@ class UpSampleBN(nn.Module):
         self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
 
     def _folded(self):
-        """Per conv block: ([dx][dy][Cout][C] TF32 filter, scale, shift) with the eval-mode BatchNorm folded into a
-        per-channel affine (scale = gamma / sqrt(var + eps), shift = beta + (conv bias - mean) * scale); cached per
+        """Per conv block: ([dx][dy][Cout][C] split-bf16 filter, scale, shift, slope) with the eval-mode BatchNorm folded into
+        a per-channel affine (scale = gamma / sqrt(var + eps), shift = beta + (conv bias - mean) * scale); cached per
         parameter / running-statistics version."""
         tensors = []
         for i in (0, 3):
@@ -55,20 +62,26 @@ class UpSampleBN(nn.Module):
                     conv, bn = self._net[i], self._net[i + 1]
                     scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
                     shift = bn.bias + (conv.bias - bn.running_mean) * scale
-                    # block 2 reads block 1's TF32-rounded output: its filter needs no truncation compensation
-                    w = ops.prepare_conv3x3_weight(conv.weight, ops.TF32_TRUNC_COMP if i == 0 else 1.0)
+                    w = ops.prepare_conv3x3_weight(conv.weight)
                     blocks.append((w, scale.contiguous(), shift.contiguous(), self._net[i + 2].negative_slope))
             cached = (key, blocks)
             self._mde_folded = cached
         return cached[1]
 
-    def forward_tc(self, x_cl, concat_with, round_out=False):
-        """Inference path on our kernels, channels_last throughout: resize + concat (one streaming pass) -> 2 x tcgen05
-        conv3x3 with BatchNorm(eval) + LeakyReLU in the epilogue."""
+    def tc_supported(self, c_up, skip):
+        c_in = self._net[0].in_channels
+        return (c_up % 4 == 0 and skip.shape[1] % 4 == 0 and c_up + skip.shape[1] == c_in and c_in % 8 == 0
+                and ops.conv3x3_cout_ok(self._net[0].out_channels, pair_out=True)
+                and ops.conv3x3_cout_ok(self._net[3].out_channels, pair_out=True))
+
+    def forward_tc(self, x_cl, concat_with, pair_out=False, name="up"):
+        """Inference path on our kernels, channels_last throughout: resize + concat (one streaming pass, written as a
+        split-bf16 pair) -> 2 x tcgen05 conv3x3 (three bf16 products per K step) with BatchNorm(eval) + LeakyReLU in the
+        epilogue.  Returns fp32 channels_last (input of the next resize) or an ops.SplitBF16 (``pair_out``)."""
         (w1, s1, b1, a1), (w2, s2, b2, a2) = self._folded()
-        y = ops.upsample_concat_nhwc(x_cl, concat_with)
-        y = ops.conv3x3_nhwc(y, w1, s1, b1, slope=a1, round_tf32=True)
-        return ops.conv3x3_nhwc(y, w2, s2, b2, slope=a2, round_tf32=round_out)
+        y = ops.upsample_concat_nhwc_pair(x_cl, concat_with)
+        y = ops.conv3x3_nhwc(y, w1, s1, b1, slope=a1, pair_out=True, name=name + ".conv_a")
+        return ops.conv3x3_nhwc(y, w2, s2, b2, slope=a2, pair_out=pair_out, name=name + ".conv_b")
 
     def forward(self, x, concat_with):
         if x.is_cuda:  # fused resize + concat kernel (ATen's align_corners bilinear kernel dominates the step otherwise)
@@ -94,33 +107,46 @@ class DecoderBN(nn.Module):
         self.mode = mode
         self.conv3 = nn.Conv2d(f // 16, num_classes if mode == "AdaBins" else 1, kernel_size=3, stride=1, padding=1)
 
-        self.conv_impl = "auto"  # "tc": tcgen05 conv3x3 path; "cudnn": stock modules; "auto": tc iff cudnn.allow_tf32
+        self.conv_impl = "auto"  # "auto" / "tc": the tcgen05 conv3x3 path in inference; "cudnn": stock modules (fp32)
 
-    def _use_tc(self, bottleneck):
-        impl = self.conv_impl
-        if impl == "auto":
-            impl = "tc" if torch.backends.cudnn.allow_tf32 else "cudnn"
-        return (impl == "tc" and bottleneck.is_cuda and not self.training and not torch.is_grad_enabled()
-                and bottleneck.dtype == torch.float32)
+    def _use_tc(self, feats):
+        if self.conv_impl == "cudnn" or self.training or torch.is_grad_enabled():
+            return False
+        s0, s1, s2, s3, bottleneck = feats
+        if not (bottleneck.is_cuda and bottleneck.dtype == torch.float32):
+            return False
+        c = self.conv2.out_channels
+        for up, skip in ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0)):
+            if not up.tc_supported(c, skip):
+                return False
+            c = up._net[3].out_channels
+        cout = self.conv3.out_channels
+        return cout <= 4 or ops.conv3x3_cout_ok(cout, pair_out=True)
 
     def _prepared_conv3(self):
         w = self.conv3.weight
         cached = getattr(self, "_mde_w3_prep", None)
         if cached is None or cached[0] != w._version or cached[1].device != w.device:
-            cached = (w._version, ops.prepare_conv3x3_weight(w, 1.0))
+            cached = (w._version, ops.prepare_conv3x3_weight(w))
             self._mde_w3_prep = cached
         return cached[1]
 
     def forward(self, features):
+        """-> unet_out: an fp32 [B,C,h,w] tensor, or (inference on our kernels, AdaBins mode) the same feature map as an
+        ops.SplitBF16, the operand format of the head's tensor-core kernels."""
         s0, s1, s2, s3, bottleneck = features[4], features[5], features[6], features[8], features[11]
-        if self._use_tc(bottleneck):
-            # (f)1: the whole decoder on our kernels, channels_last; conv2 (1x1, padding 1) is a plain library GEMM
-            y = self.conv2(bottleneck.contiguous(memory_format=torch.channels_last))
+        if self._use_tc((s0, s1, s2, s3, bottleneck)):
+            # (f)1: the whole decoder on our kernels, channels_last; conv2 (1x1, padding 1) is a plain library GEMM (fp32)
+            with ops.exact_fp32_library():
+                y = self.conv2(bottleneck.contiguous(memory_format=torch.channels_last))
             y = y.contiguous(memory_format=torch.channels_last)
+            small = self.conv3.out_channels <= 4  # noAdaBins: 1 output channel, direct fp32 kernel
             ups = ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0))
             for i, (up, skip) in enumerate(ups):
-                y = up.forward_tc(y, skip, round_out=(i == 3))
-            return ops.conv3x3_nhwc(y, self._prepared_conv3(), None, self.conv3.bias)
+                y = up.forward_tc(y, skip, pair_out=(i == 3 and not small), name="up%d" % (i + 1))
+            if small:
+                return ops.conv3x3_small(y, self.conv3.weight, self.conv3.bias)
+            return ops.conv3x3_nhwc(y, self._prepared_conv3(), None, self.conv3.bias, pair_out=True, name="decoder.conv3")
         y = self.conv2(bottleneck)
         for up, skip in ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0)):
             y = up(y, skip)
@@ -166,6 +192,9 @@ class UnetAdaptiveBins(nn.Module):
         self.encoder_name = encoder_name
         self.image_pre_encode = None
         self.fused_head = True  # False: range attention -> conv1x1 -> streaming bins (three kernels)
+        # False (default): the cuDNN passthrough bodies run in true fp32 during inference (the tolerance contract is against
+        # the fp32 reference); True: leave torch.backends.cudnn.allow_tf32 as the caller set it (PyTorch's default: TF32)
+        self.backbone_tf32 = False
 
         self.num_decoded_channels = 128
         extra = UnetAdaptiveBins.get_num_channels_to_add(encoder_name, semantics_mode, instance_segmentation_mode, image)
@@ -259,25 +288,24 @@ class UnetAdaptiveBins(nn.Module):
 
     # ---- head -------------------------------------------------------------------------------------------------
     def _head(self, unet_out):
+        """unet_out: fp32 tensor or ops.SplitBF16 (inference, from the tcgen05 decoder)."""
         head = self.adaptive_bins_layer
         conv = self.conv_out[0]
         fusable = self.fused_head and unet_out.is_cuda and self.num_classes == 256 \
             and (unet_out.shape[2] * unet_out.shape[3]) % 128 == 0 and head.conv3x3.out_channels == 128 \
             and head.n_query_channels == 128
-        needs_grad = torch.is_grad_enabled() and (unet_out.requires_grad or conv.weight.requires_grad)
+        needs_grad = torch.is_grad_enabled() and (getattr(unet_out, "requires_grad", False) or conv.weight.requires_grad)
         if needs_grad and not fusable:
             raise RuntimeError("training needs the fused head (n_bins = 256, 128 query channels, h*w % 128 == 0)")
         if fusable and not needs_grad:
-            # inference fast path: the head's two cuDNN convs read a channels_last copy of unet_out (cuDNN converts to
-            # NHWC internally anyway), the 3x3 conv runs bias-free and leaves its output in NHWC, which the tcgen05
-            # chain consumes in place as a K-major operand; the conv bias is folded into the chain's per-image bias.
-            x_cl = ops.to_channels_last(unet_out)
-            tgt, feat = head.tokens_and_features(x_cl, bias_free=True)
+            # inference: the 3x3 conv runs bias-free on the tcgen05 kernel and hands its output to the fused chain as a
+            # split-bf16 pair (K-major operand, consumed in place); the conv bias is folded into the chain's per-image bias.
+            # (Shapes the tcgen05 conv does not cover -- e.g. the 153-channel before-attn input -- take the library conv in
+            # true fp32 and the chain splits its output.)
+            tgt, feat = head.tokens_and_features(unet_out, bias_free=True, pair_out=True)
             _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
             queries = tgt[1:head.n_query_channels + 1].permute(1, 0, 2)
-            # features that come TF32-rounded from our conv need no truncation compensation on the folded operand
-            comp = 1.0 if head._conv3x3_uses_tc(x_cl) else ops.TF32_TRUNC_COMP
-            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries, feat_bias=head.conv3x3.bias, operand_scale=comp)
+            wf, biasf = ops.fold_queries(conv.weight, conv.bias, queries, feat_bias=head.conv3x3.bias)
             return bin_edges, ops.head_chain(feat, wf, biasf, centers)
         tgt, feat = head.tokens_and_features(unet_out)
         _, bin_edges, centers, _ = head.bin_widths(tgt, self.min_val, self.max_val)
@@ -285,7 +313,7 @@ class UnetAdaptiveBins(nn.Module):
         if needs_grad:
             pred = ops.head_chain_autograd(feat, queries, conv.weight, conv.bias, centers)
         else:
-            ram = ops.range_attention(feat, queries)
+            ram = ops.range_attention(feat, queries, impl="simt")
             pred = ops.bins_pred(ops.conv1x1(ram, conv.weight, conv.bias), centers)
         return bin_edges, pred
 
@@ -310,12 +338,17 @@ class UnetAdaptiveBins(nn.Module):
                 x = x.contiguous(memory_format=torch.channels_last)
             else:
                 x = ops.to_channels_last(x)
-        unet_out = self.decoder(self.encoder(x, stem_prepadded=stem_prepadded), **kwargs)
+        exact = not (self.backbone_tf32 or self.training or torch.is_grad_enabled())
+        with (ops.exact_fp32_library() if exact else contextlib.nullcontext()):
+            feats = self.encoder(x, stem_prepadded=stem_prepadded)
+        unet_out = self.decoder(feats, **kwargs)
 
         if "noAdaBins" in self.encoder_name:
             return None, ops.relu_eps(unet_out, 0.0001)
 
         if self.insertion_point == "before-attn":
+            if isinstance(unet_out, ops.SplitBF16):
+                unet_out = unet_out.float()
             size = unet_out.shape[-2:]
             near = lambda t: None if t is None else F.interpolate(t, size=size, mode='nearest').float()
             # NB: the reference's human-sizes branch here concatenates onto x instead of unet_out (a bug that makes

@@ -3,6 +3,7 @@
 Every function here launches hand-written sm_100a kernels from libmde_b200.so on torch's current CUDA stream.
 Inputs must be CUDA tensors; nothing here computes on the CPU or through a PyTorch substitute.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -11,9 +12,6 @@ from . import _lib
 
 LOG2E = 1.4426950408889634
 NUM_SMS = 148  # B200
-# mean relative mantissa loss of an fp32 value truncated to TF32 is 2^-11 * E[1/m] = 3.52e-4 (m log-uniform in [1,2));
-# the tensor core truncates the raw-fp32 activation operand, so the pre-rounded weight operand is scaled up by it
-TF32_TRUNC_COMP = 1.000352
 
 
 def _s():
@@ -34,6 +32,21 @@ def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise _lib.MdeError("mde_b200 operators take CUDA tensors only (no CPU fallback exists)")
+
+
+@contextlib.contextmanager
+def exact_fp32_library():
+    """Run the enclosed cuDNN / cuBLAS calls (the passthrough bodies: EfficientNet encoder, decoder conv2, shapes our
+    kernels do not cover) in true fp32 rather than the libraries' TF32 default, so that the whole inference path is
+    fp32-grade -- north_star's 1e-3 on depth maps is against the fp32 reference."""
+    c, m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32 = c
+        torch.backends.cuda.matmul.allow_tf32 = m
 
 
 def launch_count():
@@ -77,6 +90,74 @@ def kernel_times_ms():
     out = {}
     for name, s, e in _TIMING["records"]:
         out.setdefault(name, []).append(s.elapsed_time(e))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# split-bf16 pairs ("bf16x3"): the operand format of the tensor-core kernels (conv3x3, patch embedding, fused chain)
+# ------------------------------------------------------------------------------------------------------------
+class SplitBF16:
+    """An fp32 feature map [B,C,H,W] carried as two bf16 planes in NHWC element order: ``planes`` is a contiguous
+    torch.bfloat16 tensor [2,B,H,W,C] with planes[0] = bf16(v) and planes[1] = bf16(v - planes[0]).  The tensor-core
+    kernels multiply such operands as hi*hi + mid*hi + hi*mid with fp32 accumulation (~2^-17 relative error per product)."""
+    __slots__ = ("planes",)
+
+    def __init__(self, planes):
+        if planes.dtype != torch.bfloat16 or planes.dim() != 5 or planes.shape[0] != 2 or not planes.is_contiguous():
+            raise ValueError("SplitBF16 wraps a contiguous bfloat16 [2,B,H,W,C] tensor")
+        self.planes = planes
+
+    @property
+    def shape(self):  # logical NCHW shape
+        _, b, h, w, c = self.planes.shape
+        return torch.Size((b, c, h, w))
+
+    @property
+    def device(self):
+        return self.planes.device
+
+    @property
+    def is_cuda(self):
+        return self.planes.is_cuda
+
+    def float(self):
+        """hi + mid as a channels_last fp32 [B,C,H,W] tensor."""
+        return merge_bf16(self)
+
+
+def split_bf16_flat(x):
+    """fp32 tensor (any shape, numel % 8 == 0) -> bfloat16 [2, *x.shape] (plane 0 = hi, plane 1 = mid), same element order."""
+    lib = _lib.load()
+    _need_cuda(x)
+    x = _f32(x).contiguous()
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.mde_split_bf16(_p(x), _p(out), x.numel(), _s()), "mde_split_bf16")
+    return out
+
+
+def split_bf16(x):
+    """fp32 [B,C,H,W] (NCHW-contiguous or channels_last) -> SplitBF16 (NHWC planes); one streaming pass either way."""
+    lib = _lib.load()
+    _need_cuda(x)
+    if isinstance(x, SplitBF16):
+        return x
+    x = _f32(x)
+    b, c, h, w = x.shape
+    planes = torch.empty((2, b, h, w, c), dtype=torch.bfloat16, device=x.device)
+    with timing("split_bf16"):
+        if x.is_contiguous(memory_format=torch.channels_last) and (c * h * w * b) % 8 == 0:
+            rc = lib.mde_split_bf16(_p(x), _p(planes), x.numel(), _s())
+        else:
+            rc = lib.mde_split_bf16_nchw(_p(x.contiguous()), _p(planes), b, c, h * w, _s())
+    _lib.check(rc, "mde_split_bf16")
+    return SplitBF16(planes)
+
+
+def merge_bf16(pair):
+    lib = _lib.load()
+    _, b, h, w, c = pair.planes.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=pair.planes.device, memory_format=torch.channels_last)
+    _lib.check(lib.mde_merge_bf16(_p(pair.planes), _p(out), out.numel(), _s()), "mde_merge_bf16")
     return out
 
 
@@ -300,31 +381,32 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=Tru
 # patch embedding
 # ------------------------------------------------------------------------------------------------------------
 def prepare_patch_weight(weight):
-    """Conv filter [E,C,p,p] -> channels_last order [E,p,p,C], scaled by TF32_TRUNC_COMP and rounded to TF32 (the B
-    operand of the patch-embedding GEMM as it lies in memory)."""
-    w = weight.detach().permute(0, 2, 3, 1).contiguous()
-    return round_tf32(w, TF32_TRUNC_COMP)
+    """Conv filter [E,C,p,p] -> channels_last order [E,p,p,C] as a split-bf16 pair, bfloat16 [2,E,p,p,C] (the B operand of
+    the patch-embedding GEMM as it lies in memory)."""
+    return split_bf16_flat(weight.detach().float().permute(0, 2, 3, 1).contiguous())
 
 
 def patch_embed_supported(x, conv):
+    """x: SplitBF16 or a CUDA fp32 [B,C,H,W] tensor."""
     k = conv.kernel_size
-    return (x.is_cuda and x.dtype == torch.float32 and conv.out_channels == 128 and k[0] == k[1] and conv.stride == k
-            and conv.padding == (0, 0) and (k[0] * x.shape[1]) % 32 == 0 and x.shape[3] // k[0] <= 128
-            and -(-(x.shape[2] // k[0]) // (128 // (x.shape[3] // k[0]))) <= 4
-            and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+    b, c, h, w = x.shape
+    return (x.is_cuda and conv.out_channels == 128 and k[0] == k[1] and conv.stride == k and conv.padding == (0, 0)
+            and (k[0] * c) % 64 == 0 and c % 8 == 0 and h >= k[0] and 1 <= w // k[0] <= 128
+            and -(-(h // k[0]) // (128 // (w // k[0]))) <= 4)
 
 
-def patch_embed(x_cl, w_prepared, bias, pos, patch):
-    """tokens [S,B,E] = conv(k = s = patch)(x).flatten(2).permute(2,0,1) + pos[:S] on the tcgen05 split-K GEMM;
-    x_cl must be channels_last."""
+def patch_embed(x, w_prepared, bias, pos, patch):
+    """tokens [S,B,E] = conv(k = s = patch)(x).flatten(2).permute(2,0,1) + pos[:S] on the tcgen05 split-K GEMM (three bf16
+    products per K step).  x: SplitBF16 (or an fp32 tensor, split here)."""
     lib = _lib.load()
-    b, c, h, w = x_cl.shape
-    e = w_prepared.shape[0]
+    x = split_bf16(x)
+    b, c, h, w = x.shape
+    e = w_prepared.shape[1]
     s = (h // patch) * (w // patch)
-    tokens = torch.empty((s, b, e), dtype=torch.float32, device=x_cl.device)
-    ws = torch.empty(int(lib.mde_patch_embed_ws_floats(b, h, w, patch, c)), dtype=torch.float32, device=x_cl.device)
+    tokens = torch.empty((s, b, e), dtype=torch.float32, device=x.device)
+    ws = torch.empty(int(lib.mde_patch_embed_ws_floats(b, h, w, patch, c)), dtype=torch.float32, device=x.device)
     with timing("patch_embed"):
-        rc = lib.mde_patch_embed_fwd(_p(x_cl), _p(w_prepared), _p(bias.contiguous()), _p(pos.contiguous()), _p(tokens),
+        rc = lib.mde_patch_embed_fwd(_p(x.planes), _p(w_prepared), _p(bias.contiguous()), _p(pos.contiguous()), _p(tokens),
                                      _p(ws), b, h, w, c, patch, e, _s())
     _lib.check(rc, "mde_patch_embed_fwd")
     return tokens
@@ -363,8 +445,20 @@ def gemm_nt(a, b, out=None, splits=1, alpha=1.0):
 # ------------------------------------------------------------------------------------------------------------
 # 3x3 convolution (tcgen05 implicit GEMM, NHWC)
 # ------------------------------------------------------------------------------------------------------------
-def prepare_conv3x3_weight(weight, operand_scale=TF32_TRUNC_COMP):
-    """Conv filter [Cout,C,3,3] -> [dx][dy][Cout][C], scaled and rounded to TF32 (the B operand tiles as TMA reads them)."""
+def prepare_conv3x3_weight(weight):
+    """Conv filter [Cout,C,3,3] -> [dx][dy][Cout][C] as a split-bf16 pair, bfloat16 [2,3,3,Cout,C] (the B operand tiles as
+    TMA reads them)."""
+    lib = _lib.load()
+    _need_cuda(weight)
+    w = weight.detach().contiguous().float()
+    cout, c = w.shape[0], w.shape[1]
+    out = torch.empty((2, 3, 3, cout, c), dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.mde_conv3x3_prep_weight_x3(_p(w), _p(out), cout, c, _s()), "mde_conv3x3_prep_weight_x3")
+    return out
+
+
+def prepare_conv3x3_weight_tf32(weight, operand_scale=1.0):
+    """Conv filter [Cout,C,3,3] -> fp32 [dx][dy][Cout][C], TF32-rounded (single-pass TF32 form of the kernel)."""
     lib = _lib.load()
     _need_cuda(weight)
     w = weight.detach().contiguous().float()
@@ -374,27 +468,71 @@ def prepare_conv3x3_weight(weight, operand_scale=TF32_TRUNC_COMP):
     return out
 
 
-def conv3x3_supported(x, cout):
+def conv3x3_cout_ok(cout, pair_out=False):
     n_ok = (cout <= 256 and cout % 16 == 0) or any(cout % c == 0 for c in range(32, 257, 32))
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and n_ok
-            and x.is_contiguous(memory_format=torch.channels_last))
+    return bool(n_ok and cout % (8 if pair_out else 4) == 0)
 
 
-def conv3x3_nhwc(x_cl, w_prep, scale=None, shift=None, slope=1.0, round_tf32=False, out=None):
-    """y = lrelu(conv3x3(x, pad 1) * scale + shift) on the tcgen05 implicit GEMM.  x_cl: channels_last [B,C,H,W];
-    w_prep from prepare_conv3x3_weight; returns a channels_last [B,Cout,H,W] tensor."""
+def conv3x3_supported(x, cout, pair_out=False):
+    """x: SplitBF16 or CUDA fp32 [B,C,H,W]."""
+    return bool(x.is_cuda and x.shape[1] % 8 == 0 and conv3x3_cout_ok(cout, pair_out))
+
+
+def conv3x3_nhwc(x, w_prep, scale=None, shift=None, slope=1.0, pair_out=False, name="conv3x3"):
+    """y = lrelu(conv3x3(x, pad 1) * scale + shift) on the tcgen05 implicit GEMM, three bf16 products per K step (fp32-grade).
+    x: SplitBF16 (an fp32 [B,C,H,W] tensor is split first); w_prep from prepare_conv3x3_weight.  Returns a channels_last fp32
+    [B,Cout,H,W] tensor, or a SplitBF16 for the next tensor-core consumer when ``pair_out``."""
+    lib = _lib.load()
+    x = split_bf16(x)
+    _need_cuda(x.planes, w_prep)
+    b, c, h, w = x.shape
+    cout = w_prep.shape[3]
+    if w_prep.dtype != torch.bfloat16 or w_prep.shape[4] != c:
+        raise ValueError("conv3x3_nhwc: w_prep must come from prepare_conv3x3_weight for this input width")
+    if pair_out:
+        out = torch.empty((2, b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    else:
+        out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with timing(name):
+        rc = lib.mde_conv3x3_nhwc_x3_fwd(_p(x.planes), _p(w_prep), _p(scale), _p(shift), _p(out), 1 if pair_out else 0, b, h, w,
+                                         c, cout, float(slope), _s())
+    _lib.check(rc, "mde_conv3x3_nhwc_x3_fwd")
+    return SplitBF16(out) if pair_out else out
+
+
+def conv3x3_nhwc_tf32(x_cl, w_prep, scale=None, shift=None, slope=1.0, round_tf32=False, out=None):
+    """Single-pass TF32 form (x_cl's values must already be TF32-representable; w_prep from prepare_conv3x3_weight_tf32)."""
     lib = _lib.load()
     _need_cuda(x_cl, w_prep)
     b, c, h, w = x_cl.shape
     if x_cl.dtype != torch.float32 or not x_cl.is_contiguous(memory_format=torch.channels_last):
-        raise ValueError("conv3x3_nhwc expects a float32 channels_last tensor")
+        raise ValueError("conv3x3_nhwc_tf32 expects a float32 channels_last tensor")
     cout = w_prep.shape[2]
     if out is None:
         out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
-    with timing("conv3x3"):
+    with timing("conv3x3_tf32"):
         rc = lib.mde_conv3x3_nhwc_fwd(_p(x_cl), _p(w_prep), _p(scale), _p(shift), _p(out), b, h, w, c, cout, float(slope),
                                       1 if round_tf32 else 0, _s())
     _lib.check(rc, "mde_conv3x3_nhwc_fwd")
+    return out
+
+
+def conv3x3_small(x_cl, weight, bias=None):
+    """Exact-fp32 direct 3x3 conv for Cout <= 4 (the noAdaBins decoder's conv3): x_cl channels_last fp32, torch-layout
+    weight [Cout,C,3,3] -> [B,Cout,H,W]."""
+    lib = _lib.load()
+    _need_cuda(x_cl, weight)
+    x_cl = _f32(x_cl)
+    if not x_cl.is_contiguous(memory_format=torch.channels_last):
+        x_cl = x_cl.contiguous(memory_format=torch.channels_last)
+    b, c, h, w = x_cl.shape
+    cout = weight.shape[0]
+    out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    with timing("conv3x3_small"):
+        rc = lib.mde_conv3x3_small_nhwc_fwd(_p(x_cl), _p(weight.detach().contiguous().float()),
+                                            _p(bias.detach().contiguous().float()) if bias is not None else None, _p(out), b, h, w,
+                                            c, cout, _s())
+    _lib.check(rc, "mde_conv3x3_small_nhwc_fwd")
     return out
 
 
@@ -472,12 +610,18 @@ def round_tf32(x, scale=1.0):
     return out
 
 
+def round_tf32_(x):
+    """In place on a contiguous tensor."""
+    lib = _lib.load()
+    _lib.check(lib.mde_round_tf32(_p(x), _p(x), x.numel(), 1.0, _s()), "mde_round_tf32")
+    return x
+
+
 def range_attention(x, queries, impl="auto"):
     """y[b,n,h,w] = sum_k x[b,k,h,w] * queries[b,n,k]  (PixelWiseDotProduct).  impl: 'simt' (fp32 FMA),
-    'tc' (TMA + tcgen05 TF32) or 'auto' (tc when the shape allows)."""
+    'tc' (TMA + tcgen05, three bf16 products per K step) or 'auto' (tc when the shape allows).  x may be a SplitBF16."""
     lib = _lib.load()
     _need_cuda(x, queries)
-    x = x.contiguous().float()
     queries = queries.contiguous().float()
     b, k, h, w = x.shape
     n = queries.shape[1]
@@ -487,9 +631,18 @@ def range_attention(x, queries, impl="auto"):
         impl = "tc" if tc_ok else "simt"
     if impl == "tc" and not tc_ok:
         raise _lib.MdeError("tcgen05 range attention needs K = N = 128 and h*w % 128 == 0")
-    y = torch.empty((b, n, h, w), dtype=torch.float32, device=x.device)
-    q = round_tf32(queries, TF32_TRUNC_COMP) if impl == "tc" else queries
-    rc = lib.mde_range_attention(_p(x), _p(q), _p(y), b, k, n, p, 1 if impl == "tc" else 0, _s())
+    y = torch.empty((b, n, h, w), dtype=torch.float32, device=queries.device)
+    if impl == "tc":
+        xp = split_bf16(x)
+        qp = split_bf16_flat(queries)
+        with timing("range_attention_tc"):
+            rc = lib.mde_range_attention_tc(_p(xp.planes), _p(qp), _p(y), b, k, n, p, _s())
+        _lib.check(rc, "mde_range_attention_tc")
+        return y
+    if isinstance(x, SplitBF16):
+        x = x.float()
+    x = x.contiguous().float()
+    rc = lib.mde_range_attention(_p(x), _p(queries), _p(y), b, k, n, p, 0, _s())
     _lib.check(rc, "mde_range_attention")
     return y
 
@@ -519,10 +672,10 @@ def bins_pred(logits, centers):
     return pred
 
 
-def fold_queries(w_out, bias, queries, feat_bias=None, operand_scale=TF32_TRUNC_COMP):
-    """wf[b] = tf32(log2e * w_out @ queries[b]) [B,n_bins,K];  biasf [B,n_bins] = log2e * (bias + (w_out @ q[b]) @
-    feat_bias).  ``feat_bias`` is the bias of the conv that produced the chain's activations (folded in so that the
-    producer can run bias-free)."""
+def fold_queries_f32(w_out, bias, queries, feat_bias=None, scale=1.0, round_tf32=False):
+    """wf[b] = scale * log2e * w_out @ queries[b]  [B,n_bins,K] fp32 (optionally TF32-rounded);  biasf [B,n_bins] = log2e *
+    (bias + (w_out @ q[b]) @ feat_bias).  ``feat_bias`` is the bias of the conv that produced the chain's activations (folded
+    in so that the producer can run bias-free)."""
     lib = _lib.load()
     wt = _f32(w_out).reshape(w_out.shape[0], -1).contiguous()
     n_bins, n = wt.shape
@@ -534,24 +687,32 @@ def fold_queries(w_out, bias, queries, feat_bias=None, operand_scale=TF32_TRUNC_
     with timing("fold_queries"):
         rc = lib.mde_fold_queries(_p(wt), _p(bias.contiguous()), _p(queries), n * k,
                                   _p(feat_bias.contiguous()) if feat_bias is not None else None, _p(wf), _p(biasf), b,
-                                  n_bins, n, k, float(operand_scale), _s())
+                                  n_bins, n, k, float(scale), 1 if round_tf32 else 0, _s())
     _lib.check(rc, "mde_fold_queries")
     return wf, biasf
 
 
-def head_chain(x, wf, biasf, centers):
-    """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x [B,128,h,w], either
-    contiguous NCHW or channels_last (NHWC strides; consumed in place, no copy) -> pred [B,1,h,w]."""
+def fold_queries(w_out, bias, queries, feat_bias=None):
+    """The per-image operand of the fused chain: (split-bf16 pair of wf = log2e * w_out @ queries[b], bfloat16
+    [2,B,n_bins,K];  biasf [B,n_bins]) -- see fold_queries_f32."""
+    wf, biasf = fold_queries_f32(w_out, bias, queries, feat_bias)
+    return split_bf16_flat(wf), biasf
+
+
+def head_chain(x, wf_pair, biasf, centers):
+    """Fused range-attention -> conv_out -> softmax -> centre-weighted sum on tcgen05.  x: SplitBF16 [B,128,h,w] (what the
+    conv3x3 epilogue writes), or an fp32 tensor in either memory format (split here, one extra pass); wf_pair / biasf from
+    fold_queries -> pred [B,1,h,w]."""
     lib = _lib.load()
-    x, wf, biasf, centers = _f32(x), _f32(wf), _f32(biasf), _f32(centers)
+    x = split_bf16(x)
+    biasf, centers = _f32(biasf), _f32(centers)
+    if wf_pair.dtype != torch.bfloat16:
+        wf_pair = split_bf16_flat(wf_pair)
     b, k, h, w = x.shape
-    nhwc = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
-    if not nhwc:
-        x = x.contiguous()
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
     with timing("head_chain"):
-        rc = lib.mde_head_chain_fwd(_p(x), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers.contiguous()), _p(pred), b,
-                                    wf.shape[1], h * w, _s())
+        rc = lib.mde_head_chain_fwd(_p(x.planes), _p(wf_pair), _p(biasf.contiguous()), _p(centers.contiguous()), _p(pred), b,
+                                    wf_pair.shape[2], h * w, _s())
     _lib.check(rc, "mde_head_chain_fwd")
     return pred
 
@@ -584,25 +745,26 @@ class _HeadChainFn(torch.autograd.Function):
         if not nhwc:
             feat = feat.contiguous()
         b, k, h, w = feat.shape
+        fpair = split_bf16(feat)
         wf, biasf = fold_queries(w_out, b_out, queries)
         pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=feat.device)
         stats = torch.empty((b, h * w, 2), dtype=torch.float32, device=feat.device)
         with timing("head_chain"):
-            rc = lib.mde_head_chain_fwd_train(_p(feat), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers), _p(pred),
-                                              _p(stats), b, wf.shape[1], h * w, _s())
+            rc = lib.mde_head_chain_fwd_train(_p(fpair.planes), _p(wf), _p(biasf), _p(centers), _p(pred), _p(stats), b,
+                                              wf.shape[2], h * w, _s())
         _lib.check(rc, "mde_head_chain_fwd_train")
-        ctx.save_for_backward(feat, queries, w_out, b_out, centers, pred, stats, wf, biasf)
+        ctx.save_for_backward(feat, queries, w_out, b_out, centers, pred, stats, wf, biasf, fpair.planes)
         ctx.nhwc = nhwc
         return pred
 
     @staticmethod
     def backward(ctx, gpred):
         lib = _lib.load()
-        feat, queries, w_out, b_out, centers, pred, stats, wf, biasf = ctx.saved_tensors
+        feat, queries, w_out, b_out, centers, pred, stats, wf, biasf, fplanes = ctx.saved_tensors
         nhwc = ctx.nhwc
         b, k, h, w = feat.shape
         p = h * w
-        nb = wf.shape[1]
+        nb = wf.shape[2]
         dev = feat.device
         gpred = gpred.contiguous().float()
         gl = torch.empty((b, p, nb), dtype=torch.float32, device=dev)
@@ -610,25 +772,26 @@ class _HeadChainFn(torch.autograd.Function):
         gc = torch.empty((b, nb), dtype=torch.float32, device=dev)
         gb_img = torch.empty((b, nb), dtype=torch.float32, device=dev)
         with timing("head_chain_bwd"):
-            rc = lib.mde_head_chain_bwd_logits(_p(feat), 1 if nhwc else 0, _p(wf), _p(biasf), _p(centers), _p(pred),
-                                               _p(stats), _p(gpred), _p(gl), _p(glT), _p(gc), _p(gb_img), b, nb, p, _s())
+            rc = lib.mde_head_chain_bwd_logits(_p(fplanes), _p(wf), _p(biasf), _p(centers), _p(pred), _p(stats), _p(gpred),
+                                               _p(gl), _p(glT), _p(gc), _p(gb_img), b, nb, p, _s())
         _lib.check(rc, "mde_head_chain_bwd_logits")
         # W' = W_out Q_b without the log2(e) scale, TF32-rounded; its transpose is the K-major operand of d feat
-        wplain, _ = fold_queries(w_out, b_out, queries, operand_scale=1.0 / LOG2E)
+        wplain, _ = fold_queries_f32(w_out, b_out, queries, scale=1.0 / LOG2E, round_tf32=True)
         wpt = wplain.transpose(1, 2).contiguous()                       # [B,128,256]
         if nhwc:
             gfeat = torch.empty((b, k, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             gemm_nt(gl, wpt, out=gfeat.permute(0, 2, 3, 1).reshape(b, p, k))   # [B,P,128] = gl [B,P,256] . W'^T
             feat_t = nhwc_to_nchw(feat).reshape(b, k, p)
+            feat_t = round_tf32_(feat_t)
         else:
             gfeat = torch.empty((b, k, h, w), dtype=torch.float32, device=dev)
             gemm_nt(wpt, gl, out=gfeat.reshape(b, k, p))                        # [B,128,P] = W'^T . gl^T
-            feat_t = feat.reshape(b, k, p)
-        # d W'[j,k] = sum_p gl[p,j] feat[p,k]: K = P pixels, split over CTAs (the raw-fp32 operand is truncated by the
-        # tensor core, hence the compensation factor)
+            feat_t = round_tf32(feat.reshape(b, k, p))
+        # d W'[j,k] = sum_p gl[p,j] feat[p,k]: K = P pixels, split over CTAs; both operands are TF32-rounded (RNA), so the
+        # tensor core's operand truncation is exact
         # two 128-row output tiles per image: enough K splits to put about two CTAs on every SM
         splits = max(1, min(64, (2 * NUM_SMS) // (2 * b)))
-        gwp = gemm_nt(glT, feat_t, splits=splits, alpha=TF32_TRUNC_COMP)
+        gwp = gemm_nt(glT, feat_t, splits=splits)
         wo = w_out.reshape(w_out.shape[0], -1)
         gw = torch.einsum("bjk,bnk->jn", gwp, queries)                   # d W_out
         gq = torch.matmul(wo.t().unsqueeze(0), gwp)                      # d Q_b = W_out^T d W'_b
@@ -707,6 +870,25 @@ def upsample_concat_nhwc(x_cl, skip):
     if torch.is_grad_enabled() and (x_cl.requires_grad or skip.requires_grad):
         return _UpsampleConcatNHWC.apply(x_cl, skip)
     return _upsample_concat_nhwc_fwd(x_cl, skip)
+
+
+def upsample_concat_nhwc_pair(x_cl, skip):
+    """The inference form of upsample_concat_nhwc that writes its result as a SplitBF16 (the operand format of the conv3x3
+    that follows): bilinear(align_corners=True) resize of x_cl to skip's size, concatenated with skip."""
+    lib = _lib.load()
+    _need_cuda(x_cl, skip)
+    x_cl, skip = _f32(x_cl), _f32(skip)
+    if not x_cl.is_contiguous(memory_format=torch.channels_last):
+        x_cl = x_cl.contiguous(memory_format=torch.channels_last)
+    if not skip.is_contiguous(memory_format=torch.channels_last):
+        skip = skip.contiguous(memory_format=torch.channels_last)
+    b, c1, h, w = x_cl.shape
+    _, c2, hh, ww = skip.shape
+    planes = torch.empty((2, b, hh, ww, c1 + c2), dtype=torch.bfloat16, device=x_cl.device)
+    with timing("upsample_concat_nhwc"):
+        rc = lib.mde_upsample_concat_nhwc_pair_fwd(_p(x_cl), _p(skip), _p(planes), b, c1, c2, h, w, hh, ww, _s())
+    _lib.check(rc, "mde_upsample_concat_nhwc_pair_fwd")
+    return SplitBF16(planes)
 
 
 def _upsample_concat_nhwc_fwd(x_cl, skip):

@@ -22,35 +22,25 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 REL_DEPTH = 1e-3  # depth maps / bin edges, fp32-TF32
 REL_LOSS = 1e-4   # SILog / chamfer
-# The fused tcgen05 chain multiplies in TF32 (10-bit mantissa -- the precision PyTorch's own cuDNN convolutions use by
-# default for the reference).  With logits of magnitude ~10 entering a softmax, a single-pass TF32 contraction cannot
-# bound EVERY pixel by 1e-3: simulated with ideally rounded operands the worst pixel of the golden case already sits at
-# 1.05e-3.  The TF32 path is therefore held to: mean relative error <= 1e-4 (10x inside the
-# tolerance), 99.9th percentile <= 1.5e-3, worst pixel <= 3e-3; the exact-fp32 path (fused_head=False: SIMT range
-# attention -> conv1x1 -> streaming bins) is held to 1e-3 on EVERY pixel.
-TF32_MEAN, TF32_P999, TF32_MAX = 1e-4, 1.5e-3, 3e-3
+# Every tensor-core product of the inference path is formed from split-bf16 pairs (hi*hi + mid*hi + hi*mid, fp32
+# accumulation; ops.SplitBF16) and the cuDNN passthrough bodies run in true fp32 inside the model, so depth maps are held to
+# 1e-3 on EVERY pixel in the default mode -- the mode bench.py measures.  These tests run with PyTorch's default backend
+# flags (cudnn.allow_tf32 = True): exactness is the model's job, not the test fixture's.
 
 
-def assert_depth_close(pred, ref, tf32):
+def assert_depth_close(pred, ref, tol=REL_DEPTH):
     mx, p999 = rel_stats(pred, ref)
-    mean = float(np.mean(np.abs(np.asarray(pred, np.float64) - np.asarray(ref, np.float64)) / np.abs(np.asarray(ref, np.float64))))
-    if tf32:
-        assert mean < TF32_MEAN and p999 < TF32_P999 and mx < TF32_MAX, (mean, p999, mx)
-    else:
-        assert mx < REL_DEPTH, (mean, p999, mx)
+    assert mx < tol, (mx, p999)
+
+
+def _as_f32(t):
+    return t.float() if isinstance(t, ops.SplitBF16) else t
 
 
 class Args:
     def __init__(self, **kw):
         self.use_semantics = kw.get("use_semantics")
         self.use_instance_segmentation = kw.get("use_instance_segmentation")
-
-
-@pytest.fixture(autouse=True)
-def _strict_fp32():
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    yield
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -211,7 +201,8 @@ def test_encoder_layers_tc_vs_simt_and_fp64(golden):
 
 @pytest.mark.parametrize("shape", [(2, 128, 176, 192), (1, 128, 208, 272), (3, 128, 240, 320)])
 def test_patch_embed_tc(shape):
-    """tcgen05 split-K patch-embedding GEMM (NHWC input) vs the fp32 conv + positional rows of the reference."""
+    """tcgen05 split-K patch-embedding GEMM (split-bf16 NHWC input, three bf16 products) vs the fp32 conv + positional rows
+    of the reference."""
     m, _ = _head_state()
     pt = m.adaptive_bins_layer.patch_transformer.to(DEV)
     x = synthetic.decoder_features(*shape, seed=77)
@@ -219,25 +210,27 @@ def test_patch_embed_tc(shape):
         ref = pt.embedding_convPxP.cpu()(x).flatten(2) + pt.positional_encodings.cpu()[: (shape[2] // 16) * (shape[3] // 16)].T
         ref = ref.permute(2, 0, 1)
         pt.to(DEV)
-        x_cl = ops.to_channels_last(x.to(DEV))
-        assert ops.patch_embed_supported(x_cl, pt.embedding_convPxP)
-        tok = ops.patch_embed(x_cl, pt._prepared_weight(), pt.embedding_convPxP.bias, pt.positional_encodings, 16)
+        xp = ops.split_bf16(x.to(DEV))
+        assert ops.patch_embed_supported(xp, pt.embedding_convPxP)
+        tok = ops.patch_embed(xp, pt._prepared_weight(), pt.embedding_convPxP.bias, pt.positional_encodings, 16)
     assert tok.shape == ref.shape
     err = float((tok.cpu() - ref).abs().max()) / float(ref.abs().max())
-    assert err < 1e-3, err
+    assert err < 3e-5, err
 
 
 @pytest.mark.parametrize("cfg", [
     dict(shape=(2, 128, 48, 64), cout=128),                       # head conv3x3: NT = 2, 16-px patches, exact tiling
-    dict(shape=(1, 128, 26, 34), cout=128),                       # ragged: edge tiles zero-filled / clipped by TMA
+    dict(shape=(1, 128, 26, 34), cout=128, pair_out=True),        # ragged: edge tiles zero-filled / clipped by TMA
     dict(shape=(2, 176, 40, 24), cout=80, affine=True, slope=0.01),   # decoder up4-like: N tile 80, C % 32 != 0
-    dict(shape=(1, 344, 13, 17), cout=160, affine=True, slope=0.01),  # up3-like: N tile 160 (one patch per CTA)
+    dict(shape=(1, 344, 13, 17), cout=160, affine=True, slope=0.01, pair_out=True),  # up3-like: N tile 160 (one patch per CTA)
     dict(shape=(1, 680, 9, 11), cout=320, affine=True, slope=0.01),   # up2-like: two N tiles of 160
-    dict(shape=(1, 96, 7, 5), cout=640, affine=True, slope=0.01),     # five N tiles of 128
-    dict(shape=(1, 80, 16, 16), cout=128, round_tf32=True),
+    dict(shape=(1, 96, 7, 5), cout=640, affine=True, slope=0.01, pair_out=True),     # five N tiles of 128
+    dict(shape=(1, 80, 16, 16), cout=128, pair_out=True),
+    dict(shape=(1, 1392, 15, 19), cout=640, affine=True, slope=0.01),  # B1 up1: 44 K chunks, ragged last chunk
 ])
 def test_conv3x3_tc(cfg):
-    """tcgen05 implicit-GEMM 3x3 conv (NHWC, TF32) vs an fp64 conv of the reference's Conv2d(+BN eval affine+LeakyReLU)."""
+    """tcgen05 implicit-GEMM 3x3 conv (NHWC split-bf16 pairs, three bf16 products per K step) vs an fp64 conv of the
+    reference's Conv2d(+BN eval affine+LeakyReLU): fp32-grade, in both output formats."""
     rng = np.random.default_rng(91)
     b, c, h, w = cfg["shape"]
     cout = cfg["cout"]
@@ -253,15 +246,58 @@ def test_conv3x3_tc(cfg):
         ref = ref + bias.double().view(1, -1, 1, 1)
     slope = cfg.get("slope", 1.0)
     ref = torch.where(ref > 0, ref, ref * slope)
-    x_cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
-    assert ops.conv3x3_supported(x_cl, cout)
-    out = ops.conv3x3_nhwc(x_cl, ops.prepare_conv3x3_weight(wt.to(DEV)), None if scale is None else scale.to(DEV),
-                           bias.to(DEV), slope=slope, round_tf32=cfg.get("round_tf32", False))
+    pair_out = cfg.get("pair_out", False)
+    xp = ops.split_bf16(x.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert ops.conv3x3_supported(xp, cout, pair_out)
+    out = ops.conv3x3_nhwc(xp, ops.prepare_conv3x3_weight(wt.to(DEV)), None if scale is None else scale.to(DEV),
+                           bias.to(DEV), slope=slope, pair_out=pair_out)
+    if pair_out:
+        assert isinstance(out, ops.SplitBF16)
+        out = out.float()
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
-    assert err < 1e-3, err
-    if cfg.get("round_tf32"):
-        assert torch.equal(out, ops.round_tf32(out.contiguous()).contiguous(memory_format=torch.channels_last))
+    assert err < 5e-5, err
+
+
+def test_conv3x3_tf32_form():
+    """The single-pass TF32 form of the same kernel (operands pre-rounded by the caller, as its contract says)."""
+    rng = np.random.default_rng(94)
+    x = ops.round_tf32(torch.from_numpy(rng.standard_normal((2, 128, 24, 40)).astype(np.float32)).to(DEV))
+    wt = torch.from_numpy((rng.standard_normal((128, 128, 3, 3)) / 34.0).astype(np.float32)).to(DEV)
+    wp = ops.prepare_conv3x3_weight_tf32(wt)
+    ref = torch.nn.functional.conv2d(x.cpu().double(), wp.permute(2, 3, 1, 0).cpu().double(), None, padding=1)
+    out = ops.conv3x3_nhwc_tf32(x.contiguous(memory_format=torch.channels_last), wp, round_tf32=True)
+    err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 5e-4, err
+    assert torch.equal(out, ops.round_tf32(out.contiguous()).contiguous(memory_format=torch.channels_last))
+
+
+def test_conv3x3_small():
+    """Direct fp32 kernel for the noAdaBins decoder's 1-channel conv3 (unet_adaptive_bins.py:78-80)."""
+    rng = np.random.default_rng(97)
+    for (b, c, h, w, cout) in [(2, 80, 24, 40, 1), (1, 16, 7, 9, 3)]:
+        x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+        wt = torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
+        bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+        ref = torch.nn.functional.conv2d(x, wt, bias, padding=1)
+        out = ops.conv3x3_small(x.to(DEV).contiguous(memory_format=torch.channels_last), wt.to(DEV), bias.to(DEV))
+        assert float((out.cpu() - ref).abs().max()) < 1e-5 * float(ref.abs().max()) + 1e-6
+
+
+def test_split_bf16_roundtrip():
+    """fp32 -> (hi, mid) bf16 planes -> fp32: 16 significant bits, NCHW and channels_last sources give the same pair."""
+    rng = np.random.default_rng(98)
+    for shape in [(2, 128, 16, 24), (1, 72, 5, 7), (3, 8, 9, 2)]:
+        x = torch.from_numpy((rng.standard_normal(shape) * 10 ** rng.uniform(-3, 3, shape)).astype(np.float32)).to(DEV)
+        p1 = ops.split_bf16(x)
+        p2 = ops.split_bf16(x.contiguous(memory_format=torch.channels_last))
+        assert torch.equal(p1.planes, p2.planes)
+        hi = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        assert torch.equal(p1.planes[0], hi)
+        assert torch.equal(p1.planes[1], (x.permute(0, 2, 3, 1) - hi.float()).to(torch.bfloat16))
+        back = p1.float()
+        assert back.is_contiguous(memory_format=torch.channels_last)
+        assert float(((back - x).abs() / x.abs()).max()) < 2.0 ** -16
 
 
 @pytest.mark.parametrize("cfg", [
@@ -278,23 +314,6 @@ def test_gemm_nt_tc(cfg):
     out = ops.gemm_nt(a.to(DEV), b.to(DEV), splits=cfg["splits"], alpha=0.5).cpu().double()
     err = float((out - 0.5 * ref).abs().max()) / float(ref.abs().max())
     assert err < 1e-3, err
-
-
-def test_conv3x3_cta_pair_matches_single(monkeypatch):
-    """The cta_group::2 form of the conv (opt-in via MDE_CONV_CTAS=2; pairs along x or y, odd tile counts) gives the
-    single-CTA kernel's outputs bit for bit (same MMA order per output tile)."""
-    rng = np.random.default_rng(92)
-    for (b, c, h, w, cout) in [(2, 128, 48, 64, 128), (1, 176, 40, 24, 80), (1, 96, 26, 34, 640), (1, 344, 13, 17, 160)]:
-        x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
-        wt = ops.prepare_conv3x3_weight(torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32)).to(DEV))
-        bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(DEV)
-        monkeypatch.delenv("MDE_CONV_CTAS", raising=False)
-        y1 = ops.conv3x3_nhwc(x, wt, None, bias, slope=0.01)
-        monkeypatch.setenv("MDE_CONV_CTAS", "2")
-        y2 = ops.conv3x3_nhwc(x, wt, None, bias, slope=0.01)
-        torch.cuda.synchronize()
-        assert torch.equal(y1, y2), (b, c, h, w, cout)
-    monkeypatch.delenv("MDE_CONV_CTAS", raising=False)
 
 
 def test_regressor_bins(golden):
@@ -337,7 +356,7 @@ def test_range_attention(impl):
     out = PixelWiseDotProduct(impl=impl)(x.to(DEV), q.to(DEV)).cpu()
     scale = float(ref.abs().max())
     err = float((out - ref).abs().max()) / scale
-    assert err < (1e-5 if impl == "simt" else 2e-3), err
+    assert err < (1e-5 if impl == "simt" else 3e-5), err
 
 
 def test_range_attention_simt_ragged():
@@ -361,7 +380,9 @@ def test_conv1x1():
 
 @pytest.mark.parametrize("fused", [True, False])
 def test_head_golden(fused, golden):
-    """mViT + conv_out + bins on the golden unet_out: reference-module outputs within 1e-3 relative."""
+    """mViT + conv_out + bins on the golden unet_out (logits of magnitude ~10): reference-module outputs within 1e-3
+    relative on every pixel, for the fused tcgen05 path (patch embedding, conv3x3 and chain on split-bf16 pairs) and for the
+    un-fused exact path."""
     m, _ = _head_state()
     m.to(DEV)
     m.fused_head = fused
@@ -369,22 +390,23 @@ def test_head_golden(fused, golden):
     with torch.no_grad():
         edges, pred = m._head(x)
     assert rel_err(edges.cpu(), golden["head/edges"]) < REL_DEPTH
-    assert_depth_close(pred.cpu(), golden["head/pred"], tf32=fused)
-
-
-def test_head_golden_tf32_conv(golden):
-    """Same as test_head_golden(fused) with the 3x3 conv on the tcgen05 implicit GEMM (TF32 inputs -- what the reference's
-    cuDNN conv does under PyTorch's default allow_tf32) in front of the TF32 chain."""
-    m, _ = _head_state()
-    m.to(DEV)
-    m.adaptive_bins_layer.conv3x3_impl = "tc"
-    x = synthetic.decoder_features(2, 128, 176, 192, seed=21).to(DEV)
-    with torch.no_grad():
-        edges, pred = m._head(x)
-    assert rel_err(edges.cpu(), golden["head/edges"]) < REL_DEPTH
     mx, p999 = rel_stats(pred.cpu(), golden["head/pred"])
-    print("tf32 conv + chain: max %.3e p99.9 %.3e" % (mx, p999))
-    assert_depth_close(pred.cpu(), golden["head/pred"], tf32=True)
+    print("head golden (fused=%s): pred max %.3e p99.9 %.3e" % (fused, mx, p999))
+    assert_depth_close(pred.cpu(), golden["head/pred"], tol=2e-4 if fused else REL_DEPTH)
+
+
+@pytest.mark.parametrize("scale", [1.5, 4.0])
+def test_head_large_logits(scale):
+    """The fused head against the fp32 oracle when the logits are large (|logit| up to ~40 / ~100: sharply peaked
+    softmax, the regime of a trained network) -- the case a single TF32 pass misses by 1e-2 (scripts/precision_study_head.py)."""
+    m, sd = _head_state()
+    x = synthetic.decoder_features(1, 128, 96, 128, seed=23, scale=scale)
+    with torch.no_grad():
+        e_ref, p_ref = oracle.head(x.double(), {k: v.double() for k, v in sd.items() if v.is_floating_point()}, 1e-3, 10.0)
+        m.to(DEV)
+        edges, pred = m._head(x.to(DEV))
+    assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
+    assert_depth_close(pred.cpu(), p_ref)
 
 
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
@@ -410,32 +432,13 @@ def test_head_chain_backward(layout):
     if layout == "nhwc":
         x = x.contiguous(memory_format=torch.channels_last)
     pred = ops.head_chain_autograd(x, dev_in[1], dev_in[2], dev_in[3], dev_in[4])
-    # random operands give logits of std ~8 here (the trained-shape golden case is ~3): TF32 forward error scales with it
-    assert rel_err(pred.detach().cpu(), pred_ref.detach().float()) < 1e-2
+    # random operands give logits of std ~8 here (the trained-shape golden case is ~3)
+    assert rel_err(pred.detach().cpu(), pred_ref.detach().float()) < REL_DEPTH
     (pred * g.to(DEV)).sum().backward()
     for name, a, r in zip(("feat", "queries", "w_out", "b_out", "centers"), dev_in, ref_in):
         ga, gr = a.grad.cpu().double(), r.grad
         err = float((ga - gr).abs().max()) / float(gr.abs().max())
         assert err < 5e-3, (name, err)
-
-
-def test_head_chain_cta_pair_matches_single(monkeypatch):
-    """The cta_group::2 form of the chain (two CTAs share one M = 256 MMA stream; opt-in via MDE_CHAIN_CTAS=2) computes
-    the same predictions as the default single-CTA kernel, in both operand layouts."""
-    rng = np.random.default_rng(96)
-    b, h, w = 3, 48, 64
-    feat = torch.from_numpy(rng.standard_normal((b, 128, h, w)).astype(np.float32)).to(DEV)
-    wf = ops.round_tf32(torch.from_numpy((rng.standard_normal((b, 256, 128)) * 0.1).astype(np.float32)).to(DEV))
-    biasf = torch.from_numpy(rng.standard_normal((b, 256)).astype(np.float32)).to(DEV)
-    centers = torch.sort(torch.from_numpy(rng.random((b, 256)).astype(np.float32) * 10), dim=1).values.to(DEV)
-    for x in (feat, feat.contiguous(memory_format=torch.channels_last)):
-        monkeypatch.delenv("MDE_CHAIN_CTAS", raising=False)
-        p1 = ops.head_chain(x, wf, biasf, centers)
-        monkeypatch.setenv("MDE_CHAIN_CTAS", "2")
-        p2 = ops.head_chain(x, wf, biasf, centers)
-        torch.cuda.synchronize()
-        assert float((p1 - p2).abs().max()) <= 1e-5 * float(p1.abs().max())
-    monkeypatch.delenv("MDE_CHAIN_CTAS", raising=False)
 
 
 def test_mvit_forward_surface(golden):
@@ -447,7 +450,7 @@ def test_mvit_forward_surface(golden):
     assert rel_err(widths.cpu(), golden["head/widths"]) < REL_DEPTH
     sub = ram[:, :, ::16, ::16].cpu().numpy()
     scale = np.abs(golden["head/ram_sub"]).max()
-    assert np.abs(sub - golden["head/ram_sub"]).max() / scale < 2e-3
+    assert np.abs(sub - golden["head/ram_sub"]).max() / scale < 1e-4
 
 
 def test_full_model_golden(golden):
@@ -457,11 +460,11 @@ def test_full_model_golden(golden):
     with torch.no_grad():
         edges, pred = m(x)
     assert rel_err(edges.cpu(), golden["full/edges"]) < REL_DEPTH
-    assert_depth_close(pred.cpu(), golden["full/pred"], tf32=True)
+    assert_depth_close(pred.cpu(), golden["full/pred"])
     m.fused_head = False
     with torch.no_grad():
         _, pred = m(x)
-    assert_depth_close(pred.cpu(), golden["full/pred"], tf32=False)
+    assert_depth_close(pred.cpu(), golden["full/pred"])
 
 
 @pytest.mark.parametrize("shape", [((2, 5, 15, 19), (2, 3, 26, 34)), ((1, 4, 13, 17), (1, 2, 27, 35)), ((2, 3, 8, 8), (2, 1, 8, 8))])
@@ -526,7 +529,7 @@ def test_channels_last_model_matches_nchw():
         e1, p1 = m1(x)
         e2, p2 = m2(x)
     assert rel_err(e2.cpu(), e1.cpu()) < 1e-4
-    assert_depth_close(p2.cpu(), p1.cpu(), tf32=True)
+    assert_depth_close(p2.cpu(), p1.cpu())
     # one training-mode forward/backward in each layout (stock BatchNorm with batch statistics, our NHWC / NCHW resize+concat)
     depth = synthetic.depth(2, 352, 384, seed=39).to(DEV)
     grads = []
@@ -551,20 +554,40 @@ def test_channels_last_model_matches_nchw():
         assert float((a - b).abs().max()) <= 5e-2 * float(a.abs().max()) + 1e-7
 
 
-def test_decoder_tc_vs_stock():
-    """(f)1 DecoderBN on our kernels (channels_last, tcgen05 conv3x3 with BatchNorm(eval)+LeakyReLU folded into the
-    epilogue) vs the stock torch modules in strict fp32 on the same encoder features."""
-    m = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None).to(DEV)
-    x = synthetic.image(2, 160, 192, seed=37).to(DEV)
+def test_decoder_tc_vs_oracle():
+    """(f)1 DecoderBN on our kernels (channels_last, resize + concat written as split-bf16 pairs, tcgen05 conv3x3 with
+    BatchNorm(eval) + LeakyReLU folded into the epilogue) vs the CPU oracle's decoder_bn (models/unet_adaptive_bins.py:39-100)
+    on the same encoder features; the stock torch modules (cuDNN) are checked alongside."""
+    m = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = synthetic.image(2, 160, 192, seed=37)
     with torch.no_grad():
-        feats = m.encoder(x)
-        m.decoder.conv_impl = "cudnn"
-        ref = m.decoder(feats)
-        m.decoder.conv_impl = "tc"
+        feats_cpu = oracle.encoder_features(m.encoder.original_model, x)
+        ref = oracle.decoder_bn(feats_cpu, sd)
+        m.to(DEV).channels_last_()
+        feats = [f.to(DEV).contiguous(memory_format=torch.channels_last) for f in feats_cpu]
         out = m.decoder(feats)
+        assert isinstance(out, ops.SplitBF16), "the tcgen05 decoder path did not run"
+        out = out.float()
+        m.decoder.conv_impl = "cudnn"
+        with ops.exact_fp32_library():
+            stock = m.decoder(feats)
     assert out.shape == ref.shape
-    err = float((out - ref).abs().max()) / float(ref.abs().max())
-    assert err < 2e-3, err
+    err = float((out.cpu() - ref).abs().max()) / float(ref.abs().max())
+    err_stock = float((stock.cpu() - ref).abs().max()) / float(ref.abs().max())
+    print("decoder vs oracle: ours %.3e  stock cuDNN fp32 %.3e" % (err, err_stock))
+    assert err < 5e-5, err
+
+
+def test_upsample_concat_nhwc_pair():
+    """The pair-writing form of the resize + concat step equals split_bf16 of the fp32 form, bit for bit."""
+    rng = np.random.default_rng(40)
+    for xs, ss in [((2, 8, 15, 19), (2, 16, 26, 34)), ((1, 64, 13, 17), (1, 8, 27, 35))]:
+        x = torch.from_numpy(rng.standard_normal(xs).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
+        skip = torch.from_numpy(rng.standard_normal(ss).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
+        ref = ops.split_bf16(ops.upsample_concat_nhwc(x, skip))
+        out = ops.upsample_concat_nhwc_pair(x, skip)
+        assert torch.equal(out.planes, ref.planes)
 
 
 def test_nchw_to_nhwc():
@@ -684,8 +707,8 @@ def test_full_size_properties():
         e1, p1 = m._head(x)
         m.fused_head = False
         e2, p2 = m._head(x)
-    assert rel_err(e1.cpu(), e2.cpu()) < REL_DEPTH  # the fused path embeds patches in TF32, the other in fp32
-    assert_depth_close(p1.cpu(), p2.cpu(), tf32=True)
+    assert rel_err(e1.cpu(), e2.cpu()) < 1e-5  # same patch embedding / transformer / regressor kernels on both paths
+    assert_depth_close(p1.cpu(), p2.cpu())
     assert float(p1.min()) >= 1e-3 and float(p1.max()) <= 10.0  # a convex combination of the bin centres
 
 
@@ -777,13 +800,14 @@ def test_config4_b5_head_vs_oracle():
                    instance_segmentation_mode=None).to(DEV)
     x = synthetic.image(1, 352, 384, seed=81).to(DEV)
     with torch.no_grad():
-        unet_out = m.decoder(m.encoder(x))
+        with ops.exact_fp32_library():
+            unet_out = _as_f32(m.decoder(m.encoder(x)))
         edges, pred = m(x)
     assert unet_out.shape == (1, 128, 176, 192) and pred.shape == (1, 1, 176, 192) and edges.shape == (1, 257)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     e_ref, p_ref = oracle.head(unet_out.cpu().contiguous(), sd, 1e-3, 10.0)
     assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
-    assert_depth_close(pred.cpu(), p_ref, tf32=True)
+    assert_depth_close(pred.cpu(), p_ref)
 
 
 def test_config5_noadabins_480x640():
@@ -792,10 +816,16 @@ def test_config5_noadabins_480x640():
                    instance_segmentation_mode=None).to(DEV)
     x = synthetic.image(2, 480, 640, seed=82).to(DEV)
     with torch.no_grad():
-        unet_out = m.decoder(m.encoder(x))
+        with ops.exact_fp32_library():
+            feats = m.encoder(x)
+            unet_out = m.decoder(feats)
         edges, pred = m(x)
     assert edges is None and pred.shape == (2, 1, 240, 320)
     assert np.array_equal(pred.cpu().numpy(), oracle.noadabins_epilogue(unet_out.cpu()).numpy())
+    # the decoder itself (tcgen05 convs + the direct 1-channel conv3) against the CPU oracle on the same encoder features
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = oracle.decoder_bn([f.cpu().contiguous() for f in feats], sd)
+    assert float((unet_out.cpu() - ref).abs().max()) < 5e-5 * float(ref.abs().max())
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -867,14 +897,15 @@ def test_before_attn_insertion_vs_oracle():
     _, sem = SemanticsLoader(Args(use_semantics=mode)).get_semantics({"semantics": lab})
     with torch.no_grad():
         edges, pred = m(x, semantics=sem)
-        unet_out = m.decoder(m.encoder(x))
+        with ops.exact_fp32_library():
+            unet_out = _as_f32(m.decoder(m.encoder(x)))
         small = torch.nn.functional.interpolate(sem, size=unet_out.shape[-2:], mode="nearest").float()
         cat = torch.cat((unet_out, small), dim=1)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     e_ref, p_ref = oracle.head(cat.cpu().contiguous(), sd, 1e-3, 10.0)
     assert pred.shape == (1, 1, 176, 192)
     assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
-    assert_depth_close(pred.cpu(), p_ref, tf32=True)
+    assert_depth_close(pred.cpu(), p_ref)
 
 
 def test_config3_full_path_vs_oracle_and_training_step():
@@ -905,7 +936,7 @@ def test_config3_full_path_vs_oracle_and_training_step():
         unet = oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, xin), sd)
         e_ref, p_ref = oracle.head(unet, sd, 1e-3, 10.0)
     assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
-    assert_depth_close(pred.cpu(), p_ref, tf32=True)
+    assert_depth_close(pred.cpu(), p_ref)
     # one training step: gradients reach the aux MLPs through the channels_last input concatenation
     depth = synthetic.depth(b, h, w, seed=90).to(DEV)
     m.train()
@@ -916,3 +947,50 @@ def test_config3_full_path_vs_oracle_and_training_step():
                  "adaptive_bins_layer.conv3x3.weight", "conv_out.0.weight"):
         g = dict(m.named_parameters())[name].grad
         assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0, name
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 2 at the benchmarked size, in the benchmarked mode
+# ------------------------------------------------------------------------------------------------------------
+def test_config2_full_size_bench_mode_vs_oracle():
+    """B = 16, 416 x 544, GloVe-25d ADE20K-places semantics at the input; channels_last model, PyTorch's default backend flags
+    (cudnn.allow_tf32 = True), the whole step (loader gather -> model -> SILog + chamfer) replayed as ONE CUDA graph
+    (graphs.GraphedStep) exactly as bench.py runs it -- against the CPU oracle of the whole reference path: `pred` and
+    `bin_edges` within 1e-3 relative on every pixel, both losses within 1e-4."""
+    from mde_biological_vision_systems_b200.graphs import GraphedStep
+    assert torch.backends.cudnn.allow_tf32, "this test must run under PyTorch's default flags (the mode bench.py measures)"
+    mode = "glove-25d-ade20k-places"
+    b, h, w = 16, 416, 544
+    cpu = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None)
+    sd = {k: v.detach().clone() for k, v in cpu.state_dict().items()}
+    img = synthetic.image(b, h, w, seed=0)
+    depth = synthetic.depth(b, h, w, seed=1)
+    lab, _ = synthetic.label_maps(b, h, w, seed=2)
+    table = load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy")
+    with torch.no_grad():
+        _, sem_ref = oracle.semantics_loader(mode, lab.numpy(), table)
+        xin = oracle.input_insertion(sd, img, mode, None, "rgb", semantics=torch.from_numpy(sem_ref))
+        e_ref, p_ref, l1_ref, l2_ref = oracle.forward_and_losses(
+            lambda t: oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, t), sd), sd, xin, depth, 1e-3, 10.0)
+    m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
+    loader = SemanticsLoader(Args(use_semantics=mode))
+    silog, chamfer = SILogLoss(), BinsChamferLoss()
+
+    def step(image, depth, semantics):
+        _, sem = loader.get_semantics({"semantics": semantics})
+        edges, pred = m(image, semantics=sem)
+        return edges, pred, silog(pred, depth, mask=depth > 1e-3, interpolate=True), chamfer(edges, depth)
+
+    resident = {"image": img.to(DEV), "depth": depth.to(DEV), "semantics": lab.to(DEV)}
+    l0 = ops.launch_count()
+    g = GraphedStep(step, resident)
+    assert ops.launch_count() > l0
+    edges, pred, l1, l2 = g(**resident)
+    torch.cuda.synchronize()
+    mx, p999 = rel_stats(pred.cpu(), p_ref)
+    print("config 2 full size, graph replay: pred max %.3e p99.9 %.3e  edges %.3e  silog %.6f/%.6f  chamfer %.6f/%.6f" % (
+        mx, p999, rel_err(edges.cpu(), e_ref), float(l1), float(l1_ref), float(l2), float(l2_ref)))
+    assert rel_err(edges.cpu(), e_ref) < REL_DEPTH
+    assert_depth_close(pred.cpu(), p_ref)
+    assert abs(float(l1) - float(l1_ref)) <= REL_LOSS * abs(float(l1_ref))
+    assert abs(float(l2) - float(l2_ref)) <= REL_LOSS * abs(float(l2_ref))
