@@ -370,6 +370,11 @@ int mde_bn_bwd_reduce_p2p_nhwc(const float* x, const float* dy, int64_t N, int C
 int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_t N, int C, const float* mean,
                               const float* invstd, const float* weight, uint64_t my_base, int64_t slot_off, int64_t flag_off,
                               int world, uint64_t epoch, double count, mde_stream_t stream);
+/* Bound of the peer-flag wait inside the *_p2p kernels (seconds, default 600: all ranks must enter every BatchNorm layer
+ * within it -- the role NCCL's collective timeout plays for the reference's nn.SyncBatchNorm, train.py:296).  The wait backs
+ * off with __nanosleep; on expiry the rank counts the event (mde_bn_peer_timeouts) and traps.  Both calls synchronise. */
+int mde_bn_set_peer_timeout_seconds(double seconds);
+int mde_bn_peer_timeouts(void);
 
 #ifdef __cplusplus
 }

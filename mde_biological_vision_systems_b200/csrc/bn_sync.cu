@@ -281,15 +281,36 @@ __device__ __forceinline__ void bn_publish_if_last(double* local, int C, const B
     st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x] + flag_off) + peers.rank, epoch);
 }
 
-// Wait until every rank's partial sums of this epoch have landed in MY arena.  Bounded (~60 s: ranks can be seconds apart
-// while cuDNN autotunes in the first steps), then trap rather than hang the box.
+// Wait until every rank's partial sums of this epoch have landed in MY arena.  All ranks must enter every BatchNorm layer
+// within the bound below (default 600 s -- the order of NCCL's own collective timeout; the reference would block in NCCL
+// for rank skew such as rank-0-only validation, train.py:459-499).  The wait backs off with __nanosleep; when the bound
+// expires the rank records the event in g_bn_peer_timeouts (mde_bn_peer_timeouts()) and traps -- the equivalent of the NCCL
+// watchdog aborting the process -- rather than normalising with missing statistics.
+static __device__ unsigned long long g_bn_timeout_ns = 600ULL * 1000000000ULL;
+static __device__ unsigned int g_bn_peer_timeouts = 0;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void bn_wait_peers(unsigned long long my_base, long long flag_off, int world,
                                               unsigned long long epoch) {
   if (threadIdx.x < world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(my_base + flag_off) + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < epoch) {
-      if (clock64() - t0 > 120000000000LL) asm volatile("trap;");
+    if (ld_acquire_sys(f) < epoch) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int backoff = 32;
+      while (ld_acquire_sys(f) < epoch) {
+        __nanosleep(backoff);
+        if (backoff < 4096) backoff *= 2;
+        if (globaltimer_ns() - t0 > g_bn_timeout_ns) {
+          atomicAdd(&g_bn_peer_timeouts, 1u);
+          __threadfence_system();
+          asm volatile("trap;");
+        }
+      }
     }
   }
   __syncthreads();
@@ -522,6 +543,20 @@ int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_
                                                                            slot_off, flag_off, world, epoch, count,
                                                                            bn_cl_log2(C));
   return check_launch();
+}
+
+// Bound of the peer-flag wait of the *_p2p kernels (seconds; default 600).  Synchronous (cudaMemcpyToSymbol).
+int mde_bn_set_peer_timeout_seconds(double seconds) {
+  if (!(seconds > 0.0)) return MDE_ERR_BAD_SHAPE;
+  const unsigned long long ns = (unsigned long long)(seconds * 1e9);
+  return cudaMemcpyToSymbol(g_bn_timeout_ns, &ns, sizeof(ns)) == cudaSuccess ? MDE_OK : MDE_ERR_LAUNCH;
+}
+
+// Number of peer-flag waits that expired on this device since load (each one trapped its kernel).  Synchronises.
+int mde_bn_peer_timeouts(void) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_bn_peer_timeouts, sizeof(v)) != cudaSuccess) return -1;
+  return (int)v;
 }
 
 }  // extern "C"

@@ -362,34 +362,45 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   if (C % in_align != 0 || Cout % out_align != 0 || !aligned(x, 16) || !aligned(w_prep, 16) || !aligned(y, 16))
     return MDE_ERR_UNSUPPORTED;
   // N tile: the whole C_out when it fits one instruction (<= 256, multiple of 16), else the largest divisor of C_out
-  // that is a multiple of 32 (so that 32-channel store groups never straddle two N tiles).  Measured on B200: choosing
+  // that is a multiple of 32 (so that 32-channel store groups never straddle two N tiles) -- the first candidate, in that
+  // order, whose stage (halo box + filter taps) fits the shared-memory ring at least twice.  Measured on B200: choosing
   // narrower tiles so that two stacked patches share the filter (C_out = 640 as 5 x 128, 320 as 5 x 64) was slower
   // (up1 + up2: 1.54 vs 1.37 ms).
-  int n_tile = 0;
-  if (Cout <= 256 && Cout % 16 == 0) {
-    n_tile = Cout;
-  } else {
-    for (int cand = 256; cand >= 32; cand -= 32)
-      if (Cout % cand == 0) {
-        n_tile = cand;
-        break;
-      }
-  }
+  const int rowb = X3 ? 64 : 128, planes = X3 ? 2 : 1;
+  const int budget = 222 * 1024 - 2 * tc::CV_STG_BYTES - 2048 - 512;
+  int forced = 0;
   {
     const char* force = getenv("MDE_CONV_NTILE");  // tuning aid
-    if (force && atoi(force) > 0 && Cout % atoi(force) == 0 && atoi(force) % 32 == 0 && atoi(force) <= 256) n_tile = atoi(force);
+    if (force && atoi(force) > 0 && Cout % atoi(force) == 0 && atoi(force) % 32 == 0 && atoi(force) <= 256) forced = atoi(force);
+  }
+  int n_tile = 0, nt = 0, tw = 0, stage_bytes = 0;
+  for (int pass = 0; pass < 9 && n_tile == 0; ++pass) {
+    int cand;
+    if (forced) {
+      if (pass > 0) break;
+      cand = forced;
+    } else if (pass == 0) {
+      if (!(Cout <= 256 && Cout % 16 == 0)) continue;
+      cand = Cout;
+    } else {
+      cand = 256 - 32 * (pass - 1);
+      if (Cout % cand != 0 || cand == Cout) continue;
+    }
+    const int cnt = (4 * cand <= 512) ? 2 : 1;
+    if (2 * cnt * cand + 16 > 512 && (cand % 32) != 0) continue;
+    // patch shape: 8 rows x 16 px or 16 rows x 8 px, whichever wastes fewer padded pixels
+    auto padded = [&](int w_) {
+      const int th_ = 128 / w_, sr_ = cnt * th_;
+      return (long long)((W + w_ - 1) / w_) * w_ * ((H + sr_ - 1) / sr_) * sr_;
+    };
+    const int ctw = padded(16) <= padded(8) ? 16 : 8;
+    const int csr = cnt * (128 / ctw);
+    const int sb = planes * (csr + 2) * ctw * rowb + planes * 3 * cand * rowb;
+    if (budget / sb < 2) continue;
+    n_tile = cand; nt = cnt; tw = ctw; stage_bytes = sb;
   }
   if (n_tile == 0) return MDE_ERR_UNSUPPORTED;
-  const int nt = (4 * n_tile <= 512) ? 2 : 1;
-  if (2 * nt * n_tile + 16 > 512 && (n_tile % 32) != 0) return MDE_ERR_UNSUPPORTED;
-  // patch shape: 8 rows x 16 px or 16 rows x 8 px, whichever wastes fewer padded pixels
-  auto padded = [&](int tw) {
-    const int th = 128 / tw, sr = nt * th;
-    return (long long)((W + tw - 1) / tw) * tw * ((H + sr - 1) / sr) * sr;
-  };
-  const int tw = padded(16) <= padded(8) ? 16 : 8;
   const int th = 128 / tw, sr = nt * th;
-  const int rowb = X3 ? 64 : 128, planes = X3 ? 2 : 1;
 
   tc::ConvGeom g;
   g.B = B; g.H = H; g.W = W; g.C = C; g.Cout = Cout;
@@ -403,11 +414,8 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   g.out_mode = out_mode;
   int cols = 2 * nt * n_tile + ((n_tile % 32) ? 16 : 0);
   g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  const int a_bytes = planes * (sr + 2) * tw * rowb, stage_bytes = a_bytes + planes * 3 * n_tile * rowb;
-  const int budget = 222 * 1024 - 2 * tc::CV_STG_BYTES - 2048 - 512;
   g.nstages = budget / stage_bytes;
   if (g.nstages > 6) g.nstages = 6;
-  if (g.nstages < 2) return MDE_ERR_UNSUPPORTED;
   const int smem = g.nstages * stage_bytes + 2 * tc::CV_STG_BYTES + 32 * g.nstages + 128 + 2048;
 
   CUtensorMap mx, mw, my;

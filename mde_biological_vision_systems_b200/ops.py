@@ -55,12 +55,14 @@ def launch_count():
 
 # Optional per-kernel CUDA-event timing (bench.py's roofline numbers are measured live with this, on the launching
 # stream): timing("head_chain") returns a context manager that records an event pair when enabled, else a no-op.
-_TIMING = {"on": False, "records": []}
+_TIMING = {"on": False, "records": [], "work": {}}
 
 
 class _Timed:
-    def __init__(self, name):
+    def __init__(self, name, work=None):
         self.name = name
+        if work is not None and _TIMING["on"]:
+            _TIMING["work"][name] = work
 
     def __enter__(self):
         if _TIMING["on"]:
@@ -76,13 +78,21 @@ class _Timed:
         return False
 
 
-def timing(name):
-    return _Timed(name)
+def timing(name, work=None):
+    """``work``: algorithmic work of the launch (FLOPs or bytes), recorded next to the name for the bench's roofline table."""
+    return _Timed(name, work)
 
 
 def enable_kernel_timing(on=True):
     _TIMING["on"] = bool(on)
     _TIMING["records"] = []
+    if on:
+        _TIMING["work"] = {}
+
+
+def kernel_work():
+    """name -> algorithmic work per launch recorded by timing(name, work=...) while kernel timing was enabled."""
+    return dict(_TIMING["work"])
 
 
 def kernel_times_ms():
@@ -493,7 +503,7 @@ def conv3x3_nhwc(x, w_prep, scale=None, shift=None, slope=1.0, pair_out=False, n
         out = torch.empty((2, b, h, w, cout), dtype=torch.bfloat16, device=x.device)
     else:
         out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-    with timing(name):
+    with timing(name, work=2.0 * b * h * w * cout * 9 * c):
         rc = lib.mde_conv3x3_nhwc_x3_fwd(_p(x.planes), _p(w_prep), _p(scale), _p(shift), _p(out), 1 if pair_out else 0, b, h, w,
                                          c, cout, float(slope), _s())
     _lib.check(rc, "mde_conv3x3_nhwc_x3_fwd")

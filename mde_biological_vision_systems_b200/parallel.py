@@ -3,10 +3,10 @@
 The forward path (loaders -> model -> SILog/chamfer) needs no collective: images are independent and the reference
 computes its loss per rank on the local shard (train.py:414-426).  The only exchanges of the *training* path are the
 gradient all-reduce that DistributedDataParallel performs (train.py:298-299) and SyncBatchNorm's statistics
-(train.py:296, stock torch module).  ``GradientAverager`` is that all-reduce: gradients are packed into flat buckets,
-summed with ``torch.distributed.all_reduce`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) and divided by
-the world size -- DDP's mean semantics -- bucket by bucket so the collective of one bucket overlaps the packing of the
-next.
+(train.py:296).  ``GradientAverager`` is that all-reduce: every gradient lives in a flat per-bucket arena, each bucket is
+summed in place with ``torch.distributed.all_reduce`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) as soon as
+autograd has filled it -- overlapped with the rest of the backward pass -- and divided by the world size (DDP's mean
+semantics); ``broadcast_module_state`` is DDP's construction-time parameter / buffer broadcast.
 """
 import os
 
@@ -44,48 +44,149 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
+def broadcast_module_state(module, src=0, group=None):
+    """What DistributedDataParallel does at construction (train.py:298-299): rank ``src``'s parameters and buffers overwrite
+    every other rank's, so replicas cannot silently start from different weights / BatchNorm statistics (different seeds,
+    per-rank checkpoints).  One coalesced broadcast per dtype."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    tensors = [p.data for p in module.parameters()] + [b for b in module.buffers()]
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault((t.dtype, t.device), []).append(t)
+    total = 0
+    for ts in by_dtype.values():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in ts:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view(t.shape))
+            off += n
+        total += off
+    return total
+
+
 class GradientAverager:
-    """Bucketed mean all-reduce of ``.grad`` over all ranks (the collective of the DDP training path)."""
+    """Bucketed mean all-reduce of the gradients over all ranks -- the collective DistributedDataParallel adds to the
+    training path (train.py:298-299) -- overlapped with the backward pass:
 
-    def __init__(self, params, bucket_mb=25.0):
+    * fixed layout: ALL trainable parameters, in reverse registration order (the order their gradients become ready: head ->
+      decoder -> encoder), are packed into buckets of ``bucket_mb``; every rank therefore issues the same collectives in the
+      same order whatever subset of parameters received a gradient (a parameter that got none contributes zeros, which is
+      what DDP's find_unused_parameters=True does in the reference);
+    * gradient arena: each bucket is ONE flat tensor and every ``p.grad`` is a view into it, so autograd accumulates straight
+      into the communication buffer -- no packing, no copy-back, the all-reduce is in place;
+    * overlap: a post-accumulate hook per parameter counts the bucket down and launches its asynchronous all-reduce the
+      moment the bucket is complete (in bucket order), while autograd is still producing the gradients of the layers below;
+      ``reduce()`` after backward only launches what is left, waits and scales by 1 / world.
+
+    Use ``zero_grad()`` of this object (one fill per bucket) instead of ``optimizer.zero_grad(set_to_none=True)``, which
+    would detach the views."""
+
+    def __init__(self, params, bucket_mb=25.0, group=None, overlap=True):
         self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.overlap = overlap
         self.bucket_elems = max(1, int(bucket_mb * 1024 * 1024 / 4))
-
-    def _buckets(self):
+        self.buckets = []   # dicts: params, flat, views, pending (per step), work
         cur, n = [], 0
-        for p in reversed(self.params):  # gradients become ready roughly in reverse registration order
-            if p.grad is None:
-                continue
+        for p in reversed(self.params):
             cur.append(p)
-            n += p.grad.numel()
+            n += p.numel()
             if n >= self.bucket_elems:
-                yield cur
+                self.buckets.append(self._make_bucket(cur))
                 cur, n = [], 0
         if cur:
-            yield cur
+            self.buckets.append(self._make_bucket(cur))
+        self._index = {}
+        for bi, bk in enumerate(self.buckets):
+            for p in bk["params"]:
+                self._index[p] = bi
+        self._next_launch = 0
+        self._hooks = []
+        self.exposed_wait_ms = None  # device-side time reduce() spent waiting for collectives (last call; needs CUDA)
+        if self._active() and overlap:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.attach()
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    @staticmethod
+    def _make_bucket(params):
+        dtype, device = params[0].dtype, params[0].device
+        total = sum(p.numel() for p in params)
+        return {"params": list(params), "flat": torch.zeros(total, dtype=dtype, device=device), "views": None, "pending": 0,
+                "work": None}
+
+    def attach(self):
+        """(Re-)point every p.grad at its slice of the bucket arena (memory order = the parameter's own: channels_last conv
+        weights keep channels_last gradients)."""
+        for bk in self.buckets:
+            off = 0
+            for p in bk["params"]:
+                n = p.numel()
+                view = bk["flat"][off:off + n]
+                if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                    g = view.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+                else:
+                    g = view.view(p.shape)
+                if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                    if p.grad is not None:  # constructed after a backward pass: keep what autograd already produced
+                        g.copy_(p.grad)
+                    p.grad = g
+                off += n
+            bk["pending"] = len(bk["params"])
+        self._next_launch = 0
+
+    def zero_grad(self):
+        for bk in self.buckets:
+            bk["flat"].zero_()
+            bk["work"] = None
+        self.attach()
+
+    def _launch_ready(self, force=False):
+        while self._next_launch < len(self.buckets):
+            bk = self.buckets[self._next_launch]
+            if bk["pending"] > 0 and not force:
+                break
+            bk["work"] = dist.all_reduce(bk["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._next_launch += 1
+
+    def _on_grad(self, p):
+        bk = self.buckets[self._index[p]]
+        bk["pending"] -= 1
+        if bk["pending"] == 0:
+            self._launch_ready()
 
     def reduce(self):
-        if not (dist.is_available() and dist.is_initialized()):
+        """Call after backward: launches the buckets that are still pending (parameters without a gradient this step), waits
+        for all collectives and turns the sums into means.  Returns the number of elements exchanged."""
+        if not self._active():
             return 0
-        world = dist.get_world_size()
-        if world == 1:
-            return 0
-        pending = []
-        for bucket in self._buckets():
-            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-            pending.append((bucket, flat, work))
+        world = dist.get_world_size(self.group)
+        cuda = self.buckets and self.buckets[0]["flat"].is_cuda
+        if cuda:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+        self._launch_ready(force=True)
         total = 0
-        for bucket, flat, work in pending:
-            work.wait()
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-            total += off
-        return total  # elements exchanged
+        for bk in self.buckets:
+            bk["work"].wait()
+            bk["flat"].div_(world)
+            bk["work"] = None
+            total += bk["flat"].numel()
+        if cuda:
+            t1.record()
+            self._wait_events = (t0, t1)
+        return total
+
+    def last_exposed_wait_ms(self):
+        """Device time between the end of backward and the last bucket's mean being ready (call after a synchronize)."""
+        ev = getattr(self, "_wait_events", None)
+        return None if ev is None else ev[0].elapsed_time(ev[1])
 
 
 # ---------------------------------------------------------------------------------------------------------------

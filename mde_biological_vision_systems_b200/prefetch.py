@@ -4,7 +4,8 @@ The reference moves every batch with blocking ``.to(device)`` / ``.cuda()`` call
 SemanticsLoader.py:122-143).  ``DevicePrefetcher`` copies batch i+1 from pinned host memory into a persistent device
 slot on its own CUDA stream while the kernels of batch i run, so the PCIe transfer (87 MB / step at config 2 with int64
 labels, 61 MB with the uint8 / int32 wire formats of label_io) is hidden behind compute.  Slots are allocated once and
-recycled (no allocator traffic in the loop); a slot is rewritten only after the consumer has moved two batches on.
+recycled (no allocator traffic in the loop); a slot is refilled as soon as the consumer moves on to the next batch, ordered
+behind everything the consumer stream had enqueued by then (a release event), so with 3 slots two copies are in flight.
 """
 import torch
 
@@ -32,15 +33,22 @@ class DevicePrefetcher:
         self.next_slot = (i + 1) % self.nslots
         slot = self.slots[i]
         out = {}
+        fresh = False
         for k, v in host.items():  # allocate (first use only) on the consumer's stream, outside the side-stream context
             if isinstance(v, torch.Tensor) and not v.is_cuda:
                 buf = slot.get(k)
                 if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    # (re)allocated from the consumer stream's pool: the caching allocator may hand back a block that kernels
+                    # already enqueued on the consumer stream still read (e.g. the previous, differently shaped buffer of a
+                    # ragged last batch) -- the copy stream must run behind them
                     buf = torch.empty(v.shape, dtype=v.dtype, device=self.device)
                     slot[k] = buf
+                    fresh = True
                 out[k] = buf
             else:
                 out[k] = v
+        if fresh:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             if self.free_evt[i] is not None:
                 self.stream.wait_event(self.free_evt[i])

@@ -35,6 +35,23 @@ def _worker(rank, world, port, tmp):
         torch.save([p.grad.clone() for p in model.parameters()], os.path.join(tmp, f"g{rank}.pt"))
         t = parallel.max_over_ranks(10.0 + rank)
         assert t == 10.0 + world - 1
+        # --- the overlapped form: averager built first (gradient arena + hooks), replicas start from DIFFERENT weights and
+        # are synchronised by broadcast_module_state; a parameter that is unused on one rank only still reduces (as zeros)
+        torch.manual_seed(100 + rank)
+        net = torch.nn.ModuleDict({"a": torch.nn.Linear(8, 16), "b": torch.nn.Linear(16, 1), "side": torch.nn.Linear(8, 1)})
+        parallel.broadcast_module_state(net)
+        torch.save({k: v.clone() for k, v in net.state_dict().items()}, os.path.join(tmp, f"w{rank}.pt"))
+        avg = parallel.GradientAverager(net.parameters(), bucket_mb=0.0001)
+        assert len(avg.buckets) > 1
+        for step in range(2):
+            avg.zero_grad()
+            out = net["b"](torch.relu(net["a"](data[idx])))
+            if rank == 0:  # 'side' gets a gradient on rank 0 only
+                out = out + net["side"](data[idx])
+            torch.nn.functional.mse_loss(out, target[idx]).backward()
+            avg.reduce()
+            assert all(p.grad is not None and p.grad.data_ptr() >= 0 for p in net.parameters())
+        torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(tmp, f"h{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -68,6 +85,27 @@ def test_gradient_mean_allreduce_world2(tmp_path):
     for a, b, x, y in zip(g0, g1, grads[0], grads[1]):
         torch.testing.assert_close(a, b)
         torch.testing.assert_close(a, (x + y) / 2)
+    # overlapped form: identical start weights on both ranks (rank 0's), identical averaged gradients, and the one-sided
+    # 'side' parameter averaged against zeros
+    w0, w1 = torch.load(os.path.join(tmp_path, "w0.pt")), torch.load(os.path.join(tmp_path, "w1.pt"))
+    assert all(torch.equal(w0[k], w1[k]) for k in w0)
+    h0, h1 = torch.load(os.path.join(tmp_path, "h0.pt")), torch.load(os.path.join(tmp_path, "h1.pt"))
+    assert all(torch.equal(h0[k], h1[k]) for k in h0)
+    net = torch.nn.ModuleDict({"a": torch.nn.Linear(8, 16), "b": torch.nn.Linear(16, 1), "side": torch.nn.Linear(8, 1)})
+    net.load_state_dict(w0)
+    ref = {k: torch.zeros_like(p) for k, p in net.named_parameters()}
+    for r in range(world):
+        net.zero_grad()
+        idx = parallel.shard_indices(10, r, world)
+        out = net["b"](torch.relu(net["a"](data[idx])))
+        if r == 0:
+            out = out + net["side"](data[idx])
+        torch.nn.functional.mse_loss(out, target[idx]).backward()
+        for k, p in net.named_parameters():
+            if p.grad is not None:
+                ref[k] += p.grad / world
+    for k in ref:
+        torch.testing.assert_close(h0[k], ref[k])
 
 
 def test_convert_sync_batchnorm_keeps_state_dict():
