@@ -305,8 +305,8 @@ def build_gpu(cfg, ctx):
 
 def infer_step_fn(cfg, model, sem_loader, inst_loader, dev):
     import torch
-    from mde_biological_vision_systems_b200.loss import BinsChamferLoss, SILogLoss
-    silog, chamfer = SILogLoss(), BinsChamferLoss()
+    from mde_biological_vision_systems_b200.loss import DepthLosses, SILogLoss
+    silog, both = SILogLoss(), DepthLosses(1e-3)
 
     def step(batch):
         with torch.no_grad():
@@ -319,9 +319,11 @@ def infer_step_fn(cfg, model, sem_loader, inst_loader, dev):
                 _, emb, areas = inst_loader.get_instance_segmentation(batch)
                 kwargs.update(instance_labels=emb, instance_areas=areas)
             edges, pred = model(img, **kwargs)
-            loss = silog(pred, depth, mask=depth > 1e-3, interpolate=True)
-            if edges is not None:
-                loss = loss + 0.1 * chamfer(edges, depth)
+            if edges is not None:  # train.py:414-419: SILog(mask = depth > min_depth) + 0.1 * chamfer, one pass over the depth map
+                l_dense, l_bins = both(pred, edges, depth, interpolate=True)
+                loss = l_dense + 0.1 * l_bins
+            else:
+                loss = silog(pred, depth, mask=depth > 1e-3, interpolate=True)
         return loss
 
     return step
@@ -405,8 +407,8 @@ def run_infer(cfg, ctx, steps, warmup, batch, detail=True):
     ops.enable_kernel_timing(False)
     # ---- hot path only (loaders + head + losses on a fixed decoder output), as ONE CUDA graph
     if "noAdaBins" not in cfg["encoder"] and cfg["insertion"] == "input":
-        from mde_biological_vision_systems_b200.loss import BinsChamferLoss, SILogLoss
-        silog, chamfer = SILogLoss(), BinsChamferLoss()
+        from mde_biological_vision_systems_b200.loss import DepthLosses
+        both = DepthLosses(1e-3)
         with torch.no_grad():
             kwargs = {}
             if sem_loader is not None:
@@ -428,7 +430,8 @@ def run_infer(cfg, ctx, steps, warmup, batch, detail=True):
                 if inst_loader is not None:
                     inst_loader.get_instance_segmentation(labels)
                 edges, pred = model._head(ops.SplitBF16(planes) if planes is not None else unet)
-                return silog(pred, depth, mask=depth > 1e-3, interpolate=True) + 0.1 * chamfer(edges, depth)
+                l_dense, l_bins = both(pred, edges, depth, interpolate=True)
+                return l_dense + 0.1 * l_bins
 
         try:
             ghot = GraphedStep(hot, {k: v for k, v in resident.items() if k != "image"})

@@ -297,8 +297,9 @@ int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B, int C, int
 
 /* ---- K4: SILog loss (loss.py:12-25).  pred [B,1,h,w] float32; target [B,1,H,W] float32; mask uint8/bool
  * [B,1,H,W] or NULL (all pixels); interpolate != 0: bilinear align_corners=True resampling of pred to HxW is
- * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (zeroed by the call; holds
- * {sum g, sum g^2, n} as float64 afterwards, which mde_silog_bwd reads).  loss: float32 scalar. */
+ * fused (never materialised).  ws: >= mde_silog_ws_bytes() bytes of scratch (holds {sum g, sum g^2, n} as float64
+ * afterwards, which mde_silog_bwd reads, followed by per-block partial sums).  loss: float32 scalar.  One launch, no host
+ * synchronisation, bit-reproducible (fixed summation order). */
 int64_t mde_silog_ws_bytes(void);
 int mde_silog_fwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W,
                   int interpolate, void* ws, float* loss, mde_stream_t stream);
@@ -307,14 +308,27 @@ int mde_silog_bwd(const float* pred, const float* target, const uint8_t* mask, i
                   int interpolate, const void* ws, const float* grad_loss, float* grad_pred, mde_stream_t stream);
 
 /* ---- K5: bin-centre chamfer loss (loss.py:33-46 -> pytorch3d.loss.chamfer_distance, K=1 squared L2 both ways,
- * point mean, batch mean; targets < 1e-3 dropped).  edges [B,n_bins+1] float32 ascending; target [B,HW] float32.
- * ws: >= mde_chamfer_ws_bytes(B,n_bins) bytes scratch (zeroed by the call; keeps per-image/per-centre statistics
- * for mde_chamfer_bwd).  loss: float32 scalar (NaN if an image has no valid target, like the reference's 0/0). */
+ * point mean, batch mean; targets < min_target dropped).  edges [B,n_bins+1] float32; target [B,HW] float32.
+ * The centres must be ascending (they are for any edges the model produces: bin widths are positive); the kernel checks
+ * and returns NaN for an unsorted centre vector rather than a silently wrong value.
+ * ws: >= mde_chamfer_ws_bytes(B,n_bins) bytes scratch (keeps per-image/per-centre statistics for mde_chamfer_bwd;
+ * those per-centre sums are only collected when want_grad != 0).  loss: float32 scalar (NaN if an image has no valid
+ * target, like the reference's 0/0). */
 int64_t mde_chamfer_ws_bytes(int B, int n_bins);
-int mde_chamfer_fwd(const float* edges, const float* target, int B, int n_bins, int64_t HW, float min_target,
+int mde_chamfer_fwd(const float* edges, const float* target, int B, int n_bins, int64_t HW, float min_target, int want_grad,
                     void* ws, float* loss, mde_stream_t stream);
 int mde_chamfer_bwd(const float* edges, int B, int n_bins, const void* ws, const float* grad_loss,
                     float* grad_edges, mde_stream_t stream);
+
+/* ---- K4 + K5 fused: both losses of train.py:414-419 in ONE pass over the target depth (the depth
+ * read is shared, 1.13 MB/img): SILog with mask = target > silog_min_depth (train.py:414) and chamfer over targets >=
+ * chamfer_min_target (loss.py:40).  Same scratch buffers and backward entry points as the separate forms; the SILog
+ * backward for the derived mask is mde_silog_bwd_thr. */
+int mde_depth_losses_fwd(const float* pred, const float* edges, const float* target, int B, int h, int w, int H, int W,
+                         int n_bins, int interpolate, float silog_min_depth, float chamfer_min_target, int want_grad,
+                         void* silog_ws, void* chamfer_ws, float* silog_loss, float* chamfer_loss, mde_stream_t stream);
+int mde_silog_bwd_thr(const float* pred, const float* target, float min_depth, int B, int h, int w, int H, int W,
+                      int interpolate, const void* ws, const float* grad_loss, float* grad_pred, mde_stream_t stream);
 
 /* ---- "next" row (f)2: evaluation epilogue + metrics (evaluate.py:50-71,128-152; train.py:543-568; utils.py:119-139).
  * pred [B,1,h,w] (bilinearly up-sampled to HxW with align_corners=True inside the kernel when h,w != H,W), gt [B,1,H,W];

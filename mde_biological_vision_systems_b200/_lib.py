@@ -89,7 +89,9 @@ SIGNATURES = {
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_silog_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "mde_chamfer_ws_bytes": (_i64, [_i32, _i32]),
-    "mde_chamfer_fwd": (_i32, [_p, _p, _i32, _i32, _i64, _f32, _p, _p, _p]),
+    "mde_chamfer_fwd": (_i32, [_p, _p, _i32, _i32, _i64, _f32, _i32, _p, _p, _p]),
+    "mde_depth_losses_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _p, _p, _p, _p, _p]),
+    "mde_silog_bwd_thr": (_i32, [_p, _p, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "mde_chamfer_bwd": (_i32, [_p, _i32, _i32, _p, _p, _p, _p]),
 }
 

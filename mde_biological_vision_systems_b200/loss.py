@@ -1,6 +1,9 @@
 """Drop-in for the reference's loss.py: SILogLoss and BinsChamferLoss with the same call signatures and ``.name``
 tags (/root/reference/loss.py:7-46), each running as ONE sm_100a kernel launch without host synchronisation
 (the reference needs boolean-mask gathers, ``len()`` and ``pad_sequence`` round trips plus pytorch3d's K-NN).
+
+``DepthLosses`` (an addition, not in the reference) evaluates both criteria of the reference's training loop
+(train.py:414-419) with ONE kernel that reads the target depth once.
 """
 import torch.nn as nn
 
@@ -27,3 +30,17 @@ class BinsChamferLoss(nn.Module):  # Bin centers regularizer used in AdaBins pap
         """Bidirectional squared-L2 chamfer distance between the bin centres of ``bins`` [N, n_bins+1] and the valid
         (>= 1e-3) depths of each image, point-mean then batch-mean (pytorch3d.loss.chamfer_distance defaults)."""
         return ops.bins_chamfer(bins, target_depth_maps, min_target=1e-3)
+
+
+class DepthLosses(nn.Module):
+    """(SILogLoss()(pred, depth, mask=depth > min_depth, interpolate=True), BinsChamferLoss()(bin_edges, depth)) -- exactly
+    the pair train.py:414-419 computes -- in one pass over ``depth`` (csrc/losses.cu, mde_depth_losses_fwd): the mask is
+    derived in registers, so neither the boolean mask tensor nor a second read of the depth map exists."""
+
+    def __init__(self, min_depth=1e-3):
+        super().__init__()
+        self.min_depth = min_depth
+        self.name = "SILog+ChamferLoss"
+
+    def forward(self, pred, bin_edges, depth, interpolate=True):
+        return ops.depth_losses(pred, bin_edges, depth, min_depth=self.min_depth, min_target=1e-3, interpolate=interpolate)

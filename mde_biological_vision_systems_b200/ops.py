@@ -1026,10 +1026,12 @@ class _Chamfer(torch.autograd.Function):
         lib = _lib.load()
         b, n1 = edges.shape
         hw = target.numel() // b
+        want_grad = bool(ctx.needs_input_grad[0])  # per-centre sums are only collected for the backward
         ws = torch.empty(int(lib.mde_chamfer_ws_bytes(b, n1 - 1)), dtype=torch.uint8, device=edges.device)
         loss = torch.empty((), dtype=torch.float32, device=edges.device)
         with timing("chamfer_fwd"):
-            rc = lib.mde_chamfer_fwd(_p(edges), _p(target), b, n1 - 1, hw, float(min_target), _p(ws), _p(loss), _s())
+            rc = lib.mde_chamfer_fwd(_p(edges), _p(target), b, n1 - 1, hw, float(min_target), 1 if want_grad else 0, _p(ws),
+                                     _p(loss), _s())
         _lib.check(rc, "mde_chamfer_fwd")
         ctx.save_for_backward(edges, ws)
         return loss
@@ -1050,6 +1052,59 @@ def bins_chamfer(edges, target_depth_maps, min_target=1e-3):
     if edges.dim() != 2 or target_depth_maps.shape[0] != edges.shape[0]:
         raise ValueError("bins_chamfer expects edges [B,n_bins+1] and targets [B,...]")
     return _Chamfer.apply(edges.contiguous().float(), target_depth_maps.contiguous().float(), min_target)
+
+
+class _DepthLosses(torch.autograd.Function):
+    """SILog (mask = target > min_depth) and bins-chamfer in one pass over the target (mde_depth_losses_fwd)."""
+
+    @staticmethod
+    def forward(ctx, pred, edges, target, min_depth, min_target, interpolate):
+        lib = _lib.load()
+        b, _, h, w = pred.shape
+        hh, ww = target.shape[-2:]
+        n1 = edges.shape[1]
+        want_grad = bool(ctx.needs_input_grad[1])
+        ws_s = torch.empty(int(lib.mde_silog_ws_bytes()), dtype=torch.uint8, device=pred.device)
+        ws_c = torch.empty(int(lib.mde_chamfer_ws_bytes(b, n1 - 1)), dtype=torch.uint8, device=pred.device)
+        out = torch.empty(2, dtype=torch.float32, device=pred.device)
+        with timing("loss_fused"):
+            rc = lib.mde_depth_losses_fwd(_p(pred), _p(edges), _p(target), b, h, w, hh, ww, n1 - 1, 1 if interpolate else 0,
+                                          float(min_depth), float(min_target), 1 if want_grad else 0, _p(ws_s), _p(ws_c),
+                                          _p(out[0:1]), _p(out[1:2]), _s())
+        _lib.check(rc, "mde_depth_losses_fwd")
+        ctx.save_for_backward(pred, edges, target, ws_s, ws_c)
+        ctx.cfg = (float(min_depth), bool(interpolate))
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_silog, g_chamfer):
+        lib = _lib.load()
+        pred, edges, target, ws_s, ws_c = ctx.saved_tensors
+        min_depth, interpolate = ctx.cfg
+        b, _, h, w = pred.shape
+        hh, ww = target.shape[-2:]
+        n1 = edges.shape[1]
+        gp = ge = None
+        if ctx.needs_input_grad[0]:
+            gp = torch.empty_like(pred)
+            rc = lib.mde_silog_bwd_thr(_p(pred), _p(target), min_depth, b, h, w, hh, ww, 1 if interpolate else 0, _p(ws_s),
+                                       _p(g_silog.contiguous().float()), _p(gp), _s())
+            _lib.check(rc, "mde_silog_bwd_thr")
+        if ctx.needs_input_grad[1]:
+            ge = torch.empty_like(edges)
+            rc = lib.mde_chamfer_bwd(_p(edges), b, n1 - 1, _p(ws_c), _p(g_chamfer.contiguous().float()), _p(ge), _s())
+            _lib.check(rc, "mde_chamfer_bwd")
+        return gp, ge, None, None, None, None
+
+
+def depth_losses(pred, edges, target, min_depth=1e-3, min_target=1e-3, interpolate=True):
+    """(SILogLoss(pred, target, mask=target > min_depth, interpolate), BinsChamferLoss(edges, target)) -- the two criteria of
+    the reference's training loop (train.py:414-419) -- from ONE kernel that reads the target once."""
+    _need_cuda(pred, edges, target)
+    if pred.dim() != 4 or pred.shape[1] != 1 or target.dim() != 4 or target.shape[1] != 1 or edges.dim() != 2:
+        raise ValueError("depth_losses expects pred [B,1,h,w], edges [B,n_bins+1] and target [B,1,H,W]")
+    return _DepthLosses.apply(pred.contiguous().float(), edges.contiguous().float(), target.contiguous().float(), min_depth,
+                              min_target, bool(interpolate))
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ not a re-implementation of train.py's logging / validation / checkpoint code (ou
 import torch
 import torch.nn as nn
 
-from .loss import BinsChamferLoss, SILogLoss
+from .loss import BinsChamferLoss, DepthLosses, SILogLoss
 from .parallel import GradientAverager, broadcast_module_state
 
 
@@ -30,6 +30,7 @@ class TrainStep:
         self.min_depth = min_depth
         self.criterion_ueff = SILogLoss()
         self.criterion_bins = BinsChamferLoss() if w_chamfer > 0 else None
+        self.criterion_fused = DepthLosses(min_depth) if w_chamfer > 0 else None  # both criteria, one pass over the depth map
         if same_lr:
             params = model.parameters()
         else:  # train.py:351-352
@@ -61,10 +62,12 @@ class TrainStep:
                 kwargs.update(instance_labels=emb, instance_areas=areas)
         with torch.autocast("cuda", dtype=self.autocast, enabled=self.autocast is not None):
             bin_edges, pred = self.model(img, **kwargs)
-            mask = depth > self.min_depth
-            loss = self.criterion_ueff(pred, depth, mask=mask.to(torch.bool), interpolate=True)
-            if self.criterion_bins is not None and bin_edges is not None:
-                loss = loss + self.w_chamfer * self.criterion_bins(bin_edges, depth)
+            if self.criterion_fused is not None and bin_edges is not None:
+                l_dense, l_chamfer = self.criterion_fused(pred, bin_edges, depth, interpolate=True)  # train.py:414-419
+                loss = l_dense + self.w_chamfer * l_chamfer
+            else:
+                mask = depth > self.min_depth
+                loss = self.criterion_ueff(pred, depth, mask=mask.to(torch.bool), interpolate=True)
         loss.backward()
         self.averager.reduce()
         nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)

@@ -13,7 +13,7 @@ from oracle import adabins_oracle as oracle
 from mde_biological_vision_systems_b200 import ops, synthetic
 from mde_biological_vision_systems_b200.ExternalInfoLoaders.InstanceSegmentationLoader import InstanceSegmentationLoader
 from mde_biological_vision_systems_b200.ExternalInfoLoaders.SemanticsLoader import SemanticsLoader
-from mde_biological_vision_systems_b200.loss import BinsChamferLoss, SILogLoss
+from mde_biological_vision_systems_b200.loss import BinsChamferLoss, DepthLosses, SILogLoss
 from mde_biological_vision_systems_b200.models.layers import PixelWiseDotProduct
 
 from helpers import INST_MODES, SEM_MODES, digest, inst_labels, load_table, make_model, rel_err, rel_stats, sem_labels
@@ -673,6 +673,47 @@ def test_chamfer_backward():
     np.testing.assert_allclose(e_dev.grad.cpu().numpy(), g_ref, rtol=2e-3, atol=2e-3 * np.abs(g_ref).max())
 
 
+def test_depth_losses_fused_matches_oracle_and_separate():
+    """The fused SILog + chamfer kernel (one pass over the depth map, masks derived in registers) against the oracle and the
+    two drop-in modules, forward and backward, incl. ragged sizes (HW % 4 != 0) and an image with very few valid pixels."""
+    rng = np.random.default_rng(120)
+    for (b, h, w, H, W) in [(3, 104, 136, 208, 272), (2, 13, 17, 27, 35), (1, 8, 8, 8, 8)]:
+        depth = synthetic.depth(b, H, W, seed=121 + H)
+        if b > 1:
+            depth[1, :, 2:, :] = 0.0  # image 1: only two rows of valid pixels
+        pred = torch.from_numpy((0.3 + 9 * rng.random((b, 1, h, w), dtype=np.float32)))
+        widths = torch.from_numpy(rng.random((b, 256)).astype(np.float32) + 0.05)
+        edges = torch.cat((torch.full((b, 1), 1e-3), 1e-3 + torch.cumsum(widths / widths.sum(1, keepdim=True) * 9.999, 1)), 1)
+        interp = (h, w) != (H, W)
+        p_ref, e_ref = pred.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+        s_ref = oracle.silog(p_ref, depth, mask=depth > 1e-3, interpolate=interp)
+        c_ref = oracle.bins_chamfer(e_ref, depth)
+        (s_ref + 0.1 * c_ref).backward()
+        pd, ed, dd = pred.to(DEV).requires_grad_(True), edges.to(DEV).requires_grad_(True), depth.to(DEV)
+        s, c = DepthLosses(1e-3)(pd, ed, dd, interpolate=interp)
+        assert abs(float(s) - float(s_ref)) <= REL_LOSS * abs(float(s_ref)), (float(s), float(s_ref))
+        assert abs(float(c) - float(c_ref)) <= REL_LOSS * abs(float(c_ref)), (float(c), float(c_ref))
+        (s + 0.1 * c).backward()
+        assert float((pd.grad.cpu() - p_ref.grad).abs().max()) <= 1e-3 * float(p_ref.grad.abs().max()) + 1e-9
+        assert float((ed.grad.cpu() - e_ref.grad).abs().max()) <= 1e-3 * float(e_ref.grad.abs().max()) + 1e-9
+        # the separate drop-in modules give the same numbers (same kernel, other template flags); bit-reproducible run to run
+        s2 = SILogLoss()(pred.to(DEV), dd, mask=dd > 1e-3, interpolate=interp)
+        c2 = BinsChamferLoss()(edges.to(DEV), dd)
+        assert abs(float(s2) - float(s)) <= 1e-6 * abs(float(s)) and abs(float(c2) - float(c)) <= 1e-6 * abs(float(c))
+        s3, c3 = DepthLosses(1e-3)(pred.to(DEV), edges.to(DEV), dd, interpolate=interp)
+        assert float(s3) == float(s) and float(c3) == float(c)
+
+
+def test_chamfer_unsorted_centres_is_nan_not_wrong():
+    """The kernel's nearest-neighbour search relies on ascending centres (always true for the model's edges); an unsorted
+    vector is detected on the device and reported as NaN instead of a silently wrong loss."""
+    depth = synthetic.depth(2, 32, 48, seed=130).to(DEV)
+    edges = torch.linspace(1e-3, 10, 257).repeat(2, 1)
+    assert torch.isfinite(BinsChamferLoss()(edges.to(DEV), depth))
+    edges[1, 100], edges[1, 140] = edges[1, 140].clone(), edges[1, 100].clone()
+    assert torch.isnan(BinsChamferLoss()(edges.to(DEV), depth))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # full-size properties (config 2: B = 16, 416 x 544, n_bins = 256)
 # ------------------------------------------------------------------------------------------------------------
@@ -977,12 +1018,13 @@ def test_config2_full_size_bench_mode_vs_oracle():
             lambda t: oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, t), sd), sd, xin, depth, 1e-3, 10.0)
     m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
     loader = SemanticsLoader(Args(use_semantics=mode))
-    silog, chamfer = SILogLoss(), BinsChamferLoss()
+    both = DepthLosses(1e-3)
 
     def step(image, depth, semantics):
         _, sem = loader.get_semantics({"semantics": semantics})
         edges, pred = m(image, semantics=sem)
-        return edges, pred, silog(pred, depth, mask=depth > 1e-3, interpolate=True), chamfer(edges, depth)
+        l_dense, l_bins = both(pred, edges, depth, interpolate=True)  # train.py:414-419, one pass over the depth map
+        return edges, pred, l_dense, l_bins
 
     resident = {"image": img.to(DEV), "depth": depth.to(DEV), "semantics": lab.to(DEV)}
     l0 = ops.launch_count()
