@@ -300,6 +300,8 @@ def build_gpu(cfg, ctx):
     model = UnetAdaptiveBins.build(**model_kwargs(cfg)).to(ctx.dev)
     sem_loader = SemanticsLoader(Namespace(use_semantics=cfg["sem"]), device=ctx.dev) if cfg["sem"] else None
     inst_loader = InstanceSegmentationLoader(Namespace(use_instance_segmentation=cfg["inst"]), device=ctx.dev) if cfg["inst"] else None
+    if sem_loader is not None:
+        sem_loader.bind_encoder_input(model)  # config 2: embeddings gathered straight into the NHWC encoder input
     return model, sem_loader, inst_loader
 
 

@@ -64,6 +64,14 @@ int mde_gather_embed_labels(const void* labels, int label_dtype, int64_t* labels
                             int64_t HW, int rows, int D, int background, int out_dtype, int64_t table_image_stride,
                             int32_t* oob_flag, mde_stream_t stream);
 
+/* The same clamp + gather written straight into channels [c0, c0+D) of a (spatially padded) channels_last tensor
+ * out_nhwc [B, Ho, Wo, pitch] at pixel (y + pad_top, x + pad_left): the embedding planes land where the encoder reads them
+ * (input insertion, models/unet_adaptive_bins.py:194-211), without the planar [B,D,H,W] tensor and its transpose.  fp32
+ * table [rows, D] (<= 48 KB), clamping mode only (0 <= background < rows); labels_out int64 [B*H*W] or NULL. */
+int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_out, const float* table, float* out_nhwc,
+                          int B, int H, int W, int rows, int D, int background, int pitch, int c0, int Ho, int Wo, int pad_top,
+                          int pad_left, mde_stream_t stream);
+
 /* Per-image class histogram -> per-image table of area fractions count/HW (float64), the gather table of
  * SemanticsLoader.get_semantics_inst_areas (SemanticsLoader.py:88-99).
  *   counts int32 [B, rows] workspace (zeroed by the call); frac float64 [B, rows] output. */
@@ -139,7 +147,7 @@ int mde_patch_embed_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const fl
  * mde_conv3x3_nhwc_fwd (single-pass TF32): x_nhwc fp32 whose values are already TF32-representable (rounded by their
  *   producer -- the tensor core would otherwise truncate them), w_prep = [dx][dy][Cout][C] TF32-rounded
  *   (mde_conv3x3_prep_weight, operand_scale normally 1.0f); round_tf32 != 0 rounds the outputs to TF32.  C % 4 == 0.
- * Both: Cout either <= 256 and a multiple of 16, or divisible by a multiple of 32 that is <= 256.
+ * Both: any such Cout (N tiles of <= 256 channels; the last tile may be ragged).
  * mde_conv3x3_small_nhwc_fwd: exact-fp32 direct kernel for Cout <= 4 (the noAdaBins decoder's conv3, :78-80);
  *   w_oihw is the torch-layout filter [Cout,C,3,3], bias may be NULL. */
 int mde_conv3x3_prep_weight(const float* w_oihw, float* w_prep, int Cout, int C, float operand_scale,
@@ -209,6 +217,17 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
  * impl 0 = SIMT fp32 (exact fp32 FMA); the tensor-core form is mde_range_attention_tc (split-bf16 pair operands). */
 int mde_range_attention(const float* x, const float* q, float* y, int B, int K, int N, int64_t P, int impl,
                         mde_stream_t stream);
+
+/* ---- training: weight gradient of the 3x3 convolutions (autograd of models/miniViT.py:16 and the DecoderBN convs,
+ * models/unet_adaptive_bins.py:39-49,73) on the NT GEMM above, ONE launch for the nine taps:
+ *   dW9[ky*3+kx][co][ci] = sum_k dyT[co][k] * xT[ci][k + (ky-1)*Wp + (kx-1)]
+ * with k over the zero-padded pixel axis (b, y+1, x+1), Wp = W+2, Kp = B*(H+2)*(W+2), row pitch ld (>= Kp, % 4 == 0).
+ * mde_nhwc_to_cpad_tf32 builds dyT / xT from NHWC fp32 tensors (channel-major, padded, TF32-rounded RNA, so that the
+ * tensor cores' operand read is exact).  splits > 1: split-K with atomic accumulation (dW9 zeroed by the call).
+ * The input gradient (dgrad) is mde_conv3x3_nhwc_x3_fwd on the spatially flipped, channel-transposed filter. */
+int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int64_t ld, mde_stream_t stream);
+int mde_conv3x3_wgrad_tf32(const float* dyT, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
+                           int splits, mde_stream_t stream);
 
 /* ---- K2: streaming bin pipeline  pred[b,p] = sum_j softmax_j(logits[b,:,p]) * centers[b,j]
  * (unet_adaptive_bins.py:286 Softmax(dim=1) and :298-300).  logits [B,n_bins,P], centers [B,n_bins], pred [B,P]. */

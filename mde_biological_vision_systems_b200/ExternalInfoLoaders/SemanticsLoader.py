@@ -42,6 +42,8 @@ class SemanticsLoader():
         # The reference clamps batch['semantics'] in place on the host (SemanticsLoader.py:117-118).  Here the clamp runs
         # on the GPU and the clamped map is what get_semantics returns; set this to also rewrite the caller's host tensor.
         self.clamp_host_batch = False
+        # bind_encoder_input(model): gather the embedding planes straight into the model's channels_last encoder input
+        self._bound = None
         self.set_semantics_path()
         self.set_human_sizes_path()
         self.load_word_embeddings()
@@ -96,6 +98,20 @@ class SemanticsLoader():
             self._dev_tables[key] = host.to(dtype).contiguous().to(self.device)
         return self._dev_tables[key]
 
+    def bind_encoder_input(self, model):
+        """Input-insertion fast path (models/unet_adaptive_bins.py:194-211): with a channels_last model whose only external
+        channel group is this loader's embedding (BASELINE config 2), get_semantics gathers straight into the encoder's NHWC
+        input buffer -- RGB slots and the stem's SAME padding included -- and returns the embedding tensor as a strided view
+        into it; UnetAdaptiveBins.forward recognises the view and only adds the image planes.  Values and shapes of the
+        returned tensors are unchanged; the planar [B,25,H,W] copy and its transpose (2 x 22.6 MB per image) disappear.
+        Returns True if the fast path applies."""
+        mode = self.args.use_semantics
+        ok = (mode is not None and "ade20k-places" in mode and "glove-25d" in mode and "human-sizes" not in mode
+              and "inst-areas" not in mode and getattr(model, "_channels_last", False) and model.insertion_point == "input"
+              and model.semantics_mode == mode and model.instance_segmentation_mode is None and model.image == "rgb")
+        self._bound = model if ok else None
+        return ok
+
     def get_semantics_inst_areas(self, semantics_raw):
         rows = self.word_embeddings_semantics.shape[0]
         return ops.class_area_fraction(semantics_raw, rows)
@@ -123,6 +139,11 @@ class SemanticsLoader():
                 raw = raw.clamp_(max=100)
                 raw[raw < 0] = 100
             semantics = ops.cast_i64_f32(raw)
+        elif self._bound is not None and places and raw.dtype == torch.int64:
+            table = self._table("emb", self.word_embeddings_semantics, torch.float32)
+            pads = self._bound.stem_pads(raw.shape[2], raw.shape[3])
+            buf, semantics = ops.gather_embed_nhwc(raw, table, 100, c_before=3, pads=pads, labels_out=raw)
+            semantics._mde_encoder_input = (buf, pads)  # recognised by UnetAdaptiveBins._concat_external
         else:
             # places tables are float32 on return (.float() at :128-129); the 150-class tables stay float64
             dtype = torch.float32 if places else torch.float64

@@ -21,6 +21,7 @@ SIGNATURES = {
     "mde_launch_count": (_i64, []),
     "mde_gather_embed": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     "mde_gather_embed_labels": (_i32, [_p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
+    "mde_gather_embed_nhwc": (_i32, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_class_area_table": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p]),
     "mde_cast_i64_f32": (_i32, [_p, _p, _i64, _p]),
     "mde_aux_mlp_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i64, _f32, _p]),
@@ -45,6 +46,8 @@ SIGNATURES = {
     "mde_gemm_nt_tf32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_gemm_nt_tf32_ex": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _p]),
     "mde_gemm_nt_tf32_planes": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _i64, _p]),
+    "mde_nhwc_to_cpad_tf32": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i64, _p]),
+    "mde_conv3x3_wgrad_tf32": (_i32, [_p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _p]),
     "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),
     "mde_encoder_layer_ws_floats": (_i64, [_i32, _i32, _i32, _i32]),

@@ -374,7 +374,7 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
     if (force && atoi(force) > 0 && Cout % atoi(force) == 0 && atoi(force) % 32 == 0 && atoi(force) <= 256) forced = atoi(force);
   }
   int n_tile = 0, nt = 0, tw = 0, stage_bytes = 0;
-  for (int pass = 0; pass < 9 && n_tile == 0; ++pass) {
+  for (int pass = 0; pass < 11 && n_tile == 0; ++pass) {
     int cand;
     if (forced) {
       if (pass > 0) break;
@@ -382,9 +382,14 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
     } else if (pass == 0) {
       if (!(Cout <= 256 && Cout % 16 == 0)) continue;
       cand = Cout;
-    } else {
+    } else if (pass <= 8) {
       cand = 256 - 32 * (pass - 1);
       if (Cout % cand != 0 || cand == Cout) continue;
+    } else {
+      // no exact tiling (e.g. the 1392 / 680 / 344 input widths of the decoder, which are the OUTPUT widths of the input-
+      // gradient convolutions): ragged last tile -- filter rows and output channels beyond C_out are the TMA's zero fill /
+      // store clipping
+      cand = pass == 9 ? 128 : 64;
     }
     const int cnt = (4 * cand <= 512) ? 2 : 1;
     if (2 * cnt * cand + 16 > 512 && (cand % 32) != 0) continue;
@@ -406,7 +411,7 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   g.B = B; g.H = H; g.W = W; g.C = C; g.Cout = Cout;
   g.tiles_x = (W + tw - 1) / tw;
   g.tiles_y = (H + sr - 1) / sr;
-  g.tiles_n = Cout / n_tile;
+  g.tiles_n = (Cout + n_tile - 1) / n_tile;
   g.total = g.tiles_x * g.tiles_y * g.tiles_n * B;
   g.chunks = (C + tc::CV_KC - 1) / tc::CV_KC;
   g.n_tile = n_tile;

@@ -34,6 +34,8 @@ struct GemmGeom {
   int act;                 // 0 none, 1 ReLU (not with split-K)
   int split_out;           // 1: write rows as [v | v - trunc_tf32(v) | v] (row pitch >= 3N): the A operand of a 3xTF32 GEMM
   long long plane_stride;  // > 0: K split s writes its partial product to C + s * plane_stride (no atomics; the consumer sums)
+  int tap_wp;              // > 0: the "batch" index is a 3x3 filter tap (ky, kx) = (z / 3, z % 3): both operands are the SAME
+                           // matrices for every tap and B is read at k + (ky - 1) * tap_wp + (kx - 1) (conv3x3 weight gradient)
 };
 
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -83,12 +85,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const int zb = g.tap_wp > 0 ? 0 : batch;
+      const int kb_off = g.tap_wp > 0 ? (batch / 3 - 1) * g.tap_wp + (batch % 3 - 1) : 0;  // out-of-range k: TMA zero fill
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1, 31);
         mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
         const uint32_t dst = base + stage * stage_bytes;
-        tma_load_3d(dst, &map_a, bar_full + 8 * stage, (c_begin + c) * GM_KC, m0, batch);
-        tma_load_3d(dst + A_BYTES, &map_b, bar_full + 8 * stage, (c_begin + c) * GM_KC, n0, batch);
+        tma_load_3d(dst, &map_a, bar_full + 8 * stage, (c_begin + c) * GM_KC, m0, zb);
+        tma_load_3d(dst + A_BYTES, &map_b, bar_full + 8 * stage, (c_begin + c) * GM_KC + kb_off, n0, zb);
         if (++stage == (uint32_t)g.nstages) {
           stage = 0;
           phase ^= 1;
@@ -209,9 +213,33 @@ int mde_gemm_nt_tf32_ex(const float* A, int64_t lda, int64_t a_batch, const floa
                                  split_out, 0, stream);
 }
 
+static int gemm_nt_launch(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
+                          float* C, int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                          const float* bias, int act, int split_out, int64_t plane_stride, int tap_wp, mde_stream_t stream);
+
 int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
                             float* C, int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
                             const float* bias, int act, int split_out, int64_t plane_stride, mde_stream_t stream) {
+  return gemm_nt_launch(A, lda, a_batch, B, ldb, b_batch, C, ldc, c_batch, batch, M, N, K, splits, alpha, bias, act, split_out,
+                        plane_stride, 0, stream);
+}
+
+// Weight gradient of a 3x3 / stride 1 / pad 1 convolution as ONE launch of the NT GEMM with the nine filter taps on the grid's
+// z axis:  dW9[ky*3+kx][co][ci] = sum_k dyT[co][k] * xT[ci][k + (ky-1)*Wp + (kx-1)],  k running over the zero-PADDED pixel
+// axis (b, y+1, x+1) of pitch Wp = W+2 (mde_nhwc_to_cpad_tf32 builds both operands, TF32-rounded): a tap is then a pure shift
+// of the K coordinate, borders included, and shifts that leave the matrix are the TMA's zero fill.
+int mde_conv3x3_wgrad_tf32(const float* dyT, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
+                           int splits, mde_stream_t stream) {
+  if (!dyT || !xT || !dW9) return MDE_ERR_BAD_POINTER;
+  if (Cout <= 0 || Cin <= 0 || Kp <= 0 || Kp > 0x7fffffffLL || ld < Kp || Wp < 3) return MDE_ERR_BAD_SHAPE;
+  if (splits > 1) cudaMemsetAsync(dW9, 0, sizeof(float) * 9 * (size_t)Cout * Cin, (cudaStream_t)stream);
+  return gemm_nt_launch(dyT, ld, 0, xT, ld, 0, dW9, Cin, (int64_t)Cout * Cin, 9, Cout, Cin, (int)Kp, splits, 1.0f, nullptr, 0, 0,
+                        0, Wp, stream);
+}
+
+static int gemm_nt_launch(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
+                          float* C, int64_t ldc, int64_t c_batch, int batch, int M, int N, int K, int splits, float alpha,
+                          const float* bias, int act, int split_out, int64_t plane_stride, int tap_wp, mde_stream_t stream) {
   if (!A || !B || !C) return MDE_ERR_BAD_POINTER;
   if (batch <= 0 || batch > 65535 || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || splits > 65535) return MDE_ERR_BAD_SHAPE;
   if (act < 0 || act > 1 || (splits > 1 && (act != 0 || split_out)) || (split_out && ldc < 3 * (int64_t)N)) return MDE_ERR_BAD_SHAPE;
@@ -244,6 +272,7 @@ int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const 
   g.bias = bias;
   g.act = act;
   g.split_out = split_out;
+  g.tap_wp = tap_wp;
   g.tmem_cols = g.tn <= 32 ? 32 : g.tn <= 64 ? 64 : g.tn <= 128 ? 128 : 256;
   const int stage_bytes = 128 * 128 + g.tn * 128;
   g.nstages = (184 * 1024) / stage_bytes;
@@ -255,14 +284,14 @@ int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const 
 
   CUtensorMap ma, mb;
   {
-    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)batch};
-    const uint64_t strides[2] = {(uint64_t)lda * 4, (uint64_t)(batch > 1 ? a_batch : lda * M) * 4};
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(tap_wp > 0 ? 1 : batch)};
+    const uint64_t strides[2] = {(uint64_t)lda * 4, (uint64_t)((batch > 1 && tap_wp == 0) ? a_batch : lda * M) * 4};
     const uint32_t box[3] = {(uint32_t)tc::GM_KC, 128, 1};
     if (!tc::encode_f32(&ma, A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)batch};
-    const uint64_t strides[2] = {(uint64_t)ldb * 4, (uint64_t)(batch > 1 ? b_batch : ldb * N) * 4};
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)(tap_wp > 0 ? 1 : batch)};
+    const uint64_t strides[2] = {(uint64_t)ldb * 4, (uint64_t)((batch > 1 && tap_wp == 0) ? b_batch : ldb * N) * 4};
     const uint32_t box[3] = {(uint32_t)tc::GM_KC, (uint32_t)g.tn, 1};
     if (!tc::encode_f32(&mb, B, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }

@@ -76,6 +76,38 @@ __global__ void __launch_bounds__(256) split_bf16_nchw_kernel(const float* __res
   }
 }
 
+// fp32 NHWC [B][H][W][C] -> channel-major, zero-PADDED, TF32-rounded out[c][(b*(H+2) + y+1)*(W+2) + x+1] with row pitch ld
+// (the K-major operands of mde_conv3x3_wgrad_tf32): 64 x 64 tile transpose over the padded pixel axis, pads written as 0.
+__global__ void __launch_bounds__(256) nhwc_to_cpad_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                                int H, int W, long long Kp, long long ld) {
+  __shared__ float tile[64][65];
+  const long long k0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int Wp = W + 2, Hp = H + 2;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {  // rows of the tile = padded pixels, columns = channels (contiguous in the source)
+    const long long k = k0 + ty + i * 4;
+    const int c = c0 + tx;
+    float v = 0.f;
+    if (k < Kp && c < C) {
+      const int xp = (int)(k % Wp);
+      const long long r = k / Wp;
+      const int yp = (int)(r % Hp);
+      const long long b = r / Hp;
+      if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) v = in[((b * H + (yp - 1)) * W + (xp - 1)) * C + c];
+    }
+    tile[ty + i * 4][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = c0 + ty + i * 4;
+    const long long k = k0 + tx;
+    if (c < C && k < ld) out[(long long)c * ld + k] = k < Kp ? tc::tf32_round(tile[tx][ty + i * 4]) : 0.f;
+  }
+}
+
 }  // namespace mde
 
 using namespace mde;
@@ -107,6 +139,15 @@ int mde_split_bf16_nchw(const float* x_nchw, uint16_t* planes_nhwc, int B, int C
   if (B <= 0 || C <= 0 || P <= 0 || B > 65535 || (C + 63) / 64 > 65535 || C % 2 != 0) return MDE_ERR_BAD_SHAPE;
   dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
   split_bf16_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, planes_nhwc, C, P, (long long)B * P * C);
+  return check_launch();
+}
+
+int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int64_t ld, mde_stream_t stream) {
+  if (!x_nhwc || !out) return MDE_ERR_BAD_POINTER;
+  const long long Kp = (long long)B * (H + 2) * (W + 2);
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || ld < Kp || ld % 4 != 0 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
+  dim3 grid((unsigned)((ld + 63) / 64), (unsigned)((C + 63) / 64));
+  nhwc_to_cpad_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, out, C, H, W, Kp, ld);
   return check_launch();
 }
 

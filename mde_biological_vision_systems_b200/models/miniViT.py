@@ -63,6 +63,8 @@ class mViT(nn.Module):
         if isinstance(x, ops.SplitBF16):
             x = x.float()
         if needs_grad:
+            if self.conv3x3_impl != "cudnn" and not torch.is_autocast_enabled() and ops.conv3x3_train_supported(x, c):
+                return tgt, ops.conv3x3_autograd(x, c.weight, None if bias_free else c.bias)  # fwd, dgrad, wgrad on our kernels
             return tgt, (torch.nn.functional.conv2d(x, c.weight, None, c.stride, c.padding) if bias_free else c(x))
         with ops.exact_fp32_library():
             if bias_free:

@@ -44,6 +44,7 @@ class UpSampleBN(nn.Module):
     def __init__(self, skip_input, output_features):
         super().__init__()
         self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
+        self.train_conv_impl = "tc"  # training / autograd: "tc" = our conv kernels (fwd, dgrad, wgrad); "cudnn" = stock modules
 
     def _folded(self):
         """Per conv block: ([dx][dy][Cout][C] split-bf16 filter, scale, shift, slope) with the eval-mode BatchNorm folded into
@@ -83,11 +84,26 @@ class UpSampleBN(nn.Module):
         y = ops.conv3x3_nhwc(y, w1, s1, b1, slope=a1, pair_out=True, name=name + ".conv_a")
         return ops.conv3x3_nhwc(y, w2, s2, b2, slope=a2, pair_out=pair_out, name=name + ".conv_b")
 
+    def _net_train(self, y):
+        """The block with its two 3x3 convolutions on our kernels (forward, dgrad, wgrad: ops.conv3x3_autograd); BatchNorm
+        (batch statistics; SyncBatchNorm2d kernels when converted) and LeakyReLU stay modules."""
+        for i in (0, 3):
+            conv = self._net[i]
+            if ops.conv3x3_train_supported(y, conv):
+                y = ops.conv3x3_autograd(y, conv.weight, conv.bias)
+            else:
+                y = conv(y)
+            y = self._net[i + 2](self._net[i + 1](y))
+        return y
+
     def forward(self, x, concat_with):
         if x.is_cuda:  # fused resize + concat kernel (ATen's align_corners bilinear kernel dominates the step otherwise)
             if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous() \
                     and x.shape[1] % 4 == 0 and concat_with.shape[1] % 4 == 0:
-                return self._net(ops.upsample_concat_nhwc(x, concat_with))  # channels_last model: stay in NHWC
+                y = ops.upsample_concat_nhwc(x, concat_with)  # channels_last model: stay in NHWC
+                if self.train_conv_impl == "tc" and y.dtype == torch.float32 and not torch.is_autocast_enabled():
+                    return self._net_train(y)
+                return self._net(y)
             return self._net(ops.upsample_concat(x, concat_with))
         raise ops._lib.MdeError("UpSampleBN runs on the B200 kernels only (no CPU path)")
 
@@ -150,6 +166,9 @@ class DecoderBN(nn.Module):
         y = self.conv2(bottleneck)
         for up, skip in ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0)):
             y = up(y, skip)
+        if self.up4.train_conv_impl == "tc" and not torch.is_autocast_enabled() and y.is_cuda \
+                and y.is_contiguous(memory_format=torch.channels_last) and ops.conv3x3_train_supported(y, self.conv3):
+            return ops.conv3x3_autograd(y, self.conv3.weight, self.conv3.bias)
         return self.conv3(y)
 
 
@@ -233,6 +252,14 @@ class UnetAdaptiveBins(nn.Module):
         self._channels_last = True
         return self
 
+    def stem_pads(self, h, w):
+        """(top, bottom, left, right) zeros the TensorFlow-SAME stem convolution adds to an h x w input ((0, 0, 0, 0) for a
+        plain stem)."""
+        stem = getattr(self.encoder.original_model, "conv_stem", None)
+        if isinstance(stem, SamePadConv2d) and self.image != "none":
+            return tuple(int(v) for v in stem.same_pads(h, w))
+        return (0, 0, 0, 0)
+
     # ---- external-info insertion -------------------------------------------------------------------------------
     @staticmethod
     def _run_mlp(seq, x, in_div, out):
@@ -267,6 +294,16 @@ class UnetAdaptiveBins(nn.Module):
         only by the channels_last fast path (callers detect it by the grown spatial size)."""
         if not items:
             return x
+        bound = getattr(items[0][1], "_mde_encoder_input", None) if len(items) == 1 and items[0][0] == "copy" else None
+        if bound is not None and getattr(self, "_channels_last", False) and x.is_cuda \
+                and not (torch.is_grad_enabled() and x.requires_grad):
+            # the loader gathered the embedding planes straight into the encoder's NHWC input (SemanticsLoader.
+            # bind_encoder_input): only the image planes are missing
+            buf, bpads = bound
+            want = (0, 0, 0, 0) if pads is None else tuple(int(v) for v in pads)
+            if tuple(bpads) == want and buf.shape[1] == x.shape[1] + items[0][1].shape[1] \
+                    and buf.shape[0] == x.shape[0] and buf.shape[2] == x.shape[2] + want[0] + want[1]:
+                return ops.fill_channels_nhwc(buf, x, 0, want)
         if getattr(self, "_channels_last", False) and x.is_cuda and all(it[0] == "copy" for it in items) \
                 and not (torch.is_grad_enabled() and x.requires_grad):
             # channels_last model, pass-through groups only (config 2): the planar sources are transposed straight into

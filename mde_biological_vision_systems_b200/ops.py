@@ -219,6 +219,56 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
     return out
 
 
+def gather_embed_nhwc(labels, table, background, c_before, c_after=0, pads=(0, 0, 0, 0), labels_out=None):
+    """Clamp + gather straight into a channels_last buffer laid out like the encoder input: returns (buffer, view) where
+    ``buffer`` is a zero-bordered channels_last [B, c_before + D + c_after, H + top + bottom, W + left + right] fp32 tensor
+    whose channels [c_before, c_before + D) hold the embeddings, and ``view`` = the [B, D, H, W] embedding tensor the
+    reference's loader returns -- a strided view into the buffer (no planar copy exists).  The caller fills the other channels
+    (ops.fill_channels_nhwc) and feeds ``buffer`` to the encoder."""
+    lib = _lib.load()
+    _need_cuda(labels, table)
+    if labels.dtype not in _LABEL_DTYPES or labels.dim() != 4 or labels.shape[1] != 1 or not labels.is_contiguous():
+        raise ValueError("labels must be a contiguous int64 / int32 / uint8 [B,1,H,W] tensor")
+    if table.dtype != torch.float32 or not table.is_contiguous():
+        raise ValueError("gather_embed_nhwc takes a contiguous float32 table")
+    b, _, h, w = labels.shape
+    rows, d = table.shape
+    pt, pb, pl, pr = (int(v) for v in pads)
+    ho, wo, pitch = h + pt + pb, w + pl + pr, c_before + d + c_after
+    buf = torch.empty((b, pitch, ho, wo), dtype=torch.float32, device=labels.device, memory_format=torch.channels_last)
+    if pt:
+        buf[:, :, :pt].zero_()
+    if pb:
+        buf[:, :, h + pt:].zero_()
+    if pl:
+        buf[:, :, :, :pl].zero_()
+    if pr:
+        buf[:, :, :, w + pl:].zero_()
+    with timing("gather_embed", work=float(b * h * w * (labels.element_size() + 4 * d))):
+        rc = lib.mde_gather_embed_nhwc(_p(labels), _LABEL_DTYPES[labels.dtype], _p(labels_out), _p(table), _p(buf), b, h, w, rows,
+                                       d, int(background), pitch, c_before, ho, wo, pt, pl, _s())
+    _lib.check(rc, "mde_gather_embed_nhwc")
+    view = buf[:, c_before:c_before + d, pt:pt + h, pl:pl + w]
+    return buf, view
+
+
+def fill_channels_nhwc(buf, src, c0, pads=(0, 0, 0, 0)):
+    """Write the NCHW-contiguous fp32 ``src`` [B,C,H,W] into channels [c0, c0 + C) of the (padded) channels_last ``buf``."""
+    lib = _lib.load()
+    src = _f32(src).contiguous()
+    b, c, h, w = src.shape
+    pt, pb, pl, pr = (int(v) for v in pads)
+    ctot = buf.shape[1]
+    dst = ctypes.c_void_p(buf.data_ptr() + 4 * c0)
+    with timing("nchw_to_nhwc"):
+        if pt or pb or pl or pr:
+            rc = lib.mde_nchw_to_nhwc_slice_padded(_p(src), dst, b, c, h, w, ctot, pt, pb, pl, pr, _s())
+        else:
+            rc = lib.mde_nchw_to_nhwc_slice(_p(src), dst, b, c, h * w, ctot, _s())
+    _lib.check(rc, "mde_nchw_to_nhwc_slice")
+    return buf
+
+
 def class_area_fraction(labels, rows):
     """SemanticsLoader.get_semantics_inst_areas: float64 [B,1,H,W] of per-image class pixel fractions."""
     lib = _lib.load()
@@ -479,8 +529,7 @@ def prepare_conv3x3_weight_tf32(weight, operand_scale=1.0):
 
 
 def conv3x3_cout_ok(cout, pair_out=False):
-    n_ok = (cout <= 256 and cout % 16 == 0) or any(cout % c == 0 for c in range(32, 257, 32))
-    return bool(n_ok and cout % (8 if pair_out else 4) == 0)
+    return bool(cout >= 8 and cout % (8 if pair_out else 4) == 0)
 
 
 def conv3x3_supported(x, cout, pair_out=False):
@@ -525,6 +574,71 @@ def conv3x3_nhwc_tf32(x_cl, w_prep, scale=None, shift=None, slope=1.0, round_tf3
                                       1 if round_tf32 else 0, _s())
     _lib.check(rc, "mde_conv3x3_nhwc_fwd")
     return out
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    """Training form of the 3x3 / stride 1 / pad 1 convolution on our kernels (autograd of models/miniViT.py:16 and the
+    DecoderBN convs, models/unet_adaptive_bins.py:39-49,73):
+      forward : tcgen05 implicit GEMM on split-bf16 pairs (three bf16 products per K step, as in inference);
+      dgrad   : the SAME kernel on the spatially flipped, channel-transposed filter applied to the output gradient;
+      wgrad   : ONE launch of the TF32 NT GEMM with the nine taps on the grid (mde_conv3x3_wgrad_tf32), both operands laid out
+                channel-major over the zero-padded pixel axis and TF32-rounded by a transpose kernel (split-K over pixels);
+      dbias   : a column sum (torch)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xp = split_bf16(x)
+        y = conv3x3_nhwc(xp, prepare_conv3x3_weight(weight), None, bias, name="conv3x3_train_fwd")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, weight = ctx.saved_tensors
+        gy = _f32(gy)
+        if not gy.is_contiguous(memory_format=torch.channels_last):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        b, c, h, w = x.shape
+        cout = weight.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().flip(2, 3).transpose(0, 1).contiguous()   # [C, Cout, 3, 3]
+            gx = conv3x3_nhwc(split_bf16(gy), prepare_conv3x3_weight(wt), name="conv3x3_dgrad")
+        if ctx.needs_input_grad[1]:
+            kp = b * (h + 2) * (w + 2)
+            ld = (kp + 3) // 4 * 4
+            x_cl = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+            xt = torch.empty((c, ld), dtype=torch.float32, device=x.device)
+            gt = torch.empty((cout, ld), dtype=torch.float32, device=x.device)
+            gw9 = torch.empty((9, cout, c), dtype=torch.float32, device=x.device)
+            with timing("conv3x3_wgrad", work=2.0 * b * h * w * cout * 9 * c):
+                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(x_cl), _p(xt), b, h, w, c, ld, _s()), "mde_nhwc_to_cpad_tf32")
+                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(gy), _p(gt), b, h, w, cout, ld, _s()), "mde_nhwc_to_cpad_tf32")
+                tiles = ((cout + 127) // 128) * max(1, (c + 255) // 256) * 9
+                splits = max(1, min(64, (2 * NUM_SMS) // tiles, kp // 4096))
+                rc = lib.mde_conv3x3_wgrad_tf32(_p(gt), _p(xt), _p(gw9), cout, c, kp, ld, w + 2, splits, _s())
+            _lib.check(rc, "mde_conv3x3_wgrad_tf32")
+            gw = gw9.view(3, 3, cout, c).permute(2, 3, 0, 1).contiguous(memory_format=torch.channels_last) \
+                if weight.is_contiguous(memory_format=torch.channels_last) and not weight.is_contiguous() \
+                else gw9.view(3, 3, cout, c).permute(2, 3, 0, 1).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(dim=(0, 2, 3))
+        return gx, gw, gb
+
+
+def conv3x3_train_supported(x, conv):
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+                and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and x.shape[1] % 8 == 0
+                and conv.out_channels % 8 == 0 and conv3x3_cout_ok(conv.out_channels) and conv3x3_cout_ok(x.shape[1]))
+
+
+def conv3x3_autograd(x, weight, bias=None):
+    """conv2d(x, weight, bias, padding=1) with forward, input gradient and weight gradient on the tcgen05 kernels; returns a
+    channels_last fp32 tensor."""
+    _need_cuda(x, weight)
+    return _Conv3x3Fn.apply(_f32(x), weight, bias)
 
 
 def conv3x3_small(x_cl, weight, bias=None):

@@ -89,6 +89,29 @@ def test_gather_full_size_and_ragged():
         assert np.array_equal(out.cpu().numpy(), oracle.gather_rows(t, lab.numpy()))
 
 
+def test_gather_into_encoder_input_matches_planar():
+    """SemanticsLoader.bind_encoder_input: the embedding planes gathered straight into the channels_last encoder input (with
+    the stem's SAME padding) are bit-identical to the planar gather, the returned tensors keep the reference's shapes, and the
+    model's output does not change by a bit."""
+    mode = "glove-25d-ade20k-places"
+    m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
+    lab, _ = sem_labels(mode, 2, 352, 384, seed=150, n_rect=(20, 40))
+    plain, bound = SemanticsLoader(Args(use_semantics=mode)), SemanticsLoader(Args(use_semantics=mode))
+    assert bound.bind_encoder_input(m)
+    raw1, sem1 = plain.get_semantics({"semantics": lab.clone()})
+    raw2, sem2 = bound.get_semantics({"semantics": lab.clone()})
+    assert sem2.shape == sem1.shape and torch.equal(sem2, sem1) and torch.equal(raw2, raw1)
+    assert hasattr(sem2, "_mde_encoder_input")
+    x = synthetic.image(2, 352, 384, seed=151).to(DEV)
+    with torch.no_grad():
+        e1, p1 = m(x, semantics=sem1)
+        e2, p2 = m(x, semantics=sem2)
+    assert torch.equal(p1, p2) and torch.equal(e1, e2)
+    # a loader bound to a model it does not fit declines
+    other = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None).to(DEV).channels_last_()
+    assert not SemanticsLoader(Args(use_semantics=mode)).bind_encoder_input(other)
+
+
 def test_gather_out_of_range_raises():
     lab = torch.zeros(1, 1, 8, 8, dtype=torch.int64)
     lab[0, 0, 3, 3] = 150
@@ -259,6 +282,40 @@ def test_conv3x3_tc(cfg):
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
     assert err < 5e-5, err
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 128, 24, 40), cout=128),                 # head conv
+    dict(shape=(2, 176, 20, 28), cout=80),                  # decoder up4 conv_a (C_in = 176: dgrad with a 176-wide output)
+    dict(shape=(1, 344, 13, 17), cout=160),                 # up3 conv_a: dgrad output width 344 (ragged N tiles)
+    dict(shape=(3, 80, 9, 11), cout=128, bias=False),       # conv3-like, bias-free
+])
+def test_conv3x3_autograd(cfg):
+    """Training form of the 3x3 conv (ops.conv3x3_autograd): forward on split-bf16 pairs, dgrad = the same kernel on the
+    flipped / transposed filter, wgrad = tap-shifted TF32 NT GEMM over the padded pixel axis -- vs float64 autograd of
+    F.conv2d (the reference's nn.Conv2d, models/miniViT.py:16, unet_adaptive_bins.py:43-48)."""
+    rng = np.random.default_rng(140)
+    b, c, h, w = cfg["shape"]
+    cout = cfg["cout"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)) if cfg.get("bias", True) else None
+    g = torch.from_numpy(rng.standard_normal((b, cout, h, w)).astype(np.float32))
+    xr, wr = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    br = bias.double().requires_grad_(True) if bias is not None else None
+    yr = torch.nn.functional.conv2d(xr, wr, br, padding=1)
+    yr.backward(g.double())
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wd = wt.to(DEV).requires_grad_(True)
+    bd = bias.to(DEV).requires_grad_(True) if bias is not None else None
+    conv = torch.nn.Conv2d(c, cout, 3, padding=1)
+    assert ops.conv3x3_train_supported(xd, conv)
+    y = ops.conv3x3_autograd(xd, wd, bd)
+    assert float((y.detach().cpu().double() - yr.detach()).abs().max()) < 5e-5 * float(yr.abs().max())
+    y.backward(g.to(DEV))
+    for name, a, r in (("x", xd.grad, xr.grad), ("w", wd.grad, wr.grad)) + ((("b", bd.grad, br.grad),) if bias is not None else ()):
+        err = float((a.cpu().double() - r).abs().max()) / float(r.abs().max())
+        assert err < (1e-4 if name == "x" else 2e-3), (name, err)
 
 
 def test_conv3x3_tf32_form():
@@ -1018,6 +1075,7 @@ def test_config2_full_size_bench_mode_vs_oracle():
             lambda t: oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, t), sd), sd, xin, depth, 1e-3, 10.0)
     m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
     loader = SemanticsLoader(Args(use_semantics=mode))
+    assert loader.bind_encoder_input(m)  # as bench.py: embeddings gathered straight into the NHWC encoder input
     both = DepthLosses(1e-3)
 
     def step(image, depth, semantics):
