@@ -388,6 +388,17 @@ def run_infer(cfg, ctx, steps, warmup, batch, detail=True):
         out["loss"] = got
     except Exception as exc:  # reported, never fatal: the eager numbers stand on their own
         out["graph_error"] = repr(exc)[:200]
+    if detail and "graph_ms" in out:
+        # the same graph with the cuDNN passthrough bodies left on the library default (TF32) -- reported alongside; the
+        # headline runs them in true fp32 (the tolerance contract is against the fp32 reference)
+        try:
+            model.backbone_tf32 = True
+            g2 = GraphedStep(lambda **kw: step(kw), resident)
+            out["tf32_backbone_ms"] = ctx.timed(lambda: g2(**resident), steps) / steps
+            del g2
+        except Exception as exc:  # noqa: BLE001
+            out["tf32_backbone_error"] = repr(exc)[:120]
+        model.backbone_tf32 = False
     out["ms"] = out.get("graph_ms", ms_eager)
     out["e2e_ms"] = out.get("e2e_graph_ms", out["e2e_eager_ms"])
     pix = ctx.world * batch * h * w
@@ -618,6 +629,9 @@ def run_ours(args):
             if "hot_ms" in r:
                 line["hot_path"] = {"what": "loaders + mViT head + bins + SILog + chamfer on a fixed decoder output, one CUDA graph",
                                     "ms_per_step": r["hot_ms"], "value": batch * h * w / (r["hot_ms"] * 1e-3) / 1e6, "unit": "Mpix/s per GPU"}
+            if "tf32_backbone_ms" in r:
+                line["tf32_backbone"] = {"value": pix / (r["tf32_backbone_ms"] * 1e-3) / 1e6, "ms_per_step": r["tf32_backbone_ms"],
+                                         "note": "cuDNN encoder / conv2 on the library's TF32 default instead of true fp32"}
             for k in ("graph_error", "hot_error", "a6_error"):
                 if k in r:
                     line[k] = r[k]

@@ -29,7 +29,7 @@
 
 namespace mde {
 
-constexpr int LS_THREADS = 256;
+constexpr int LS_THREADS = 512;
 constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_MAX_BLOCKS = MDE_NUM_SMS * 16;  // bound of blocks per launch (scratch sizing)
 constexpr unsigned int F_INF = 0x7f800000u;
@@ -58,9 +58,11 @@ struct ChamferWs {  // offsets into the caller's scratch buffer (nn_t, sum_t, cn
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Blocks per image: two 512-thread CTAs per SM over the whole batch.  More, smaller blocks stream no faster (the pass is
+// ~10 us of HBM time) but lengthen the finishing block's reduction over the per-block rows, which is the serial tail.
 inline int loss_blocks_per_image(int B, long long HW) {
-  long long bx = (HW / 4 + LS_THREADS * 2 - 1) / (LS_THREADS * 2);  // ~8 pixels per thread
-  const long long cap = (MDE_NUM_SMS * 8 + B - 1) / B;              // ~8 resident CTAs per SM
+  long long bx = (HW / 4 + LS_THREADS * 2 - 1) / (LS_THREADS * 2);  // >= 8 pixels per thread
+  const long long cap = (MDE_NUM_SMS * 2 + B - 1) / B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return (int)bx;
@@ -129,6 +131,7 @@ struct LossArgs {
   // chamfer
   const float* edges;           // [B][n+1]
   int n;
+  int search_step;              // largest power of two <= n
   float min_target;
   ChamferWs cw;
   float* chamfer_loss;
@@ -236,18 +239,21 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
       }
     }
     if (CHAMFER) {
+      // j = number of centres <= t (upper bound), interval j = [c_{j-1}, c_j): branch-free binary search, the four pixels of
+      // the group in lockstep so that their shared-memory loads overlap
+      int j4[4] = {0, 0, 0, 0};
+      for (int step = a.search_step; step > 0; step >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int probe = j4[i] + step;
+          if (probe <= n && sc[skew(probe - 1)] <= t4[i]) j4[i] = probe;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float t = t4[i];
         if (!(p0 + i < a.HW) || !(t >= a.min_target)) continue;  // loss.py:40  mask = target.ge(1e-3)
-        // j = number of centres <= t  (upper bound) ; interval j = [c_{j-1}, c_j)
-        int lo = 0, hi = n;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (sc[skew(mid)] <= t) lo = mid + 1;
-          else hi = mid;
-        }
-        const int j = lo;
+        const int j = j4[i];
         float best = INFINITY;
         int kbest = 0;
         if (j > 0) {
@@ -414,15 +420,22 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
       a.cw.nn_t[(long long)b * n + k] = tn;
       dx += (double)best;
     }
+    double psy = 0.0, pny = 0.0;
+    for (int i = threadIdx.x; i < bx; i += LS_THREADS) {
+      psy += __ldcg(a.cw.blk_part + ((long long)b * bx + i) * 2);
+      pny += __ldcg(a.cw.blk_part + ((long long)b * bx + i) * 2 + 1);
+    }
     dx = warp_sum(dx);
-    if (lane == 0) red[warp][0] = dx;
+    psy = warp_sum(psy);
+    pny = warp_sum(pny);
+    if (lane == 0) {
+      red[warp][0] = dx; red[warp][1] = psy; red[warp][2] = pny;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       double ax = 0.0, sy = 0.0, ny = 0.0;
-      for (int i = 0; i < LS_WARPS; ++i) ax += red[i][0];
-      for (int i = 0; i < bx; ++i) {
-        sy += __ldcg(a.cw.blk_part + ((long long)b * bx + i) * 2);
-        ny += __ldcg(a.cw.blk_part + ((long long)b * bx + i) * 2 + 1);
+      for (int i = 0; i < LS_WARPS; ++i) {
+        ax += red[i][0]; sy += red[i][1]; ny += red[i][2];
       }
       a.cw.n_y[b] = (unsigned long long)ny;
       a.cw.cham[2 * b + 0] = ax / (double)n;
@@ -587,6 +600,8 @@ int launch_losses(bool silog, bool chamfer, const float* pred, const float* targ
   size_t sm = 0;
   if (chamfer) {
     a.edges = edges; a.n = n_bins; a.min_target = min_target; a.chamfer_loss = chamfer_loss;
+    a.search_step = 1;
+    while (a.search_step * 2 <= n_bins) a.search_step *= 2;
     const size_t zero = chamfer_layout(chamfer_ws, B, n_bins, bx, &a.cw);
     cudaMemsetAsync(chamfer_ws, 0, zero, st);
     sm = chamfer_smem(n_bins, want_grad != 0);
