@@ -220,13 +220,16 @@ int mde_range_attention(const float* x, const float* q, float* y, int B, int K, 
 
 /* ---- training: weight gradient of the 3x3 convolutions (autograd of models/miniViT.py:16 and the DecoderBN convs,
  * models/unet_adaptive_bins.py:39-49,73) on the NT GEMM above, ONE launch for the nine taps:
- *   dW9[ky*3+kx][co][ci] = sum_k dyT[co][k] * xT[ci][k + (ky-1)*Wp + (kx-1)]
- * with k over the zero-padded pixel axis (b, y+1, x+1), Wp = W+2, Kp = B*(H+2)*(W+2), row pitch ld (>= Kp, % 4 == 0).
- * mde_nhwc_to_cpad_tf32 builds dyT / xT from NHWC fp32 tensors (channel-major, padded, TF32-rounded RNA, so that the
- * tensor cores' operand read is exact).  splits > 1: split-K with atomic accumulation (dW9 zeroed by the call).
+ *   dW9[ky*3+kx][co][ci] = sum_k dyT3[kx][co][k] * xT[ci][k + (ky-1)*Wp]
+ * with k over the zero-padded pixel axis (b, y+1, x+1) of pitch Wp (>= W+2, % 4 == 0), Kp = ld = B*(H+2)*Wp.
+ * mde_nhwc_to_cpad_tf32 builds the operands from NHWC fp32 tensors (channel-major, padded, TF32-rounded RNA so that the
+ * tensor cores' operand read is exact): xT [Cin][ld] with shift3 == 0, and dyT3 [3][Cout][ld] with shift3 != 0 -- three
+ * copies shifted by kx-1 along k, which bakes the horizontal tap into the data (the TMA cannot start a box at an
+ * unaligned element of the contiguous axis; the vertical tap is an aligned shift of its K coordinate).
+ * splits > 1: split-K with atomic accumulation (dW9 zeroed by the call).
  * The input gradient (dgrad) is mde_conv3x3_nhwc_x3_fwd on the spatially flipped, channel-transposed filter. */
-int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int64_t ld, mde_stream_t stream);
-int mde_conv3x3_wgrad_tf32(const float* dyT, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
+int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int Wp, int shift3, mde_stream_t stream);
+int mde_conv3x3_wgrad_tf32(const float* dyT3, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
                            int splits, mde_stream_t stream);
 
 /* ---- K2: streaming bin pipeline  pred[b,p] = sum_j softmax_j(logits[b,:,p]) * centers[b,j]

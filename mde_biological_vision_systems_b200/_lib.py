@@ -46,7 +46,7 @@ SIGNATURES = {
     "mde_gemm_nt_tf32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     "mde_gemm_nt_tf32_ex": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _p]),
     "mde_gemm_nt_tf32_planes": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _p, _i32, _i32, _i64, _p]),
-    "mde_nhwc_to_cpad_tf32": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i64, _p]),
+    "mde_nhwc_to_cpad_tf32": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_conv3x3_wgrad_tf32": (_i32, [_p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _p]),
     "mde_linear_fwd": (_i32, [_p, _i32, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_bins_finalize_fwd": (_i32, [_p, _i32, _i32, _i32, _f32, _f32, _p, _p, _p, _p]),

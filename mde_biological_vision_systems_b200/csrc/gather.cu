@@ -138,7 +138,7 @@ static int launch_gather(const void* labels, int64_t* labels_out, const void* ta
 // (pixel, d): a warp's 32 stores are consecutive addresses (25 floats of a pixel, then the next pixel's after the c0-wide
 // gap); labels are read once per pixel through L1.  Removes the planar [B,D,H,W] intermediate and its transpose
 // (2 x 22.6 MB/img at config 2).  fp32 tables in shared memory, clamping mode only.
-template <typename L>
+template <typename L, bool VEC>
 __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restrict__ labels, long long* labels_out,
                                                                  const float* __restrict__ table, float* __restrict__ out,
                                                                  int H, int W, int rows, int D, int background, int pitch,
@@ -152,15 +152,44 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
   const L* lab = labels + (long long)b * HW;
   long long* lab_out = labels_out ? labels_out + (long long)b * HW : nullptr;
   float* o = out + (long long)b * Ho * Wo * pitch;
-  const int total = HW * D;
   bool oob = false;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int p = i / D, d = i - p * D;
-    const long long raw = (long long)lab[p];
-    const int l = clamp_label(raw, rows, background, oob);
-    if (d == 0 && lab_out) lab_out[p] = l;
-    const int y = p / W, x = p - y * W;
-    o[((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch + c0 + d] = stab[l * D + d];
+  if (VEC) {
+    // pitch % 4 == 0 and 16-byte aligned rows: the D channels of a pixel are `head` leading scalars up to the next 16-byte
+    // boundary, then float4 groups, then `tail` scalars.  One thread per (pixel, piece): a warp's stores are consecutive
+    // 16-byte pieces of consecutive pixels.
+    const int head = (4 - (c0 & 3)) & 3;           // scalars before the first aligned float4
+    const int nvec = (D - head) >> 2;              // float4 groups
+    const int tail = D - head - 4 * nvec;
+    const int pieces = nvec + (head ? 1 : 0) + (tail ? 1 : 0);
+    const int total = HW * pieces;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int p = i / pieces, q = i - p * pieces;
+      const long long raw = (long long)lab[p];
+      const int l = clamp_label(raw, rows, background, oob);
+      if (q == 0 && lab_out) lab_out[p] = l;
+      const int y = p / W, x = p - y * W;
+      float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch + c0;
+      const float* row = stab + l * D;
+      const int qv = q - (head ? 1 : 0);
+      if (head && q == 0) {
+        for (int d = 0; d < head; ++d) dst[d] = row[d];
+      } else if (qv < nvec) {
+        const int d = head + 4 * qv;
+        *reinterpret_cast<float4*>(dst + d) = make_float4(row[d], row[d + 1], row[d + 2], row[d + 3]);
+      } else {
+        for (int d = head + 4 * nvec; d < D; ++d) dst[d] = row[d];
+      }
+    }
+  } else {
+    const int total = HW * D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int p = i / D, d = i - p * D;
+      const long long raw = (long long)lab[p];
+      const int l = clamp_label(raw, rows, background, oob);
+      if (d == 0 && lab_out) lab_out[p] = l;
+      const int y = p / W, x = p - y * W;
+      o[((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch + c0 + d] = stab[l * D + d];
+    }
   }
 }
 
@@ -304,17 +333,25 @@ int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_o
   if (background < 0 || background >= rows) return MDE_ERR_UNSUPPORTED;  // clamping mode only
   const size_t sm = (size_t)rows * D * sizeof(float);
   if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
-  long long gx = ((long long)H * W * D + 256 * 8 - 1) / (256 * 8);
+  long long gx = ((long long)H * W * ((D + 3) / 4 + 1) + 256 * 4 - 1) / (256 * 4);
   const long long cap = (MDE_NUM_SMS * 16 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-#define MDE_GN(LT) gather_embed_nhwc_kernel<LT><<<grid, 256, sm, st>>>(reinterpret_cast<const LT*>(labels), \
-    reinterpret_cast<long long*>(labels_out), table, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left)
-  if (label_dtype == MDE_I64) MDE_GN(long long);
-  else if (label_dtype == MDE_I32) MDE_GN(int);
-  else if (label_dtype == MDE_U8) MDE_GN(unsigned char);
+  const bool vec = (pitch % 4 == 0) && aligned(out_nhwc, 16) && D >= 8;
+#define MDE_GN(LT)                                                                                                     \
+  {                                                                                                                    \
+    if (vec)                                                                                                           \
+      gather_embed_nhwc_kernel<LT, true><<<grid, 256, sm, st>>>(reinterpret_cast<const LT*>(labels),                   \
+          reinterpret_cast<long long*>(labels_out), table, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
+    else                                                                                                               \
+      gather_embed_nhwc_kernel<LT, false><<<grid, 256, sm, st>>>(reinterpret_cast<const LT*>(labels),                  \
+          reinterpret_cast<long long*>(labels_out), table, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
+  }
+  if (label_dtype == MDE_I64) MDE_GN(long long)
+  else if (label_dtype == MDE_I32) MDE_GN(int)
+  else if (label_dtype == MDE_U8) MDE_GN(unsigned char)
   else return MDE_ERR_UNSUPPORTED;
 #undef MDE_GN
   return check_launch();

@@ -34,8 +34,9 @@ struct GemmGeom {
   int act;                 // 0 none, 1 ReLU (not with split-K)
   int split_out;           // 1: write rows as [v | v - trunc_tf32(v) | v] (row pitch >= 3N): the A operand of a 3xTF32 GEMM
   long long plane_stride;  // > 0: K split s writes its partial product to C + s * plane_stride (no atomics; the consumer sums)
-  int tap_wp;              // > 0: the "batch" index is a 3x3 filter tap (ky, kx) = (z / 3, z % 3): both operands are the SAME
-                           // matrices for every tap and B is read at k + (ky - 1) * tap_wp + (kx - 1) (conv3x3 weight gradient)
+  int tap_wp;              // > 0: the "batch" index is a 3x3 filter tap (ky, kx) = (z / 3, z % 3) of a conv3x3 weight gradient:
+                           // A is the kx-th of three pre-shifted copies of one matrix, B one matrix read at k + (ky - 1) * tap_wp
+                           // (tap_wp % 4 == 0: the TMA needs 16-byte aligned box starts along the contiguous axis)
 };
 
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
@@ -85,13 +86,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const int zb = g.tap_wp > 0 ? 0 : batch;
-      const int kb_off = g.tap_wp > 0 ? (batch / 3 - 1) * g.tap_wp + (batch % 3 - 1) : 0;  // out-of-range k: TMA zero fill
+      const int za = g.tap_wp > 0 ? batch % 3 : batch, zb = g.tap_wp > 0 ? 0 : batch;
+      const int kb_off = g.tap_wp > 0 ? (batch / 3 - 1) * g.tap_wp : 0;  // out-of-range k: TMA zero fill
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1, 31);
         mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
         const uint32_t dst = base + stage * stage_bytes;
-        tma_load_3d(dst, &map_a, bar_full + 8 * stage, (c_begin + c) * GM_KC, m0, zb);
+        tma_load_3d(dst, &map_a, bar_full + 8 * stage, (c_begin + c) * GM_KC, m0, za);
         tma_load_3d(dst + A_BYTES, &map_b, bar_full + 8 * stage, (c_begin + c) * GM_KC + kb_off, n0, zb);
         if (++stage == (uint32_t)g.nstages) {
           stage = 0;
@@ -225,16 +226,18 @@ int mde_gemm_nt_tf32_planes(const float* A, int64_t lda, int64_t a_batch, const 
 }
 
 // Weight gradient of a 3x3 / stride 1 / pad 1 convolution as ONE launch of the NT GEMM with the nine filter taps on the grid's
-// z axis:  dW9[ky*3+kx][co][ci] = sum_k dyT[co][k] * xT[ci][k + (ky-1)*Wp + (kx-1)],  k running over the zero-PADDED pixel
-// axis (b, y+1, x+1) of pitch Wp = W+2 (mde_nhwc_to_cpad_tf32 builds both operands, TF32-rounded): a tap is then a pure shift
-// of the K coordinate, borders included, and shifts that leave the matrix are the TMA's zero fill.
-int mde_conv3x3_wgrad_tf32(const float* dyT, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
+// z axis:  dW9[ky*3+kx][co][ci] = sum_k dyT3[kx][co][k] * xT[ci][k + (ky-1)*Wp],  k running over the zero-PADDED pixel axis
+// (b, y+1, x+1) of pitch Wp (>= W+2, a multiple of 4).  mde_nhwc_to_cpad_tf32 builds both operands (TF32-rounded): xT as is,
+// dyT3 as three copies shifted by kx-1 along k (dyT3[kx][co][k] = dy_pad[co][k - (kx-1)]), so that the horizontal tap is
+// baked into the data and the vertical tap is a 16-byte aligned shift of the TMA's K coordinate -- the TMA cannot start a
+// box at an unaligned element of the contiguous axis.  Shifts that leave the matrix are the TMA's zero fill.
+int mde_conv3x3_wgrad_tf32(const float* dyT3, const float* xT, float* dW9, int Cout, int Cin, int64_t Kp, int64_t ld, int Wp,
                            int splits, mde_stream_t stream) {
-  if (!dyT || !xT || !dW9) return MDE_ERR_BAD_POINTER;
-  if (Cout <= 0 || Cin <= 0 || Kp <= 0 || Kp > 0x7fffffffLL || ld < Kp || Wp < 3) return MDE_ERR_BAD_SHAPE;
+  if (!dyT3 || !xT || !dW9) return MDE_ERR_BAD_POINTER;
+  if (Cout <= 0 || Cin <= 0 || Kp <= 0 || Kp > 0x7fffffffLL || ld < Kp || Wp < 4 || Wp % 4 != 0) return MDE_ERR_BAD_SHAPE;
   if (splits > 1) cudaMemsetAsync(dW9, 0, sizeof(float) * 9 * (size_t)Cout * Cin, (cudaStream_t)stream);
-  return gemm_nt_launch(dyT, ld, 0, xT, ld, 0, dW9, Cin, (int64_t)Cout * Cin, 9, Cout, Cin, (int)Kp, splits, 1.0f, nullptr, 0, 0,
-                        0, Wp, stream);
+  return gemm_nt_launch(dyT3, ld, (int64_t)Cout * ld, xT, ld, 0, dW9, Cin, (int64_t)Cout * Cin, 9, Cout, Cin, (int)Kp, splits,
+                        1.0f, nullptr, 0, 0, 0, Wp, stream);
 }
 
 static int gemm_nt_launch(const float* A, int64_t lda, int64_t a_batch, const float* B, int64_t ldb, int64_t b_batch,
@@ -284,8 +287,8 @@ static int gemm_nt_launch(const float* A, int64_t lda, int64_t a_batch, const fl
 
   CUtensorMap ma, mb;
   {
-    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(tap_wp > 0 ? 1 : batch)};
-    const uint64_t strides[2] = {(uint64_t)lda * 4, (uint64_t)((batch > 1 && tap_wp == 0) ? a_batch : lda * M) * 4};
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, (uint64_t)(tap_wp > 0 ? 3 : batch)};
+    const uint64_t strides[2] = {(uint64_t)lda * 4, (uint64_t)(batch > 1 ? a_batch : lda * M) * 4};
     const uint32_t box[3] = {(uint32_t)tc::GM_KC, 128, 1};
     if (!tc::encode_f32(&ma, A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
   }

@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
     }
     if (SILOG) {
       int y = p0 / a.W, x = p0 - y * a.W;
+      int y0 = 0, y1 = 0;
+      float ly0 = 0.f, ly1 = 0.f;
+      bool row_ready = false;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool in = p0 + i < a.HW;
@@ -218,16 +221,21 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
         if (valid) {
           float v;
           if (INTERP) {
-            int y0, y1, x0, x1;
-            float ly0, ly1, lx0, lx1;
-            src_index(y, a.sy, a.h, y0, y1, ly0, ly1);
+            if (!row_ready) {  // the four pixels of a group share their row except across a row end
+              src_index(y, a.sy, a.h, y0, y1, ly0, ly1);
+              row_ready = true;
+            }
+            int x0, x1;
+            float lx0, lx1;
             src_index(x, a.sx, a.w, x0, x1, lx0, lx1);
             v = ly0 * (lx0 * __ldg(pb + y0 * a.w + x0) + lx1 * __ldg(pb + y0 * a.w + x1)) +
                 ly1 * (lx0 * __ldg(pb + y1 * a.w + x0) + lx1 * __ldg(pb + y1 * a.w + x1));
           } else {
             v = __ldg(pb + p0 + i);
           }
-          const float g = logf(v) - logf(t4[i]);
+          // log(v) - log(t) on the SFU (lg2.approx, ~2^-22 absolute in log2 units): the rounding of each pixel's term is far
+          // below the 1e-4 the loss is held to and unbiased over the ~10^6 pixels of the sum
+          const float g = (__log2f(v) - __log2f(t4[i])) * 0.6931471805599453f;
           s_g += g;
           s_gg = fmaf(g, g, s_gg);
           ++n_g;
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
         if (++x == a.W) {
           x = 0;
           ++y;
+          row_ready = false;
         }
       }
     }

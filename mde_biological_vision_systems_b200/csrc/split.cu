@@ -76,21 +76,24 @@ __global__ void __launch_bounds__(256) split_bf16_nchw_kernel(const float* __res
   }
 }
 
-// fp32 NHWC [B][H][W][C] -> channel-major, zero-PADDED, TF32-rounded out[c][(b*(H+2) + y+1)*(W+2) + x+1] with row pitch ld
-// (the K-major operands of mde_conv3x3_wgrad_tf32): 64 x 64 tile transpose over the padded pixel axis, pads written as 0.
+// fp32 NHWC [B][H][W][C] -> channel-major, zero-PADDED, TF32-rounded out[c][(b*(H+2) + y+1)*Wp + x+1] with row pitch
+// ld = B*(H+2)*Wp (the K-major operands of mde_conv3x3_wgrad_tf32; Wp >= W+2): 64 x 64 tile transpose over the padded pixel
+// axis, pads written as 0.  SHIFT3: three copies are written, copy s (0..2) shifted by s-1 along k (out3[s][c][k] =
+// pad[c][k - (s-1)]), i.e. the horizontal filter tap baked into the data.
+template <bool SHIFT3>
 __global__ void __launch_bounds__(256) nhwc_to_cpad_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                                                int H, int W, long long Kp, long long ld) {
+                                                                int H, int W, int Wp, long long ld) {
   __shared__ float tile[64][65];
   const long long k0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  const int Wp = W + 2, Hp = H + 2;
+  const int Hp = H + 2;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {  // rows of the tile = padded pixels, columns = channels (contiguous in the source)
     const long long k = k0 + ty + i * 4;
     const int c = c0 + tx;
     float v = 0.f;
-    if (k < Kp && c < C) {
+    if (k < ld && c < C) {
       const int xp = (int)(k % Wp);
       const long long r = k / Wp;
       const int yp = (int)(r % Hp);
@@ -104,7 +107,19 @@ __global__ void __launch_bounds__(256) nhwc_to_cpad_tf32_kernel(const float* __r
   for (int i = 0; i < 16; ++i) {
     const int c = c0 + ty + i * 4;
     const long long k = k0 + tx;
-    if (c < C && k < ld) out[(long long)c * ld + k] = k < Kp ? tc::tf32_round(tile[tx][ty + i * 4]) : 0.f;
+    if (c >= C || k >= ld) continue;
+    const float v = tc::tf32_round(tile[tx][ty + i * 4]);
+    if (!SHIFT3) {
+      out[(long long)c * ld + k] = v;
+    } else {
+      const long long plane = (long long)C * ld;
+      float* row = out + (long long)c * ld;
+      if (k >= 1) row[k - 1] = v;                       // copy 0: out3[0][c][k'] = pad[c][k' + 1]
+      row[plane + k] = v;                               // copy 1
+      if (k + 1 < ld) row[2 * plane + k + 1] = v;       // copy 2: out3[2][c][k'] = pad[c][k' - 1]
+      if (k == ld - 1) row[k] = 0.f;                    // the two elements no source position maps to
+      if (k == 0) row[2 * plane] = 0.f;
+    }
   }
 }
 
@@ -142,12 +157,14 @@ int mde_split_bf16_nchw(const float* x_nchw, uint16_t* planes_nhwc, int B, int C
   return check_launch();
 }
 
-int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int64_t ld, mde_stream_t stream) {
+int mde_nhwc_to_cpad_tf32(const float* x_nhwc, float* out, int B, int H, int W, int C, int Wp, int shift3,
+                          mde_stream_t stream) {
   if (!x_nhwc || !out) return MDE_ERR_BAD_POINTER;
-  const long long Kp = (long long)B * (H + 2) * (W + 2);
-  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || ld < Kp || ld % 4 != 0 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Wp < W + 2 || Wp % 4 != 0 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
+  const long long ld = (long long)B * (H + 2) * Wp;
   dim3 grid((unsigned)((ld + 63) / 64), (unsigned)((C + 63) / 64));
-  nhwc_to_cpad_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, out, C, H, W, Kp, ld);
+  if (shift3) nhwc_to_cpad_tf32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, out, C, H, W, Wp, ld);
+  else nhwc_to_cpad_tf32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nhwc, out, C, H, W, Wp, ld);
   return check_launch();
 }
 

@@ -607,18 +607,18 @@ class _Conv3x3Fn(torch.autograd.Function):
             wt = weight.detach().flip(2, 3).transpose(0, 1).contiguous()   # [C, Cout, 3, 3]
             gx = conv3x3_nhwc(split_bf16(gy), prepare_conv3x3_weight(wt), name="conv3x3_dgrad")
         if ctx.needs_input_grad[1]:
-            kp = b * (h + 2) * (w + 2)
-            ld = (kp + 3) // 4 * 4
+            wp = (w + 2 + 3) // 4 * 4           # padded row pitch: vertical taps become 16-byte aligned shifts
+            kp = b * (h + 2) * wp
             x_cl = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
-            xt = torch.empty((c, ld), dtype=torch.float32, device=x.device)
-            gt = torch.empty((cout, ld), dtype=torch.float32, device=x.device)
+            xt = torch.empty((c, kp), dtype=torch.float32, device=x.device)
+            gt3 = torch.empty((3, cout, kp), dtype=torch.float32, device=x.device)   # horizontal taps baked in
             gw9 = torch.empty((9, cout, c), dtype=torch.float32, device=x.device)
             with timing("conv3x3_wgrad", work=2.0 * b * h * w * cout * 9 * c):
-                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(x_cl), _p(xt), b, h, w, c, ld, _s()), "mde_nhwc_to_cpad_tf32")
-                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(gy), _p(gt), b, h, w, cout, ld, _s()), "mde_nhwc_to_cpad_tf32")
+                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(x_cl), _p(xt), b, h, w, c, wp, 0, _s()), "mde_nhwc_to_cpad_tf32")
+                _lib.check(lib.mde_nhwc_to_cpad_tf32(_p(gy), _p(gt3), b, h, w, cout, wp, 1, _s()), "mde_nhwc_to_cpad_tf32")
                 tiles = ((cout + 127) // 128) * max(1, (c + 255) // 256) * 9
                 splits = max(1, min(64, (2 * NUM_SMS) // tiles, kp // 4096))
-                rc = lib.mde_conv3x3_wgrad_tf32(_p(gt), _p(xt), _p(gw9), cout, c, kp, ld, w + 2, splits, _s())
+                rc = lib.mde_conv3x3_wgrad_tf32(_p(gt3), _p(xt), _p(gw9), cout, c, kp, kp, wp, splits, _s())
             _lib.check(rc, "mde_conv3x3_wgrad_tf32")
             gw = gw9.view(3, 3, cout, c).permute(2, 3, 0, 1).contiguous(memory_format=torch.channels_last) \
                 if weight.is_contiguous(memory_format=torch.channels_last) and not weight.is_contiguous() \

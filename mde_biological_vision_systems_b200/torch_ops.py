@@ -141,10 +141,11 @@ def silog_fwd(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor | Non
 
 @silog_fwd.register_fake
 def _(pred, target, mask, interpolate):
-    return pred.new_empty((), dtype=torch.float32), pred.new_empty((_SILOG_WS_BYTES,), dtype=torch.uint8)
+    return pred.new_empty((), dtype=torch.float32), pred.new_empty((_silog_ws_bytes(),), dtype=torch.uint8)
 
 
-_SILOG_WS_BYTES = 64 + 8 * 3 * 148 * 16  # mde_silog_ws_bytes(): SilogWs + per-block partials (csrc/losses.cu)
+def _silog_ws_bytes():
+    return int(_lib.load(check_device=False).mde_silog_ws_bytes())
 
 
 @custom_op("mde::silog_bwd", mutates_args=())
@@ -213,7 +214,7 @@ def _(pred, edges, target, min_depth, min_target, interpolate, want_edge_grad):
     b, n1 = edges.shape
     lib = _lib.load(check_device=False)
     return (pred.new_empty((), dtype=torch.float32), pred.new_empty((), dtype=torch.float32),
-            pred.new_empty((_SILOG_WS_BYTES,), dtype=torch.uint8),
+            pred.new_empty((_silog_ws_bytes(),), dtype=torch.uint8),
             pred.new_empty((int(lib.mde_chamfer_ws_bytes(b, n1 - 1)),), dtype=torch.uint8))
 
 

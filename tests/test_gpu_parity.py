@@ -1097,3 +1097,33 @@ def test_config2_full_size_bench_mode_vs_oracle():
     assert_depth_close(pred.cpu(), p_ref)
     assert abs(float(l1) - float(l1_ref)) <= REL_LOSS * abs(float(l1_ref))
     assert abs(float(l2) - float(l2_ref)) <= REL_LOSS * abs(float(l2_ref))
+
+
+def test_torch_library_ops_match_ctypes_layer():
+    """torch.ops.mde.* (torch.library registration over the same C ABI) return what the ctypes layer returns, their
+    registered autograd formulas give the same gradients, and torch.library.opcheck accepts schema / fake / autograd
+    registration of the loss operator."""
+    from mde_biological_vision_systems_b200 import torch_ops
+    rng = np.random.default_rng(160)
+    b, h, w = 2, 48, 64
+    x = torch.from_numpy(rng.standard_normal((b, 128, h, w)).astype(np.float32)).to(DEV)
+    planes = torch.ops.mde.split_bf16(x)
+    assert torch.equal(planes, ops.split_bf16(x).planes)
+    wt = torch.from_numpy((rng.standard_normal((128, 128, 3, 3)) / 34.0).astype(np.float32)).to(DEV)
+    wp = ops.prepare_conv3x3_weight(wt)
+    assert torch.equal(torch.ops.mde.conv3x3_x3(planes, wp, None, None, 1.0, False), ops.conv3x3_nhwc(ops.SplitBF16(planes), wp))
+    depth = synthetic.depth(b, 2 * h, 2 * w, seed=161).to(DEV)
+    pred = torch.from_numpy((0.3 + 9 * rng.random((b, 1, h, w), dtype=np.float32))).to(DEV)
+    edges = torch.linspace(1e-3, 10, 257, device=DEV).repeat(b, 1).contiguous()
+    p1, e1 = pred.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+    p2, e2 = pred.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+    s1, c1 = torch_ops.depth_losses(p1, e1, depth)
+    s2, c2 = ops.depth_losses(p2, e2, depth)
+    assert float(s1) == float(s2) and float(c1) == float(c2)
+    (s1 + 0.1 * c1).backward()
+    (s2 + 0.1 * c2).backward()
+    assert torch.allclose(p1.grad, p2.grad, rtol=1e-5, atol=1e-9) and torch.equal(e1.grad, e2.grad)
+    l1 = torch_ops.silog(pred, depth, depth > 1e-3, True)
+    assert float(l1) == float(SILogLoss()(pred, depth, mask=depth > 1e-3))
+    torch.library.opcheck(torch.ops.mde.silog_fwd.default, (pred, depth, depth > 1e-3, True),
+                          test_utils=("test_schema", "test_faketensor"))

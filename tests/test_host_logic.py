@@ -187,3 +187,36 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "BASELINE config 2" in line["config"]["workload"]
+
+
+def test_torch_library_ops_registered_with_fake_impls():
+    """torch.ops.mde.*: every hot-path operator is registered with torch.library (schema + fake implementation), so shapes
+    propagate under FakeTensorMode without a GPU; a real CPU tensor is rejected (there is no CPU implementation)."""
+    import pytest
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from mde_biological_vision_systems_b200 import _lib, torch_ops
+    for name in torch_ops.OPS:
+        assert hasattr(torch.ops.mde, name), name
+    with FakeTensorMode():
+        lab = torch.empty((2, 1, 32, 48), dtype=torch.int64, device="cuda")
+        table = torch.empty((101, 25), dtype=torch.float32, device="cuda")
+        assert torch.ops.mde.gather_embed(lab, table, 100).shape == (2, 25, 32, 48)
+        x = torch.empty((2, 128, 32, 48), device="cuda")
+        planes = torch.ops.mde.split_bf16(x)
+        assert planes.shape == (2, 2, 32, 48, 128) and planes.dtype == torch.bfloat16
+        w = torch.empty((2, 3, 3, 128, 128), dtype=torch.bfloat16, device="cuda")
+        y = torch.ops.mde.conv3x3_x3(planes, w, None, None, 1.0, False)
+        assert y.shape == (2, 128, 32, 48) and y.is_contiguous(memory_format=torch.channels_last)
+        assert torch.ops.mde.conv3x3_x3(planes, w, None, None, 1.0, True).shape == (2, 2, 32, 48, 128)
+        wq, bq = torch.ops.mde.fold_queries(torch.empty((256, 128, 1, 1), device="cuda"), torch.empty(256, device="cuda"),
+                                            torch.empty((2, 128, 128), device="cuda"), None)
+        assert wq.shape == (2, 2, 256, 128) and bq.shape == (2, 256)
+        pred = torch.ops.mde.head_chain(planes, wq, bq, torch.empty((2, 256), device="cuda"))
+        assert pred.shape == (2, 1, 32, 48)
+        depth = torch.empty((2, 1, 64, 96), device="cuda")
+        loss, ws = torch.ops.mde.silog_fwd(pred, depth, None, True)
+        assert loss.shape == () and ws.dtype == torch.uint8
+        s, c, _, _ = torch.ops.mde.depth_losses_fwd(pred, torch.empty((2, 257), device="cuda"), depth, 1e-3, 1e-3, True, False)
+        assert s.shape == () and c.shape == ()
+    with pytest.raises(_lib.MdeError):
+        torch.ops.mde.split_bf16(torch.zeros(1, 8, 4, 4))
