@@ -315,8 +315,8 @@ def infer_step_fn(cfg, model, sem_loader, inst_loader, dev):
             img = batch["image"].to(dev, non_blocking=True)
             depth = batch["depth"].to(dev, non_blocking=True)
             kwargs = {}
-            if sem_loader is not None:
-                kwargs["semantics"] = sem_loader.get_semantics(batch)[1]
+            if sem_loader is not None:  # the device image rides along: a bound loader writes it with the embeddings
+                kwargs["semantics"] = sem_loader.get_semantics(dict(batch, image=img))[1]
             if inst_loader is not None:
                 _, emb, areas = inst_loader.get_instance_segmentation(batch)
                 kwargs.update(instance_labels=emb, instance_areas=areas)

@@ -67,10 +67,12 @@ int mde_gather_embed_labels(const void* labels, int label_dtype, int64_t* labels
 /* The same clamp + gather written straight into channels [c0, c0+D) of a (spatially padded) channels_last tensor
  * out_nhwc [B, Ho, Wo, pitch] at pixel (y + pad_top, x + pad_left): the embedding planes land where the encoder reads them
  * (input insertion, models/unet_adaptive_bins.py:194-211), without the planar [B,D,H,W] tensor and its transpose.  fp32
- * table [rows, D] (<= 48 KB), clamping mode only (0 <= background < rows); labels_out int64 [B*H*W] or NULL. */
-int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_out, const float* table, float* out_nhwc,
-                          int B, int H, int W, int rows, int D, int background, int pitch, int c0, int Ho, int Wo, int pad_top,
-                          int pad_left, mde_stream_t stream);
+ * table [rows, D] (<= 48 KB), clamping mode only (0 <= background < rows); labels_out int64 [B*H*W] or NULL.
+ * image_nchw (optional, fp32 [B, c0, H, W], 1 <= c0 <= 3): the leading channels [0, c0) -- the RGB planes the reference
+ * concatenates in front (x = cat(x, semantics)) -- are written by the same pass, so the whole input row is one store stream. */
+int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_out, const float* table, const float* image_nchw,
+                          float* out_nhwc, int B, int H, int W, int rows, int D, int background, int pitch, int c0, int Ho,
+                          int Wo, int pad_top, int pad_left, mde_stream_t stream);
 
 /* Per-image class histogram -> per-image table of area fractions count/HW (float64), the gather table of
  * SemanticsLoader.get_semantics_inst_areas (SemanticsLoader.py:88-99).

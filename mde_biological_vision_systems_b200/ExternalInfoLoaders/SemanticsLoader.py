@@ -142,8 +142,14 @@ class SemanticsLoader():
         elif self._bound is not None and places and raw.dtype == torch.int64:
             table = self._table("emb", self.word_embeddings_semantics, torch.float32)
             pads = self._bound.stem_pads(raw.shape[2], raw.shape[3])
-            buf, semantics = ops.gather_embed_nhwc(raw, table, 100, c_before=3, pads=pads, labels_out=raw)
-            semantics._mde_encoder_input = (buf, pads)  # recognised by UnetAdaptiveBins._concat_external
+            # an image that is already on the device (resident batches, DevicePrefetcher) is written by the same kernel
+            img = batch.get("image") if isinstance(batch, dict) else None
+            if not (isinstance(img, torch.Tensor) and img.is_cuda and img.dtype == torch.float32 and img.dim() == 4
+                    and img.shape[1] == 3 and img.shape[0] == raw.shape[0] and img.shape[2:] == raw.shape[2:]):
+                img = None
+            buf, semantics = ops.gather_embed_nhwc(raw, table, 100, c_before=3, pads=pads, labels_out=raw, image=img)
+            # recognised by UnetAdaptiveBins._concat_external: (buffer, pads, the image tensor already written or None)
+            semantics._mde_encoder_input = (buf, pads, img)
         else:
             # places tables are float32 on return (.float() at :128-129); the 150-class tables stay float64
             dtype = torch.float32 if places else torch.float64

@@ -21,7 +21,7 @@ SIGNATURES = {
     "mde_launch_count": (_i64, []),
     "mde_gather_embed": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     "mde_gather_embed_labels": (_i32, [_p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
-    "mde_gather_embed_nhwc": (_i32, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_gather_embed_nhwc": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_class_area_table": (_i32, [_p, _i32, _i64, _i32, _p, _p, _p]),
     "mde_cast_i64_f32": (_i32, [_p, _p, _i64, _p]),
     "mde_aux_mlp_fwd": (_i32, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i64, _f32, _p]),

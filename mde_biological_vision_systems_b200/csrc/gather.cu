@@ -138,51 +138,63 @@ static int launch_gather(const void* labels, int64_t* labels_out, const void* ta
 // (pixel, d): a warp's 32 stores are consecutive addresses (25 floats of a pixel, then the next pixel's after the c0-wide
 // gap); labels are read once per pixel through L1.  Removes the planar [B,D,H,W] intermediate and its transpose
 // (2 x 22.6 MB/img at config 2).  fp32 tables in shared memory, clamping mode only.
+// VEC: pitch % 4 == 0: a pixel's [c0, c0+D) channels are `head` leading scalars up to the next 16-byte boundary, then
+// float4 groups, then `tail` scalars.  Thread layout (8, 32): threadIdx.x = piece (up to 8 pieces per pixel), threadIdx.y =
+// pixel of a 32-pixel run of one image row -- a warp covers 4 consecutive pixels, i.e. one contiguous span of the output;
+// no integer division per element.  With ``image`` (NCHW fp32 [B][c0][H][W], 1 <= c0 <= 3) the leading channels [0, c0) are
+// written by the same kernel (piece 0 becomes the float4 {img..., emb_0...}), so the whole encoder input row comes from
+// one pass.
 template <typename L, bool VEC>
 __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restrict__ labels, long long* labels_out,
-                                                                 const float* __restrict__ table, float* __restrict__ out,
+                                                                 const float* __restrict__ table,
+                                                                 const float* __restrict__ image, float* __restrict__ out,
                                                                  int H, int W, int rows, int D, int background, int pitch,
                                                                  int c0, int Ho, int Wo, int pad_top, int pad_left) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* stab = reinterpret_cast<float*>(smem_raw);
-  for (int i = threadIdx.x; i < rows * D; i += blockDim.x) stab[i] = table[i];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < rows * D; i += blockDim.x * blockDim.y) stab[i] = table[i];
   __syncthreads();
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   const int HW = H * W;
   const L* lab = labels + (long long)b * HW;
   long long* lab_out = labels_out ? labels_out + (long long)b * HW : nullptr;
   float* o = out + (long long)b * Ho * Wo * pitch;
   bool oob = false;
   if (VEC) {
-    // pitch % 4 == 0 and 16-byte aligned rows: the D channels of a pixel are `head` leading scalars up to the next 16-byte
-    // boundary, then float4 groups, then `tail` scalars.  One thread per (pixel, piece): a warp's stores are consecutive
-    // 16-byte pieces of consecutive pixels.
-    const int head = (4 - (c0 & 3)) & 3;           // scalars before the first aligned float4
-    const int nvec = (D - head) >> 2;              // float4 groups
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * 32 + threadIdx.y;
+    if (x >= W) return;
+    const int q = threadIdx.x;
+    const int p = y * W + x;
+    const int l = clamp_label((long long)lab[p], rows, background, oob);
+    if (q == 0 && lab_out) lab_out[p] = l;
+    float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch;
+    const float* row = stab + l * D;
+    const bool fused = image != nullptr;           // then c0 <= 3 leading image channels complete the first float4
+    const int head = fused ? 4 - c0 : ((4 - (c0 & 3)) & 3);   // embedding scalars before the first aligned float4
+    const int nvec = (D - head) >> 2;
     const int tail = D - head - 4 * nvec;
-    const int pieces = nvec + (head ? 1 : 0) + (tail ? 1 : 0);
-    const int total = HW * pieces;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      const int p = i / pieces, q = i - p * pieces;
-      const long long raw = (long long)lab[p];
-      const int l = clamp_label(raw, rows, background, oob);
-      if (q == 0 && lab_out) lab_out[p] = l;
-      const int y = p / W, x = p - y * W;
-      float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch + c0;
-      const float* row = stab + l * D;
-      const int qv = q - (head ? 1 : 0);
-      if (head && q == 0) {
-        for (int d = 0; d < head; ++d) dst[d] = row[d];
-      } else if (qv < nvec) {
-        const int d = head + 4 * qv;
-        *reinterpret_cast<float4*>(dst + d) = make_float4(row[d], row[d + 1], row[d + 2], row[d + 3]);
+    const int first = (fused || head) ? 1 : 0;
+    if (q == 0 && first) {
+      if (fused) {
+        const float* ip = image + (long long)b * c0 * HW + p;
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = c < c0 ? __ldg(ip + (long long)c * HW) : row[c - c0];
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
-        for (int d = head + 4 * nvec; d < D; ++d) dst[d] = row[d];
+        for (int d = 0; d < head; ++d) dst[c0 + d] = row[d];
       }
+    } else if (q - first < nvec) {
+      const int d = head + 4 * (q - first);
+      *reinterpret_cast<float4*>(dst + c0 + d) = make_float4(row[d], row[d + 1], row[d + 2], row[d + 3]);
+    } else if (q - first == nvec && tail) {
+      for (int d = head + 4 * nvec; d < D; ++d) dst[c0 + d] = row[d];
     }
   } else {
     const int total = HW * D;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {
       const int p = i / D, d = i - p * D;
       const long long raw = (long long)lab[p];
       const int l = clamp_label(raw, rows, background, oob);
@@ -323,31 +335,41 @@ int mde_relu_eps_fwd(const float* x, float* y, int64_t n, float eps, mde_stream_
   return check_launch();
 }
 
-int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_out, const float* table, float* out_nhwc,
-                          int B, int H, int W, int rows, int D, int background, int pitch, int c0, int Ho, int Wo, int pad_top,
-                          int pad_left, mde_stream_t stream) {
+int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_out, const float* table, const float* image_nchw,
+                          float* out_nhwc, int B, int H, int W, int rows, int D, int background, int pitch, int c0, int Ho,
+                          int Wo, int pad_top, int pad_left, mde_stream_t stream) {
   if (!labels || !table || !out_nhwc) return MDE_ERR_BAD_POINTER;
-  if (B <= 0 || B > 65535 || H <= 0 || W <= 0 || rows <= 0 || D <= 0 || c0 < 0 || c0 + D > pitch || pad_top < 0 || pad_left < 0 ||
-      Ho < H + pad_top || Wo < W + pad_left || (long long)H * W * D > 0x7fffffffLL)
+  if (B <= 0 || B > 65535 || H <= 0 || H > 65535 || W <= 0 || rows <= 0 || D <= 0 || c0 < 0 || c0 + D > pitch || pad_top < 0 ||
+      pad_left < 0 || Ho < H + pad_top || Wo < W + pad_left || (long long)H * W * D > 0x7fffffffLL)
     return MDE_ERR_BAD_SHAPE;
   if (background < 0 || background >= rows) return MDE_ERR_UNSUPPORTED;  // clamping mode only
   const size_t sm = (size_t)rows * D * sizeof(float);
   if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
-  long long gx = ((long long)H * W * ((D + 3) / 4 + 1) + 256 * 4 - 1) / (256 * 4);
-  const long long cap = (MDE_NUM_SMS * 16 + B - 1) / B;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec = (pitch % 4 == 0) && aligned(out_nhwc, 16) && D >= 8;
+  const bool fused = image_nchw != nullptr;
+  if (fused && !(c0 >= 1 && c0 <= 3 && D >= 4 - c0)) return MDE_ERR_UNSUPPORTED;
+  const int head = fused ? 4 - c0 : ((4 - (c0 & 3)) & 3);
+  const int pieces = ((fused || head) ? 1 : 0) + (D - head) / 4 + (((D - head) % 4) ? 1 : 0);
+  const bool vec = (pitch % 4 == 0) && aligned(out_nhwc, 16) && D >= head && pieces <= 8;
+  if (fused && !vec) return MDE_ERR_UNSUPPORTED;
+  dim3 grid, block;
+  if (vec) {
+    block = dim3(8, 32);
+    grid = dim3((unsigned)((W + 31) / 32), (unsigned)H, (unsigned)B);
+  } else {
+    long long gx = ((long long)H * W * D + 256 * 8 - 1) / (256 * 8);
+    if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;
+    block = dim3(256, 1);
+    grid = dim3((unsigned)gx, 1, (unsigned)B);
+  }
 #define MDE_GN(LT)                                                                                                     \
   {                                                                                                                    \
     if (vec)                                                                                                           \
-      gather_embed_nhwc_kernel<LT, true><<<grid, 256, sm, st>>>(reinterpret_cast<const LT*>(labels),                   \
-          reinterpret_cast<long long*>(labels_out), table, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
+      gather_embed_nhwc_kernel<LT, true><<<grid, block, sm, st>>>(reinterpret_cast<const LT*>(labels),                 \
+          reinterpret_cast<long long*>(labels_out), table, image_nchw, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
     else                                                                                                               \
-      gather_embed_nhwc_kernel<LT, false><<<grid, 256, sm, st>>>(reinterpret_cast<const LT*>(labels),                  \
-          reinterpret_cast<long long*>(labels_out), table, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
+      gather_embed_nhwc_kernel<LT, false><<<grid, block, sm, st>>>(reinterpret_cast<const LT*>(labels),                \
+          reinterpret_cast<long long*>(labels_out), table, image_nchw, out_nhwc, H, W, rows, D, background, pitch, c0, Ho, Wo, pad_top, pad_left); \
   }
   if (label_dtype == MDE_I64) MDE_GN(long long)
   else if (label_dtype == MDE_I32) MDE_GN(int)

@@ -33,6 +33,7 @@ constexpr int LS_THREADS = 512;
 constexpr int LS_WARPS = LS_THREADS / 32;
 constexpr int LS_MAX_BLOCKS = MDE_NUM_SMS * 16;  // bound of blocks per launch (scratch sizing)
 constexpr unsigned int F_INF = 0x7f800000u;
+constexpr int LS_LUT = 1024;                    // cells of the search accelerator
 
 struct SilogWs {  // read by silog_bwd_kernel
   double sum, sumsq, count;
@@ -159,6 +160,8 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
   __shared__ double red[LS_WARPS][5];
   __shared__ bool last_block, last_image;
   __shared__ unsigned int bad_order;
+  __shared__ unsigned short lut[LS_LUT];
+  float lut_lo = 0.f, lut_scale = 0.f;
 
   if (CHAMFER) {
     const float* e = a.edges + (long long)b * (n + 1);
@@ -180,6 +183,26 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
       }
     __syncthreads();
     if (threadIdx.x == 0 && bad_order && blockIdx.x == 0) atomicExch(a.cw.unsorted, 1u);
+    // search accelerator: lut[c] = number of centres <= the left edge of cell c of a uniform grid over [edge_0, edge_n]
+    // (binary search per cell, 2 cells per thread); a target then starts its search at lut[cell(t)] and walks forward --
+    // 0-2 steps for any reasonable bin layout, instead of log2(n) dependent shared-memory probes per pixel
+    lut_lo = e[0];
+    {
+      const float span = e[n] - e[0];
+      lut_scale = span > 0.f ? (float)LS_LUT / span : 0.f;
+    }
+    for (int c = threadIdx.x; c < LS_LUT; c += LS_THREADS) {
+      const float left = lut_lo + (float)c / lut_scale;
+      int j = 0;
+      for (int step = a.search_step; step > 0; step >>= 1) {
+        const int probe = j + step;
+        if (probe <= n && sc[skew(probe - 1)] <= left) j = probe;
+      }
+      // the walk only moves forward, so the start must not overshoot: step back over centres equal to `left` (rounding of
+      // the cell edge) -- one position is enough, the forward walk re-adds it
+      lut[c] = (unsigned short)(j > 0 ? j - 1 : 0);
+    }
+    __syncthreads();
   }
 
   // ---- stream this block's share of image b: groups of 4 consecutive pixels ------------------------------------
@@ -248,15 +271,19 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
       }
     }
     if (CHAMFER) {
-      // j = number of centres <= t (upper bound), interval j = [c_{j-1}, c_j): branch-free binary search, the four pixels of
-      // the group in lockstep so that their shared-memory loads overlap
-      int j4[4] = {0, 0, 0, 0};
-      for (int step = a.search_step; step > 0; step >>= 1) {
+      // j = number of centres <= t (upper bound), interval j = [c_{j-1}, c_j): start from the uniform-grid table and walk
+      int j4[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int probe = j4[i] + step;
-          if (probe <= n && sc[skew(probe - 1)] <= t4[i]) j4[i] = probe;
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float f = (t4[i] - lut_lo) * lut_scale;
+        const int cell = f > 0.f ? (f < (float)(LS_LUT - 1) ? (int)f : LS_LUT - 1) : 0;
+        j4[i] = lut[cell];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int j = j4[i];
+        while (j < n && sc[skew(j)] <= t4[i]) ++j;
+        j4[i] = j;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

@@ -299,10 +299,12 @@ class UnetAdaptiveBins(nn.Module):
                 and not (torch.is_grad_enabled() and x.requires_grad):
             # the loader gathered the embedding planes straight into the encoder's NHWC input (SemanticsLoader.
             # bind_encoder_input): only the image planes are missing
-            buf, bpads = bound
+            buf, bpads, filled = bound
             want = (0, 0, 0, 0) if pads is None else tuple(int(v) for v in pads)
             if tuple(bpads) == want and buf.shape[1] == x.shape[1] + items[0][1].shape[1] \
                     and buf.shape[0] == x.shape[0] and buf.shape[2] == x.shape[2] + want[0] + want[1]:
+                if filled is not None and filled.data_ptr() == x.data_ptr() and filled._version == x._version:
+                    return buf  # the loader's kernel already wrote these very image planes
                 return ops.fill_channels_nhwc(buf, x, 0, want)
         if getattr(self, "_channels_last", False) and x.is_cuda and all(it[0] == "copy" for it in items) \
                 and not (torch.is_grad_enabled() and x.requires_grad):

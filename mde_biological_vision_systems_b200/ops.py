@@ -219,12 +219,13 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
     return out
 
 
-def gather_embed_nhwc(labels, table, background, c_before, c_after=0, pads=(0, 0, 0, 0), labels_out=None):
+def gather_embed_nhwc(labels, table, background, c_before, c_after=0, pads=(0, 0, 0, 0), labels_out=None, image=None):
     """Clamp + gather straight into a channels_last buffer laid out like the encoder input: returns (buffer, view) where
     ``buffer`` is a zero-bordered channels_last [B, c_before + D + c_after, H + top + bottom, W + left + right] fp32 tensor
     whose channels [c_before, c_before + D) hold the embeddings, and ``view`` = the [B, D, H, W] embedding tensor the
-    reference's loader returns -- a strided view into the buffer (no planar copy exists).  The caller fills the other channels
-    (ops.fill_channels_nhwc) and feeds ``buffer`` to the encoder."""
+    reference's loader returns -- a strided view into the buffer (no planar copy exists).  With ``image`` (NCHW fp32
+    [B, c_before, H, W]) the leading channels are written by the same kernel; otherwise the caller fills them
+    (ops.fill_channels_nhwc) before feeding ``buffer`` to the encoder."""
     lib = _lib.load()
     _need_cuda(labels, table)
     if labels.dtype not in _LABEL_DTYPES or labels.dim() != 4 or labels.shape[1] != 1 or not labels.is_contiguous():
@@ -244,9 +245,13 @@ def gather_embed_nhwc(labels, table, background, c_before, c_after=0, pads=(0, 0
         buf[:, :, :, :pl].zero_()
     if pr:
         buf[:, :, :, w + pl:].zero_()
+    if image is not None:
+        if image.dtype != torch.float32 or tuple(image.shape) != (b, c_before, h, w) or not image.is_cuda:
+            raise ValueError("image must be a CUDA float32 [B, c_before, H, W] tensor")
+        image = image.contiguous()
     with timing("gather_embed", work=float(b * h * w * (labels.element_size() + 4 * d))):
-        rc = lib.mde_gather_embed_nhwc(_p(labels), _LABEL_DTYPES[labels.dtype], _p(labels_out), _p(table), _p(buf), b, h, w, rows,
-                                       d, int(background), pitch, c_before, ho, wo, pt, pl, _s())
+        rc = lib.mde_gather_embed_nhwc(_p(labels), _LABEL_DTYPES[labels.dtype], _p(labels_out), _p(table), _p(image), _p(buf), b,
+                                       h, w, rows, d, int(background), pitch, c_before, ho, wo, pt, pl, _s())
     _lib.check(rc, "mde_gather_embed_nhwc")
     view = buf[:, c_before:c_before + d, pt:pt + h, pl:pl + w]
     return buf, view

@@ -53,7 +53,7 @@ class TrainStep:
         depth = batch["depth"].to(device, non_blocking=True)
         kwargs = {}
         if self.semantics_loader is not None:
-            _, sem = self.semantics_loader.get_semantics(batch)
+            _, sem = self.semantics_loader.get_semantics(dict(batch, image=img))  # (a bound loader also writes the image planes)
             if sem is not None:
                 kwargs["semantics"] = sem
         if self.instance_loader is not None:

@@ -107,6 +107,13 @@ def test_gather_into_encoder_input_matches_planar():
         e1, p1 = m(x, semantics=sem1)
         e2, p2 = m(x, semantics=sem2)
     assert torch.equal(p1, p2) and torch.equal(e1, e2)
+    # with the device image in the batch dict the same kernel also writes the RGB planes (nothing left for the model to copy)
+    raw3, sem3 = bound.get_semantics({"semantics": lab.clone(), "image": x})
+    assert torch.equal(sem3, sem1) and sem3._mde_encoder_input[2] is x
+    assert torch.equal(sem3._mde_encoder_input[0][:, :3, :352, :384], x)
+    with torch.no_grad():
+        e3, p3 = m(x, semantics=sem3)
+    assert torch.equal(p1, p3) and torch.equal(e1, e3)
     # a loader bound to a model it does not fit declines
     other = make_model(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None).to(DEV).channels_last_()
     assert not SemanticsLoader(Args(use_semantics=mode)).bind_encoder_input(other)
