@@ -162,10 +162,10 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
   float* o = out + (long long)b * Ho * Wo * pitch;
   bool oob = false;
   if (VEC) {
-    const int y = blockIdx.y;
     const int x = blockIdx.x * 32 + threadIdx.y;
     if (x >= W) return;
     const int q = threadIdx.x;
+   for (int y = blockIdx.y; y < H; y += gridDim.y) {  // a block walks a strip of rows: the table staging is amortised
     const int p = y * W + x;
     const int l = clamp_label((long long)lab[p], rows, background, oob);
     if (q == 0 && lab_out) lab_out[p] = l;
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
     } else if (q - first == nvec && tail) {
       for (int d = head + 4 * nvec; d < D; ++d) dst[c0 + d] = row[d];
     }
+   }
   } else {
     const int total = HW * D;
     for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {
@@ -355,7 +356,11 @@ int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_o
   dim3 grid, block;
   if (vec) {
     block = dim3(8, 32);
-    grid = dim3((unsigned)((W + 31) / 32), (unsigned)H, (unsigned)B);
+    const int gx = (W + 31) / 32;
+    int gy = (MDE_NUM_SMS * 16 + gx * B - 1) / (gx * B);  // ~16 blocks per SM over the whole batch, each walking H / gy rows
+    if (gy > H) gy = H;
+    if (gy < 1) gy = 1;
+    grid = dim3((unsigned)gx, (unsigned)gy, (unsigned)B);
   } else {
     long long gx = ((long long)H * W * D + 256 * 8 - 1) / (256 * 8);
     if (gx > MDE_NUM_SMS * 16) gx = MDE_NUM_SMS * 16;

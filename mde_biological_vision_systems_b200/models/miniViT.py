@@ -31,6 +31,7 @@ class mViT(nn.Module):
         # 3x3 conv of the inference path: "tc" = tcgen05 implicit GEMM on split-bf16 pairs (three bf16 products per K step,
         # fp32-grade), "cudnn" = library conv in true fp32, "auto" = "tc" whenever the shape allows
         self.conv3x3_impl = "auto"
+        self.train_conv_impl = "cudnn"  # training: "cudnn" (default) or "tc" (ops.conv3x3_autograd), see UpSampleBN
 
     def _conv3x3_uses_tc(self, x, pair_out=False):
         return self.conv3x3_impl != "cudnn" and ops.conv3x3_supported(x, self.conv3x3.out_channels, pair_out)
@@ -63,7 +64,7 @@ class mViT(nn.Module):
         if isinstance(x, ops.SplitBF16):
             x = x.float()
         if needs_grad:
-            if self.conv3x3_impl != "cudnn" and not torch.is_autocast_enabled() and ops.conv3x3_train_supported(x, c):
+            if self.train_conv_impl == "tc" and not torch.is_autocast_enabled() and ops.conv3x3_train_supported(x, c):
                 return tgt, ops.conv3x3_autograd(x, c.weight, None if bias_free else c.bias)  # fwd, dgrad, wgrad on our kernels
             return tgt, (torch.nn.functional.conv2d(x, c.weight, None, c.stride, c.padding) if bias_free else c(x))
         with ops.exact_fp32_library():

@@ -44,7 +44,11 @@ class UpSampleBN(nn.Module):
     def __init__(self, skip_input, output_features):
         super().__init__()
         self._net = nn.Sequential(*_block(skip_input, output_features), *_block(output_features, output_features))
-        self.train_conv_impl = "tc"  # training / autograd: "tc" = our conv kernels (fwd, dgrad, wgrad); "cudnn" = stock modules
+        # training / autograd: "cudnn" = stock modules (default); "tc" = our conv kernels (ops.conv3x3_autograd: forward and
+        # dgrad on the bf16x3 tcgen05 kernel, wgrad on the tap-shifted TF32 NT GEMM) -- parity-tested, but measured 3x slower
+        # than cuDNN's TF32 kernels on B200 (29 vs 9.5 ms of the config-2 training step: the nine taps re-read both operands),
+        # see DESIGN.md section 6
+        self.train_conv_impl = "cudnn"
 
     def _folded(self):
         """Per conv block: ([dx][dy][Cout][C] split-bf16 filter, scale, shift, slope) with the eval-mode BatchNorm folded into

@@ -14,8 +14,7 @@ impl = os.environ.get("MDE_TRAIN_CONV", "tc")
 for m in model.modules():
     if hasattr(m, "train_conv_impl"):
         m.train_conv_impl = impl
-if impl != "tc":
-    model.adaptive_bins_layer.conv3x3_impl = "cudnn"
+model.adaptive_bins_layer.train_conv_impl = impl
 stepper = TrainStep(model, semantics_loader=sem_loader, total_steps=100)
 host = bench.host_batch(cfg, batch, 0, pin=True)
 for _ in range(3):
