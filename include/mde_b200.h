@@ -162,6 +162,15 @@ int mde_conv3x3_nhwc_x3_fwd(const uint16_t* x_pair, const uint16_t* w_pair, cons
 int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const float* bias, float* y_nhwc, int B, int H, int W,
                                int C, int Cout, mde_stream_t stream);
 
+/* ---- 1x1 convolution on channels_last activations as a tcgen05 GEMM with fp32-grade accuracy (DecoderBN.conv2,
+ * models/unet_adaptive_bins.py:61; the point-wise convolutions of the EfficientNet passthrough body):
+ *   y[m][n] = act(sum_k x[m][k] * w[n][k] + bias[n]) (+ residual[m][n])
+ * x fp32 [M][K] (M = B*H*W pixels, K = C_in contiguous, K % 8 == 0); w_pair = split-bf16 pair of the [N][K] filter, planes
+ * [2][N][K] (mde_split_bf16); bias [N] or NULL; act 0 none / 1 SiLU; residual fp32 [M][ldr] or NULL; y fp32 [M][ldc].
+ * The activations are split into (hi, mid) bf16 inside the kernel (in shared memory), so callers pass plain fp32. */
+int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bias, int act, const float* residual, float* y,
+                         int64_t M, int N, int K, int64_t ldc, int64_t ldr, mde_stream_t stream);
+
 /* Batched NT GEMM on tcgen05 (TF32 inputs, fp32 accumulate):  C[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k].
  * A [batch][M][K] with row pitch lda and batch stride a_batch (floats; multiples of 4), B [batch][N][K] likewise,
  * C [batch][M][N] with row pitch ldc / batch stride c_batch.  splits > 1 splits the K range over CTAs and accumulates

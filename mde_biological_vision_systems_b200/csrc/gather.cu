@@ -165,34 +165,52 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
     const int x = blockIdx.x * 32 + threadIdx.y;
     if (x >= W) return;
     const int q = threadIdx.x;
-   for (int y = blockIdx.y; y < H; y += gridDim.y) {  // a block walks a strip of rows: the table staging is amortised
-    const int p = y * W + x;
-    const int l = clamp_label((long long)lab[p], rows, background, oob);
-    if (q == 0 && lab_out) lab_out[p] = l;
-    float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch;
-    const float* row = stab + l * D;
     const bool fused = image != nullptr;           // then c0 <= 3 leading image channels complete the first float4
     const int head = fused ? 4 - c0 : ((4 - (c0 & 3)) & 3);   // embedding scalars before the first aligned float4
     const int nvec = (D - head) >> 2;
     const int tail = D - head - 4 * nvec;
     const int first = (fused || head) ? 1 : 0;
-    if (q == 0 && first) {
-      if (fused) {
-        const float* ip = image + (long long)b * c0 * HW + p;
-        float v[4];
+    constexpr int U = 4;  // rows in flight per thread: the label (and image) loads of U rows are issued before any is used
+    // a block walks a strip of rows (the table staging is amortised over H / gridDim.y rows)
+    for (int yb = blockIdx.y; yb < H; yb += U * gridDim.y) {
+      long long raw[U];
+      float img[U][3];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = c < c0 ? __ldg(ip + (long long)c * HW) : row[c - c0];
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        for (int d = 0; d < head; ++d) dst[c0 + d] = row[d];
+      for (int u = 0; u < U; ++u) {
+        const int y = yb + u * gridDim.y;
+        raw[u] = y < H ? (long long)lab[y * W + x] : 0;
+        if (fused && q == 0 && y < H) {
+          const float* ip = image + (long long)b * c0 * HW + y * W + x;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) img[u][c] = c < c0 ? __ldg(ip + (long long)c * HW) : 0.f;
+        }
       }
-    } else if (q - first < nvec) {
-      const int d = head + 4 * (q - first);
-      *reinterpret_cast<float4*>(dst + c0 + d) = make_float4(row[d], row[d + 1], row[d + 2], row[d + 3]);
-    } else if (q - first == nvec && tail) {
-      for (int d = head + 4 * nvec; d < D; ++d) dst[c0 + d] = row[d];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int y = yb + u * gridDim.y;
+        if (y >= H) break;
+        const int p = y * W + x;
+        const int l = clamp_label(raw[u], rows, background, oob);
+        if (q == 0 && lab_out) lab_out[p] = l;
+        float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch;
+        const float* row = stab + l * D;
+        if (q == 0 && first) {
+          if (fused) {
+            float v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = c < c0 ? img[u][c < 3 ? c : 2] : row[c - c0];
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int d = 0; d < head; ++d) dst[c0 + d] = row[d];
+          }
+        } else if (q - first < nvec) {
+          const int d = head + 4 * (q - first);
+          *reinterpret_cast<float4*>(dst + c0 + d) = make_float4(row[d], row[d + 1], row[d + 2], row[d + 3]);
+        } else if (q - first == nvec && tail) {
+          for (int d = head + 4 * nvec; d < D; ++d) dst[c0 + d] = row[d];
+        }
+      }
     }
-   }
   } else {
     const int total = HW * D;
     for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {

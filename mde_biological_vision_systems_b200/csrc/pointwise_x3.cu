@@ -1,0 +1,266 @@
+// 1x1 convolution on channels_last activations as a tcgen05 GEMM with fp32-grade accuracy:
+//     y[m][n] = act( sum_k x[m][k] * w[n][k] + bias[n] ) (+ residual[m][n]),   m = (b, y, x) pixels, k = C_in, n = C_out.
+//
+// Reference: DecoderBN.conv2 (models/unet_adaptive_bins.py:61, Conv2d(bottleneck, features, kernel_size=1, padding=1): the
+// caller pads the 13x17 input spatially, border pixels then come out as the bias, exactly like the padded conv) and -- through
+// the same operator -- the point-wise convolutions of the EfficientNet passthrough body (expansion / projection / head conv with
+// their folded BatchNorm bias, SiLU and residual in the epilogue), which the library otherwise runs either in TF32 (outside
+// the 1e-3 contract for sharply peaked softmaxes) or on its slow legacy fp32 kernels (7.7 ms of an 18 ms step at config 2).
+//
+// Operands: the weights travel as a split-bf16 pair (prepared once per parameter version); the activations arrive as plain
+// fp32 from whatever produced them, are staged by TMA as raw fp32 and are SPLIT IN SHARED MEMORY by the four epilogue warps,
+// in place: thread r owns row r of the 128-row tile, reads its 64 floats of the K chunk (two 128-byte swizzled rows) into
+// registers and writes the hi bf16 row over the first box and the mid bf16 row over the second -- the same 256 bytes, now two
+// K-major SWIZZLE_128B operand tiles.  Every K step then issues the three products hi*hi + mid*hi + hi*mid (kind::f16).
+// No extra pass over HBM, no pair tensors in the callers.
+//   warp 0: TMA producer (raw activation boxes + the weight pair), warp 1: MMA issuer, warp 2: TMEM allocator,
+//   warps 3-6: converter while the K loop runs, then the epilogue (tcgen05.ld -> bias / SiLU -> shared-memory transpose ->
+//   coalesced float4 stores, residual added there).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mde {
+namespace tc {
+
+constexpr int PW_THREADS = 224;
+constexpr int PW_KC = 64;                    // K elements per chunk
+constexpr int PW_A_BYTES = 128 * PW_KC * 4;  // raw fp32 tile = afterwards [hi tile 16 KB][mid tile 16 KB]
+
+struct PwGeom {
+  long long M;
+  int N, K;
+  long long ldc, ldr;
+  int tn, n_tiles, chunks, nstages, tmem_cols, act;
+  const float* bias;
+  const float* residual;
+};
+
+__global__ void __launch_bounds__(PW_THREADS, 1)
+    pointwise_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        float* __restrict__ Y, const PwGeom g) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+  const int b_plane = g.tn * 128;
+  const int stage_bytes = PW_A_BYTES + 2 * b_plane;
+  const uint32_t s_bar = base + g.nstages * stage_bytes;
+  const uint32_t bar_raw = s_bar, bar_ops = s_bar + 8 * g.nstages, bar_empty = s_bar + 16 * g.nstages,
+                 bar_acc = s_bar + 24 * g.nstages;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 24 * g.nstages + 16);
+  float* stg_all = reinterpret_cast<float*>(gbase + (s_bar - base) + 24 * g.nstages + 64);  // [4 warps][32][33]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long mt = blockIdx.x / g.n_tiles;
+  const int nt = (int)(blockIdx.x - mt * g.n_tiles);
+  const long long m0 = mt * 128;
+  const int n0 = nt * g.tn;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.nstages; ++i) {
+      mbar_init(bar_raw + 8 * i, 1);
+      mbar_init(bar_ops + 8 * i, 4);  // one arrive per converter warp
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < g.chunks; ++c) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1, 41);
+        mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)stage_bytes);
+        const uint32_t dst = base + stage * stage_bytes;
+        tma_load_2d(dst, &map_x, bar_raw + 8 * stage, c * PW_KC, (int)m0);             // k [0, 32) of the chunk
+        tma_load_2d(dst + 16384, &map_x, bar_raw + 8 * stage, c * PW_KC + 32, (int)m0);  // k [32, 64)
+        tma_load_3d(dst + PW_A_BYTES, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 0);
+        tma_load_3d(dst + PW_A_BYTES + b_plane, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 1);
+        if (++stage == (uint32_t)g.nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(FMT_BF16, 128, (uint32_t)g.tn, 0, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < g.chunks; ++c) {
+        mbar_wait(bar_raw + 8 * stage, phase, 42);  // the weight pair (written by the TMA) ...
+        mbar_wait(bar_ops + 8 * stage, phase, 43);  // ... and the converted activation tiles
+        tc_fence_after();
+        const uint32_t a0 = base + stage * stage_bytes, b0 = a0 + PW_A_BYTES;
+#pragma unroll
+        for (int j = 0; j < PW_KC / 16; ++j) {
+          const uint64_t ahi = make_smem_desc(a0 + j * 32, 16, 1024, SWZ_128B);
+          const uint64_t amid = make_smem_desc(a0 + 16384 + j * 32, 16, 1024, SWZ_128B);
+          const uint64_t bhi = make_smem_desc(b0 + j * 32, 16, 1024, SWZ_128B);
+          const uint64_t bmid = make_smem_desc(b0 + b_plane + j * 32, 16, 1024, SWZ_128B);
+          umma_f16_ss(tmem_base, ahi, bhi, idesc, (c | j) != 0);
+          umma_f16_ss(tmem_base, amid, bhi, idesc, 1);
+          umma_f16_ss(tmem_base, ahi, bmid, idesc, 1);
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (++stage == (uint32_t)g.nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(bar_acc);
+    }
+  } else if (warp >= 3) {
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int r = quarter * 32 + lane;     // row of the tile this thread converts and later reads from TMEM
+    // ---- converter: fp32 -> (hi, mid) bf16, in place -------------------------------------------------------------
+    {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t sw = (uint32_t)(r & 7);
+      for (int c = 0; c < g.chunks; ++c) {
+        mbar_wait(bar_raw + 8 * stage, phase, 44);
+        const uint32_t row0 = base + stage * stage_bytes + r * 128, row1 = row0 + 16384;
+        float v[64];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3])
+                       : "r"(row0 + ((q ^ sw) << 4)));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[32 + 4 * q]), "=f"(v[33 + 4 * q]), "=f"(v[34 + 4 * q]), "=f"(v[35 + 4 * q])
+                       : "r"(row1 + ((q ^ sw) << 4)));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of the bf16 rows = k [8j, 8j + 8)
+          uint32_t hi[4], mid[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], mid[e]);
+          const uint32_t off = (uint32_t)((j ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row0 + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row1 + off), "r"(mid[0]), "r"(mid[1]), "r"(mid[2]),
+                       "r"(mid[3])
+                       : "memory");
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ops + 8 * stage);
+        if (++stage == (uint32_t)g.nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    mbar_wait(bar_acc, 0, 45);
+    tc_fence_after();
+    float* stg = stg_all + quarter * (32 * 33);
+#pragma unroll 1
+    for (int c0 = 0; c0 < g.tn; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(quarter * 32) << 16), acc);
+      tmem_ld_wait();
+      const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = __uint_as_float(acc[i]);
+        if (g.bias != nullptr && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
+        if (g.act == 1) t = t / (1.f + __expf(-t));  // SiLU
+        stg[lane * 33 + i] = t;
+      }
+      __syncwarp();
+      // 8 lanes write one row's 128 bytes: every store instruction covers 4 whole lines
+      const int cc = (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const long long mm = m0 + quarter * 32 + rr;
+        if (mm >= g.M || cc >= nvalid) continue;
+        const float* sp = stg + rr * 33 + cc;
+        float o[4] = {sp[0], sp[1], sp[2], sp[3]};
+        float* dst = Y + mm * g.ldc + n0 + c0 + cc;
+        const float* res = g.residual ? g.residual + mm * g.ldr + n0 + c0 + cc : nullptr;
+        if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+            (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+          if (res) {
+            const float4 rv = *reinterpret_cast<const float4*>(res);
+            o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int q = 0; q < 4 && cc + q < nvalid; ++q) dst[q] = o[q] + (res ? res[q] : 0.f);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  }
+}
+
+}  // namespace tc
+}  // namespace mde
+
+using namespace mde;
+
+extern "C" {
+
+int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bias, int act, const float* residual, float* y,
+                         int64_t M, int N, int K, int64_t ldc, int64_t ldr, mde_stream_t stream) {
+  if (!x || !w_pair || !y) return MDE_ERR_BAD_POINTER;
+  if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0 || ldc < N || (residual && ldr < N) || act < 0 || act > 1)
+    return MDE_ERR_BAD_SHAPE;
+  if (K % 8 != 0 || !aligned(x, 16) || !aligned(w_pair, 16)) return MDE_ERR_UNSUPPORTED;  // TMA: 16-byte global strides
+  tc::PwGeom g;
+  g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldr = ldr; g.act = act; g.bias = bias; g.residual = residual;
+  // N tile: 256 columns when that still leaves >= 2 CTAs per SM (each N tile converts the activation tile again), else 128
+  const long long m_tiles = (M + 127) / 128;
+  int tn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  if (tn == 256 && m_tiles * ((N + 255) / 256) < 2 * MDE_NUM_SMS) tn = 128;
+  g.tn = tn;
+  g.n_tiles = (N + tn - 1) / tn;
+  g.chunks = (K + tc::PW_KC - 1) / tc::PW_KC;
+  g.tmem_cols = tn <= 32 ? 32 : tn <= 64 ? 64 : tn <= 128 ? 128 : 256;
+  const int stage_bytes = tc::PW_A_BYTES + 2 * tn * 128;
+  g.nstages = (200 * 1024) / stage_bytes;
+  if (g.nstages > 4) g.nstages = 4;
+  if (g.nstages > g.chunks) g.nstages = g.chunks;
+  const int smem = g.nstages * stage_bytes + 24 * g.nstages + 64 + 4 * 32 * 33 * 4 + 1024;
+  if (m_tiles * g.n_tiles > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
+  CUtensorMap mx, mw;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)K * 4};
+    const uint32_t box[2] = {32, 128};
+    if (!tc::encode_f32(&mx, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 2};
+    const uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
+    const uint32_t box[3] = {(uint32_t)tc::PW_KC, (uint32_t)tn, 1};
+    if (!tc::encode_bf16(&mw, w_pair, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return MDE_ERR_DRIVER;
+  }
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(tc::pointwise_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+      return MDE_ERR_LAUNCH;
+    attr = true;
+  }
+  tc::pointwise_x3_kernel<<<(unsigned)(m_tiles * g.n_tiles), tc::PW_THREADS, smem, (cudaStream_t)stream>>>(mx, mw, y, g);
+  return check_launch();
+}
+
+}  // extern "C"

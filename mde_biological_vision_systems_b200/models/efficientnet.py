@@ -89,6 +89,25 @@ def _folded_conv_bn(conv, bn):
     return cached[1], cached[2]
 
 
+def _pointwise_exact(conv, x, act, residual, out_pads):
+    from .. import ops
+    return (not torch.backends.cudnn.allow_tf32 and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1
+            and conv.padding in ((0, 0), 0) and (act is None or isinstance(act, nn.SiLU))
+            and (out_pads is None or not any(out_pads)) and ops.pointwise_supported(x, conv.in_channels, conv.out_channels)
+            and (residual is None or (residual.dtype == torch.float32 and residual.is_contiguous(memory_format=torch.channels_last))))
+
+
+def _folded_pointwise_pair(conv, bn, w_folded):
+    """split-bf16 pair of the BatchNorm-folded 1x1 filter, cached next to the fold (same version key)."""
+    from .. import ops
+    key = conv._mde_fold[0]
+    cached = getattr(conv, "_mde_fold_pair", None)
+    if cached is None or cached[0] != key:
+        cached = (key, ops.prepare_pointwise_weight(w_folded))
+        conv._mde_fold_pair = cached
+    return cached[1]
+
+
 def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False):
     """act(bn(conv(x))) (+ residual); in inference (eval-mode statistics, no autograd) as ONE convolution with the folded
     filter -- the 69 per-block BatchNorm passes of EfficientNet-B1 are 3 ms of a 14 ms step otherwise -- followed, on
@@ -103,6 +122,11 @@ def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False
         return y + residual if residual is not None else y
     from .. import ops
     w, b = _folded_conv_bn(conv, bn)
+    if _pointwise_exact(conv, x, act, residual, out_pads):
+        # exact mode (the caller switched the library's TF32 off: UnetAdaptiveBins inference): the 1x1 convolution, its folded
+        # BatchNorm bias, SiLU and the residual run as ONE tcgen05 GEMM with fp32-grade products (ops.pointwise_conv) instead
+        # of the library's legacy fp32 kernels + a bias/activation pass
+        return ops.pointwise_conv(x, _folded_pointwise_pair(conv, bn, w), b, 1 if act is not None else 0, residual)
     fused = (act is None or isinstance(act, nn.SiLU)) and x.is_cuda
     y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
         else conv._conv_forward(x, w, None if fused else b)

@@ -143,6 +143,14 @@ class DecoderBN(nn.Module):
         cout = self.conv3.out_channels
         return cout <= 4 or ops.conv3x3_cout_ok(cout, pair_out=True)
 
+    def _prepared_conv2(self):
+        w = self.conv2.weight
+        cached = getattr(self, "_mde_w2_prep", None)
+        if cached is None or cached[0] != w._version or cached[1].device != w.device:
+            cached = (w._version, ops.prepare_pointwise_weight(w))
+            self._mde_w2_prep = cached
+        return cached[1]
+
     def _prepared_conv3(self):
         w = self.conv3.weight
         cached = getattr(self, "_mde_w3_prep", None)
@@ -156,10 +164,15 @@ class DecoderBN(nn.Module):
         ops.SplitBF16, the operand format of the head's tensor-core kernels."""
         s0, s1, s2, s3, bottleneck = features[4], features[5], features[6], features[8], features[11]
         if self._use_tc((s0, s1, s2, s3, bottleneck)):
-            # (f)1: the whole decoder on our kernels, channels_last; conv2 (1x1, padding 1) is a plain library GEMM (fp32)
-            with ops.exact_fp32_library():
-                y = self.conv2(bottleneck.contiguous(memory_format=torch.channels_last))
-            y = y.contiguous(memory_format=torch.channels_last)
+            # (f)1: the whole decoder on our kernels, channels_last.  conv2 is a 1x1 conv with padding 1 (:61): pad the 13x17
+            # input by one zero pixel and run the point-wise GEMM -- border pixels come out as the bias, as in the padded conv
+            xb = F.pad(bottleneck, (1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+            if ops.pointwise_supported(xb, self.conv2.in_channels, self.conv2.out_channels):
+                y = ops.pointwise_conv(xb, self._prepared_conv2(), self.conv2.bias, name="decoder.conv2")
+            else:
+                with ops.exact_fp32_library():
+                    y = self.conv2(bottleneck.contiguous(memory_format=torch.channels_last))
+                y = y.contiguous(memory_format=torch.channels_last)
             small = self.conv3.out_channels <= 4  # noAdaBins: 1 output channel, direct fp32 kernel
             ups = ((self.up1, s3), (self.up2, s2), (self.up3, s1), (self.up4, s0))
             for i, (up, skip) in enumerate(ups):

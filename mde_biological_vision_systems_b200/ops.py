@@ -666,6 +666,43 @@ def conv3x3_small(x_cl, weight, bias=None):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# 1x1 convolution (tcgen05 GEMM, activations split to bf16 pairs inside the kernel)
+# ------------------------------------------------------------------------------------------------------------
+def prepare_pointwise_weight(weight):
+    """Conv filter [Cout,Cin,1,1] (or [Cout,Cin]) -> split-bf16 pair, bfloat16 [2,Cout,Cin]."""
+    w = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+    return split_bf16_flat(w)
+
+
+def pointwise_supported(x, cin, cout):
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and cin % 8 == 0 and cout % 4 == 0
+                and x.is_contiguous(memory_format=torch.channels_last) and x.shape[0] * x.shape[2] * x.shape[3] < 2 ** 31)
+
+
+def pointwise_conv(x_cl, w_pair, bias=None, act=0, residual=None, name="pointwise"):
+    """act(conv1x1(x) + bias) (+ residual) on the tcgen05 GEMM, three bf16 products per K step (fp32-grade): x_cl channels_last
+    fp32 [B,Cin,H,W], w_pair from prepare_pointwise_weight; act 0 none / 1 SiLU; residual channels_last [B,Cout,H,W].
+    Returns a channels_last fp32 [B,Cout,H,W] tensor."""
+    lib = _lib.load()
+    _need_cuda(x_cl, w_pair)
+    b, c, h, w = x_cl.shape
+    cout = w_pair.shape[1]
+    if w_pair.dtype != torch.bfloat16 or w_pair.shape[2] != c:
+        raise ValueError("pointwise_conv: w_pair must come from prepare_pointwise_weight for this input width")
+    if not x_cl.is_contiguous(memory_format=torch.channels_last) or x_cl.dtype != torch.float32:
+        raise ValueError("pointwise_conv expects a float32 channels_last tensor")
+    if residual is not None and not (residual.is_contiguous(memory_format=torch.channels_last) and residual.dtype == torch.float32
+                                     and residual.shape == (b, cout, h, w)):
+        raise ValueError("pointwise_conv: residual must be a float32 channels_last [B,Cout,H,W] tensor")
+    out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    m = b * h * w
+    with timing(name, work=2.0 * m * cout * c):
+        rc = lib.mde_pointwise_x3_fwd(_p(x_cl), _p(w_pair), _p(bias), int(act), _p(residual), _p(out), m, cout, c, cout, cout, _s())
+    _lib.check(rc, "mde_pointwise_x3_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # transformer encoder layer
 # ------------------------------------------------------------------------------------------------------------
 def encoder_layer(x, layer, ws=None):

@@ -325,6 +325,38 @@ def test_conv3x3_autograd(cfg):
         assert err < (1e-4 if name == "x" else 2e-3), (name, err)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 16, 40, 56), cout=96, act=1),                    # EfficientNet expansion: K = 16 (one partial K chunk), SiLU
+    dict(shape=(1, 96, 26, 34), cout=24, res=True),                 # projection with residual, N = 24 (ragged N tile)
+    dict(shape=(2, 1280, 15, 19), cout=1280),                       # DecoderBN.conv2 (input already padded): 20 K chunks
+    dict(shape=(1, 672, 13, 17), cout=112, res=True),
+    dict(shape=(1, 1152, 7, 9), cout=320, act=1),
+    dict(shape=(3, 40, 9, 11), cout=240, act=1),                    # K = 40: not a multiple of the 32-float TMA box
+])
+def test_pointwise_conv_x3(cfg):
+    """1x1 conv as a tcgen05 GEMM whose fp32 activations are split into bf16 pairs in shared memory (ops.pointwise_conv):
+    bias + SiLU + residual epilogue, vs a float64 evaluation -- fp32-grade."""
+    rng = np.random.default_rng(180)
+    b, c, h, w = cfg["shape"]
+    cout = cfg["cout"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 1, 1)) / np.sqrt(c)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    res = torch.from_numpy(rng.standard_normal((b, cout, h, w)).astype(np.float32)) if cfg.get("res") else None
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), bias.double())
+    if cfg.get("act"):
+        ref = ref * torch.sigmoid(ref)
+    if res is not None:
+        ref = ref + res.double()
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert ops.pointwise_supported(xd, c, cout)
+    out = ops.pointwise_conv(xd, ops.prepare_pointwise_weight(wt.to(DEV)), bias.to(DEV), cfg.get("act", 0),
+                             None if res is None else res.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 5e-5, err
+
+
 def test_conv3x3_tf32_form():
     """The single-pass TF32 form of the same kernel (operands pre-rounded by the caller, as its contract says)."""
     rng = np.random.default_rng(94)
@@ -1140,8 +1172,8 @@ def test_training_step_with_own_conv_kernels_matches_cudnn():
     """train_conv_impl = "tc" routes every 3x3 convolution of the decoder and the head (forward, dgrad, wgrad) through
     ops.conv3x3_autograd inside the real model: same loss and gradients as the stock cuDNN modules."""
     kw = dict(insertion_point="input", semantics_mode=None, instance_segmentation_mode=None)
-    x = synthetic.image(2, 160, 192, seed=170).to(DEV)
-    depth = synthetic.depth(2, 160, 192, seed=171).to(DEV)
+    x = synthetic.image(2, 352, 384, seed=170).to(DEV)   # 22 x 24 = 528 tokens >= 1 + 128 queries
+    depth = synthetic.depth(2, 352, 384, seed=171).to(DEV)
     out = {}
     for impl in ("cudnn", "tc"):
         m = make_model(**kw).to(DEV).channels_last_()
