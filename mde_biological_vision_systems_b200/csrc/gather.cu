@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
       for (int u = 0; u < U; ++u) {
         const int y = yb + u * gridDim.y;
         raw[u] = y < H ? (long long)lab[y * W + x] : 0;
+        img[u][0] = img[u][1] = img[u][2] = 0.f;
         if (fused && q == 0 && y < H) {
           const float* ip = image + (long long)b * c0 * HW + y * W + x;
 #pragma unroll
@@ -194,7 +195,20 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
         if (q == 0 && lab_out) lab_out[p] = l;
         float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch;
         const float* row = stab + l * D;
-        if (q == 0 && first) {
+        if (fused && tail == 0) {
+          // uniform (divergence-free) path of the encoder-input case: piece q covers channels [4q, 4q + 4) of the pixel's row;
+          // channel c < c0 is an image plane, channel c >= c0 is embedding element c - c0
+          if (q < 1 + nvec) {
+            const int ch = 4 * q;
+            float v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int e = ch + c - c0;
+              v[c] = e >= 0 ? row[e] : img[u][(ch + c) < 3 ? (ch + c) : 2];
+            }
+            *reinterpret_cast<float4*>(dst + ch) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        } else if (q == 0 && first) {
           if (fused) {
             float v[4];
 #pragma unroll

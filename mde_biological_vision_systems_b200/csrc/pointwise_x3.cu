@@ -8,21 +8,22 @@
 // the 1e-3 contract for sharply peaked softmaxes) or on its slow legacy fp32 kernels (7.7 ms of an 18 ms step at config 2).
 //
 // Operands: the weights travel as a split-bf16 pair (prepared once per parameter version); the activations arrive as plain
-// fp32 from whatever produced them, are staged by TMA as raw fp32 and are SPLIT IN SHARED MEMORY by the four epilogue warps,
+// fp32 from whatever produced them, are staged by TMA as raw fp32 and are SPLIT IN SHARED MEMORY by four converter warps,
 // in place: thread r owns row r of the 128-row tile, reads its 64 floats of the K chunk (two 128-byte swizzled rows) into
 // registers and writes the hi bf16 row over the first box and the mid bf16 row over the second -- the same 256 bytes, now two
 // K-major SWIZZLE_128B operand tiles.  Every K step then issues the three products hi*hi + mid*hi + hi*mid (kind::f16).
 // No extra pass over HBM, no pair tensors in the callers.
-//   warp 0: TMA producer (raw activation boxes + the weight pair), warp 1: MMA issuer, warp 2: TMEM allocator,
-//   warps 3-6: converter while the K loop runs, then the epilogue (tcgen05.ld -> bias / SiLU -> shared-memory transpose ->
-//   coalesced float4 stores, residual added there).
+// Persistent, 1 CTA / SM: warp 0 TMA producer (raw activation boxes + the weight pair), warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 3-6 converter, warps 7-10 epilogue (tcgen05.ld -> bias / SiLU -> shared-memory transpose -> coalesced
+// float4 stores, residual added there); two TMEM accumulator buffers, so the epilogue of one tile overlaps the next tile's
+// loads, conversion and MMAs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace mde {
 namespace tc {
 
-constexpr int PW_THREADS = 224;
+constexpr int PW_THREADS = 352;              // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3-6 converter, 7-10 epilogue
 constexpr int PW_KC = 64;                    // K elements per chunk
 constexpr int PW_A_BYTES = 128 * PW_KC * 4;  // raw fp32 tile = afterwards [hi tile 16 KB][mid tile 16 KB]
 
@@ -31,10 +32,13 @@ struct PwGeom {
   int N, K;
   long long ldc, ldr;
   int tn, n_tiles, chunks, nstages, tmem_cols, act;
+  long long total_tiles;
   const float* bias;
   const float* residual;
 };
 
+// Persistent: a CTA walks output tiles (m tile major, n tile minor) with ONE continuous operand pipeline; two TMEM
+// accumulator buffers let the epilogue of tile i overlap the loads / conversion / MMAs of tile i+1.
 __global__ void __launch_bounds__(PW_THREADS, 1)
     pointwise_x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         float* __restrict__ Y, const PwGeom g) {
@@ -45,14 +49,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
   const int stage_bytes = PW_A_BYTES + 2 * b_plane;
   const uint32_t s_bar = base + g.nstages * stage_bytes;
   const uint32_t bar_raw = s_bar, bar_ops = s_bar + 8 * g.nstages, bar_empty = s_bar + 16 * g.nstages,
-                 bar_acc = s_bar + 24 * g.nstages;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 24 * g.nstages + 16);
+                 bar_acc_full = s_bar + 24 * g.nstages, bar_acc_empty = bar_acc_full + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 24 * g.nstages + 32);
   float* stg_all = reinterpret_cast<float*>(gbase + (s_bar - base) + 24 * g.nstages + 64);  // [4 warps][32][33]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long mt = blockIdx.x / g.n_tiles;
-  const int nt = (int)(blockIdx.x - mt * g.n_tiles);
-  const long long m0 = mt * 128;
-  const int n0 = nt * g.tn;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.nstages; ++i) {
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
       mbar_init(bar_ops + 8 * i, 4);  // one arrive per converter warp
       mbar_init(bar_empty + 8 * i, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 4);  // one arrive per epilogue warp
+    }
     fence_barrier_init();
     fence_proxy_async();
     tma_prefetch_desc(&map_x);
@@ -78,54 +81,64 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int c = 0; c < g.chunks; ++c) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1, 41);
-        mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)stage_bytes);
-        const uint32_t dst = base + stage * stage_bytes;
-        tma_load_2d(dst, &map_x, bar_raw + 8 * stage, c * PW_KC, (int)m0);             // k [0, 32) of the chunk
-        tma_load_2d(dst + 16384, &map_x, bar_raw + 8 * stage, c * PW_KC + 32, (int)m0);  // k [32, 64)
-        tma_load_3d(dst + PW_A_BYTES, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 0);
-        tma_load_3d(dst + PW_A_BYTES + b_plane, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 1);
-        if (++stage == (uint32_t)g.nstages) {
-          stage = 0;
-          phase ^= 1;
+      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const long long mt = tile / g.n_tiles;
+        const int n0 = (int)(tile - mt * g.n_tiles) * g.tn;
+        const int m0 = (int)(mt * 128);
+        for (int c = 0; c < g.chunks; ++c) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 41);
+          mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)stage_bytes);
+          const uint32_t dst = base + stage * stage_bytes;
+          tma_load_2d(dst, &map_x, bar_raw + 8 * stage, c * PW_KC, m0);               // k [0, 32) of the chunk
+          tma_load_2d(dst + 16384, &map_x, bar_raw + 8 * stage, c * PW_KC + 32, m0);  // k [32, 64)
+          tma_load_3d(dst + PW_A_BYTES, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 0);
+          tma_load_3d(dst + PW_A_BYTES + b_plane, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 1);
+          if (++stage == (uint32_t)g.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(FMT_BF16, 128, (uint32_t)g.tn, 0, 0);
-      uint32_t stage = 0, phase = 0;
-      for (int c = 0; c < g.chunks; ++c) {
-        mbar_wait(bar_raw + 8 * stage, phase, 42);  // the weight pair (written by the TMA) ...
-        mbar_wait(bar_ops + 8 * stage, phase, 43);  // ... and the converted activation tiles
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(bar_acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1, 46);
         tc_fence_after();
-        const uint32_t a0 = base + stage * stage_bytes, b0 = a0 + PW_A_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * g.tn;
+        for (int c = 0; c < g.chunks; ++c) {
+          mbar_wait(bar_raw + 8 * stage, phase, 42);  // the weight pair (written by the TMA) ...
+          mbar_wait(bar_ops + 8 * stage, phase, 43);  // ... and the converted activation tiles
+          tc_fence_after();
+          const uint32_t a0 = base + stage * stage_bytes, b0 = a0 + PW_A_BYTES;
 #pragma unroll
-        for (int j = 0; j < PW_KC / 16; ++j) {
-          const uint64_t ahi = make_smem_desc(a0 + j * 32, 16, 1024, SWZ_128B);
-          const uint64_t amid = make_smem_desc(a0 + 16384 + j * 32, 16, 1024, SWZ_128B);
-          const uint64_t bhi = make_smem_desc(b0 + j * 32, 16, 1024, SWZ_128B);
-          const uint64_t bmid = make_smem_desc(b0 + b_plane + j * 32, 16, 1024, SWZ_128B);
-          umma_f16_ss(tmem_base, ahi, bhi, idesc, (c | j) != 0);
-          umma_f16_ss(tmem_base, amid, bhi, idesc, 1);
-          umma_f16_ss(tmem_base, ahi, bmid, idesc, 1);
+          for (int j = 0; j < PW_KC / 16; ++j) {
+            const uint64_t ahi = make_smem_desc(a0 + j * 32, 16, 1024, SWZ_128B);
+            const uint64_t amid = make_smem_desc(a0 + 16384 + j * 32, 16, 1024, SWZ_128B);
+            const uint64_t bhi = make_smem_desc(b0 + j * 32, 16, 1024, SWZ_128B);
+            const uint64_t bmid = make_smem_desc(b0 + b_plane + j * 32, 16, 1024, SWZ_128B);
+            umma_f16_ss(d_tmem, ahi, bhi, idesc, (c | j) != 0);
+            umma_f16_ss(d_tmem, amid, bhi, idesc, 1);
+            umma_f16_ss(d_tmem, ahi, bmid, idesc, 1);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == (uint32_t)g.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(bar_empty + 8 * stage);
-        if (++stage == (uint32_t)g.nstages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(bar_acc_full + 8 * buf);
       }
-      umma_commit(bar_acc);
     }
-  } else if (warp >= 3) {
-    const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are accessible to this warp
-    const int r = quarter * 32 + lane;     // row of the tile this thread converts and later reads from TMEM
-    // ---- converter: fp32 -> (hi, mid) bf16, in place -------------------------------------------------------------
-    {
-      uint32_t stage = 0, phase = 0;
-      const uint32_t sw = (uint32_t)(r & 7);
+  } else if (warp >= 3 && warp < 7) {
+    // ---- converter: fp32 -> (hi, mid) bf16, in place; thread r owns row r of the 128-row tile ----------------------
+    const int r = (warp - 3) * 32 + lane;
+    uint32_t stage = 0, phase = 0;
+    const uint32_t sw = (uint32_t)(r & 7);
+    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       for (int c = 0; c < g.chunks; ++c) {
         mbar_wait(bar_raw + 8 * stage, phase, 44);
         const uint32_t row0 = base + stage * stage_bytes + r * 128, row1 = row0 + 16384;
@@ -160,47 +173,61 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
         }
       }
     }
-    // ---- epilogue ---------------------------------------------------------------------------------------------
-    mbar_wait(bar_acc, 0, 45);
-    tc_fence_after();
+  } else if (warp >= 7) {
+    // ---- epilogue: tcgen05.ld -> bias / SiLU -> shared-memory transpose -> coalesced stores (+ residual) -------------
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are accessible to this warp
     float* stg = stg_all + quarter * (32 * 33);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+      const long long mt = tile / g.n_tiles;
+      const int n0 = (int)(tile - mt * g.n_tiles) * g.tn;
+      const long long m0 = mt * 128;
+      const uint32_t buf = it & 1;
+      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1, 45);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < g.tn; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(quarter * 32) << 16), acc);
-      tmem_ld_wait();
-      const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float t = __uint_as_float(acc[i]);
-        if (g.bias != nullptr && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
-        if (g.act == 1) t = t / (1.f + __expf(-t));  // SiLU
-        stg[lane * 33 + i] = t;
-      }
-      __syncwarp();
-      // 8 lanes write one row's 128 bytes: every store instruction covers 4 whole lines
-      const int cc = (lane & 7) * 4;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + (lane >> 3);
-        const long long mm = m0 + quarter * 32 + rr;
-        if (mm >= g.M || cc >= nvalid) continue;
-        const float* sp = stg + rr * 33 + cc;
-        float o[4] = {sp[0], sp[1], sp[2], sp[3]};
-        float* dst = Y + mm * g.ldc + n0 + c0 + cc;
-        const float* res = g.residual ? g.residual + mm * g.ldr + n0 + c0 + cc : nullptr;
-        if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-            (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
-          if (res) {
-            const float4 rv = *reinterpret_cast<const float4*>(res);
-            o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-          }
-          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int q = 0; q < 4 && cc + q < nvalid; ++q) dst[q] = o[q] + (res ? res[q] : 0.f);
+      for (int c0 = 0; c0 < g.tn; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + buf * g.tn + c0 + ((uint32_t)(quarter * 32) << 16), acc);
+        tmem_ld_wait();
+        if (c0 + 32 >= g.tn) {  // accumulator fully read: hand the buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
+        const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(acc[i]);
+          if (g.bias != nullptr && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
+          if (g.act == 1) t = t / (1.f + __expf(-t));  // SiLU
+          stg[lane * 33 + i] = t;
+        }
+        __syncwarp();
+        // 8 lanes write one row's 128 bytes: every store instruction covers 4 whole lines
+        const int cc = (lane & 7) * 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = k * 4 + (lane >> 3);
+          const long long mm = m0 + quarter * 32 + rr;
+          if (mm >= g.M || cc >= nvalid) continue;
+          const float* sp = stg + rr * 33 + cc;
+          float o[4] = {sp[0], sp[1], sp[2], sp[3]};
+          float* dst = Y + mm * g.ldc + n0 + c0 + cc;
+          const float* res = g.residual ? g.residual + mm * g.ldr + n0 + c0 + cc : nullptr;
+          if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+              (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+            if (res) {
+              const float4 rv = *reinterpret_cast<const float4*>(res);
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+            }
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int q = 0; q < 4 && cc + q < nvalid; ++q) dst[q] = o[q] + (res ? res[q] : 0.f);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   tc_fence_before();
@@ -233,13 +260,13 @@ int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bi
   g.tn = tn;
   g.n_tiles = (N + tn - 1) / tn;
   g.chunks = (K + tc::PW_KC - 1) / tc::PW_KC;
-  g.tmem_cols = tn <= 32 ? 32 : tn <= 64 ? 64 : tn <= 128 ? 128 : 256;
+  g.tmem_cols = 2 * tn <= 32 ? 32 : 2 * tn <= 64 ? 64 : 2 * tn <= 128 ? 128 : 2 * tn <= 256 ? 256 : 512;  // two accumulator buffers
+  g.total_tiles = m_tiles * g.n_tiles;
   const int stage_bytes = tc::PW_A_BYTES + 2 * tn * 128;
   g.nstages = (200 * 1024) / stage_bytes;
   if (g.nstages > 4) g.nstages = 4;
   if (g.nstages > g.chunks) g.nstages = g.chunks;
   const int smem = g.nstages * stage_bytes + 24 * g.nstages + 64 + 4 * 32 * 33 * 4 + 1024;
-  if (m_tiles * g.n_tiles > 0x7fffffffLL) return MDE_ERR_BAD_SHAPE;
   CUtensorMap mx, mw;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -259,7 +286,8 @@ int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bi
       return MDE_ERR_LAUNCH;
     attr = true;
   }
-  tc::pointwise_x3_kernel<<<(unsigned)(m_tiles * g.n_tiles), tc::PW_THREADS, smem, (cudaStream_t)stream>>>(mx, mw, y, g);
+  const long long grid = g.total_tiles < MDE_NUM_SMS ? g.total_tiles : MDE_NUM_SMS;
+  tc::pointwise_x3_kernel<<<(unsigned)grid, tc::PW_THREADS, smem, (cudaStream_t)stream>>>(mx, mw, y, g);
   return check_launch();
 }
 
