@@ -108,6 +108,26 @@ def _folded_pointwise_pair(conv, bn, w_folded):
     return cached[1]
 
 
+class _depthwise_engine:
+    """A depthwise convolution (groups == channels) has no channel reduction and cuDNN computes it with fp32 FMAs whatever
+    the TF32 switch says -- but with the switch OFF (exact mode) the library falls back to an NCHW engine behind two layout
+    conversions per call (0.55 ms + slower kernels per config-2 step).  For depthwise convs only, the switch is therefore left
+    on, which selects the direct NHWC fp32 kernel; tests/test_gpu_parity.py::test_depthwise_engine_is_exact checks that the
+    two settings give bit-identical outputs on this cuDNN."""
+
+    def __init__(self, conv, x):
+        self.on = bool(x.is_cuda and conv.groups > 1 and conv.groups == conv.in_channels and not torch.backends.cudnn.allow_tf32)
+
+    def __enter__(self):
+        if self.on:
+            torch.backends.cudnn.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.backends.cudnn.allow_tf32 = False
+        return False
+
+
 def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False):
     """act(bn(conv(x))) (+ residual); in inference (eval-mode statistics, no autograd) as ONE convolution with the folded
     filter -- the 69 per-block BatchNorm passes of EfficientNet-B1 are 3 ms of a 14 ms step otherwise -- followed, on
@@ -128,8 +148,9 @@ def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False
         # of the library's legacy fp32 kernels + a bias/activation pass
         return ops.pointwise_conv(x, _folded_pointwise_pair(conv, bn, w), b, 1 if act is not None else 0, residual)
     fused = (act is None or isinstance(act, nn.SiLU)) and x.is_cuda
-    y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
-        else conv._conv_forward(x, w, None if fused else b)
+    with _depthwise_engine(conv, x):
+        y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
+            else conv._conv_forward(x, w, None if fused else b)
     if fused and ops.bias_act_supported(y, residual):
         if out_pads is not None and residual is None and any(out_pads):
             return ops.bias_act_pad_nhwc(y, b, 1 if act is not None else 0, out_pads)

@@ -1196,3 +1196,18 @@ def test_training_step_with_own_conv_kernels_matches_cudnn():
     assert abs(out["tc"][0] - out["cudnn"][0]) <= 1e-3 * abs(out["cudnn"][0])
     for a, b in zip(out["tc"][1:4], out["cudnn"][1:4]):
         assert float((a - b).abs().max()) <= 3e-2 * float(b.abs().max()) + 1e-8  # train-mode BatchNorm at batch 2 (see above)
+
+
+def test_depthwise_engine_is_exact():
+    """models/efficientnet.py leaves cuDNN's TF32 switch on for DEPTHWISE convolutions inside the exact-fp32 region (it only
+    selects the NHWC engine; depthwise math is fp32 FMAs either way): the two settings must give bit-identical outputs."""
+    rng = np.random.default_rng(190)
+    for (c, k, s, hw) in [(96, 3, 2, (104, 136)), (240, 5, 1, (52, 68)), (672, 5, 2, (26, 34)), (32, 3, 1, (208, 272))]:
+        x = torch.from_numpy(rng.standard_normal((2, c, *hw)).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
+        w = torch.from_numpy(rng.standard_normal((c, 1, k, k)).astype(np.float32)).to(DEV)
+        outs = []
+        for flag in (False, True):
+            torch.backends.cudnn.allow_tf32 = flag
+            outs.append(torch.nn.functional.conv2d(x, w, None, s, k // 2, 1, c))
+        torch.backends.cudnn.allow_tf32 = True
+        assert torch.equal(outs[0], outs[1]), (c, k, s)
