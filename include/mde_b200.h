@@ -6,6 +6,11 @@
  * Return value: MDE_OK (0) or a negative MDE_ERR_* code; mde_error_string() names it.  There is no CPU
  * fallback anywhere behind this header.
  *
+ * Process model: ONE process drives ONE device (the one-process-per-GPU layout of the reference's mp.spawn / DDP,
+ * train.py:576-640).  The library keeps a little process-global state that is neither per-device nor thread-safe: the launch
+ * counter, "shared-memory attribute already set" flags per kernel instantiation, the profiling buffer of
+ * mde_tc_debug_profile and the SyncBatchNorm wait bound.  Calls from several host threads must be serialised by the caller.
+ *
  * Each declaration cites the reference interface it replaces (paths relative to the reference tree
  * DylanAuty/MDE-biological-vision-systems).
  */
