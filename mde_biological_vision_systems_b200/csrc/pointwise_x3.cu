@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
         const int n0 = (int)(tile - mt * g.n_tiles) * g.tn;
         const int m0 = (int)(mt * 128);
         for (int c = 0; c < g.chunks; ++c) {
+          const bool two = g.K - c * PW_KC > 32;  // the chunk's second 32-float box holds data (else it is skipped altogether)
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 41);
-          mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)stage_bytes);
+          mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)(stage_bytes - (two ? 0 : 16384)));
           const uint32_t dst = base + stage * stage_bytes;
           tma_load_2d(dst, &map_x, bar_raw + 8 * stage, c * PW_KC, m0);               // k [0, 32) of the chunk
-          tma_load_2d(dst + 16384, &map_x, bar_raw + 8 * stage, c * PW_KC + 32, m0);  // k [32, 64)
+          if (two) tma_load_2d(dst + 16384, &map_x, bar_raw + 8 * stage, c * PW_KC + 32, m0);  // k [32, 64)
           tma_load_3d(dst + PW_A_BYTES, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 0);
           tma_load_3d(dst + PW_A_BYTES + b_plane, &map_w, bar_raw + 8 * stage, c * PW_KC, n0, 1);
           if (++stage == (uint32_t)g.nstages) {
@@ -114,8 +115,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
           mbar_wait(bar_ops + 8 * stage, phase, 43);  // ... and the converted activation tiles
           tc_fence_after();
           const uint32_t a0 = base + stage * stage_bytes, b0 = a0 + PW_A_BYTES;
-#pragma unroll
-          for (int j = 0; j < PW_KC / 16; ++j) {
+          const int kvalid = min(PW_KC, g.K - c * PW_KC);
+          const int nj = (kvalid + 15) >> 4;  // K = 16 steps that hold data (the rest of the chunk is zero)
+#pragma unroll 1
+          for (int j = 0; j < nj; ++j) {
             const uint64_t ahi = make_smem_desc(a0 + j * 32, 16, 1024, SWZ_128B);
             const uint64_t amid = make_smem_desc(a0 + 16384 + j * 32, 16, 1024, SWZ_128B);
             const uint64_t bhi = make_smem_desc(b0 + j * 32, 16, 1024, SWZ_128B);
@@ -142,18 +145,24 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
       for (int c = 0; c < g.chunks; ++c) {
         mbar_wait(bar_raw + 8 * stage, phase, 44);
         const uint32_t row0 = base + stage * stage_bytes + r * 128, row1 = row0 + 16384;
+        const bool two = g.K - c * PW_KC > 32;
         float v[64];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3])
                        : "r"(row0 + ((q ^ sw) << 4)));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v[32 + 4 * q]), "=f"(v[33 + 4 * q]), "=f"(v[34 + 4 * q]), "=f"(v[35 + 4 * q])
-                       : "r"(row1 + ((q ^ sw) << 4)));
+        }
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[32 + 4 * q]), "=f"(v[33 + 4 * q]), "=f"(v[34 + 4 * q]), "=f"(v[35 + 4 * q])
+                         : "r"(row1 + ((q ^ sw) << 4)));
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of the bf16 rows = k [8j, 8j + 8)
+          if (j >= 4 && !two) break;   // k >= 32 of a one-box chunk is never read by the MMAs
           uint32_t hi[4], mid[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], hi[e], mid[e]);
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
         for (int i = 0; i < 32; ++i) {
           float t = __uint_as_float(acc[i]);
           if (g.bias != nullptr && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
-          if (g.act == 1) t = t / (1.f + __expf(-t));  // SiLU
+          if (g.act == 1) t = __fdividef(t, 1.f + __expf(-t));  // SiLU
           stg[lane * 33 + i] = t;
         }
         __syncwarp();
