@@ -304,21 +304,22 @@ __global__ void __launch_bounds__(256) conv3x3_prep_weight_kernel(const float* _
 }
 
 // Direct fp32 convolution for a handful of output channels (the noAdaBins decoder's conv3: C -> 1,
-// models/unet_adaptive_bins.py:78-80): one warp per output pixel, lanes over channels (coalesced NHWC reads), shuffle
-// reduction; the 9*C*Cout filter sits in shared memory.  Memory bound (reads x once through L1/L2), exact fp32.
+// models/unet_adaptive_bins.py:78-80): ONE THREAD per output pixel, 16-byte loads along the channel axis of the nine taps
+// (neighbouring pixels' taps overlap, so L1 serves 8 of 9 reads), the 9*C*Cout filter in shared memory (every lane reads the
+// same filter word: a broadcast).  Exact fp32; ~0.7 kFLOP per pixel, bound by L1 load issue.
 template <int COUT_MAX>
 __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restrict__ x, const float* __restrict__ w_oihw,
                                                             const float* __restrict__ bias, float* __restrict__ y, int B,
                                                             int H, int W, int C, int Cout) {
-  extern __shared__ float sw[];  // [Cout][9][C]
+  extern __shared__ __align__(16) float sw[];  // [Cout][9][C]
   for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) {
     const int c = i % C, tap = (i / C) % 9, co = i / (9 * C);
     sw[i] = w_oihw[((long long)co * C + c) * 9 + tap];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
   const long long npix = (long long)B * H * W;
-  for (long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); p < npix; p += (long long)gridDim.x * 8) {
+  const int c4 = C >> 2;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(p % W), yy = (int)((p / W) % H);
     const long long b = p / ((long long)W * H);
     float acc[COUT_MAX];
@@ -327,21 +328,22 @@ __global__ void __launch_bounds__(256) conv3x3_small_kernel(const float* __restr
     for (int tap = 0; tap < 9; ++tap) {
       const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
       if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
-      const float* src = x + ((b * H + sy) * W + sx) * C;
-      for (int c = lane; c < C; c += 32) {
-        const float v = __ldg(src + c);
+      const float4* src = reinterpret_cast<const float4*>(x + ((b * H + sy) * W + sx) * C);
+#pragma unroll 4
+      for (int c = 0; c < c4; ++c) {
+        const float4 v = __ldg(src + c);
 #pragma unroll
-        for (int co = 0; co < COUT_MAX; ++co)
-          if (co < Cout) acc[co] = fmaf(v, sw[(co * 9 + tap) * C + c], acc[co]);
+        for (int co = 0; co < COUT_MAX; ++co) {
+          if (co < Cout) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw + (co * 9 + tap) * C + 4 * c);
+            acc[co] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[co]))));
+          }
+        }
       }
     }
 #pragma unroll
-    for (int co = 0; co < COUT_MAX; ++co) {
-      if (co < Cout) {
-        const float s = warp_sum(acc[co]);
-        if (lane == 0) y[p * Cout + co] = s + (bias ? bias[co] : 0.f);
-      }
-    }
+    for (int co = 0; co < COUT_MAX; ++co)
+      if (co < Cout) y[p * Cout + co] = acc[co] + (bias ? bias[co] : 0.f);
   }
 }
 
@@ -522,7 +524,7 @@ int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const f
                                int C, int Cout, mde_stream_t stream) {
   if (!x_nhwc || !w_oihw || !y_nhwc) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0) return MDE_ERR_BAD_SHAPE;
-  if (Cout > 4 || (size_t)Cout * 9 * C * sizeof(float) > 200 * 1024) return MDE_ERR_UNSUPPORTED;
+  if (Cout > 4 || C % 4 != 0 || !aligned(x_nhwc, 16) || (size_t)Cout * 9 * C * sizeof(float) > 200 * 1024) return MDE_ERR_UNSUPPORTED;
   const size_t sm = (size_t)Cout * 9 * C * sizeof(float);
   static bool attr = false;
   if (!attr) {
@@ -531,7 +533,7 @@ int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const f
     attr = true;
   }
   const long long npix = (long long)B * H * W;
-  long long grid = (npix + 7) / 8;
+  long long grid = (npix + 255) / 256;
   if (grid > MDE_NUM_SMS * 8) grid = MDE_NUM_SMS * 8;
   tc::conv3x3_small_kernel<4><<<(unsigned)grid, 256, sm, (cudaStream_t)stream>>>(x_nhwc, w_oihw, bias, y_nhwc, B, H, W, C, Cout);
   return check_launch();

@@ -81,12 +81,30 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      // The ring is shallow (2-3 stages of 64-96 KB), far less than the ~90 KB per SM that must be in flight to cover the DRAM
+      // latency at full bandwidth.  The activation boxes of the next PF chunks are therefore prefetched into L2
+      // (cp.async.bulk.prefetch.tensor: no shared memory, no barrier), so the ring's own loads only pay the L2 latency.
+      constexpr int PF = 6;
+      long long pf_tile = blockIdx.x;
+      int pf_c = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile >= g.total_tiles) return;
+        const int pm0 = (int)((pf_tile / g.n_tiles) * 128);
+        tma_prefetch_l2_2d(&map_x, pf_c * PW_KC, pm0);
+        if (g.K - pf_c * PW_KC > 32) tma_prefetch_l2_2d(&map_x, pf_c * PW_KC + 32, pm0);
+        if (++pf_c == g.chunks) {
+          pf_c = 0;
+          pf_tile += gridDim.x;
+        }
+      };
+      for (int i = 0; i < PF; ++i) prefetch_next();
       for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         const long long mt = tile / g.n_tiles;
         const int n0 = (int)(tile - mt * g.n_tiles) * g.tn;
         const int m0 = (int)(mt * 128);
         for (int c = 0; c < g.chunks; ++c) {
           const bool two = g.K - c * PW_KC > 32;  // the chunk's second 32-float box holds data (else it is skipped altogether)
+          prefetch_next();
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 41);
           mbar_expect_tx(bar_raw + 8 * stage, (uint32_t)(stage_bytes - (two ? 0 : 16384)));
           const uint32_t dst = base + stage * stage_bytes;

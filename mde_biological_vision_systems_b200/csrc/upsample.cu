@@ -249,14 +249,39 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
     }
   }
 }
+// C <= 4 (the RGB planes of the encoder input): one thread per pixel reads the C planes (coalesced across the warp) and writes C
+// consecutive floats -- the 64 x 64 tile kernel above would idle 61 of its 64 channel lanes.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                                  long long P, int pitch, int W, int Wo, long long Po, int pt,
+                                                                  int pl) {
+  const int b = blockIdx.y;
+  const float* src = in + (long long)b * C * P;
+  float* dst = out + (long long)b * pitch * (W > 0 ? Po : P);
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long po = W > 0 ? ((p / W + pt) * Wo + (p % W + pl)) : p;
+    for (int c = 0; c < C; ++c) dst[po * pitch + c] = __ldg(src + (long long)c * P + p);
+  }
+}
+
+static int launch_nchw_to_nhwc(const float* in, float* out, int B, int C, long long P, int pitch, int W, int Wo, long long Po,
+                               int pt, int pl, cudaStream_t st) {
+  if (C <= 4) {
+    long long gx = (P + 255) / 256;
+    const long long cap = (MDE_NUM_SMS * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    nchw_to_nhwc_smallc_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(in, out, C, P, pitch, W, Wo, Po, pt, pl);
+  } else {
+    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, C, P, pitch, W, Wo, Po, pt, pl);
+  }
+  return check_launch();
+}
 }  // namespace mde
 
 extern "C" int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream) {
   if (!in || !out) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || C <= 0 || P <= 0 || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
-  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, C);
-  return mde::check_launch();
+  return mde::launch_nchw_to_nhwc(in, out, B, C, P, C, 0, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -327,9 +352,7 @@ extern "C" int mde_nchw_to_nhwc_slice(const float* in, float* out, int B, int C,
                                       mde_stream_t stream) {
   if (!in || !out) return MDE_ERR_BAD_POINTER;
   if (B <= 0 || C <= 0 || P <= 0 || out_pitch < C || B > 65535 || (C + 63) / 64 > 65535) return MDE_ERR_BAD_SHAPE;
-  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, out_pitch);
-  return mde::check_launch();
+  return mde::launch_nchw_to_nhwc(in, out, B, C, P, out_pitch, 0, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
 // ... and into a padded channels_last image [B, H + pad_top + pad_bottom, W + pad_left + pad_right, out_pitch] (the border
@@ -343,9 +366,7 @@ extern "C" int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B,
   const long long P = (long long)H * W;
   const int Wo = W + pad_left + pad_right;
   const long long Po = (long long)(H + pad_top + pad_bottom) * Wo;
-  dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64), (unsigned)B);
-  mde::nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, P, out_pitch, W, Wo, Po, pad_top, pad_left);
-  return mde::check_launch();
+  return mde::launch_nchw_to_nhwc(in, out, B, C, P, out_pitch, W, Wo, Po, pad_top, pad_left, (cudaStream_t)stream);
 }
 
 static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, int skip_channels_last, void* out, bool pair,

@@ -19,7 +19,10 @@ def launches(src, dst, cmd):
     vals = [float(r[idx["Metric Value"]].replace(",", "")) for r in rows]
     grids = [r[idx["Grid Size"]] + " " + r[idx["Block Size"]] for r in rows]
     marks = [i for i, n in enumerate(names) if "gather_embed" in n]
-    a, b = marks[-3], marks[-2]  # one whole step between two loader gathers, late in the run
+    if len(marks) >= 3:
+        a, b = marks[-3], marks[-2]  # one whole step between two loader gathers, late in the run
+    else:
+        a, b = 0, len(names)  # scripts/ncu_step.py: the capture IS one step (cudaProfilerStart/Stop around it)
     agg = collections.OrderedDict()
     for n, v, g in zip(names[a:b], vals[a:b], grids[a:b]):
         k = (n[:118], g)
@@ -30,7 +33,7 @@ def launches(src, dst, cmd):
     ours = sum(v for (n, _), (_, v) in agg.items() if "mde::" in n or "tc::" in n or n.startswith("void tc::") or "mde" in n.split("(")[0])
     with open(dst, "w") as f:
         f.write(f"# {cmd}\n# one inference step of BASELINE config 2 (B=16, 416x544): launches {a}..{b} of the capture "
-                f"(between two loader gathers)\n# {b - a} launches, {tot / 1000:.1f} us total (cold-cache, serialised: compare shares); "
+                f"\n# {b - a} launches, {tot / 1000:.1f} us total (cold-cache, serialised: compare shares); "
                 f"hand-written kernels (mde::*, tc::*): {ours / 1000:.1f} us = {100 * ours / tot:.1f} %\n")
         for (n, g), (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{v / 1000:9.1f} us {100 * v / tot:5.1f}%  x{c:<3d} {n}  grid/block {g}\n")
