@@ -172,9 +172,27 @@ int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const f
  *   y[m][n] = act(sum_k x[m][k] * w[n][k] + bias[n]) (+ residual[m][n])
  * x fp32 [M][K] (M = B*H*W pixels, K = C_in contiguous, K % 8 == 0); w_pair = split-bf16 pair of the [N][K] filter, planes
  * [2][N][K] (mde_split_bf16); bias [N] or NULL; act 0 none / 1 SiLU; residual fp32 [M][ldr] or NULL; y fp32 [M][ldc].
- * The activations are split into (hi, mid) bf16 inside the kernel (in shared memory), so callers pass plain fp32. */
-int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bias, int act, const float* residual, float* y,
-                         int64_t M, int N, int K, int64_t ldc, int64_t ldr, mde_stream_t stream);
+ * The activations are split into (hi, mid) bf16 inside the kernel (in shared memory), so callers pass plain fp32.
+ * gate (optional, with rows_per_image = H*W): fp32 [M / rows_per_image][K] per-image channel scale multiplied into x (in fp32)
+ * before the product -- the squeeze-excite gate of the MBConv block the 1x1 projection closes (geffnet SqueezeExcite.forward:
+ * x * sigmoid(...)), saving the pass that would materialise x * gate.
+ * out_pad (optional, host array {H, W, pad_top, pad_bottom, pad_left, pad_right}; residual must be NULL): row m = (b, y, x) is
+ * written at (b, y + pad_top, x + pad_left) of a [B][H + pt + pb][W + pl + pr][ldc] map (the TensorFlow-SAME padding of the
+ * stride-2 depthwise convolution that consumes it); the border is NOT written -- the caller zeroes it. */
+int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_image, const uint16_t* w_pair, const float* bias,
+                         int act, const float* residual, float* y, int64_t M, int N, int K, int64_t ldc, int64_t ldr,
+                         const int* out_pad, mde_stream_t stream);
+
+/* ---- squeeze-excite helpers of the EfficientNet passthrough body (inference):
+ * mde_bias_act_pool_nhwc: y[p][c] = act(x[p][c] + bias[c]) on [B][HW][C] (in place allowed) and, in the same pass, the
+ *   per-(image, slab, channel) sums partial[B][slabs][C] of y (slabs = mde_pool_slabs(B, HW)); fixed summation order.
+ * mde_se_gate: gate[b][c] = sigmoid(w2[c][:] . silu(w1 . mean_b + b1) + b2[c]) with mean_b = inv_hw * sum_s partial[b][s][:];
+ *   w1 [R][C], w2 [C][R] (the 1x1 conv_reduce / conv_expand filters of geffnet's SqueezeExcite). */
+int mde_pool_slabs(int B, int64_t HW);
+int mde_bias_act_pool_nhwc(const float* x, const float* bias, float* y, float* partial, int B, int64_t HW, int C, int act,
+                           mde_stream_t stream);
+int mde_se_gate(const float* partial, int slabs, float inv_hw, const float* w1, const float* b1, const float* w2,
+                const float* b2, float* gate, int B, int C, int R, mde_stream_t stream);
 
 /* Batched NT GEMM on tcgen05 (TF32 inputs, fp32 accumulate):  C[b][m][n] (+)= alpha * sum_k A[b][m][k] * B[b][n][k].
  * A [batch][M][K] with row pitch lda and batch stride a_batch (floats; multiples of 4), B [batch][N][K] likewise,

@@ -302,3 +302,125 @@ extern "C" int mde_bias_act_pad_nhwc(const float* x, const float* bias, float* y
                                                                           total4, act);
   return check_launch();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Squeeze-excite of the MBConv blocks (geffnet SqueezeExcite: x * sigmoid(conv_expand(silu(conv_reduce(mean_hw(x)))))) in
+// inference: the spatial mean rides on the bias + SiLU pass that follows the depthwise convolution, the two tiny 1x1
+// convolutions run as one kernel, and the gate is multiplied into the activations inside the projection GEMM
+// (mde_pointwise_x3_fwd) -- 4 launches and 1 read + 1 write of the expanded tensor per block instead of 10 launches and 4
+// reads + 2 writes.
+namespace mde {
+
+// grid (slabs, B); warp = 32 consecutive float4 channel groups of one row, 8 rows in flight per block
+__global__ void __launch_bounds__(256) bias_act_pool_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                                 float* __restrict__ y, float* __restrict__ partial,
+                                                                 long long HW, int c4, long long rows_per_slab, int act) {
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long b = blockIdx.y, slab = blockIdx.x;
+  const long long r0 = slab * rows_per_slab;
+  const long long r1 = r0 + rows_per_slab < HW ? r0 + rows_per_slab : HW;
+  for (int cg0 = 0; cg0 < c4; cg0 += 32) {
+    const int cg = cg0 + tx;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cg < c4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + cg);
+#pragma unroll 4
+      for (long long r = r0 + ty; r < r1; r += 8) {
+        const long long idx = (b * HW + r) * c4 + cg;
+        const float4 v = reinterpret_cast<const float4*>(x)[idx];
+        float o[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
+        if (act == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
+        }
+        reinterpret_cast<float4*>(y)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+        acc.x += o[0]; acc.y += o[1]; acc.z += o[2]; acc.w += o[3];
+      }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && cg < c4) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        const float4 t = red[k][tx];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      reinterpret_cast<float4*>(partial)[(b * gridDim.x + slab) * c4 + cg] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// grid (splits, B): every block recomputes the squeezed vector h (R <= 256 values), then fills its slice of the gate
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ partial, int slabs, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      float* __restrict__ gate, int C, int R) {
+  extern __shared__ float se_sm[];  // mean[C] | h[R]
+  float* mean = se_sm;
+  float* h = se_sm + C;
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < slabs; ++i) s += partial[((long long)b * slabs + i) * C + c];
+    mean[c] = s * inv_hw;
+  }
+  __syncthreads();
+  for (int r = warp; r < R; r += 8) {
+    float d = 0.f;
+    for (int c = lane; c < C; c += 32) d = fmaf(__ldg(w1 + (long long)r * C + c), mean[c], d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      d += b1 ? b1[r] : 0.f;
+      h[r] = d / (1.f + expf(-d));
+    }
+  }
+  __syncthreads();
+  const int per = (C + gridDim.x - 1) / gridDim.x;
+  const int c_lo = blockIdx.x * per, c_hi = min(C, c_lo + per);
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    float d = b2 ? b2[c] : 0.f;
+    const float* wr = w2 + (long long)c * R;
+    for (int r = 0; r < R; ++r) d = fmaf(__ldg(wr + r), h[r], d);
+    gate[(long long)b * C + c] = 1.f / (1.f + expf(-d));
+  }
+}
+}  // namespace mde
+
+extern "C" int mde_pool_slabs(int B, int64_t HW) {
+  if (B <= 0 || HW <= 0) return 0;
+  long long s = (MDE_NUM_SMS * 4 + B - 1) / B;  // ~4 blocks per SM over the batch
+  const long long cap = (HW + 31) / 32;          // >= 32 rows per slab
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return (int)s;
+}
+
+extern "C" int mde_bias_act_pool_nhwc(const float* x, const float* bias, float* y, float* partial, int B, int64_t HW, int C,
+                                      int act, mde_stream_t stream) {
+  using namespace mde;
+  if (!x || !bias || !y || !partial) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || B > 65535 || HW <= 0 || C <= 0 || act < 0 || act > 1) return MDE_ERR_BAD_SHAPE;
+  if (C % 4 != 0 || !aligned(x, 16) || !aligned(y, 16) || !aligned(bias, 16) || !aligned(partial, 16)) return MDE_ERR_UNSUPPORTED;
+  const int slabs = mde_pool_slabs(B, HW);
+  const long long rps = (HW + slabs - 1) / slabs;
+  bias_act_pool_nhwc_kernel<<<dim3((unsigned)slabs, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(x, bias, y, partial, HW, C / 4,
+                                                                                                 rps, act);
+  return check_launch();
+}
+
+extern "C" int mde_se_gate(const float* partial, int slabs, float inv_hw, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float* gate, int B, int C, int R, mde_stream_t stream) {
+  using namespace mde;
+  if (!partial || !w1 || !w2 || !gate) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || B > 65535 || C <= 0 || R <= 0 || slabs <= 0) return MDE_ERR_BAD_SHAPE;
+  const size_t sm = (size_t)(C + R) * sizeof(float);
+  if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
+  const int splits = C >= 512 ? 4 : (C >= 128 ? 2 : 1);
+  se_gate_kernel<<<dim3((unsigned)splits, (unsigned)B), 256, sm, (cudaStream_t)stream>>>(partial, slabs, inv_hw, w1, b1, w2, b2,
+                                                                                         gate, C, R);
+  return check_launch();
+}

@@ -153,7 +153,17 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* stab = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < rows * D; i += blockDim.x * blockDim.y) stab[i] = table[i];
+  // encoder-input case (image planes + embedding, whole float4 pieces): the table is staged as OUTPUT ROWS, 8 float4 pieces
+  // per label with the embedding shifted by c0 channels, so that a thread's piece is one 16-byte shared-memory read
+  const bool rowform = VEC && image != nullptr && ((D - (4 - c0)) & 3) == 0;
+  if (rowform) {
+    for (int i = tid; i < rows * 32; i += blockDim.x * blockDim.y) {
+      const int e = (i & 31) - c0;
+      stab[i] = (e >= 0 && e < D) ? table[(i >> 5) * D + e] : 0.f;
+    }
+  } else {
+    for (int i = tid; i < rows * D; i += blockDim.x * blockDim.y) stab[i] = table[i];
+  }
   __syncthreads();
   const int b = blockIdx.z;
   const int HW = H * W;
@@ -195,18 +205,17 @@ __global__ void __launch_bounds__(256) gather_embed_nhwc_kernel(const L* __restr
         if (q == 0 && lab_out) lab_out[p] = l;
         float* dst = o + ((long long)(y + pad_top) * Wo + (x + pad_left)) * pitch;
         const float* row = stab + l * D;
-        if (fused && tail == 0) {
+        if (rowform) {
           // uniform (divergence-free) path of the encoder-input case: piece q covers channels [4q, 4q + 4) of the pixel's row;
-          // channel c < c0 is an image plane, channel c >= c0 is embedding element c - c0
+          // channel c < c0 is an image plane (piece 0 only), channel c >= c0 is embedding element c - c0
           if (q < 1 + nvec) {
-            const int ch = 4 * q;
-            float v[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int e = ch + c - c0;
-              v[c] = e >= 0 ? row[e] : img[u][(ch + c) < 3 ? (ch + c) : 2];
+            float4 v = *reinterpret_cast<const float4*>(stab + l * 32 + 4 * q);
+            if (q == 0) {
+              v.x = img[u][0];
+              if (c0 > 1) v.y = img[u][1];
+              if (c0 > 2) v.z = img[u][2];
             }
-            *reinterpret_cast<float4*>(dst + ch) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4 * q) = v;
           }
         } else if (q == 0 && first) {
           if (fused) {
@@ -376,10 +385,10 @@ int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_o
       pad_left < 0 || Ho < H + pad_top || Wo < W + pad_left || (long long)H * W * D > 0x7fffffffLL)
     return MDE_ERR_BAD_SHAPE;
   if (background < 0 || background >= rows) return MDE_ERR_UNSUPPORTED;  // clamping mode only
-  const size_t sm = (size_t)rows * D * sizeof(float);
+  const bool fused = image_nchw != nullptr;
+  const size_t sm = (size_t)rows * (fused && D <= 32 - c0 ? 32 : D) * sizeof(float);  // fused: staged as 32-float output rows
   if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fused = image_nchw != nullptr;
   if (fused && !(c0 >= 1 && c0 <= 3 && D >= 4 - c0)) return MDE_ERR_UNSUPPORTED;
   const int head = fused ? 4 - c0 : ((4 - (c0 & 3)) & 3);
   const int pieces = ((fused || head) ? 1 : 0) + (D - head) / 4 + (((D - head) % 4) ? 1 : 0);

@@ -35,6 +35,9 @@ struct PwGeom {
   long long total_tiles;
   const float* bias;
   const float* residual;
+  const float* gate;            // optional [M / rows_per_image][K] per-image channel scale applied to x before the product
+  long long rows_per_image;
+  int out_W, out_H, out_Wp, out_Hp, out_pt, out_pl;  // out_W > 0: row m = (b, y, x) is written at (b, y + pt, x + pl) of a padded map
 };
 
 // Persistent: a CTA walks output tiles (m tile major, n tile minor) with ONE continuous operand pipeline; two TMEM
@@ -160,7 +163,21 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
     uint32_t stage = 0, phase = 0;
     const uint32_t sw = (uint32_t)(r & 7);
     for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const float* grow = nullptr;  // this row's squeeze-excite gate (rows of one image share it)
+      if (g.gate != nullptr) {
+        long long m = (tile / g.n_tiles) * 128 + r;
+        if (m >= g.M) m = g.M - 1;
+        grow = g.gate + (m / g.rows_per_image) * g.K;
+      }
       for (int c = 0; c < g.chunks; ++c) {
+        float4 gv[16];
+        if (grow != nullptr) {  // issued before the wait: the loads fly while the TMA box lands
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int k = c * PW_KC + 4 * q;
+            gv[q] = k < g.K ? __ldg(reinterpret_cast<const float4*>(grow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         mbar_wait(bar_raw + 8 * stage, phase, 44);
         const uint32_t row0 = base + stage * stage_bytes + r * 128, row1 = row0 + 16384;
         const bool two = g.K - c * PW_KC > 32;
@@ -177,6 +194,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(v[32 + 4 * q]), "=f"(v[33 + 4 * q]), "=f"(v[34 + 4 * q]), "=f"(v[35 + 4 * q])
                          : "r"(row1 + ((q ^ sw) << 4)));
+        }
+        if (grow != nullptr) {  // x * gate in fp32, exactly the product the reference's SqueezeExcite forms before the conv
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (q >= 8 && !two) break;
+            v[4 * q] *= gv[q].x; v[4 * q + 1] *= gv[q].y; v[4 * q + 2] *= gv[q].z; v[4 * q + 3] *= gv[q].w;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 16-byte chunk j of the bf16 rows = k [8j, 8j + 8)
@@ -212,6 +236,18 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
       const uint32_t buf = it & 1;
       mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1, 45);
       tc_fence_after();
+      long long orow[8];  // output row of the 8 tile rows this thread stores (identity, or the position inside a padded map)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        long long mm = m0 + quarter * 32 + k * 4 + (lane >> 3);
+        if (g.out_W > 0 && mm < g.M) {
+          const long long img = mm / ((long long)g.out_W * g.out_H);
+          const int rem = (int)(mm - img * g.out_W * g.out_H);
+          const int yy = rem / g.out_W, xx = rem - yy * g.out_W;
+          mm = (img * g.out_Hp + yy + g.out_pt) * g.out_Wp + xx + g.out_pl;
+        }
+        orow[k] = mm;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < g.tn; c0 += 32) {
         uint32_t acc[32];
@@ -240,7 +276,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
           if (mm >= g.M || cc >= nvalid) continue;
           const float* sp = stg + rr * 33 + cc;
           float o[4] = {sp[0], sp[1], sp[2], sp[3]};
-          float* dst = Y + mm * g.ldc + n0 + c0 + cc;
+          float* dst = Y + orow[k] * g.ldc + n0 + c0 + cc;
           const float* res = g.residual ? g.residual + mm * g.ldr + n0 + c0 + cc : nullptr;
           if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
               (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
@@ -272,14 +308,26 @@ using namespace mde;
 
 extern "C" {
 
-int mde_pointwise_x3_fwd(const float* x, const uint16_t* w_pair, const float* bias, int act, const float* residual, float* y,
-                         int64_t M, int N, int K, int64_t ldc, int64_t ldr, mde_stream_t stream) {
+int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_image, const uint16_t* w_pair, const float* bias,
+                         int act, const float* residual, float* y, int64_t M, int N, int K, int64_t ldc, int64_t ldr,
+                         const int* out_pad, mde_stream_t stream) {
   if (!x || !w_pair || !y) return MDE_ERR_BAD_POINTER;
+  if (out_pad && (out_pad[0] <= 0 || out_pad[1] <= 0 || out_pad[2] < 0 || out_pad[3] < 0 || out_pad[4] < 0 || out_pad[5] < 0 ||
+                  M % ((int64_t)out_pad[0] * out_pad[1]) != 0 || residual))
+    return MDE_ERR_BAD_SHAPE;
+  if (gate && (rows_per_image <= 0 || M % rows_per_image != 0)) return MDE_ERR_BAD_SHAPE;
+  if (gate && !aligned(gate, 16)) return MDE_ERR_BAD_POINTER;
   if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0 || ldc < N || (residual && ldr < N) || act < 0 || act > 1)
     return MDE_ERR_BAD_SHAPE;
   if (K % 8 != 0 || !aligned(x, 16) || !aligned(w_pair, 16)) return MDE_ERR_UNSUPPORTED;  // TMA: 16-byte global strides
   tc::PwGeom g;
   g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldr = ldr; g.act = act; g.bias = bias; g.residual = residual;
+  g.gate = gate; g.rows_per_image = gate ? rows_per_image : 1;
+  g.out_W = 0; g.out_H = g.out_Wp = g.out_Hp = g.out_pt = g.out_pl = 0;
+  if (out_pad) {  // {H, W, pad_top, pad_bottom, pad_left, pad_right}: the caller zeroes the border
+    g.out_H = out_pad[0]; g.out_W = out_pad[1]; g.out_pt = out_pad[2]; g.out_pl = out_pad[4];
+    g.out_Hp = out_pad[0] + out_pad[2] + out_pad[3]; g.out_Wp = out_pad[1] + out_pad[4] + out_pad[5];
+  }
   // N tile: 256 columns when that still leaves >= 2 CTAs per SM (each N tile converts the activation tile again), else 128
   const long long m_tiles = (M + 127) / 128;
   int tn = N >= 256 ? 256 : ((N + 15) / 16) * 16;

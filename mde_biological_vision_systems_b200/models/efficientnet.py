@@ -93,7 +93,8 @@ def _pointwise_exact(conv, x, act, residual, out_pads):
     from .. import ops
     return (not torch.backends.cudnn.allow_tf32 and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1
             and conv.padding in ((0, 0), 0) and (act is None or isinstance(act, nn.SiLU))
-            and (out_pads is None or not any(out_pads)) and ops.pointwise_supported(x, conv.in_channels, conv.out_channels)
+            and (out_pads is None or not any(out_pads) or residual is None)
+            and ops.pointwise_supported(x, conv.in_channels, conv.out_channels)
             and (residual is None or (residual.dtype == torch.float32 and residual.is_contiguous(memory_format=torch.channels_last))))
 
 
@@ -128,37 +129,50 @@ class _depthwise_engine:
         return False
 
 
-def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False):
+def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False, gate=None, pool=False):
     """act(bn(conv(x))) (+ residual); in inference (eval-mode statistics, no autograd) as ONE convolution with the folded
     filter -- the 69 per-block BatchNorm passes of EfficientNet-B1 are 3 ms of a 14 ms step otherwise -- followed, on
     channels_last CUDA tensors, by one fused bias + SiLU (+ residual) pass (ops.bias_act_nhwc_) instead of separate bias,
     activation and add kernels.  Same values up to fp32 rounding.
     ``out_pads`` (top, bottom, left, right): on the fused path the result is written zero-padded (the SAME padding of the
-    stride-2 convolution that consumes it; callers detect it by the grown spatial size and pass ``prepadded`` on)."""
+    stride-2 convolution that consumes it; callers detect it by the grown spatial size and pass ``prepadded`` on).
+    ``gate`` [B, C_in]: the convolution's input is x * gate[:, :, None, None] (squeeze-excite), multiplied inside the GEMM
+    where that kernel runs.  ``pool``: return (y, slab sums of y or None) -- the spatial mean the following squeeze-excite
+    needs, taken from the bias/activation pass."""
+    def ret(y, partial=None):
+        return (y, partial) if pool else y
+
     if bn.training or torch.is_grad_enabled() or not isinstance(bn, nn.BatchNorm2d) or not bn.track_running_stats \
             or not bn.affine:
+        if gate is not None:
+            x = x * gate[:, :, None, None]
         y = bn(conv(x))
         y = act(y) if act is not None else y
-        return y + residual if residual is not None else y
+        return ret(y + residual if residual is not None else y)
     from .. import ops
     w, b = _folded_conv_bn(conv, bn)
     if _pointwise_exact(conv, x, act, residual, out_pads):
         # exact mode (the caller switched the library's TF32 off: UnetAdaptiveBins inference): the 1x1 convolution, its folded
-        # BatchNorm bias, SiLU and the residual run as ONE tcgen05 GEMM with fp32-grade products (ops.pointwise_conv) instead
-        # of the library's legacy fp32 kernels + a bias/activation pass
-        return ops.pointwise_conv(x, _folded_pointwise_pair(conv, bn, w), b, 1 if act is not None else 0, residual)
+        # BatchNorm bias, SiLU, the squeeze-excite gate on its input and the residual run as ONE tcgen05 GEMM with fp32-grade
+        # products (ops.pointwise_conv) instead of the library's legacy fp32 kernels + a bias/activation pass
+        return ret(ops.pointwise_conv(x, _folded_pointwise_pair(conv, bn, w), b, 1 if act is not None else 0, residual,
+                                      gate=gate, out_pads=out_pads))
+    if gate is not None:
+        x = x * gate[:, :, None, None]
     fused = (act is None or isinstance(act, nn.SiLU)) and x.is_cuda
     with _depthwise_engine(conv, x):
         y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
             else conv._conv_forward(x, w, None if fused else b)
     if fused and ops.bias_act_supported(y, residual):
         if out_pads is not None and residual is None and any(out_pads):
-            return ops.bias_act_pad_nhwc(y, b, 1 if act is not None else 0, out_pads)
-        return ops.bias_act_nhwc_(y, b, 1 if act is not None else 0, residual)
+            return ret(ops.bias_act_pad_nhwc(y, b, 1 if act is not None else 0, out_pads))
+        if pool and residual is None:
+            return ops.bias_act_pool_nhwc_(y, b, 1 if act is not None else 0)
+        return ret(ops.bias_act_nhwc_(y, b, 1 if act is not None else 0, residual))
     if fused:
         y = y + b.view(1, -1, 1, 1)
     y = act(y) if act is not None else y
-    return y + residual if residual is not None else y
+    return ret(y + residual if residual is not None else y)
 
 
 def _conv(cin, cout, k, stride=1, groups=1, bias=False):
@@ -176,17 +190,23 @@ class SqueezeExcite(nn.Module):
 
     def forward(self, x):
         g = x.mean((2, 3), keepdim=True)
-        if x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32:
-            # inference: the two 1x1 convolutions act on a [B, C, 1, 1] tensor, i.e. they are [B, C] x [C, R] products; as
-            # convolutions the library's exact-fp32 path spends ~48 us on each of the 46 (2.2 ms per config-2 step), as
-            # exact-fp32 linear maps (ops.linear, fp32 FMA) a few microseconds.  Same arithmetic, same parameters.
-            from .. import ops
-            r, e = self.conv_reduce, self.conv_expand
-            h = ops.linear(g.flatten(1), r.weight.flatten(1), r.bias)
-            h = ops.linear(h * torch.sigmoid(h), e.weight.flatten(1), e.bias)
-            return x * torch.sigmoid(h)[:, :, None, None]
         g = self.conv_expand(self.act1(self.conv_reduce(g)))
         return x * torch.sigmoid(g)
+
+    def gate_from(self, partial, hw):
+        """[B, C] gate sigmoid(conv_expand(silu(conv_reduce(mean)))) from the slab sums the preceding bias/activation pass left
+        (inference; the two 1x1 convolutions act on a [B, C, 1, 1] tensor, i.e. they are two tiny dense layers -- as library
+        convolutions in exact fp32 they cost ~48 us each, 2.2 ms per config-2 step)."""
+        from .. import ops
+        r, e = self.conv_reduce, self.conv_expand
+        return ops.se_gate(partial, hw, r.weight.flatten(1), r.bias, e.weight.flatten(1), e.bias)
+
+
+def _se_project(se, conv, bn, y, partial, residual):
+    """squeeze-excite + the 1x1 projection that follows it; with the slab sums at hand the gate goes into the GEMM"""
+    if partial is not None:
+        return conv_bn(conv, bn, y, None, residual, gate=se.gate_from(partial, y.shape[2] * y.shape[3]))
+    return conv_bn(conv, bn, se(y), None, residual)
 
 
 class DepthwiseSeparableConv(nn.Module):
@@ -202,8 +222,8 @@ class DepthwiseSeparableConv(nn.Module):
         self.act2 = nn.Identity()
 
     def forward(self, x):
-        y = conv_bn(self.conv_dw, self.bn1, x, self.act1)
-        return conv_bn(self.conv_pw, self.bn2, self.se(y), None, x if self.has_residual else None)
+        y, partial = conv_bn(self.conv_dw, self.bn1, x, self.act1, pool=True)
+        return _se_project(self.se, self.conv_pw, self.bn2, y, partial, x if self.has_residual else None)
 
 
 class InvertedResidual(nn.Module):
@@ -225,8 +245,8 @@ class InvertedResidual(nn.Module):
         # a stride-2 SAME depthwise conv follows the 1x1 expansion: let the expansion's epilogue write its output padded
         pads = self.conv_dw.same_pads(x.shape[-2], x.shape[-1]) if isinstance(self.conv_dw, SamePadConv2d) else None
         y = conv_bn(self.conv_pw, self.bn1, x, self.act1, out_pads=pads)
-        y = conv_bn(self.conv_dw, self.bn2, y, self.act2, prepadded=(y.shape[-2:] != x.shape[-2:]))
-        return conv_bn(self.conv_pwl, self.bn3, self.se(y), None, x if self.has_residual else None)
+        y, partial = conv_bn(self.conv_dw, self.bn2, y, self.act2, prepadded=(y.shape[-2:] != x.shape[-2:]), pool=True)
+        return _se_project(self.se, self.conv_pwl, self.bn3, y, partial, x if self.has_residual else None)
 
 
 class GenEfficientNet(nn.Module):

@@ -197,7 +197,16 @@ class Encoder(nn.Module):
         self.original_model = backend
 
     def forward(self, x, stem_prepadded=False):
-        """``stem_prepadded``: x already carries the zero border the TensorFlow-SAME stem convolution would add."""
+        """``stem_prepadded``: x already carries the zero border the TensorFlow-SAME stem convolution would add.
+        Inference on CUDA (no autograd, eval-mode BatchNorm) takes a shorter walk that leaves the entries no consumer reads as
+        ``None``: conv_stem + bn1 + act1 run as one folded convolution (entries 1 and 2 are None, entry 3 is the activation),
+        conv_head as the fp32-grade tcgen05 1x1 GEMM when the library's TF32 is off, and whatever follows conv_head (bn2, act2,
+        pooling, classifier -- the decoder's deepest tap is conv_head's own output, entry 11) is not computed."""
+        om = self.original_model
+        if (x.is_cuda and not torch.is_grad_enabled() and not om.training and isinstance(getattr(om, 'bn1', None), nn.BatchNorm2d)
+                and list(om._modules)[:5] == ['conv_stem', 'bn1', 'act1', 'blocks', 'conv_head']
+                and isinstance(om.act1, nn.SiLU)):
+            return self._forward_inference(x, stem_prepadded)
         feats = [x]
         for name, child in self.original_model._modules.items():
             stages = child._modules.values() if name == 'blocks' else (child,)
@@ -206,6 +215,27 @@ class Encoder(nn.Module):
                     feats.append(stage.forward_with(feats[-1], stage.weight, stage.bias, prepadded=True))
                 else:
                     feats.append(stage(feats[-1]))
+        return feats
+
+    def _forward_inference(self, x, stem_prepadded):
+        from .efficientnet import conv_bn
+        om = self.original_model
+        y = conv_bn(om.conv_stem, om.bn1, x, om.act1, prepadded=stem_prepadded and isinstance(om.conv_stem, SamePadConv2d))
+        feats = [x, None, None, y]
+        for stage in om.blocks._modules.values():
+            feats.append(stage(feats[-1]))
+        head, y = om.conv_head, feats[-1]
+        if (not torch.backends.cudnn.allow_tf32 and head.kernel_size == (1, 1) and head.bias is None
+                and ops.pointwise_supported(y, head.in_channels, head.out_channels)):
+            key = head.weight._version
+            cached = getattr(head, "_mde_pair", None)
+            if cached is None or cached[0] != key or cached[1].device != y.device:
+                cached = (key, ops.prepare_pointwise_weight(head.weight.detach().flatten(1)))
+                head._mde_pair = cached
+            feats.append(ops.pointwise_conv(y, cached[1], None, 0, None, name="pointwise"))
+        else:
+            feats.append(head(y))
+        feats.extend([None] * (len(om._modules) - 5))
         return feats
 
 

@@ -679,10 +679,13 @@ def pointwise_supported(x, cin, cout):
                 and x.is_contiguous(memory_format=torch.channels_last) and x.shape[0] * x.shape[2] * x.shape[3] < 2 ** 31)
 
 
-def pointwise_conv(x_cl, w_pair, bias=None, act=0, residual=None, name="pointwise"):
-    """act(conv1x1(x) + bias) (+ residual) on the tcgen05 GEMM, three bf16 products per K step (fp32-grade): x_cl channels_last
-    fp32 [B,Cin,H,W], w_pair from prepare_pointwise_weight; act 0 none / 1 SiLU; residual channels_last [B,Cout,H,W].
-    Returns a channels_last fp32 [B,Cout,H,W] tensor."""
+def pointwise_conv(x_cl, w_pair, bias=None, act=0, residual=None, name="pointwise", gate=None, out_pads=None):
+    """act(conv1x1(x * gate) + bias) (+ residual) on the tcgen05 GEMM, three bf16 products per K step (fp32-grade): x_cl
+    channels_last fp32 [B,Cin,H,W], w_pair from prepare_pointwise_weight; act 0 none / 1 SiLU; residual channels_last
+    [B,Cout,H,W]; gate fp32 [B,Cin] (the squeeze-excite scale, multiplied into x in fp32 inside the kernel); out_pads
+    (top, bottom, left, right): the result is written inside a zero border of that size.
+    Returns a channels_last fp32 [B,Cout,H(+pads),W(+pads)] tensor."""
+    import ctypes
     lib = _lib.load()
     _need_cuda(x_cl, w_pair)
     b, c, h, w = x_cl.shape
@@ -694,12 +697,54 @@ def pointwise_conv(x_cl, w_pair, bias=None, act=0, residual=None, name="pointwis
     if residual is not None and not (residual.is_contiguous(memory_format=torch.channels_last) and residual.dtype == torch.float32
                                      and residual.shape == (b, cout, h, w)):
         raise ValueError("pointwise_conv: residual must be a float32 channels_last [B,Cout,H,W] tensor")
-    out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    if gate is not None and not (gate.dtype == torch.float32 and gate.shape == (b, c) and gate.is_contiguous()):
+        raise ValueError("pointwise_conv: gate must be a contiguous float32 [B,Cin] tensor")
+    pad_arg = None
+    if out_pads is not None and any(out_pads):
+        if residual is not None:
+            raise ValueError("pointwise_conv: out_pads and residual are exclusive")
+        pt, pb, pl, pr = (int(v) for v in out_pads)
+        out = torch.empty((b, cout, h + pt + pb, w + pl + pr), dtype=torch.float32, device=x_cl.device,
+                          memory_format=torch.channels_last)
+        for sl in ((slice(0, pt), slice(None)), (slice(h + pt, None), slice(None)), (slice(None), slice(0, pl)),
+                   (slice(None), slice(w + pl, None))):
+            border = out[:, :, sl[0], sl[1]]
+            if border.numel():
+                border.zero_()
+        pad_arg = (ctypes.c_int * 6)(h, w, pt, pb, pl, pr)
+    else:
+        out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
     m = b * h * w
     with timing(name, work=2.0 * m * cout * c):
-        rc = lib.mde_pointwise_x3_fwd(_p(x_cl), _p(w_pair), _p(bias), int(act), _p(residual), _p(out), m, cout, c, cout, cout, _s())
+        rc = lib.mde_pointwise_x3_fwd(_p(x_cl), _p(gate), h * w, _p(w_pair), _p(bias), int(act), _p(residual), _p(out), m, cout,
+                                      c, cout, cout, pad_arg, _s())
     _lib.check(rc, "mde_pointwise_x3_fwd")
     return out
+
+
+def bias_act_pool_nhwc_(x_cl, bias, act):
+    """In place x = act(x + bias[c]) on a channels_last tensor and, from the same pass, the per-slab channel sums
+    [B, slabs, C] of the result (ops.se_gate turns them into the squeeze-excite gate)."""
+    lib = _lib.load()
+    b, c, h, w = x_cl.shape
+    slabs = int(lib.mde_pool_slabs(b, h * w))
+    partial = torch.empty((b, slabs, c), dtype=torch.float32, device=x_cl.device)
+    rc = lib.mde_bias_act_pool_nhwc(_p(x_cl), _p(bias), _p(x_cl), _p(partial), b, h * w, c, int(act), _s())
+    _lib.check(rc, "mde_bias_act_pool_nhwc")
+    return x_cl, partial
+
+
+def se_gate(partial, hw, w_reduce, b_reduce, w_expand, b_expand):
+    """sigmoid(expand(silu(reduce(mean)))) of a squeeze-excite block from the slab sums of bias_act_pool_nhwc_:
+    partial [B, slabs, C], w_reduce [R, C], w_expand [C, R] -> gate [B, C]."""
+    lib = _lib.load()
+    b, slabs, c = partial.shape
+    r = w_reduce.shape[0]
+    gate = torch.empty((b, c), dtype=torch.float32, device=partial.device)
+    rc = lib.mde_se_gate(_p(partial), slabs, 1.0 / float(hw), _p(w_reduce), _p(b_reduce), _p(w_expand), _p(b_expand), _p(gate),
+                         b, c, r, _s())
+    _lib.check(rc, "mde_se_gate")
+    return gate
 
 
 # ------------------------------------------------------------------------------------------------------------

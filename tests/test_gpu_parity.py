@@ -357,6 +357,101 @@ def test_pointwise_conv_x3(cfg):
     assert err < 5e-5, err
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 96, 23, 31), cout=24, gate=True),
+    dict(shape=(3, 144, 13, 17), cout=40, gate=True, res=True),       # 3 images inside / across 128-row tiles
+    dict(shape=(2, 16, 24, 40), cout=96, act=1, pads=(0, 1, 0, 1)),
+    dict(shape=(2, 24, 13, 17), cout=144, act=1, pads=(1, 2, 2, 1), gate=True),
+])
+def test_pointwise_conv_gate_and_padded_output(cfg):
+    """ops.pointwise_conv with the squeeze-excite gate multiplied into its input inside the GEMM and / or the result written
+    inside a zero border (TensorFlow-SAME padding of the stride-2 depthwise conv that follows), vs float64."""
+    rng = np.random.default_rng(181)
+    b, c, h, w = cfg["shape"]
+    cout = cfg["cout"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 1, 1)) / np.sqrt(c)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    gate = torch.from_numpy(rng.random((b, c)).astype(np.float32)) if cfg.get("gate") else None
+    res = torch.from_numpy(rng.standard_normal((b, cout, h, w)).astype(np.float32)) if cfg.get("res") else None
+    xin = x if gate is None else x * gate[:, :, None, None]  # fp32 product, as the reference forms it
+    ref = torch.nn.functional.conv2d(xin.double(), wt.double(), bias.double())
+    if cfg.get("act"):
+        ref = ref * torch.sigmoid(ref)
+    if res is not None:
+        ref = ref + res.double()
+    pads = cfg.get("pads")
+    if pads:
+        ref = torch.nn.functional.pad(ref, (pads[2], pads[3], pads[0], pads[1]))
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = ops.pointwise_conv(xd, ops.prepare_pointwise_weight(wt.to(DEV)), bias.to(DEV), cfg.get("act", 0),
+                             None if res is None else res.to(DEV).contiguous(memory_format=torch.channels_last),
+                             gate=None if gate is None else gate.to(DEV), out_pads=pads)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 5e-5, err
+    if pads:  # the border is exactly zero
+        inner = torch.zeros_like(out, dtype=torch.bool)
+        inner[:, :, pads[0]:pads[0] + h, pads[2]:pads[2] + w] = True
+        assert float(out[~inner].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,r", [((2, 96, 23, 31), 4), ((16, 1152, 13, 17), 48), ((3, 40, 5, 7), 10)])
+def test_squeeze_excite_kernels(shape, r):
+    """bias + SiLU + slab sums in one pass (ops.bias_act_pool_nhwc_) and the fused gate kernel (ops.se_gate) vs torch."""
+    rng = np.random.default_rng(182)
+    b, c, h, w = shape
+    x = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.from_numpy(rng.standard_normal(c).astype(np.float32)).to(DEV)
+    w1 = torch.from_numpy((rng.standard_normal((r, c)) / np.sqrt(c)).astype(np.float32)).to(DEV)
+    b1 = torch.from_numpy(rng.standard_normal(r).astype(np.float32)).to(DEV)
+    w2 = torch.from_numpy((rng.standard_normal((c, r)) / np.sqrt(r)).astype(np.float32)).to(DEV)
+    b2 = torch.from_numpy(rng.standard_normal(c).astype(np.float32)).to(DEV)
+    ref_y = torch.nn.functional.silu(x.double() + bias.double()[None, :, None, None])
+    m = ref_y.mean((2, 3))
+    hdn = torch.nn.functional.silu(m @ w1.double().T + b1.double())
+    ref_gate = torch.sigmoid(hdn @ w2.double().T + b2.double())
+    y, partial = ops.bias_act_pool_nhwc_(x.clone(memory_format=torch.channels_last), bias, 1)
+    assert float((y.double() - ref_y).abs().max()) < 1e-5
+    assert partial.shape[0] == b and partial.shape[2] == c
+    assert float((partial.double().sum(1) / (h * w) - m).abs().max()) < 1e-5
+    gate = ops.se_gate(partial, h * w, w1, b1, w2, b2)
+    assert float((gate.double() - ref_gate).abs().max()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_encoder_inference_walk_matches_generic_walk():
+    """Encoder._forward_inference (folded stem, squeeze-excite gate inside the projection GEMM, padded expansion output,
+    conv_head on the tcgen05 GEMM) yields the same decoder taps as walking the backbone module by module in exact fp32."""
+    from mde_biological_vision_systems_b200.models import UnetAdaptiveBins
+    torch.manual_seed(3)
+    model = UnetAdaptiveBins.build(n_bins=256, min_val=1e-3, max_val=10.0, norm="linear", encoder_name="efficientnet-b1",
+                                   semantics_mode=None, instance_segmentation_mode=None).to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    for mod in model.encoder.modules():  # non-trivial BatchNorm statistics so that the folds are exercised
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+            mod.running_var.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+            mod.weight.data.copy_(0.5 + torch.rand(mod.num_features, generator=g))
+            mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+    x = torch.rand(2, 3, 96, 128, device=DEV).contiguous(memory_format=torch.channels_last)
+    enc = model.encoder
+    with ops.exact_fp32_library():
+        with torch.no_grad():
+            fast = enc(x)
+        with torch.enable_grad():  # autograd on: every block takes its plain torch path (bn(conv(x)), SqueezeExcite.forward)
+            ref = [x]
+            for name, child in enc.original_model._modules.items():  # the reference's walk (unet_adaptive_bins.py:118-128)
+                for stage in (child._modules.values() if name == "blocks" else (child,)):
+                    ref.append(stage(ref[-1]).detach())
+    assert len(fast) == len(ref) and fast[1] is None
+    for i in (3, 4, 5, 6, 8, 11):
+        err = float((fast[i].double() - ref[i].double()).abs().max()) / float(ref[i].abs().max())
+        assert err < 2e-5, (i, err)
+
+
 def test_conv3x3_tf32_form():
     """The single-pass TF32 form of the same kernel (operands pre-rounded by the caller, as its contract says)."""
     rng = np.random.default_rng(94)
