@@ -334,10 +334,12 @@ int mde_upsample_bwd(const float* gout, float* gx, int channels_last, int B, int
  * [B,C2,H,W]; out_nhwc [B,H,W,C1+C2].  C1 % 4 == 0 and C2 % 4 == 0. */
 int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last, float* out_nhwc, int B,
                                  int C1, int C2, int h, int w, int H, int W, mde_stream_t stream);
-/* the same step writing its result as a split-bf16 pair planes[2][B,H,W,C1+C2] (feeds mde_conv3x3_nhwc_x3_fwd);
- * skip must be NHWC */
+/* the same step writing its result as a split-bf16 pair planes[2][B,H,W,Cpitch] (feeds mde_conv3x3_nhwc_x3_fwd);
+ * skip must be NHWC.  Cpitch >= C1 + C2, Cpitch % 8 == 0; channels [C1 + C2, Cpitch) are written as zeros -- a pitch rounded up
+ * to 32 channels keeps every 64-byte TMA box row of the convolution sector-aligned (the conv then runs with C = Cpitch and a
+ * filter zero-padded to match: same K chunks, same result). */
 int mde_upsample_concat_nhwc_pair_fwd(const float* x_nhwc, const float* skip_nhwc, uint16_t* out_pair, int B, int C1, int C2,
-                                      int h, int w, int H, int W, mde_stream_t stream);
+                                      int Cpitch, int h, int w, int H, int W, mde_stream_t stream);
 
 /* NCHW [B,C,P] -> NHWC [B,P,C] transpose (feeds the head's cuDNN convs and the K-major chain operand) */
 int mde_nchw_to_nhwc(const float* in, float* out, int B, int C, int64_t P, mde_stream_t stream);

@@ -42,7 +42,7 @@ SIGNATURES = {
     "mde_merge_bf16": (_i32, [_p, _p, _i64, _p]),
     "mde_split_bf16_nchw": (_i32, [_p, _p, _i32, _i32, _i64, _p]),
     "mde_range_attention_tc": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _p]),
-    "mde_upsample_concat_nhwc_pair_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "mde_upsample_concat_nhwc_pair_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_pointwise_x3_fwd": (_i32, [_p, _p, _i64, _p, _p, _i32, _p, _p, _i64, _i32, _i32, _i64, _i64, _p, _p]),
     "mde_pool_slabs": (_i32, [_i32, _i64]),
     "mde_bias_act_pool_nhwc": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _p]),

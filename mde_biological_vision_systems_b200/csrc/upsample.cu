@@ -305,26 +305,24 @@ __device__ __forceinline__ void store4(void* out, long long elem, long long plan
   }
 }
 
+// grid (ceil(W * C1/4 / 256), H, B): the row and the image come from the block index, so a thread needs one 32-bit division
+// (the 64-bit index arithmetic of a flat launch cost more than the interpolation itself)
 template <bool PAIR>
 __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ x, void* __restrict__ out, int C1,
                                                             int Ctot, int h, int w, int H, int W, float sy, float sx,
-                                                            long long total, long long plane_elems) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+                                                            long long plane_elems) {
   const int c4 = C1 >> 2;
-  const int cg = (int)(idx % c4);
-  long long p = idx / c4;
-  const int X = (int)(p % W);
-  p /= W;
-  const int Y = (int)(p % H);
-  const int b = (int)(p / H);
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= (unsigned)(W * c4)) return;
+  const int X = (int)(t / (unsigned)c4), cg = (int)(t - (unsigned)X * c4);
+  const int Y = blockIdx.y, b = blockIdx.z;
   int y0, y1, xa, xb;
   float ly0, ly1, lx0, lx1;
   up_src(Y, sy, h, y0, y1, ly0, ly1);
   up_src(X, sx, w, xa, xb, lx0, lx1);
   const float4* src = reinterpret_cast<const float4*>(x + (long long)b * h * w * C1) + cg;
-  const float4 v00 = __ldg(src + ((long long)y0 * w + xa) * c4), v01 = __ldg(src + ((long long)y0 * w + xb) * c4);
-  const float4 v10 = __ldg(src + ((long long)y1 * w + xa) * c4), v11 = __ldg(src + ((long long)y1 * w + xb) * c4);
+  const float4 v00 = __ldg(src + (y0 * w + xa) * c4), v01 = __ldg(src + (y0 * w + xb) * c4);
+  const float4 v10 = __ldg(src + (y1 * w + xa) * c4), v11 = __ldg(src + (y1 * w + xb) * c4);
   float4 o;  // same association as ATen: ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * c + lx1 * d)
   o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
   o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
@@ -333,16 +331,20 @@ __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restr
   store4<PAIR>(out, (((long long)b * H + Y) * W + X) * Ctot + 4 * cg, plane_elems, o);
 }
 
+// skip channels [C1, C1 + C2) of every pixel, then zeros up to the row pitch Ctot (>= C1 + C2: a pitch padded to whole
+// 64-byte groups keeps the conv's TMA boxes sector-aligned).  grid (ceil(P * (Ctot - C1)/4 / 256), B)
 template <bool PAIR>
 __global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __restrict__ skip, void* __restrict__ out,
-                                                                 int C1, int C2, int Ctot, long long total,
-                                                                 long long plane_elems) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c4 = C2 >> 2;
-  const int cg = (int)(idx % c4);
-  const long long p = idx / c4;
-  store4<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg));
+                                                                 int C1, int C2, int Ctot, unsigned per_image,
+                                                                 long long P, long long plane_elems) {
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= per_image) return;
+  const unsigned c4 = (unsigned)(Ctot - C1) >> 2;
+  const unsigned pl = t / c4, cg = t - pl * c4;
+  const long long p = (long long)blockIdx.y * P + pl;
+  const float4 v = 4 * cg < (unsigned)C2 ? ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  store4<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, v);
 }
 }  // namespace mde
 
@@ -370,33 +372,38 @@ extern "C" int mde_nchw_to_nhwc_slice_padded(const float* in, float* out, int B,
 }
 
 static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, int skip_channels_last, void* out, bool pair,
-                                       int B, int C1, int C2, int h, int w, int H, int W, cudaStream_t st) {
+                                       int B, int C1, int C2, int Cpitch, int h, int w, int H, int W, cudaStream_t st) {
   using namespace mde;
   if (!x_nhwc || !out || (C2 > 0 && !skip)) return MDE_ERR_BAD_POINTER;
-  if (B <= 0 || C1 <= 0 || C2 < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return MDE_ERR_BAD_SHAPE;
-  if (C1 % 4 != 0 || C2 % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(out, 16) || (C2 > 0 && !aligned(skip, 16)))
+  if (B <= 0 || C1 <= 0 || C2 < 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535 || H > 65535 || Cpitch < C1 + C2)
+    return MDE_ERR_BAD_SHAPE;
+  if (C1 % 4 != 0 || C2 % 4 != 0 || Cpitch % 4 != 0 || !aligned(x_nhwc, 16) || !aligned(out, 16) || (C2 > 0 && !aligned(skip, 16)))
     return MDE_ERR_UNSUPPORTED;
   if (pair && C2 > 0 && !skip_channels_last) return MDE_ERR_UNSUPPORTED;  // pair output takes an NHWC skip
-  const int Ctot = C1 + C2;
+  if (Cpitch != C1 + C2 && !skip_channels_last) return MDE_ERR_UNSUPPORTED;
+  const int Ctot = Cpitch;
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const long long P = (long long)H * W;
   const long long plane = (long long)B * P * Ctot;
-  const long long total = (long long)B * P * (C1 / 4);
+  if ((long long)W * (C1 / 4) > 0x7fffffffLL || (long long)h * w * (C1 / 4) > 0x7fffffffLL || P * ((Ctot - C1) / 4) > 0x7fffffffLL)
+    return MDE_ERR_BAD_SHAPE;
+  const dim3 grid((unsigned)((W * (C1 / 4) + 255) / 256), (unsigned)H, (unsigned)B);
   if (pair)
-    upsample_nhwc_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, total, plane);
+    upsample_nhwc_kernel<true><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
   else
-    upsample_nhwc_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, total, plane);
+    upsample_nhwc_kernel<false><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
   int rc = check_launch();
-  if (rc || C2 == 0) return rc;
+  if (rc || Ctot == C1) return rc;
   if (skip_channels_last) {
-    const long long t2 = (long long)B * P * (C2 / 4);
+    const unsigned per_image = (unsigned)(P * ((Ctot - C1) / 4));
+    const dim3 g2((per_image + 255) / 256, (unsigned)B);
     if (pair)
-      copy_channels_nhwc_kernel<true><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out, C1, C2, Ctot, t2, plane);
+      copy_channels_nhwc_kernel<true><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
     else
-      copy_channels_nhwc_kernel<false><<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(skip, out, C1, C2, Ctot, t2, plane);
+      copy_channels_nhwc_kernel<false><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
   } else {
-    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(skip, reinterpret_cast<float*>(out) + C1, C2, P, Ctot);
+    dim3 grid2((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
+    nchw_to_nhwc_kernel<<<grid2, 256, 0, st>>>(skip, reinterpret_cast<float*>(out) + C1, C2, P, Ctot);
   }
   return check_launch();
 }
@@ -404,12 +411,14 @@ static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, i
 extern "C" int mde_upsample_concat_nhwc_fwd(const float* x_nhwc, const float* skip, int skip_channels_last,
                                             float* out_nhwc, int B, int C1, int C2, int h, int w, int H, int W,
                                             mde_stream_t stream) {
-  return upsample_concat_nhwc_launch(x_nhwc, skip, skip_channels_last, out_nhwc, false, B, C1, C2, h, w, H, W,
+  return upsample_concat_nhwc_launch(x_nhwc, skip, skip_channels_last, out_nhwc, false, B, C1, C2, C1 + C2, h, w, H, W,
                                      (cudaStream_t)stream);
 }
 
-// the same step writing a split-bf16 pair (planes[2][B,H,W,C1+C2]) for mde_conv3x3_nhwc_x3_fwd; skip must be NHWC
+// the same step writing a split-bf16 pair (planes[2][B,H,W,Cpitch], Cpitch >= C1 + C2, the channels beyond C1 + C2 zeroed) for
+// mde_conv3x3_nhwc_x3_fwd; skip must be NHWC
 extern "C" int mde_upsample_concat_nhwc_pair_fwd(const float* x_nhwc, const float* skip_nhwc, uint16_t* out_pair, int B, int C1,
-                                                 int C2, int h, int w, int H, int W, mde_stream_t stream) {
-  return upsample_concat_nhwc_launch(x_nhwc, skip_nhwc, 1, out_pair, true, B, C1, C2, h, w, H, W, (cudaStream_t)stream);
+                                                 int C2, int Cpitch, int h, int w, int H, int W, mde_stream_t stream) {
+  if (Cpitch % 8 != 0) return MDE_ERR_UNSUPPORTED;
+  return upsample_concat_nhwc_launch(x_nhwc, skip_nhwc, 1, out_pair, true, B, C1, C2, Cpitch, h, w, H, W, (cudaStream_t)stream);
 }

@@ -67,7 +67,9 @@ class UpSampleBN(nn.Module):
                     conv, bn = self._net[i], self._net[i + 1]
                     scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
                     shift = bn.bias + (conv.bias - bn.running_mean) * scale
-                    w = ops.prepare_conv3x3_weight(conv.weight)
+                    # the concatenated input of the first conv is written with its channel pitch rounded up to 32 (64-byte
+                    # operand rows stay sector-aligned: 680- and 344-channel rows otherwise start at 16-byte offsets)
+                    w = ops.prepare_conv3x3_weight(conv.weight, cin_pad_to=32 if i == 0 else 1)
                     blocks.append((w, scale.contiguous(), shift.contiguous(), self._net[i + 2].negative_slope))
             cached = (key, blocks)
             self._mde_folded = cached
@@ -84,7 +86,7 @@ class UpSampleBN(nn.Module):
         split-bf16 pair) -> 2 x tcgen05 conv3x3 (three bf16 products per K step) with BatchNorm(eval) + LeakyReLU in the
         epilogue.  Returns fp32 channels_last (input of the next resize) or an ops.SplitBF16 (``pair_out``)."""
         (w1, s1, b1, a1), (w2, s2, b2, a2) = self._folded()
-        y = ops.upsample_concat_nhwc_pair(x_cl, concat_with)
+        y = ops.upsample_concat_nhwc_pair(x_cl, concat_with, pad_to=32)
         y = ops.conv3x3_nhwc(y, w1, s1, b1, slope=a1, pair_out=True, name=name + ".conv_a")
         return ops.conv3x3_nhwc(y, w2, s2, b2, slope=a2, pair_out=pair_out, name=name + ".conv_b")
 

@@ -510,12 +510,16 @@ def gemm_nt(a, b, out=None, splits=1, alpha=1.0):
 # ------------------------------------------------------------------------------------------------------------
 # 3x3 convolution (tcgen05 implicit GEMM, NHWC)
 # ------------------------------------------------------------------------------------------------------------
-def prepare_conv3x3_weight(weight):
+def prepare_conv3x3_weight(weight, cin_pad_to=1):
     """Conv filter [Cout,C,3,3] -> [dx][dy][Cout][C] as a split-bf16 pair, bfloat16 [2,3,3,Cout,C] (the B operand tiles as
-    TMA reads them)."""
+    TMA reads them).  ``cin_pad_to``: C is rounded up to a multiple of it with zero input channels (for an input whose
+    channel pitch was padded the same way, ops.upsample_concat_nhwc_pair(pad_to=...))."""
     lib = _lib.load()
     _need_cuda(weight)
-    w = weight.detach().contiguous().float()
+    w = weight.detach().float()
+    if w.shape[1] % cin_pad_to:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad_to - w.shape[1] % cin_pad_to))
+    w = w.contiguous()
     cout, c = w.shape[0], w.shape[1]
     out = torch.empty((2, 3, 3, cout, c), dtype=torch.bfloat16, device=w.device)
     _lib.check(lib.mde_conv3x3_prep_weight_x3(_p(w), _p(out), cout, c, _s()), "mde_conv3x3_prep_weight_x3")
@@ -1083,9 +1087,11 @@ def upsample_concat_nhwc(x_cl, skip):
     return _upsample_concat_nhwc_fwd(x_cl, skip)
 
 
-def upsample_concat_nhwc_pair(x_cl, skip):
+def upsample_concat_nhwc_pair(x_cl, skip, pad_to=1):
     """The inference form of upsample_concat_nhwc that writes its result as a SplitBF16 (the operand format of the conv3x3
-    that follows): bilinear(align_corners=True) resize of x_cl to skip's size, concatenated with skip."""
+    that follows): bilinear(align_corners=True) resize of x_cl to skip's size, concatenated with skip.  ``pad_to``: the channel
+    count is rounded up to a multiple of it with zero channels (32 keeps the conv's 64-byte operand rows sector-aligned; the
+    conv's filter is zero-padded to match, see prepare_conv3x3_weight(cin_pad_to=...))."""
     lib = _lib.load()
     _need_cuda(x_cl, skip)
     x_cl, skip = _f32(x_cl), _f32(skip)
@@ -1095,9 +1101,10 @@ def upsample_concat_nhwc_pair(x_cl, skip):
         skip = skip.contiguous(memory_format=torch.channels_last)
     b, c1, h, w = x_cl.shape
     _, c2, hh, ww = skip.shape
-    planes = torch.empty((2, b, hh, ww, c1 + c2), dtype=torch.bfloat16, device=x_cl.device)
+    cp = -(-(c1 + c2) // pad_to) * pad_to
+    planes = torch.empty((2, b, hh, ww, cp), dtype=torch.bfloat16, device=x_cl.device)
     with timing("upsample_concat_nhwc"):
-        rc = lib.mde_upsample_concat_nhwc_pair_fwd(_p(x_cl), _p(skip), _p(planes), b, c1, c2, h, w, hh, ww, _s())
+        rc = lib.mde_upsample_concat_nhwc_pair_fwd(_p(x_cl), _p(skip), _p(planes), b, c1, c2, cp, h, w, hh, ww, _s())
     _lib.check(rc, "mde_upsample_concat_nhwc_pair_fwd")
     return SplitBF16(planes)
 

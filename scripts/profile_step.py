@@ -39,21 +39,22 @@ def table(prof, title, rows=45):
 
 
 if what in ("infer", "both"):
-    model.eval()
-
-    def infer():
-        with torch.no_grad():
-            _, sem = loader.get_semantics(batch)
-            edges, pred = model(batch["image"], semantics=sem)
-            return silog(pred, batch["depth"], mask=batch["depth"] > 1e-3, interpolate=True) + 0.1 * chamfer(edges, batch["depth"])
-
+    # the benchmarked mode: loader bound to the encoder input, fused losses (bench.build_gpu / bench.infer_step_fn)
+    import bench
+    cfg = dict(bench.CONFIGS[2], batch=B)
+    ctx = bench.Ctx()
+    bmodel, sem_loader, inst_loader = bench.build_gpu(cfg, ctx)
+    bmodel.eval()
+    step = bench.infer_step_fn(cfg, bmodel, sem_loader, inst_loader, ctx.dev)
+    hb = bench.host_batch(cfg, B)
+    dbatch = {k: v.to(dev) for k, v in hb.items()}
     for _ in range(3):
-        infer()
+        step(dbatch)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        infer()
+        step(dbatch)
         torch.cuda.synchronize()
-    table(prof, f"inference step B={B}")
+    table(prof, f"inference step B={B} (bench mode)", rows=60)
 
 if what in ("train", "both"):
     model.train()

@@ -782,6 +782,10 @@ def test_upsample_concat_nhwc_pair():
         ref = ops.split_bf16(ops.upsample_concat_nhwc(x, skip))
         out = ops.upsample_concat_nhwc_pair(x, skip)
         assert torch.equal(out.planes, ref.planes)
+        padded = ops.upsample_concat_nhwc_pair(x, skip, pad_to=32)  # zero channels up to the next multiple of 32
+        c = ref.planes.shape[-1]
+        assert padded.planes.shape[-1] == -(-c // 32) * 32
+        assert torch.equal(padded.planes[..., :c], ref.planes) and float(padded.planes[..., c:].float().abs().max()) == 0.0
 
 
 def test_nchw_to_nhwc():
@@ -1059,7 +1063,7 @@ def test_config5_noadabins_480x640():
     assert np.array_equal(pred.cpu().numpy(), oracle.noadabins_epilogue(unet_out.cpu()).numpy())
     # the decoder itself (tcgen05 convs + the direct 1-channel conv3) against the CPU oracle on the same encoder features
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-    ref = oracle.decoder_bn([f.cpu().contiguous() for f in feats], sd)
+    ref = oracle.decoder_bn([None if f is None else f.cpu().contiguous() for f in feats], sd)  # None: entries no consumer reads
     assert float((unet_out.cpu() - ref).abs().max()) < 5e-5 * float(ref.abs().max())
 
 
