@@ -399,6 +399,15 @@ def run_infer(cfg, ctx, steps, warmup, batch, detail=True):
         except Exception as exc:  # noqa: BLE001
             out["tf32_backbone_error"] = repr(exc)[:120]
         model.backbone_tf32 = False
+        # the north star's bf16 mode (2e-2 tolerance): one bf16 product per K step in the tensor-core kernels
+        try:
+            model.precision = "bf16"
+            g3 = GraphedStep(lambda **kw: step(kw), resident)
+            out["bf16_mode_ms"] = ctx.timed(lambda: g3(**resident), steps) / steps
+            del g3
+        except Exception as exc:  # noqa: BLE001
+            out["bf16_mode_error"] = repr(exc)[:120]
+        model.precision = "fp32"
     out["ms"] = out.get("graph_ms", ms_eager)
     out["e2e_ms"] = out.get("e2e_graph_ms", out["e2e_eager_ms"])
     pix = ctx.world * batch * h * w
@@ -632,7 +641,10 @@ def run_ours(args):
             if "tf32_backbone_ms" in r:
                 line["tf32_backbone"] = {"value": pix / (r["tf32_backbone_ms"] * 1e-3) / 1e6, "ms_per_step": r["tf32_backbone_ms"],
                                          "note": "cuDNN encoder / conv2 on the library's TF32 default instead of true fp32"}
-            for k in ("graph_error", "hot_error", "a6_error"):
+            if "bf16_mode_ms" in r:
+                line["bf16_mode"] = {"value": pix / (r["bf16_mode_ms"] * 1e-3) / 1e6, "ms_per_step": r["bf16_mode_ms"],
+                                     "note": "model.precision = 'bf16': one bf16 product per K step (2e-2 tolerance), library bodies TF32"}
+            for k in ("graph_error", "hot_error", "a6_error", "bf16_mode_error", "tf32_backbone_error"):
                 if k in r:
                     line[k] = r[k]
             line["clocks"] = clocks

@@ -150,7 +150,9 @@ int mde_patch_embed_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const fl
  * mde_conv3x3_nhwc_x3_fwd (the model's default): x_pair planes[2][B,H,W,C] and w_pair planes[2][dx][dy][Cout][C]
  *   (mde_conv3x3_prep_weight_x3) are split-bf16 pairs, three bf16 products per K step; y is fp32 [B,H,W,Cout]
  *   (y_is_pair == 0) or a pair planes[2][B,H,W,Cout] for the next tensor-core consumer (y_is_pair != 0).
- *   Requires C % 8 == 0, Cout % 4 == 0 (% 8 for pair output).
+ *   Requires C % 8 == 0, Cout % 4 == 0 (% 8 for pair output).  products = 3: hi*hi + mid*hi + hi*mid (fp32-grade, the 1e-3
+ *   contract); products = 1: the hi planes only, ONE bf16 product per K step -- the bf16 mode of the north star (depth within
+ *   2e-2 of the fp32 reference): a third of the tensor work and half the operand traffic.
  * mde_conv3x3_nhwc_fwd (single-pass TF32): x_nhwc fp32 whose values are already TF32-representable (rounded by their
  *   producer -- the tensor core would otherwise truncate them), w_prep = [dx][dy][Cout][C] TF32-rounded
  *   (mde_conv3x3_prep_weight, operand_scale normally 1.0f); round_tf32 != 0 rounds the outputs to TF32.  C % 4 == 0.
@@ -163,7 +165,8 @@ int mde_conv3x3_prep_weight_x3(const float* w_oihw, uint16_t* w_pair, int Cout, 
 int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* scale, const float* shift, float* y_nhwc,
                          int B, int H, int W, int C, int Cout, float lrelu_slope, int round_tf32, mde_stream_t stream);
 int mde_conv3x3_nhwc_x3_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* scale, const float* shift, void* y,
-                            int y_is_pair, int B, int H, int W, int C, int Cout, float lrelu_slope, mde_stream_t stream);
+                            int y_is_pair, int B, int H, int W, int C, int Cout, float lrelu_slope, int products,
+                            mde_stream_t stream);
 int mde_conv3x3_small_nhwc_fwd(const float* x_nhwc, const float* w_oihw, const float* bias, float* y_nhwc, int B, int H, int W,
                                int C, int Cout, mde_stream_t stream);
 
@@ -285,6 +288,10 @@ int mde_conv1x1_fwd(const float* ram, const float* w, const float* bias, float* 
  *   centers  [B,n_bins], pred [B,P].   Requires P % 128 == 0, n_bins == 256. */
 int mde_head_chain_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers, float* pred,
                        int B, int n_bins, int64_t P, mde_stream_t stream);
+/* the same fused head with ONE bf16 product per K step (hi planes only; the mid planes are neither read nor multiplied): the
+ * bf16 mode -- depth within 2e-2 of the fp32 reference (north star), half the operand traffic and a third of the MMAs */
+int mde_head_chain_bf16_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers,
+                            float* pred, int B, int n_bins, int64_t P, mde_stream_t stream);
 /* Training forms of the fused chain (autograd of layers.py:31-36 + unet_adaptive_bins.py:286-300 in hand-written form):
  *  - mde_head_chain_fwd_train: the forward, additionally storing the per-pixel softmax state stats [B,P,2]
  *    (max logit in log2 units, sum_j 2^(z_j - max));

@@ -36,7 +36,7 @@ SIGNATURES = {
     "mde_conv3x3_prep_weight": (_i32, [_p, _p, _i32, _i32, _f32, _p]),
     "mde_conv3x3_nhwc_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
     "mde_conv3x3_prep_weight_x3": (_i32, [_p, _p, _i32, _i32, _p]),
-    "mde_conv3x3_nhwc_x3_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    "mde_conv3x3_nhwc_x3_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _p]),
     "mde_conv3x3_small_nhwc_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_split_bf16": (_i32, [_p, _p, _i64, _p]),
     "mde_merge_bf16": (_i32, [_p, _p, _i64, _p]),
@@ -63,6 +63,7 @@ SIGNATURES = {
     "mde_bins_pred_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_conv1x1_fwd": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i64, _p]),
     "mde_head_chain_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
+    "mde_head_chain_bf16_fwd": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_head_chain_fwd_train": (_i32, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_head_chain_bwd_logits": (_i32, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i64, _p]),
     "mde_fold_queries": (_i32, [_p, _p, _p, _i64, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _i32, _p]),

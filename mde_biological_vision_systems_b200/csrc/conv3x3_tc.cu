@@ -37,7 +37,7 @@ namespace tc {
 constexpr int CV_THREADS = 224;
 constexpr int CV_KC = 32;                // channels per K chunk
 constexpr int CV_STG_BYTES = 128 * 128;  // one staged output group: 128 pixels x 32 channels (fp32, or 2 bf16 planes)
-enum { PREC_TF32 = 0, PREC_X3 = 1 };
+enum { PREC_TF32 = 0, PREC_X3 = 1, PREC_BF16 = 2 };  // BF16: the hi planes only, one bf16 product per K step (2e-2 mode)
 enum { OUT_F32 = 0, OUT_TF32 = 1, OUT_PAIR = 2 };  // epilogue output: fp32, fp32 rounded to TF32, split-bf16 pair
 
 struct ConvGeom {
@@ -58,13 +58,14 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
                    const __grid_constant__ CUtensorMap map_y, const float* __restrict__ scale,
                    const float* __restrict__ shift, const ConvGeom g) {
   constexpr bool X3 = PREC == PREC_X3;
+  constexpr bool BF = PREC != PREC_TF32;       // bf16 operands (pair planes); BF && !X3: plane 0 (hi) only
   constexpr int TH = 128 / TW;
   constexpr int SR = NT * TH;                  // pixel rows per super tile
-  constexpr int ROWB = X3 ? 64 : 128;          // bytes of one shared-memory operand row (32 channels)
+  constexpr int ROWB = BF ? 64 : 128;          // bytes of one shared-memory operand row (32 channels)
   constexpr int PLANES = X3 ? 2 : 1;
   constexpr int A_PLANE = (SR + 2) * TW * ROWB;  // halo box of one stage, one plane
   constexpr int A_BYTES = PLANES * A_PLANE;
-  constexpr uint32_t SWZ = X3 ? SWZ_64B : SWZ_128B;
+  constexpr uint32_t SWZ = BF ? SWZ_64B : SWZ_128B;
   constexpr uint32_t SBO = 8 * ROWB;           // 8-row swizzle atom
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 21);
             mbar_expect_tx(bar_full + 8 * stage, (uint32_t)stage_bytes);
             const uint32_t dst = base + stage * stage_bytes;
-            if constexpr (X3) {  // both planes of the pair in one box (outermost box dimension)
+            if constexpr (BF) {  // the planes of the pair this precision reads in one box (outermost box dimension)
               tma_load_5d(dst, &map_x, bar_full + 8 * stage, c * CV_KC, x0 + dx - 1, y0 - 1, b, 0);
               tma_load_5d(dst + A_BYTES, &map_w, bar_full + 8 * stage, c * CV_KC, n0, 0, dx, 0);
             } else {
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(X3 ? FMT_BF16 : FMT_TF32, 128, (uint32_t)g.n_tile, 0, 0);
+      const uint32_t idesc = make_idesc(BF ? FMT_BF16 : FMT_TF32, 128, (uint32_t)g.n_tile, 0, 0);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = unit0; tile < g.total; tile += ustep, ++it) {
         const uint32_t buf = it & 1, aphase = (it >> 1) & 1;
@@ -166,6 +167,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
                     umma_f16_ss(d0 + t * g.n_tile, ahi, bhi, idesc, first ^ 1);
                     umma_f16_ss(d0 + t * g.n_tile, amid, bhi, idesc, 1);
                     umma_f16_ss(d0 + t * g.n_tile, ahi, bmid, idesc, 1);
+                  }
+                  first = 0;
+                }
+              } else if constexpr (BF) {
+#pragma unroll
+                for (int j = 0; j < CV_KC / 16; ++j) {
+                  const uint64_t bdesc = make_smem_desc(b0 + dy * nb * ROWB + j * 32, 16, SBO, SWZ);
+#pragma unroll
+                  for (int t = 0; t < NT; ++t) {
+                    const uint64_t adesc = make_smem_desc(a0 + (t * TH + dy) * TW * ROWB + j * 32, 16, SBO, SWZ);
+                    umma_f16_ss(d0 + t * g.n_tile, adesc, bdesc, idesc, first ^ 1);
                   }
                   first = 0;
                 }
@@ -359,7 +371,8 @@ template <int PREC>
 int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const float* shift, void* y, int B, int H, int W,
                    int C, int Cout, float lrelu_slope, int out_mode, cudaStream_t st) {
   constexpr bool X3 = PREC == tc::PREC_X3;
-  const int in_align = X3 ? 8 : 4;                                   // TMA: 16-byte global strides
+  constexpr bool BF = PREC != tc::PREC_TF32;
+  const int in_align = BF ? 8 : 4;                                   // TMA: 16-byte global strides
   const int out_align = out_mode == tc::OUT_PAIR ? 8 : 4;
   if (C % in_align != 0 || Cout % out_align != 0 || !aligned(x, 16) || !aligned(w_prep, 16) || !aligned(y, 16))
     return MDE_ERR_UNSUPPORTED;
@@ -368,7 +381,7 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   // order, whose stage (halo box + filter taps) fits the shared-memory ring at least twice.  Measured on B200: choosing
   // narrower tiles so that two stacked patches share the filter (C_out = 640 as 5 x 128, 320 as 5 x 64) was slower
   // (up1 + up2: 1.54 vs 1.37 ms).
-  const int rowb = X3 ? 64 : 128, planes = X3 ? 2 : 1;
+  const int rowb = BF ? 64 : 128, planes = X3 ? 2 : 1;
   const int budget = 222 * 1024 - 2 * tc::CV_STG_BYTES - 2048 - 512;
   int forced = 0;
   {
@@ -426,16 +439,17 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   const int smem = g.nstages * stage_bytes + 2 * tc::CV_STG_BYTES + 32 * g.nstages + 128 + 2048;
 
   CUtensorMap mx, mw, my;
-  const uint64_t es = X3 ? 2 : 4;  // operand element size
-  if (X3) {
+  const uint64_t es = BF ? 2 : 4;  // operand element size
+  if (BF) {
+    const uint32_t pl = X3 ? 2 : 1;  // planes per box: the hi plane alone in the single-product mode
     const uint64_t xplane = (uint64_t)B * H * W * C * es, wplane = (uint64_t)9 * Cout * C * es;
     const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B, 2};
     const uint64_t strides[4] = {(uint64_t)C * es, (uint64_t)W * C * es, (uint64_t)H * W * C * es, xplane};
-    const uint32_t box[5] = {(uint32_t)tc::CV_KC, (uint32_t)tw, (uint32_t)(sr + 2), 1, 2};
+    const uint32_t box[5] = {(uint32_t)tc::CV_KC, (uint32_t)tw, (uint32_t)(sr + 2), 1, pl};
     if (!tc::encode_bf16(&mx, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return MDE_ERR_DRIVER;
     const uint64_t wdims[5] = {(uint64_t)C, (uint64_t)Cout, 3, 3, 2};
     const uint64_t wstrides[4] = {(uint64_t)C * es, (uint64_t)Cout * C * es, (uint64_t)3 * Cout * C * es, wplane};
-    const uint32_t wbox[5] = {(uint32_t)tc::CV_KC, (uint32_t)n_tile, 3, 1, 2};
+    const uint32_t wbox[5] = {(uint32_t)tc::CV_KC, (uint32_t)n_tile, 3, 1, pl};
     if (!tc::encode_bf16(&mw, w_prep, 5, wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_64B)) return MDE_ERR_DRIVER;
   } else {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -513,9 +527,13 @@ int mde_conv3x3_nhwc_fwd(const float* x_nhwc, const float* w_prep, const float* 
 }
 
 int mde_conv3x3_nhwc_x3_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* scale, const float* shift, void* y,
-                            int y_is_pair, int B, int H, int W, int C, int Cout, float lrelu_slope, mde_stream_t stream) {
+                            int y_is_pair, int B, int H, int W, int C, int Cout, float lrelu_slope, int products,
+                            mde_stream_t stream) {
   if (!x_pair || !w_pair || !y) return MDE_ERR_BAD_POINTER;
-  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0) return MDE_ERR_BAD_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || (products != 3 && products != 1)) return MDE_ERR_BAD_SHAPE;
+  if (products == 1)
+    return conv3x3_launch<tc::PREC_BF16>(x_pair, w_pair, scale, shift, y, B, H, W, C, Cout, lrelu_slope,
+                                         y_is_pair ? tc::OUT_PAIR : tc::OUT_F32, (cudaStream_t)stream);
   return conv3x3_launch<tc::PREC_X3>(x_pair, w_pair, scale, shift, y, B, H, W, C, Cout, lrelu_slope,
                                      y_is_pair ? tc::OUT_PAIR : tc::OUT_F32, (cudaStream_t)stream);
 }

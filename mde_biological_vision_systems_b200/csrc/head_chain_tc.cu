@@ -57,6 +57,7 @@ struct ChainTrain {
   float* glT;
   float* gc;
   float* gb;
+  int single;  // != 0: the hi planes only, one bf16 product per K step (the 2e-2 bf16 mode): mid units are neither loaded nor multiplied
 };
 
 // column sums over the 32 lanes of a warp of v[32] (lane = row): afterwards v[0] of lane l holds sum_rows v[l]
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
         const int row0 = (int)((long long)img * P + p0);
 #pragma unroll
         for (int u = 0; u < UNITS_PER_TILE; ++u) {  // u = 2 * kc + plane
+          if (tr.single && (u & 1)) continue;
           const long long c0 = w_empty.begin();
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
           w_empty.end(c0);
@@ -191,10 +193,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
         if (img == cur) continue;
         cur = img;
         mbar_wait(bar_wempty, wphase ^ 1, 2);  // previous image's MMAs have drained
-        mbar_expect_tx(bar_wfull, Plan::W_BYTES);
+        mbar_expect_tx(bar_wfull, tr.single ? Plan::W_BYTES / 2 : Plan::W_BYTES);
 #pragma unroll
         for (int u = 0; u < UNITS_PER_TILE; ++u)  // smem block u = 2 * kc + plane
-          tma_load_4d(s_w + u * Plan::W_UNIT, &map_w, bar_wfull, (u >> 1) * KC, 0, img, u & 1);
+          if (!(tr.single && (u & 1))) tma_load_4d(s_w + u * Plan::W_UNIT, &map_w, bar_wfull, (u >> 1) * KC, 0, img, u & 1);
         wphase ^= 1;
       }
     }
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
         const uint32_t d_tmem = tmem_base + buf * NB;
 #pragma unroll
         for (int u = 0; u < UNITS_PER_TILE; ++u) {
+          if (tr.single && (u & 1)) continue;
           {
             const long long c0 = w_full.begin();
             mbar_wait(bar_full + 8 * stage, phase, 5);
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
             const uint64_t adesc = make_smem_desc(a_base + j * 32, 16, 1024, SWZ_128B);
             const uint64_t bdesc = make_smem_desc(b_hi + j * 32, 16, 1024, SWZ_128B);
             umma_f16_ss(d_tmem, adesc, bdesc, idesc, (u | j) != 0);   // A_hi B_hi (u even) / A_mid B_hi (u odd)
-            if ((u & 1) == 0) umma_f16_ss(d_tmem, adesc, make_smem_desc(b_mid + j * 32, 16, 1024, SWZ_128B), idesc, 1);  // A_hi B_mid
+            if ((u & 1) == 0 && !tr.single)
+              umma_f16_ss(d_tmem, adesc, make_smem_desc(b_mid + j * 32, 16, 1024, SWZ_128B), idesc, 1);  // A_hi B_mid
           }
           umma_commit(bar_empty + 8 * stage);  // frees the unit when these MMAs complete
           if (++stage == NS) {
@@ -505,6 +509,17 @@ __global__ void round_tf32_kernel(const float* __restrict__ in, float* __restric
 using namespace mde;
 
 extern "C" {
+
+// the bf16 mode of the fused head (north star: depth within 2e-2 of the fp32 reference): same operands, hi planes only
+int mde_head_chain_bf16_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers,
+                            float* pred, int B, int n_bins, int64_t P, mde_stream_t stream) {
+  if (!x_pair || !w_pair || !biasf || !centers || !pred) return MDE_ERR_BAD_POINTER;
+  if (B <= 0 || P <= 0) return MDE_ERR_BAD_SHAPE;
+  if (n_bins != 256) return MDE_ERR_UNSUPPORTED;
+  tc::ChainTrain tr{};
+  tr.single = 1;
+  return tc::launch_chain<256, tc::EPI_SOFTMAX>(x_pair, w_pair, biasf, centers, pred, B, P, (cudaStream_t)stream, tr);
+}
 
 int mde_head_chain_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const float* biasf, const float* centers, float* pred,
                        int B, int n_bins, int64_t P, mde_stream_t stream) {

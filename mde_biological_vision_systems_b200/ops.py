@@ -49,6 +49,28 @@ def exact_fp32_library():
         torch.backends.cuda.matmul.allow_tf32 = m
 
 
+_PRODUCTS = [3]
+
+
+@contextlib.contextmanager
+def bf16_products(enabled=True):
+    """The bf16 mode of the tensor-core kernels (north star: depth and bin edges within 2e-2 of the fp32 reference): inside this
+    context conv3x3_nhwc and head_chain multiply the hi planes of their split-bf16 operands only -- ONE bf16 product per K
+    step, fp32 accumulation -- instead of the three products of the fp32-grade default.  Operand formats do not change."""
+    old = _PRODUCTS[0]
+    if enabled:
+        _PRODUCTS[0] = 1
+    try:
+        yield
+    finally:
+        _PRODUCTS[0] = old
+
+
+def products():
+    """3 (fp32-grade, default) or 1 (inside ops.bf16_products())."""
+    return _PRODUCTS[0]
+
+
 def launch_count():
     return int(_lib.load(False).mde_launch_count())
 
@@ -563,7 +585,7 @@ def conv3x3_nhwc(x, w_prep, scale=None, shift=None, slope=1.0, pair_out=False, n
         out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
     with timing(name, work=2.0 * b * h * w * cout * 9 * c):
         rc = lib.mde_conv3x3_nhwc_x3_fwd(_p(x.planes), _p(w_prep), _p(scale), _p(shift), _p(out), 1 if pair_out else 0, b, h, w,
-                                         c, cout, float(slope), _s())
+                                         c, cout, float(slope), products(), _s())
     _lib.check(rc, "mde_conv3x3_nhwc_x3_fwd")
     return SplitBF16(out) if pair_out else out
 
@@ -925,9 +947,10 @@ def head_chain(x, wf_pair, biasf, centers):
         wf_pair = split_bf16_flat(wf_pair)
     b, k, h, w = x.shape
     pred = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
+    fn = lib.mde_head_chain_fwd if products() == 3 else lib.mde_head_chain_bf16_fwd
     with timing("head_chain"):
-        rc = lib.mde_head_chain_fwd(_p(x.planes), _p(wf_pair), _p(biasf.contiguous()), _p(centers.contiguous()), _p(pred), b,
-                                    wf_pair.shape[2], h * w, _s())
+        rc = fn(_p(x.planes), _p(wf_pair), _p(biasf.contiguous()), _p(centers.contiguous()), _p(pred), b, wf_pair.shape[2], h * w,
+                _s())
     _lib.check(rc, "mde_head_chain_fwd")
     return pred
 

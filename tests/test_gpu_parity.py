@@ -1237,6 +1237,63 @@ def test_config2_full_size_bench_mode_vs_oracle():
     assert abs(float(l2) - float(l2_ref)) <= REL_LOSS * abs(float(l2_ref))
 
 
+def test_bf16_mode_within_2e_2_of_fp32_reference():
+    """north star: "depth maps and bin edges within 1e-3 relative in fp32/TF32 (2e-2 in bf16)".  model.precision = "bf16" runs
+    the decoder convolutions, the head convolution and the fused chain with ONE bf16 product per K step (hi planes only) and
+    the library bodies at their TF32 default; pred / edges vs the CPU fp32 oracle of the reference path within 2e-2, and the
+    mode really is a different computation from the fp32-grade default."""
+    mode = "glove-25d-ade20k-places"
+    b, h, w = 4, 416, 544
+    cpu = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None)
+    sd = {k: v.detach().clone() for k, v in cpu.state_dict().items()}
+    img = synthetic.image(b, h, w, seed=0)
+    lab, _ = synthetic.label_maps(b, h, w, seed=2)
+    table = load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy")
+    with torch.no_grad():
+        _, sem_ref = oracle.semantics_loader(mode, lab.numpy(), table)
+        xin = oracle.input_insertion(sd, img, mode, None, "rgb", semantics=torch.from_numpy(sem_ref))
+        e_ref, p_ref = oracle.head(oracle.decoder_bn(oracle.encoder_features(cpu.encoder.original_model, xin), sd), sd, 1e-3, 10.0,
+                                   "linear")
+    m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
+    loader = SemanticsLoader(Args(use_semantics=mode))
+    with torch.no_grad():
+        _, sem = loader.get_semantics({"semantics": lab.to(DEV)})
+        e32, p32 = m(img.to(DEV), semantics=sem)
+        m.precision = "bf16"
+        e16, p16 = m(img.to(DEV), semantics=sem)
+    mx, p999 = rel_stats(p16.cpu(), p_ref)
+    print("bf16 mode: pred max %.3e p99.9 %.3e  edges %.3e   (fp32 mode: pred max %.3e)" % (
+        mx, p999, rel_err(e16.cpu(), e_ref), rel_stats(p32.cpu(), p_ref)[0]))
+    assert rel_err(e16.cpu(), e_ref) < 2e-2
+    assert_depth_close(p16.cpu(), p_ref, 2e-2)
+    assert not torch.equal(p16, p32)
+    m.precision = "fp64"
+    with pytest.raises(ValueError):
+        m(img.to(DEV), semantics=sem)
+
+
+@pytest.mark.parametrize("cfg", [dict(b=2, c=128, h=24, w=40, cout=128), dict(b=1, c=352, h=13, w=17, cout=160, pair=True)])
+def test_conv3x3_single_bf16_product(cfg):
+    """products = 1 (ops.bf16_products): the kernel multiplies the hi planes only -- equal, up to fp32 accumulation, to a float64
+    convolution of the bf16-rounded operands."""
+    rng = np.random.default_rng(191)
+    b, c, h, w, cout = cfg["b"], cfg["c"], cfg["h"], cfg["w"], cfg["cout"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32)).to(DEV)
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32)).to(DEV)
+    xp, wp = ops.split_bf16(x), ops.prepare_conv3x3_weight(wt)
+    ref = torch.nn.functional.conv2d(xp.planes[0].float().permute(0, 3, 1, 2).cpu().double(),
+                                     wt.bfloat16().float().cpu().double(), None, padding=1)
+    with ops.bf16_products():
+        assert ops.products() == 1
+        out = ops.conv3x3_nhwc(xp, wp, pair_out=bool(cfg.get("pair")))
+    assert ops.products() == 3
+    out = out.float() if cfg.get("pair") else out
+    err = float((out.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < (1e-4 if cfg.get("pair") else 2e-5), err  # a pair output is itself rounded to ~2^-17
+    full = ops.conv3x3_nhwc(xp, wp)
+    assert float((full.cpu().double() - ref).abs().max()) / float(ref.abs().max()) > 1e-4  # the default is a different product
+
+
 def test_torch_library_ops_match_ctypes_layer():
     """torch.ops.mde.* (torch.library registration over the same C ABI) return what the ctypes layer returns, their
     registered autograd formulas give the same gradients, and torch.library.opcheck accepts schema / fake / autograd
