@@ -311,40 +311,46 @@ extern "C" int mde_bias_act_pad_nhwc(const float* x, const float* bias, float* y
 // reads + 2 writes.
 namespace mde {
 
-// grid (slabs, B); warp = 32 consecutive float4 channel groups of one row, 8 rows in flight per block
+// grid (slabs, B).  A slab is a contiguous run of rows, i.e. a contiguous run of rows * C/4 float4s.  The block's first
+// c4 * RY threads (RY = 256 / c4 whole rows per pass) walk it with stride c4 * RY: consecutive threads touch consecutive
+// float4s, every thread keeps ONE channel group (the stride is a multiple of c4), so its running sum needs no indexing.
+// C > 1024 (c4 > 256): the channel groups are covered in passes of 256.
 __global__ void __launch_bounds__(256) bias_act_pool_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ bias,
                                                                  float* __restrict__ y, float* __restrict__ partial,
                                                                  long long HW, int c4, long long rows_per_slab, int act) {
-  __shared__ float4 red[8][32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float4 red[256];
   const long long b = blockIdx.y, slab = blockIdx.x;
   const long long r0 = slab * rows_per_slab;
   const long long r1 = r0 + rows_per_slab < HW ? r0 + rows_per_slab : HW;
-  for (int cg0 = 0; cg0 < c4; cg0 += 32) {
-    const int cg = cg0 + tx;
+  const float4* xs = reinterpret_cast<const float4*>(x) + (b * HW + r0) * c4;
+  float4* ys = reinterpret_cast<float4*>(y) + (b * HW + r0) * c4;
+  const int t = threadIdx.x;
+  for (int cg0 = 0; cg0 < c4; cg0 += 256) {
+    const int cw = min(256, c4 - cg0);           // channel groups of this pass
+    const int ry = 256 / cw;                     // rows per sweep of the block
+    const int cg = cg0 + t % cw, row = t / cw;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cg < c4) {
+    if (row < ry) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + cg);
 #pragma unroll 4
-      for (long long r = r0 + ty; r < r1; r += 8) {
-        const long long idx = (b * HW + r) * c4 + cg;
-        const float4 v = reinterpret_cast<const float4*>(x)[idx];
+      for (long long r = row; r < r1 - r0; r += ry) {
+        const long long idx = r * c4 + cg;
+        const float4 v = ldg_stream(xs + idx);
         float o[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
         if (act == 1) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
+          for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.f + __expf(-o[k]));
         }
-        reinterpret_cast<float4*>(y)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+        ys[idx] = make_float4(o[0], o[1], o[2], o[3]);
         acc.x += o[0]; acc.y += o[1]; acc.z += o[2]; acc.w += o[3];
       }
     }
-    red[ty][tx] = acc;
+    red[t] = acc;
     __syncthreads();
-    if (ty == 0 && cg < c4) {
-#pragma unroll
-      for (int k = 1; k < 8; ++k) {
-        const float4 t = red[k][tx];
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    if (t < cw) {  // fixed order: rows 0 .. ry-1 of the sweep
+      for (int k = 1; k < ry; ++k) {
+        const float4 u = red[t + k * cw];
+        acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
       }
       reinterpret_cast<float4*>(partial)[(b * gridDim.x + slab) * c4 + cg] = acc;
     }
@@ -363,15 +369,31 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < slabs; ++i) s += partial[((long long)b * slabs + i) * C + c];
-    mean[c] = s * inv_hw;
+    const float* pp = partial + (long long)b * slabs * C + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four loads in flight; the association is fixed, so results are reproducible
+    int i = 0;
+    for (; i + 3 < slabs; i += 4) {
+      s0 += pp[(long long)i * C];
+      s1 += pp[(long long)(i + 1) * C];
+      s2 += pp[(long long)(i + 2) * C];
+      s3 += pp[(long long)(i + 3) * C];
+    }
+    for (; i < slabs; ++i) s0 += pp[(long long)i * C];
+    mean[c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
   }
   __syncthreads();
   for (int r = warp; r < R; r += 8) {
-    float d = 0.f;
-    for (int c = lane; c < C; c += 32) d = fmaf(__ldg(w1 + (long long)r * C + c), mean[c], d);
-    d = warp_sum(d);
+    const float* wr = w1 + (long long)r * C;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    int c = lane;
+    for (; c + 96 < C; c += 128) {  // four independent loads per lane per trip
+      d0 = fmaf(__ldg(wr + c), mean[c], d0);
+      d1 = fmaf(__ldg(wr + c + 32), mean[c + 32], d1);
+      d2 = fmaf(__ldg(wr + c + 64), mean[c + 64], d2);
+      d3 = fmaf(__ldg(wr + c + 96), mean[c + 96], d3);
+    }
+    for (; c < C; c += 32) d0 = fmaf(__ldg(wr + c), mean[c], d0);
+    float d = warp_sum((d0 + d1) + (d2 + d3));
     if (lane == 0) {
       d += b1 ? b1[r] : 0.f;
       h[r] = d / (1.f + expf(-d));
@@ -381,9 +403,17 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   const int per = (C + gridDim.x - 1) / gridDim.x;
   const int c_lo = blockIdx.x * per, c_hi = min(C, c_lo + per);
   for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
-    float d = b2 ? b2[c] : 0.f;
     const float* wr = w2 + (long long)c * R;
-    for (int r = 0; r < R; ++r) d = fmaf(__ldg(wr + r), h[r], d);
+    float d0 = b2 ? b2[c] : 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    int r = 0;
+    for (; r + 3 < R; r += 4) {
+      d0 = fmaf(__ldg(wr + r), h[r], d0);
+      d1 = fmaf(__ldg(wr + r + 1), h[r + 1], d1);
+      d2 = fmaf(__ldg(wr + r + 2), h[r + 2], d2);
+      d3 = fmaf(__ldg(wr + r + 3), h[r + 3], d3);
+    }
+    for (; r < R; ++r) d0 = fmaf(__ldg(wr + r), h[r], d0);
+    const float d = (d0 + d1) + (d2 + d3);
     gate[(long long)b * C + c] = 1.f / (1.f + expf(-d));
   }
 }
@@ -419,7 +449,7 @@ extern "C" int mde_se_gate(const float* partial, int slabs, float inv_hw, const 
   if (B <= 0 || B > 65535 || C <= 0 || R <= 0 || slabs <= 0) return MDE_ERR_BAD_SHAPE;
   const size_t sm = (size_t)(C + R) * sizeof(float);
   if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
-  const int splits = C >= 512 ? 4 : (C >= 128 ? 2 : 1);
+  const int splits = C >= 512 ? 8 : (C >= 128 ? 4 : 1);
   se_gate_kernel<<<dim3((unsigned)splits, (unsigned)B), 256, sm, (cudaStream_t)stream>>>(partial, slabs, inv_hw, w1, b1, w2, b2,
                                                                                          gate, C, R);
   return check_launch();

@@ -338,9 +338,10 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
   g.tmem_cols = 2 * tn <= 32 ? 32 : 2 * tn <= 64 ? 64 : 2 * tn <= 128 ? 128 : 2 * tn <= 256 ? 256 : 512;  // two accumulator buffers
   g.total_tiles = m_tiles * g.n_tiles;
   const int stage_bytes = tc::PW_A_BYTES + 2 * tn * 128;
+  // the ring runs ACROSS tiles (a CTA's chunk stream is continuous), so its depth is set by shared memory alone -- capping it
+  // at the chunks of one tile (K <= 64: one) serialises load -> convert -> MMA per tile behind a full DRAM round trip
   g.nstages = (200 * 1024) / stage_bytes;
-  if (g.nstages > 4) g.nstages = 4;
-  if (g.nstages > g.chunks) g.nstages = g.chunks;
+  if (g.nstages > 6) g.nstages = 6;
   const int smem = g.nstages * stage_bytes + 24 * g.nstages + 64 + 4 * 32 * 33 * 4 + 1024;
   CUtensorMap mx, mw;
   {
