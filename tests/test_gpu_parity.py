@@ -119,6 +119,34 @@ def test_gather_into_encoder_input_matches_planar():
     assert not SemanticsLoader(Args(use_semantics=mode)).bind_encoder_input(other)
 
 
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.uint8])
+@pytest.mark.parametrize("shape,pads,c_after", [((3, 37, 50), (1, 2, 2, 1), 0), ((2, 64, 96), (0, 1, 0, 1), 0),
+                                                ((2, 19, 33), (0, 0, 0, 0), 4)])
+def test_gather_embed_nhwc_kernels_bit_exact(dtype, shape, pads, c_after):
+    """ops.gather_embed_nhwc with the image planes fused in: dense pixel records (c_after = 0: the warp-staged kernel, ragged
+    row ends, every label type) and records inside a wider pitch (c_after > 0: the per-piece kernel) -- bit-exact against
+    torch indexing, borders zero, labels_out clamped."""
+    b, h, w = shape
+    rng = np.random.default_rng(170)
+    table = torch.from_numpy(load_table("ade20k_places_classes_glove_twitter_27b_25d_embeddings.npy")).float().to(DEV)
+    rows, d = table.shape
+    hi = 255 if dtype == torch.uint8 else 400
+    lab = torch.from_numpy(rng.integers(0 if dtype == torch.uint8 else -3, hi, size=(b, 1, h, w))).to(dtype).to(DEV)
+    img = torch.from_numpy(rng.standard_normal((b, 3, h, w)).astype(np.float32)).to(DEV)
+    lab_out = torch.empty((b, 1, h, w), dtype=torch.int64, device=DEV)
+    buf, view = ops.gather_embed_nhwc(lab, table, rows - 1, 3, c_after, pads, labels_out=lab_out, image=img)
+    l64 = lab.long()
+    clamped = torch.where((l64 < 0) | (l64 > rows - 1), torch.full_like(l64, rows - 1), l64)
+    ref = table[clamped[:, 0]].permute(0, 3, 1, 2)
+    pt, pb, pl, pr = pads
+    assert torch.equal(lab_out, clamped)
+    assert torch.equal(view, ref) and torch.equal(buf[:, :3, pt:pt + h, pl:pl + w], img)
+    inner = torch.zeros_like(buf, dtype=torch.bool)
+    inner[:, :, pt:pt + h, pl:pl + w] = True
+    if any(pads):
+        assert float(buf[:, :3 + d][~inner[:, :3 + d]].abs().max()) == 0.0
+
+
 def test_gather_out_of_range_raises():
     lab = torch.zeros(1, 1, 8, 8, dtype=torch.int64)
     lab[0, 0, 3, 3] = 150
