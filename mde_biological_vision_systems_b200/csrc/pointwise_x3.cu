@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
   const uint32_t bar_raw = s_bar, bar_ops = s_bar + 8 * g.nstages, bar_empty = s_bar + 16 * g.nstages,
                  bar_acc_full = s_bar + 24 * g.nstages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + (s_bar - base) + 24 * g.nstages + 32);
-  float* stg_all = reinterpret_cast<float*>(gbase + (s_bar - base) + 24 * g.nstages + 64);  // [4 warps][32][33]
+  float* stg_all = reinterpret_cast<float*>(gbase + (s_bar - base) + ((24 * g.nstages + 64 + 15) & ~15));  // [4 warps][32][36], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -226,67 +226,84 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
     }
   } else if (warp >= 7) {
     // ---- epilogue: tcgen05.ld -> bias / SiLU -> shared-memory transpose -> coalesced stores (+ residual) -------------
+    // One warp per scheduler does this work, so it lives on instruction-level parallelism: the 32 elements of a thread's
+    // row are handled by BRANCH-FREE code (bias as 8 float4 loads up front, the activation switch hoisted out of the
+    // element loop, raw ex2 / rcp) that the compiler can interleave.  (With a bias test and an activation test per
+    // element every element was its own load -> add -> ex2 -> rcp chain: 880 instructions and ~3200 clocks per 32 columns.)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are accessible to this warp
-    float* stg = stg_all + quarter * (32 * 33);
+    float* stg = stg_all + quarter * (32 * 36);  // [32 rows][36]: 144-byte rows keep the 16-byte accesses of both phases conflict-free
+    const int cc = (lane & 7) * 4;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
       const long long mt = tile / g.n_tiles;
       const int n0 = (int)(tile - mt * g.n_tiles) * g.tn;
       const long long m0 = mt * 128;
       const uint32_t buf = it & 1;
-      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1, 45);
-      tc_fence_after();
-      long long orow[8];  // output row of the 8 tile rows this thread stores (identity, or the position inside a padded map)
+      // destination / residual pointers of the 8 tile rows this thread stores (rows k*4 + lane/8), once per tile
+      float* drow[8];
+      const float* rrow[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        long long mm = m0 + quarter * 32 + k * 4 + (lane >> 3);
-        if (g.out_W > 0 && mm < g.M) {
-          const long long img = mm / ((long long)g.out_W * g.out_H);
-          const int rem = (int)(mm - img * g.out_W * g.out_H);
-          const int yy = rem / g.out_W, xx = rem - yy * g.out_W;
-          mm = (img * g.out_Hp + yy + g.out_pt) * g.out_Wp + xx + g.out_pl;
+        const long long mm = m0 + quarter * 32 + k * 4 + (lane >> 3);
+        long long om = mm;
+        if (g.out_W > 0 && mm < g.M) {  // position inside the zero-bordered map (M < 2^31: 32-bit divisions)
+          const unsigned hw = (unsigned)(g.out_W * g.out_H);
+          const unsigned img = (unsigned)mm / hw, rem = (unsigned)mm - img * hw;
+          const unsigned yy = rem / (unsigned)g.out_W, xx = rem - yy * (unsigned)g.out_W;
+          om = ((long long)img * g.out_Hp + yy + g.out_pt) * g.out_Wp + xx + g.out_pl;
         }
-        orow[k] = mm;
+        drow[k] = mm < g.M ? Y + om * g.ldc + n0 + cc : nullptr;
+        rrow[k] = (g.residual != nullptr && mm < g.M) ? g.residual + mm * g.ldr + n0 + cc : nullptr;
       }
+      mbar_wait(bar_acc_full + 8 * buf, (it >> 1) & 1, 45);
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < g.tn; c0 += 32) {
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + buf * g.tn + c0 + ((uint32_t)(quarter * 32) << 16), acc);
+        const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));  // a multiple of 4
+        float bv[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = (g.bias != nullptr && 4 * q < nvalid) ? __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c0) + q)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          bv[4 * q] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
+        }
         tmem_ld_wait();
         if (c0 + 32 >= g.tn) {  // accumulator fully read: hand the buffer back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
-        const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));
+        float o[32];
+        if (g.act == 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(acc[i]);
-          if (g.bias != nullptr && i < nvalid) t += __ldg(g.bias + n0 + c0 + i);
-          if (g.act == 1) t = __fdividef(t, 1.f + __expf(-t));  // SiLU
-          stg[lane * 33 + i] = t;
+          for (int i = 0; i < 32; ++i) {  // SiLU: t / (1 + 2^(-t log2 e)); ex2 flushes to 0 / overflows to inf at the ends, both limits exact
+            const float t = __uint_as_float(acc[i]) + bv[i];
+            float e, r;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * -1.4426950408889634f));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+            o[i] = t * r;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(acc[i]) + bv[i];
         }
+        float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) srow[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         __syncwarp();
         // 8 lanes write one row's 128 bytes: every store instruction covers 4 whole lines
-        const int cc = (lane & 7) * 4;
+        if (cc < nvalid) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int rr = k * 4 + (lane >> 3);
-          const long long mm = m0 + quarter * 32 + rr;
-          if (mm >= g.M || cc >= nvalid) continue;
-          const float* sp = stg + rr * 33 + cc;
-          float o[4] = {sp[0], sp[1], sp[2], sp[3]};
-          float* dst = Y + orow[k] * g.ldc + n0 + c0 + cc;
-          const float* res = g.residual ? g.residual + mm * g.ldr + n0 + c0 + cc : nullptr;
-          if (cc + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-              (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
-            if (res) {
-              const float4 rv = *reinterpret_cast<const float4*>(res);
-              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+          for (int k = 0; k < 8; ++k) {
+            if (drow[k] == nullptr) continue;
+            float4 v = *reinterpret_cast<const float4*>(stg + (k * 4 + (lane >> 3)) * 36 + cc);
+            if (rrow[k] != nullptr) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow[k] + c0));
+              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
             }
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int q = 0; q < 4 && cc + q < nvalid; ++q) dst[q] = o[q] + (res ? res[q] : 0.f);
+            *reinterpret_cast<float4*>(drow[k] + c0) = v;
           }
         }
         __syncwarp();
@@ -320,6 +337,10 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
   if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0 || ldc < N || (residual && ldr < N) || act < 0 || act > 1)
     return MDE_ERR_BAD_SHAPE;
   if (K % 8 != 0 || !aligned(x, 16) || !aligned(w_pair, 16)) return MDE_ERR_UNSUPPORTED;  // TMA: 16-byte global strides
+  // 16-byte epilogue accesses: whole float4 groups of output channels, aligned rows
+  if (N % 4 != 0 || ldc % 4 != 0 || !aligned(y, 16) || (bias && !aligned(bias, 16)) ||
+      (residual && (ldr % 4 != 0 || !aligned(residual, 16))))
+    return MDE_ERR_UNSUPPORTED;
   tc::PwGeom g;
   g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.ldr = ldr; g.act = act; g.bias = bias; g.residual = residual;
   g.gate = gate; g.rows_per_image = gate ? rows_per_image : 1;
@@ -342,7 +363,7 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
   // at the chunks of one tile (K <= 64: one) serialises load -> convert -> MMA per tile behind a full DRAM round trip
   g.nstages = (200 * 1024) / stage_bytes;
   if (g.nstages > 6) g.nstages = 6;
-  const int smem = g.nstages * stage_bytes + 24 * g.nstages + 64 + 4 * 32 * 33 * 4 + 1024;
+  const int smem = g.nstages * stage_bytes + 24 * g.nstages + 64 + 4 * 32 * 36 * 4 + 1024;
   CUtensorMap mx, mw;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
