@@ -227,18 +227,30 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
         for (int cg = 0; cg < groups; ++cg) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (buf * NT + t) * g.n_tile + cg * 32 + lane_addr, v);
-          tmem_ld_wait();
           const int ch0 = n0 + cg * 32;
+          // the group's 32 scale / shift values as 16-byte loads issued before the accumulator arrives (C_out % 4 == 0, ch0 % 32
+          // == 0): the element loop below is then pure register arithmetic the compiler interleaves freely
+          float sc[32], sh[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool in = ch0 + 4 * q < g.Cout;
+            const float4 a = (scale != nullptr && in) ? __ldg(reinterpret_cast<const float4*>(scale + ch0) + q)
+                                                      : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 c = (shift != nullptr && in) ? __ldg(reinterpret_cast<const float4*>(shift + ch0) + q)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[4 * q] = a.x; sc[4 * q + 1] = a.y; sc[4 * q + 2] = a.z; sc[4 * q + 3] = a.w;
+            sh[4 * q] = c.x; sh[4 * q + 1] = c.y; sh[4 * q + 2] = c.z; sh[4 * q + 3] = c.w;
+          }
+          tmem_ld_wait();
           float o[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int ch = ch0 + i;
-            const bool in = ch < g.Cout;
-            const float sc = (scale != nullptr && in) ? __ldg(scale + ch) : 1.0f;
-            const float sh = (shift != nullptr && in) ? __ldg(shift + ch) : 0.0f;
-            float y = fmaf(__uint_as_float(v[i]), sc, sh);
-            y = y > 0.0f ? y : y * g.slope;
-            o[i] = g.out_mode == OUT_TF32 ? tf32_round(y) : y;
+            const float y = fmaf(__uint_as_float(v[i]), sc[i], sh[i]);
+            o[i] = y > 0.0f ? y : y * g.slope;
+          }
+          if (g.out_mode == OUT_TF32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = tf32_round(o[i]);
           }
           const uint32_t sbuf = s_stg + (nstore & 1) * CV_STG_BYTES;
           if (etid == 0) tma_store_wait_read<1>();  // the store that last read this staging buffer has drained
@@ -374,7 +386,8 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
   constexpr bool BF = PREC != tc::PREC_TF32;
   const int in_align = BF ? 8 : 4;                                   // TMA: 16-byte global strides
   const int out_align = out_mode == tc::OUT_PAIR ? 8 : 4;
-  if (C % in_align != 0 || Cout % out_align != 0 || !aligned(x, 16) || !aligned(w_prep, 16) || !aligned(y, 16))
+  if (C % in_align != 0 || Cout % out_align != 0 || !aligned(x, 16) || !aligned(w_prep, 16) || !aligned(y, 16) ||
+      (scale && !aligned(scale, 16)) || (shift && !aligned(shift, 16)))
     return MDE_ERR_UNSUPPORTED;
   // N tile: the whole C_out when it fits one instruction (<= 256, multiple of 16), else the largest divisor of C_out
   // that is a multiple of 32 (so that 32-channel store groups never straddle two N tiles) -- the first candidate, in that
