@@ -192,6 +192,13 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
  * mde_se_gate: gate[b][c] = sigmoid(w2[c][:] . silu(w1 . mean_b + b1) + b2[c]) with mean_b = inv_hw * sum_s partial[b][s][:];
  *   w1 [R][C], w2 [C][R] (the 1x1 conv_reduce / conv_expand filters of geffnet's SqueezeExcite). */
 int mde_pool_slabs(int B, int64_t HW);
+/* mde_depthwise_bias_act_pool_nhwc: the depthwise k x k convolution (k = 3 / 5, stride 1 / 2, zero padding pad_top / pad_left and
+ * whatever the output size implies at the far edges -- TensorFlow-SAME included), its folded-BatchNorm bias, SiLU (act = 1) and
+ * the slab sums of the result in ONE pass: x [B][Hi][Wi][C] fp32 NHWC, w [k][k][C] (channel innermost), y [B][Ho][Wo][C],
+ * partial [B][mde_pool_slabs(B, Ho*Wo)][C].  Plain fp32 FMAs (a depthwise convolution has no channel reduction). */
+int mde_depthwise_bias_act_pool_nhwc(const float* x, const float* w, const float* bias, float* y, float* partial, int B, int Hi,
+                                     int Wi, int C, int k, int stride, int pad_top, int pad_left, int Ho, int Wo, int act,
+                                     mde_stream_t stream);
 int mde_bias_act_pool_nhwc(const float* x, const float* bias, float* y, float* partial, int B, int64_t HW, int C, int act,
                            mde_stream_t stream);
 int mde_se_gate(const float* partial, int slabs, float inv_hw, const float* w1, const float* b1, const float* w2,

@@ -363,56 +363,77 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w1, const float* __restrict__ b1,
                                                       const float* __restrict__ w2, const float* __restrict__ b2,
                                                       float* __restrict__ gate, int C, int R) {
-  extern __shared__ float se_sm[];  // mean[C] | h[R]
+  extern __shared__ __align__(16) float se_sm[];  // mean[C] | h[R]
   float* mean = se_sm;
   float* h = se_sm + C;
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* pp = partial + (long long)b * slabs * C + c;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four loads in flight; the association is fixed, so results are reproducible
+    float sacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // eight loads in flight; fixed association -> reproducible
     int i = 0;
-    for (; i + 3 < slabs; i += 4) {
-      s0 += pp[(long long)i * C];
-      s1 += pp[(long long)(i + 1) * C];
-      s2 += pp[(long long)(i + 2) * C];
-      s3 += pp[(long long)(i + 3) * C];
+    for (; i + 7 < slabs; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sacc[u] += pp[(long long)(i + u) * C];
     }
-    for (; i < slabs; ++i) s0 += pp[(long long)i * C];
-    mean[c] = ((s0 + s1) + (s2 + s3)) * inv_hw;
+    for (; i < slabs; ++i) sacc[0] += pp[(long long)i * C];
+    mean[c] = (((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]))) * inv_hw;
   }
   __syncthreads();
-  for (int r = warp; r < R; r += 8) {
-    const float* wr = w1 + (long long)r * C;
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    int c = lane;
-    for (; c + 96 < C; c += 128) {  // four independent loads per lane per trip
-      d0 = fmaf(__ldg(wr + c), mean[c], d0);
-      d1 = fmaf(__ldg(wr + c + 32), mean[c + 32], d1);
-      d2 = fmaf(__ldg(wr + c + 64), mean[c + 64], d2);
-      d3 = fmaf(__ldg(wr + c + 96), mean[c + 96], d3);
+  // squeeze: h[r] = silu(w1[r, :] . mean + b1[r]).  The rows of w1 come from L2 (~600 clocks): a warp works on TWO rows at once
+  // with 16-byte loads, eight in flight per row, so a row costs one or two round trips instead of C / 32.
+  const bool v4 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0;
+  for (int r = warp; r < R; r += 16) {
+    const int r2 = r + 8 < R ? r + 8 : r;
+    float da = 0.f, db = 0.f;
+    if (v4) {
+      const float4* wa = reinterpret_cast<const float4*>(w1 + (long long)r * C);
+      const float4* wb = reinterpret_cast<const float4*>(w1 + (long long)r2 * C);
+      const float4* m4 = reinterpret_cast<const float4*>(mean);
+#pragma unroll 8
+      for (int c = lane; c < (C >> 2); c += 32) {
+        const float4 a = __ldg(wa + c), bq = __ldg(wb + c), m = m4[c];
+        da = fmaf(a.x, m.x, fmaf(a.y, m.y, fmaf(a.z, m.z, fmaf(a.w, m.w, da))));
+        db = fmaf(bq.x, m.x, fmaf(bq.y, m.y, fmaf(bq.z, m.z, fmaf(bq.w, m.w, db))));
+      }
+    } else {
+#pragma unroll 4
+      for (int c = lane; c < C; c += 32) {
+        da = fmaf(__ldg(w1 + (long long)r * C + c), mean[c], da);
+        db = fmaf(__ldg(w1 + (long long)r2 * C + c), mean[c], db);
+      }
     }
-    for (; c < C; c += 32) d0 = fmaf(__ldg(wr + c), mean[c], d0);
-    float d = warp_sum((d0 + d1) + (d2 + d3));
+    da = warp_sum(da);
+    db = warp_sum(db);
     if (lane == 0) {
-      d += b1 ? b1[r] : 0.f;
-      h[r] = d / (1.f + expf(-d));
+      da += b1 ? b1[r] : 0.f;
+      h[r] = da / (1.f + expf(-da));
+      if (r2 != r) {
+        db += b1 ? b1[r2] : 0.f;
+        h[r2] = db / (1.f + expf(-db));
+      }
     }
   }
   __syncthreads();
   const int per = (C + gridDim.x - 1) / gridDim.x;
   const int c_lo = blockIdx.x * per, c_hi = min(C, c_lo + per);
+  const bool r4 = (R & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
   for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
     const float* wr = w2 + (long long)c * R;
     float d0 = b2 ? b2[c] : 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    int r = 0;
-    for (; r + 3 < R; r += 4) {
-      d0 = fmaf(__ldg(wr + r), h[r], d0);
-      d1 = fmaf(__ldg(wr + r + 1), h[r + 1], d1);
-      d2 = fmaf(__ldg(wr + r + 2), h[r + 2], d2);
-      d3 = fmaf(__ldg(wr + r + 3), h[r + 3], d3);
+    if (r4) {
+#pragma unroll 8
+      for (int r = 0; r < R; r += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wr + r));
+        d0 = fmaf(w.x, h[r], d0);
+        d1 = fmaf(w.y, h[r + 1], d1);
+        d2 = fmaf(w.z, h[r + 2], d2);
+        d3 = fmaf(w.w, h[r + 3], d3);
+      }
+    } else {
+#pragma unroll 8
+      for (int r = 0; r < R; ++r) d0 = fmaf(__ldg(wr + r), h[r], d0);
     }
-    for (; r < R; ++r) d0 = fmaf(__ldg(wr + r), h[r], d0);
     const float d = (d0 + d1) + (d2 + d3);
     gate[(long long)b * C + c] = 1.f / (1.f + expf(-d));
   }

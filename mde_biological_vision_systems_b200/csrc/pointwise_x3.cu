@@ -262,6 +262,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + buf * g.tn + c0 + ((uint32_t)(quarter * 32) << 16), acc);
         const int nvalid = min(32, min(g.tn - c0, g.N - n0 - c0));  // a multiple of 4
+        // the residual pieces this thread will add, all eight loads issued now (as dependent load -> add -> store chains inside
+        // the store loop they cost eight L2 round trips per 32 columns)
+        float4 rv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          rv[k] = (rrow[k] != nullptr && cc < nvalid) ? __ldg(reinterpret_cast<const float4*>(rrow[k] + c0))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         float bv[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -299,10 +306,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
           for (int k = 0; k < 8; ++k) {
             if (drow[k] == nullptr) continue;
             float4 v = *reinterpret_cast<const float4*>(stg + (k * 4 + (lane >> 3)) * 36 + cc);
-            if (rrow[k] != nullptr) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow[k] + c0));
-              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-            }
+            v.x += rv[k].x; v.y += rv[k].y; v.z += rv[k].z; v.w += rv[k].w;
             *reinterpret_cast<float4*>(drow[k] + c0) = v;
           }
         }

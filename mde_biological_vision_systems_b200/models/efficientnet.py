@@ -98,6 +98,29 @@ def _pointwise_exact(conv, x, act, residual, out_pads):
             and (residual is None or (residual.dtype == torch.float32 and residual.is_contiguous(memory_format=torch.channels_last))))
 
 
+def _depthwise_module_ok(conv, act):
+    return (conv.groups > 1 and conv.groups == conv.in_channels == conv.out_channels and (act is None or isinstance(act, nn.SiLU))
+            and conv.kernel_size in ((3, 3), (5, 5)) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1)
+            and conv.in_channels % 4 == 0
+            and (isinstance(conv, SamePadConv2d) or (isinstance(conv.padding, tuple) and conv.padding_mode == "zeros")))
+
+
+def _depthwise_ours(conv, x, act):
+    from .. import ops
+    return _depthwise_module_ok(conv, act) and ops.depthwise_supported(x, conv.in_channels, conv.kernel_size, conv.stride,
+                                                                       conv.dilation)
+
+
+def _folded_depthwise_kkc(conv, w_folded):
+    """the BatchNorm-folded depthwise filter [C,1,k,k] as [k,k,C] (channel innermost), cached next to the fold"""
+    key = conv._mde_fold[0]
+    cached = getattr(conv, "_mde_fold_kkc", None)
+    if cached is None or cached[0] != key:
+        cached = (key, w_folded.detach()[:, 0].permute(1, 2, 0).contiguous().float())
+        conv._mde_fold_kkc = cached
+    return cached[1]
+
+
 def _folded_pointwise_pair(conv, bn, w_folded):
     """split-bf16 pair of the BatchNorm-folded 1x1 filter, cached next to the fold (same version key)."""
     from .. import ops
@@ -159,6 +182,19 @@ def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False
                                       gate=gate, out_pads=out_pads))
     if gate is not None:
         x = x * gate[:, :, None, None]
+    if pool and residual is None and gate is None and out_pads is None and _depthwise_ours(conv, x, act):
+        # the depthwise convolution of an MBConv block: convolution + folded bias + SiLU + the squeeze-excite pooling in one
+        # pass of our own fp32 kernel (ops.depthwise_bias_act_pool) instead of the library kernel, a bias/activation pass and a
+        # mean pass over the same tensor
+        k, s = conv.kernel_size[0], conv.stride[0]
+        h_in, w_in = x.shape[-2:]
+        if isinstance(conv, SamePadConv2d):
+            pt, pb, pl, pr = (0, 0, 0, 0) if prepadded else conv.same_pads(h_in, w_in)
+        else:
+            pt = pb = conv.padding[0]
+            pl = pr = conv.padding[1]
+        out_hw = ((h_in + pt + pb - k) // s + 1, (w_in + pl + pr - k) // s + 1)
+        return ops.depthwise_bias_act_pool(x, _folded_depthwise_kkc(conv, w), b, 1 if act is not None else 0, s, pt, pl, out_hw)
     fused = (act is None or isinstance(act, nn.SiLU)) and x.is_cuda
     with _depthwise_engine(conv, x):
         y = conv.forward_with(x, w, None if fused else b, prepadded) if isinstance(conv, SamePadConv2d) \
@@ -244,6 +280,9 @@ class InvertedResidual(nn.Module):
     def forward(self, x):
         # a stride-2 SAME depthwise conv follows the 1x1 expansion: let the expansion's epilogue write its output padded
         pads = self.conv_dw.same_pads(x.shape[-2], x.shape[-1]) if isinstance(self.conv_dw, SamePadConv2d) else None
+        if (pads is not None and not torch.is_grad_enabled() and not self.bn2.training and _depthwise_module_ok(self.conv_dw, self.act2)
+                and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)):
+            pads = None  # our depthwise kernel applies the SAME padding through its bounds test: nothing to pre-pad
         y = conv_bn(self.conv_pw, self.bn1, x, self.act1, out_pads=pads)
         y, partial = conv_bn(self.conv_dw, self.bn2, y, self.act2, prepadded=(y.shape[-2:] != x.shape[-2:]), pool=True)
         return _se_project(self.se, self.conv_pwl, self.bn3, y, partial, x if self.has_residual else None)

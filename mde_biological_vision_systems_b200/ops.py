@@ -760,6 +760,33 @@ def bias_act_pool_nhwc_(x_cl, bias, act):
     return x_cl, partial
 
 
+def depthwise_supported(x, channels, kernel_size, stride, dilation=(1, 1)):
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == channels and channels % 4 == 0
+                and x.is_contiguous(memory_format=torch.channels_last) and tuple(kernel_size) in ((3, 3), (5, 5))
+                and tuple(stride) in ((1, 1), (2, 2)) and tuple(dilation) == (1, 1))
+
+
+def depthwise_bias_act_pool(x_cl, w_kkc, bias, act, stride, pad_top, pad_left, out_hw):
+    """act(depthwise_conv(x) + bias) and, from the same pass, the per-slab channel sums of the result (for ops.se_gate).
+    x_cl channels_last fp32 [B,C,Hi,Wi]; w_kkc fp32 [k,k,C] (the depthwise filter, channel innermost); zero padding pad_top /
+    pad_left (and whatever ``out_hw`` implies at the bottom / right).  Returns (y channels_last [B,C,Ho,Wo], partial [B,slabs,C])."""
+    lib = _lib.load()
+    _need_cuda(x_cl, w_kkc)
+    b, c, hi, wi = x_cl.shape
+    ho, wo = (int(v) for v in out_hw)
+    k = w_kkc.shape[0]
+    if w_kkc.shape != (k, k, c) or w_kkc.dtype != torch.float32 or not w_kkc.is_contiguous():
+        raise ValueError("depthwise_bias_act_pool: w_kkc must be a contiguous float32 [k,k,C] tensor")
+    y = torch.empty((b, c, ho, wo), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    slabs = int(lib.mde_pool_slabs(b, ho * wo))
+    partial = torch.empty((b, slabs, c), dtype=torch.float32, device=x_cl.device)
+    with timing("depthwise", work=float(b * ho * wo * c * 8)):
+        rc = lib.mde_depthwise_bias_act_pool_nhwc(_p(x_cl), _p(w_kkc), _p(bias), _p(y), _p(partial), b, hi, wi, c, k, int(stride),
+                                                  int(pad_top), int(pad_left), ho, wo, int(act), _s())
+    _lib.check(rc, "mde_depthwise_bias_act_pool_nhwc")
+    return y, partial
+
+
 def se_gate(partial, hw, w_reduce, b_reduce, w_expand, b_expand):
     """sigmoid(expand(silu(reduce(mean)))) of a squeeze-excite block from the slab sums of bias_act_pool_nhwc_:
     partial [B, slabs, C], w_reduce [R, C], w_expand [C, R] -> gate [B, C]."""

@@ -449,6 +449,37 @@ def test_squeeze_excite_kernels(shape, r):
     assert float((gate.double() - ref_gate).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 96, 23, 31), k=3, stride=1), dict(shape=(2, 144, 24, 32), k=5, stride=2), dict(shape=(3, 32, 17, 19), k=3, stride=2),
+    dict(shape=(2, 1152, 7, 9), k=5, stride=1), dict(shape=(1, 40, 9, 33), k=5, stride=2),
+])
+def test_depthwise_bias_act_pool(cfg):
+    """ops.depthwise_bias_act_pool (depthwise conv + bias + SiLU + slab sums in one pass) vs float64 torch: stride 1 with
+    symmetric padding and stride 2 with TensorFlow-SAME (asymmetric) padding, k = 3 / 5, C up to 1152 (two channel passes)."""
+    rng = np.random.default_rng(183)
+    b, c, h, w = cfg["shape"]
+    k, s = cfg["k"], cfg["stride"]
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((c, 1, k, k)) / k).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(c).astype(np.float32))
+    if s == 1:
+        pt = pb = pl = pr = k // 2
+    else:  # TensorFlow SAME: total = max((ceil(n / s) - 1) * s + k - n, 0), the extra pixel goes to the bottom / right
+        th = max((-(-h // s) - 1) * s + k - h, 0)
+        tw = max((-(-w // s) - 1) * s + k - w, 0)
+        pt, pb, pl, pr = th // 2, th - th // 2, tw // 2, tw - tw // 2
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.double(), (pl, pr, pt, pb)), wt.double(), bias.double(), stride=s,
+                                     groups=c)
+    ref = ref * torch.sigmoid(ref)
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert ops.depthwise_supported(xd, c, (k, k), (s, s))
+    y, partial = ops.depthwise_bias_act_pool(xd, wt[:, 0].permute(1, 2, 0).contiguous().to(DEV), bias.to(DEV), 1, s, pt, pl,
+                                             ref.shape[-2:])
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert float((y.cpu().double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    assert float((partial.cpu().double().sum(1) - ref.sum((2, 3))).abs().max()) < 1e-4 * max(1.0, float(ref.sum((2, 3)).abs().max()))
+
+
 @pytest.mark.gpu
 def test_encoder_inference_walk_matches_generic_walk():
     """Encoder._forward_inference (folded stem, squeeze-excite gate inside the projection GEMM, padded expansion output,
