@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
 extern "C" int mde_pool_slabs(int B, int64_t HW) {
   if (B <= 0 || HW <= 0) return 0;
   long long s = (MDE_NUM_SMS * 4 + B - 1) / B;  // ~4 blocks per SM over the batch
-  const long long cap = (HW + 31) / 32;          // >= 32 rows per slab
+  const long long cap = (HW + 7) / 8;            // >= 8 rows per slab
   if (s > cap) s = cap;
   if (s < 1) s = 1;
   if (s > 256) s = 256;

@@ -51,18 +51,28 @@ __global__ void __launch_bounds__(256) depthwise_bias_act_pool_kernel(const floa
         const int oy = p / Wo, ox = p - oy * Wo;
         const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
         float4 o = bb;
+        // branch-free taps: out-of-range taps read a clamped (valid) address and are multiplied by zero, so that the K loads
+        // of a filter row issue back to back (a bounds `continue` per tap made every tap its own load -> fma round trip)
 #pragma unroll
         for (int dy = 0; dy < K; ++dy) {
           const int iy = iy0 + dy;
-          if (iy < 0 || iy >= Hi) continue;
-          const float4* row = xb + (long long)iy * Wi * c4 + cg;
+          const int iyc = min(max(iy, 0), Hi - 1);
+          const float my = iy == iyc ? 1.f : 0.f;
+          const float4* row = xb + (long long)iyc * Wi * c4 + cg;
+          float4 v[K];
+          float m[K];
 #pragma unroll
           for (int dx = 0; dx < K; ++dx) {
             const int ix = ix0 + dx;
-            if (ix < 0 || ix >= Wi) continue;
-            const float4 v = __ldg(row + (long long)ix * c4);
+            const int ixc = min(max(ix, 0), Wi - 1);
+            m[dx] = ix == ixc ? my : 0.f;
+            v[dx] = __ldg(row + (long long)ixc * c4);
+          }
+#pragma unroll
+          for (int dx = 0; dx < K; ++dx) {
             const float4 q = WREG ? wt[WREG ? dy * K + dx : 0] : __ldg(wg + (long long)(dy * K + dx) * c4);
-            o.x = fmaf(v.x, q.x, o.x); o.y = fmaf(v.y, q.y, o.y); o.z = fmaf(v.z, q.z, o.z); o.w = fmaf(v.w, q.w, o.w);
+            o.x = fmaf(v[dx].x * m[dx], q.x, o.x); o.y = fmaf(v[dx].y * m[dx], q.y, o.y);
+            o.z = fmaf(v[dx].z * m[dx], q.z, o.z); o.w = fmaf(v[dx].w * m[dx], q.w, o.w);
           }
         }
         if (act == 1) {
