@@ -98,8 +98,16 @@ def _pointwise_exact(conv, x, act, residual, out_pads):
             and (residual is None or (residual.dtype == torch.float32 and residual.is_contiguous(memory_format=torch.channels_last))))
 
 
+# "cudnn" (default): the depthwise convolutions stay on the library's NHWC fp32 kernel, followed by ONE bias + SiLU + pooling pass
+# of ours (ops.bias_act_pool_nhwc_).  "fused": ops.depthwise_bias_act_pool does convolution + bias + SiLU + pooling in one pass.
+# Measured on B200 at config 2 (23 layers): cudnn + pool 1.68 ms, fused 2.15 ms -- the one-output-per-thread mapping of the fused
+# kernel issues ~240 instructions per output float4 and re-reads every input row k times through L2; until it computes a strip of
+# outputs per thread (sharing taps) the library kernel is the faster body, so the fused form is opt-in (tested either way).
+DEPTHWISE_IMPL = "cudnn"
+
+
 def _depthwise_module_ok(conv, act):
-    return (conv.groups > 1 and conv.groups == conv.in_channels == conv.out_channels and (act is None or isinstance(act, nn.SiLU))
+    return (DEPTHWISE_IMPL == "fused" and conv.groups > 1 and conv.groups == conv.in_channels == conv.out_channels and (act is None or isinstance(act, nn.SiLU))
             and conv.kernel_size in ((3, 3), (5, 5)) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1)
             and conv.in_channels % 4 == 0
             and (isinstance(conv, SamePadConv2d) or (isinstance(conv.padding, tuple) and conv.padding_mode == "zeros")))

@@ -497,9 +497,17 @@ def test_encoder_inference_walk_matches_generic_walk():
             mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=g))
     x = torch.rand(2, 3, 96, 128, device=DEV).contiguous(memory_format=torch.channels_last)
     enc = model.encoder
+    from mde_biological_vision_systems_b200.models import efficientnet as E
     with ops.exact_fp32_library():
         with torch.no_grad():
             fast = enc(x)
+            E.DEPTHWISE_IMPL = "fused"  # the opt-in one-pass depthwise kernel gives the same taps
+            try:
+                fused = enc(x)
+            finally:
+                E.DEPTHWISE_IMPL = "cudnn"
+        for i in (4, 5, 6, 8, 11):
+            assert float((fused[i] - fast[i]).abs().max()) < 2e-5 * float(fast[i].abs().max()), i
         with torch.enable_grad():  # autograd on: every block takes its plain torch path (bn(conv(x)), SqueezeExcite.forward)
             ref = [x]
             for name, child in enc.original_model._modules.items():  # the reference's walk (unet_adaptive_bins.py:118-128)
