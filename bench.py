@@ -507,7 +507,13 @@ def run_train(cfg, ctx, steps, batch, sync_bn="kernels"):
     def one():
         box["loss"] = stepper(host, ctx.dev)
 
+    import ctypes
+    from mde_biological_vision_systems_b200 import _lib
+    lib = _lib.load()
+    wait_ns, waits = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    lib.mde_bn_wait_stats(None, None, 1)
     ms = ctx.timed(one, steps) / steps
+    lib.mde_bn_wait_stats(ctypes.byref(wait_ns), ctypes.byref(waits), 1)
     res = {"config": cfg["name"].split(":")[0].replace("BASELINE config ", "cfg"), "imgs_s": round(ctx.world * batch / (ms * 1e-3), 1),
            "ms": round(ms, 2), "batch_per_gpu": batch, "loss": round(float(box["loss"].item()), 4),
            "launches": int((ops.launch_count() - l0) / steps), "dtype": cfg["autocast"] or "f32"}
@@ -515,6 +521,9 @@ def run_train(cfg, ctx, steps, batch, sync_bn="kernels"):
         res["sync_bn"] = sync_bn
         w = stepper.averager.last_exposed_wait_ms()
         res["exposed_allreduce_ms"] = None if w is None else round(w, 3)
+        # SyncBatchNorm's peer-flag waits of this rank (rank skew + NVLink latency), per step
+        res["syncbn_wait_ms"] = round(wait_ns.value / 1e6 / steps, 3)
+        res["syncbn_waits"] = int(waits.value / steps)
     del stepper, model
     torch.cuda.empty_cache()
     return res

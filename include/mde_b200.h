@@ -461,6 +461,9 @@ int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_
  * off with __nanosleep; on expiry the rank counts the event (mde_bn_peer_timeouts) and traps.  Both calls synchronise. */
 int mde_bn_set_peer_timeout_seconds(double seconds);
 int mde_bn_peer_timeouts(void);
+/* diagnostic: time (ns) block (0,0) of the consuming kernels spent waiting for peer flags, and the number of waits, since the
+ * last reset -- the rank skew + NVLink latency SyncBatchNorm adds to a training step (bench.py reports it per step) */
+int mde_bn_wait_stats(uint64_t* wait_ns, uint64_t* waits, int reset);
 
 #ifdef __cplusplus
 }

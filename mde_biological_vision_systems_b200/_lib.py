@@ -95,6 +95,7 @@ SIGNATURES = {
                                          ctypes.c_uint64, ctypes.c_double, _p]),
     "mde_bn_set_peer_timeout_seconds": (_i32, [ctypes.c_double]),
     "mde_bn_peer_timeouts": (_i32, []),
+    "mde_bn_wait_stats": (_i32, [_p, _p, _i32]),
     "mde_silog_ws_bytes": (_i64, []),
     "mde_silog_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "mde_silog_bwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -288,6 +288,10 @@ __device__ __forceinline__ void bn_publish_if_last(double* local, int C, const B
 // watchdog aborting the process -- rather than normalising with missing statistics.
 static __device__ unsigned long long g_bn_timeout_ns = 600ULL * 1000000000ULL;
 static __device__ unsigned int g_bn_peer_timeouts = 0;
+// time block (0, 0) of the consuming kernels spent waiting for the peers' flags, and the number of such waits (diagnostic:
+// mde_bn_wait_stats; the wait is rank skew + NVLink store latency -- the part of a training step SyncBatchNorm adds)
+static __device__ unsigned long long g_bn_wait_ns = 0;
+static __device__ unsigned long long g_bn_waits = 0;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -297,6 +301,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 __device__ __forceinline__ void bn_wait_peers(unsigned long long my_base, long long flag_off, int world,
                                               unsigned long long epoch) {
+  const bool probe = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  const unsigned long long t_in = probe ? globaltimer_ns() : 0ULL;
   if (threadIdx.x < world) {
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(my_base + flag_off) + threadIdx.x;
     if (ld_acquire_sys(f) < epoch) {
@@ -304,7 +310,7 @@ __device__ __forceinline__ void bn_wait_peers(unsigned long long my_base, long l
       unsigned int backoff = 32;
       while (ld_acquire_sys(f) < epoch) {
         __nanosleep(backoff);
-        if (backoff < 4096) backoff *= 2;
+        if (backoff < 512) backoff *= 2;  // the expected wait is microseconds: a longer sleep only adds wake-up overshoot
         if (globaltimer_ns() - t0 > g_bn_timeout_ns) {
           atomicAdd(&g_bn_peer_timeouts, 1u);
           __threadfence_system();
@@ -314,6 +320,10 @@ __device__ __forceinline__ void bn_wait_peers(unsigned long long my_base, long l
     }
   }
   __syncthreads();
+  if (probe) {
+    atomicAdd(&g_bn_wait_ns, globaltimer_ns() - t_in);
+    atomicAdd(&g_bn_waits, 1ULL);
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_stats_p2p_kernel(const float* __restrict__ x, long long N, int C,
@@ -550,6 +560,22 @@ int mde_bn_set_peer_timeout_seconds(double seconds) {
   if (!(seconds > 0.0)) return MDE_ERR_BAD_SHAPE;
   const unsigned long long ns = (unsigned long long)(seconds * 1e9);
   return cudaMemcpyToSymbol(g_bn_timeout_ns, &ns, sizeof(ns)) == cudaSuccess ? MDE_OK : MDE_ERR_LAUNCH;
+}
+
+// Diagnostic: nanoseconds block (0, 0) of the consuming SyncBatchNorm kernels has spent waiting for peer flags and the number of
+// waits since the last reset (reset != 0 zeroes both after reading).  Synchronises.
+int mde_bn_wait_stats(uint64_t* wait_ns, uint64_t* waits, int reset) {
+  unsigned long long a = 0, b = 0;
+  if (cudaMemcpyFromSymbol(&a, g_bn_wait_ns, sizeof(a)) != cudaSuccess || cudaMemcpyFromSymbol(&b, g_bn_waits, sizeof(b)) != cudaSuccess)
+    return MDE_ERR_LAUNCH;
+  if (wait_ns) *wait_ns = a;
+  if (waits) *waits = b;
+  if (reset) {
+    const unsigned long long z = 0;
+    if (cudaMemcpyToSymbol(g_bn_wait_ns, &z, sizeof(z)) != cudaSuccess || cudaMemcpyToSymbol(g_bn_waits, &z, sizeof(z)) != cudaSuccess)
+      return MDE_ERR_LAUNCH;
+  }
+  return MDE_OK;
 }
 
 // Number of peer-flag waits that expired on this device since load (each one trapped its kernel).  Synchronises.
