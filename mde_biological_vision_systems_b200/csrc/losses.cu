@@ -215,7 +215,83 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
   unsigned int* my_max = wmax + warp * (n + 1);
   const int groups = (a.HW + 3) >> 2;
   const bool vec = (a.HW & 3) == 0;
-  for (int gidx = blockIdx.x * LS_THREADS + threadIdx.x; gidx < groups; gidx += bx * LS_THREADS) {
+  // ---- fast path: whole groups, the four pixels of a group share their image row (W % 4 == 0), mask derived from the target.
+  // Branch-free per pixel -- an invalid pixel computes with a harmless stand-in and its contribution is selected away, so the
+  // compiler interleaves the four pixels and the next group's depth is already in flight while this one is reduced.  (The
+  // general path below keeps a validity branch, a row-end test and a search loop per pixel: ~190 warp instructions per pixel,
+  // one dependent chain per group -- profiles/r2_ncu_full_summary.txt.)
+  const bool fast = vec && MASK != 1 && (!SILOG || !INTERP || (a.W & 3) == 0);
+  if (fast) {
+    const int stride = bx * LS_THREADS;
+    int gidx = blockIdx.x * LS_THREADS + threadIdx.x;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gidx < groups) nxt = ldg_stream(reinterpret_cast<const float4*>(tg) + gidx);
+    for (; gidx < groups; gidx += stride) {
+      const float4 v4 = nxt;
+      if (gidx + stride < groups) nxt = ldg_stream(reinterpret_cast<const float4*>(tg) + gidx + stride);
+      const float t4[4] = {v4.x, v4.y, v4.z, v4.w};
+      const int p0 = gidx << 2;
+      if (SILOG) {
+        float pv[4];
+        if (INTERP) {
+          const int y = p0 / a.W, x = p0 - y * a.W;
+          int y0, y1;
+          float ly0, ly1;
+          src_index(y, a.sy, a.h, y0, y1, ly0, ly1);
+          const float* r0 = pb + y0 * a.w;
+          const float* r1 = pb + y1 * a.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int x0, x1;
+            float lx0, lx1;
+            src_index(x + i, a.sx, a.w, x0, x1, lx0, lx1);
+            pv[i] = ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+          }
+        } else {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(pb) + gidx);
+          pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool valid = MASK == 0 || t4[i] > a.mask_thr;
+          const float g = (__log2f(pv[i]) - __log2f(t4[i])) * 0.6931471805599453f;
+          const float gs = valid ? g : 0.f;  // a select: the inf / NaN of an invalid pixel never enters the sums
+          s_g += gs;
+          s_gg = fmaf(gs, gs, s_gg);
+          n_g += valid ? 1u : 0u;
+        }
+      }
+      if (CHAMFER) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool valid = t4[i] >= a.min_target;       // loss.py:40  mask = target.ge(1e-3)
+          const float t = valid ? t4[i] : lut_lo;         // stand-in inside the table's range
+          const float f = (t - lut_lo) * lut_scale;
+          const int cell = f > 0.f ? (f < (float)(LS_LUT - 1) ? (int)f : LS_LUT - 1) : 0;
+          int j = lut[cell];                               // number of centres <= t is >= j: walk forward
+          j += (j < n && sc[skew(j)] <= t) ? 1 : 0;
+          j += (j < n && sc[skew(j)] <= t) ? 1 : 0;
+          while (j < n && sc[skew(j)] <= t) ++j;           // rare: more than two centres inside one cell of the grid
+          // nearest centre: c_{j-1} or c_j; at the ends the clamped index repeats the only candidate
+          const int jl = j > 0 ? j - 1 : 0, jr = j < n ? j : n - 1;
+          const float dl = t - sc[skew(jl)], dr = t - sc[skew(jr)];
+          const float ddl = dl * dl, ddr = dr * dr;
+          const bool right = ddr < ddl;                    // the left candidate wins ties, as in the general path
+          s_d += valid ? (right ? ddr : ddl) : 0.f;
+          n_t += valid ? 1u : 0u;
+          const unsigned int bits = __float_as_uint(t4[i]);
+          atomicMin(&my_min[j], valid ? bits : F_INF);     // neutral elements for an invalid pixel
+          atomicMax(&my_max[j], valid ? bits : 0u);
+          if (GRAD && valid) {
+            const int kbest = right ? jr : jl;
+            atomicAdd(&wsum[warp * n + kbest], t);
+            atomicAdd(&wcnt[warp * n + kbest], 1u);
+          }
+        }
+      }
+    }
+  }
+  for (int gidx = blockIdx.x * LS_THREADS + threadIdx.x; !fast && gidx < groups; gidx += bx * LS_THREADS) {
     const int p0 = gidx << 2;
     float t4[4];
     if (vec) {
