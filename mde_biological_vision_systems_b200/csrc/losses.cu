@@ -280,8 +280,12 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
           s_d += valid ? (right ? ddr : ddl) : 0.f;
           n_t += valid ? 1u : 0u;
           const unsigned int bits = __float_as_uint(t4[i]);
-          atomicMin(&my_min[j], valid ? bits : F_INF);     // neutral elements for an invalid pixel
-          atomicMax(&my_max[j], valid ? bits : 0u);
+          // interval tables: a plain read first -- the entries only move one way, so a stale read can cause a redundant
+          // atomic but never a missed one; once the tables have warmed up almost no pixel improves its interval and the
+          // shared-memory atomics (the kernel's scarcest resource: two per pixel, 32 scattered addresses per warp) disappear
+          const unsigned int lo_new = valid ? bits : F_INF, hi_new = valid ? bits : 0u;  // neutral for an invalid pixel
+          if (lo_new < my_min[j]) atomicMin(&my_min[j], lo_new);
+          if (hi_new > my_max[j]) atomicMax(&my_max[j], hi_new);
           if (GRAD && valid) {
             const int kbest = right ? jr : jl;
             atomicAdd(&wsum[warp * n + kbest], t);
@@ -384,8 +388,8 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
         s_d += best;
         ++n_t;
         const unsigned int bits = __float_as_uint(t);
-        atomicMin(&my_min[j], bits);
-        atomicMax(&my_max[j], bits);
+        if (bits < my_min[j]) atomicMin(&my_min[j], bits);  // see the fast path: read first, atomics only on improvement
+        if (bits > my_max[j]) atomicMax(&my_max[j], bits);
         if (GRAD) {
           atomicAdd(&wsum[warp * n + kbest], t);
           atomicAdd(&wcnt[warp * n + kbest], 1u);
