@@ -468,7 +468,10 @@ int mde_gather_embed_nhwc(const void* labels, int label_dtype, int64_t* labels_o
     const size_t smd = ((size_t)rows * np + 8 * 32 * np) * sizeof(float4);
     if (smd <= 96 * 1024) {
       long long gx = ((long long)H * segs + 7) / 8;
-      const long long cap = (MDE_NUM_SMS * 8 + B - 1) / B;
+      // one resident wave: a block holds the table (rows * np float4) + 8 staging tiles, i.e. ~40 KB -> 5 blocks per SM
+      const int per_sm = (int)((200 * 1024) / smd) < 8 ? (int)((200 * 1024) / smd) : 8;
+      long long cap = ((long long)MDE_NUM_SMS * (per_sm < 1 ? 1 : per_sm)) / B;
+      if (cap < 1) cap = 1;
       if (gx > cap) gx = cap;
       const dim3 gd((unsigned)gx, (unsigned)B);
 #define MDE_GD(LT, NPV)                                                                                                  \

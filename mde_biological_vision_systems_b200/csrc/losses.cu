@@ -63,7 +63,10 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // ~10 us of HBM time) but lengthen the finishing block's reduction over the per-block rows, which is the serial tail.
 inline int loss_blocks_per_image(int B, long long HW) {
   long long bx = (HW / 4 + LS_THREADS * 2 - 1) / (LS_THREADS * 2);  // >= 8 pixels per thread
-  const long long cap = (MDE_NUM_SMS * 2 + B - 1) / B;
+  // the whole grid must be resident at once (2 CTAs of 512 threads per SM): rounding the cap UP put 304 blocks on 296 slots at
+  // B = 16 and the eight stragglers doubled the kernel's duration (sm__cycles_active = half of elapsed in the ncu capture)
+  long long cap = (MDE_NUM_SMS * 2) / B;
+  if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return (int)bx;
@@ -458,9 +461,20 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
     unsigned int* smax = wmax;
     for (int k = threadIdx.x; k <= n; k += LS_THREADS) {
       unsigned int lo = F_INF, hi = 0u;
-      for (int i = 0; i < bx; ++i) {
-        lo = min(lo, __ldcg(a.cw.blk_min + ((long long)b * bx + i) * (n + 1) + k));
-        hi = max(hi, __ldcg(a.cw.blk_max + ((long long)b * bx + i) * (n + 1) + k));
+      const unsigned int* pmin = a.cw.blk_min + (long long)b * bx * (n + 1) + k;
+      const unsigned int* pmax = a.cw.blk_max + (long long)b * bx * (n + 1) + k;
+      int i = 0;
+      for (; i + 3 < bx; i += 4) {  // eight independent L2 loads per trip (this is the serial tail of the launch)
+        const unsigned int l0 = __ldcg(pmin + (long long)i * (n + 1)), l1 = __ldcg(pmin + (long long)(i + 1) * (n + 1));
+        const unsigned int l2 = __ldcg(pmin + (long long)(i + 2) * (n + 1)), l3 = __ldcg(pmin + (long long)(i + 3) * (n + 1));
+        const unsigned int h0 = __ldcg(pmax + (long long)i * (n + 1)), h1 = __ldcg(pmax + (long long)(i + 1) * (n + 1));
+        const unsigned int h2 = __ldcg(pmax + (long long)(i + 2) * (n + 1)), h3 = __ldcg(pmax + (long long)(i + 3) * (n + 1));
+        lo = min(min(lo, min(l0, l1)), min(l2, l3));
+        hi = max(max(hi, max(h0, h1)), max(h2, h3));
+      }
+      for (; i < bx; ++i) {
+        lo = min(lo, __ldcg(pmin + (long long)i * (n + 1)));
+        hi = max(hi, __ldcg(pmax + (long long)i * (n + 1)));
       }
       smin[k] = lo;
       smax[k] = hi;
