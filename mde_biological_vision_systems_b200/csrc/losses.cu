@@ -13,8 +13,8 @@
 //   * SILog: the bilinear sample of the quarter-size prediction (L1/L2 resident) is taken in registers; sum g, sum g^2, n
 //     are carried in fp32 per thread (<= a few dozen pixels) and widened to fp64 at the warp / block merge;
 //   * chamfer, targets -> nearest centre: the centres are sorted (bin widths are positive; verified on the device, see
-//     `unsorted`), so it is a binary search in the shared-memory-resident centres (skewed by one word per 32 so the top
-//     levels of the search do not collide on one bank);
+//     `unsorted`): a uniform-grid table over [edge_0, edge_n] (built per block by binary search) gives the starting centre
+//     and the search walks 0-2 steps forward in the shared-memory-resident centres;
 //   * chamfer, centres -> nearest target: every target falls in one of n+1 intervals between consecutive centres; per
 //     interval the min and max target are kept in WARP-PRIVATE shared-memory tables (atomicMin/Max on the float bits --
 //     targets are positive so integer order == float order), merged per block, written to a per-block row of the scratch
@@ -144,7 +144,17 @@ struct LossArgs {
   int B, HW;
 };
 
-__device__ __forceinline__ int skew(int k) { return k + (k >> 5); }
+// (the centres used to be stored skewed by one word per 32 for the binary search; with the uniform-grid table in front of it
+// the search touches 1-3 neighbouring centres per pixel and the extra address arithmetic cost more than the conflicts)
+__device__ __forceinline__ int skew(int k) { return k; }
+
+// log2 of a positive NORMAL float on the SFU (depths and predictions are >= 1e-3): the bare instruction, without the
+// denormal rescaling __log2f wraps around it (4 extra instructions per call, 8 calls per group)
+__device__ __forceinline__ float lg2_fast(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // MASK: 0 none, 1 explicit uint8 mask, 2 derived (target > mask_thr).  dynamic smem (CHAMFER): centres[skew(n)+1] |
 // wmin[LS_WARPS][n+1] | wmax[LS_WARPS][n+1] | (GRAD) wsum[LS_WARPS][n] float | wcnt[LS_WARPS][n]
@@ -241,14 +251,14 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
           int y0, y1;
           float ly0, ly1;
           src_index(y, a.sy, a.h, y0, y1, ly0, ly1);
-          const float* r0 = pb + y0 * a.w;
-          const float* r1 = pb + y1 * a.w;
+          const unsigned int o0 = (unsigned int)(y0 * a.w), o1 = (unsigned int)(y1 * a.w);  // 32-bit offsets: one LEA pair per load
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             int x0, x1;
             float lx0, lx1;
             src_index(x + i, a.sx, a.w, x0, x1, lx0, lx1);
-            pv[i] = ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+            pv[i] = ly0 * (lx0 * __ldg(pb + (o0 + (unsigned int)x0)) + lx1 * __ldg(pb + (o0 + (unsigned int)x1))) +
+                    ly1 * (lx0 * __ldg(pb + (o1 + (unsigned int)x0)) + lx1 * __ldg(pb + (o1 + (unsigned int)x1)));
           }
         } else {
           const float4 q = __ldg(reinterpret_cast<const float4*>(pb) + gidx);
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool valid = MASK == 0 || t4[i] > a.mask_thr;
-          const float g = (__log2f(pv[i]) - __log2f(t4[i])) * 0.6931471805599453f;
+          const float g = (lg2_fast(pv[i]) - lg2_fast(t4[i])) * 0.6931471805599453f;
           const float gs = valid ? g : 0.f;  // a select: the inf / NaN of an invalid pixel never enters the sums
           s_g += gs;
           s_gg = fmaf(gs, gs, s_gg);
@@ -576,16 +586,22 @@ __global__ void __launch_bounds__(LS_THREADS) depth_losses_kernel(const LossArgs
     __syncthreads();
     if (!last_image) return;
     __threadfence();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      // one warp: lane i reads image i (+32, ...) -- all L2 loads in flight at once (a scalar loop paid one round trip per
+      // image at the very end of the launch); the shuffle tree adds in a fixed order, so the result is reproducible
       double cx = 0, cy = 0;
-      for (int i = 0; i < a.B; ++i) {
+      for (int i = threadIdx.x; i < a.B; i += 32) {
         cx += __ldcg(a.cw.cham + 2 * i);
         cy += __ldcg(a.cw.cham + 2 * i + 1);
       }
-      // an unsorted centre vector (never produced by the model: widths are positive) would make the search above
-      // meaningless: report NaN instead of a silently wrong loss
-      const bool bad = __ldcg(a.cw.unsorted) != 0u;
-      *a.chamfer_loss = bad ? __int_as_float(0x7fc00000) : (float)(cx / a.B + cy / a.B);
+      cx = warp_sum(cx);
+      cy = warp_sum(cy);
+      if (threadIdx.x == 0) {
+        // an unsorted centre vector (never produced by the model: widths are positive) would make the search above
+        // meaningless: report NaN instead of a silently wrong loss
+        const bool bad = __ldcg(a.cw.unsorted) != 0u;
+        *a.chamfer_loss = bad ? __int_as_float(0x7fc00000) : (float)(cx / a.B + cy / a.B);
+      }
     }
   }
   if (SILOG) {
