@@ -357,10 +357,6 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
   const long long m_tiles = (M + 127) / 128;
   int tn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (tn == 256 && m_tiles * ((N + 255) / 256) < 2 * MDE_NUM_SMS) tn = 128;
-  // few rows (the 13 x 17 maps of the last stages: 28 M tiles): such a layer is latency-bound, so narrower N tiles put more
-  // CTAs to work and deepen the ring (a 192-column tile leaves room for 2 stages, a 32-column tile for 5); the activation tile
-  // is converted once per N tile, which costs nothing here
-  while (tn > 32 && m_tiles * ((N + tn - 1) / tn) < MDE_NUM_SMS) tn = tn / 2 <= 32 ? 32 : ((tn / 2 + 15) / 16) * 16;
   g.tn = tn;
   g.n_tiles = (N + tn - 1) / tn;
   g.chunks = (K + tc::PW_KC - 1) / tc::PW_KC;
