@@ -19,6 +19,7 @@ for spec in "head_chain|depth_losses|gather_embed_dense|patch_embed|upsample_nhw
       python scripts/ncu_step.py 2 > gpurun_out/ncu_full_$i.log 2>&1
   echo "ncu full $i rc=$?"
   ncu -i gpurun_out/prof_final_$i.ncu-rep --page raw --csv > gpurun_out/prof_final_${i}_raw.csv 2>/dev/null
+  if [ $i -eq 4 ]; then ncu -i gpurun_out/prof_final_$i.ncu-rep --page source --csv > gpurun_out/prof_final_${i}_source.csv 2>/dev/null; fi
   rm -f gpurun_out/prof_final_$i.ncu-rep
 done
 ls -la gpurun_out | head -40
