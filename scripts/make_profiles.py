@@ -49,16 +49,33 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def full(src, dst, traffic=None, B=None, P=None):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
+    """src: one .ncu-rep, or a comma-separated list of raw-page csv exports (ncu -i rep --page raw --csv), concatenated"""
     seen, tr = set(), {}
     with open(dst, "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on ... ({src}); one entry per distinct kernel\n")
-        for r in rows[2:]:
+        f.write(f"# ncu --set full --clock-control none ... ({src}); one entry per distinct (kernel, grid)\n")
+        for part in src.split(","):
+            if part.endswith(".csv"):
+                raw = open(part).read()
+            else:
+                raw = subprocess.run(["ncu", "-i", part, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+            rows = list(csv.reader(raw.splitlines()))
+            if len(rows) < 3:
+                continue
+            hdr, units = rows[0], rows[1]
+            idx = {h: i for i, h in enumerate(hdr)}
+            _full_rows(f, rows[2:], idx, units, seen, tr)
+    if traffic:
+        for v in tr.values():
+            v["batch"], v["P"] = int(B), int(P)
+        json.dump(tr, open(traffic, "w"), indent=1)
+    print(dst, "kernels:", len(seen))
+
+
+def _full_rows(f, data, idx, units, seen, tr):
+    if True:
+        for r in data:
             name = r[idx["Kernel Name"]]
-            key = name[:90]
+            key = name[:90] + (r[idx["Grid Size"]] if "Grid Size" in idx else "") + r[idx["gpu__time_duration.sum"]][:2]
             if key in seen:
                 continue
             seen.add(key)
@@ -72,11 +89,6 @@ def full(src, dst, traffic=None, B=None, P=None):
                 return v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get(u, 1)
             tr.setdefault(short, {"dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
                                   "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]].replace(",", "")), "kernel": name[:120]})
-    if traffic:
-        for v in tr.values():
-            v["batch"], v["P"] = int(B), int(P)
-        json.dump(tr, open(traffic, "w"), indent=1)
-    print(dst, "kernels:", len(seen))
 
 
 if __name__ == "__main__":
