@@ -126,6 +126,7 @@ class GradientAverager:
         weights keep channels_last gradients)."""
         for bk in self.buckets:
             off = 0
+            views = []
             for p in bk["params"]:
                 n = p.numel()
                 view = bk["flat"][off:off + n]
@@ -137,15 +138,38 @@ class GradientAverager:
                     if p.grad is not None:  # constructed after a backward pass: keep what autograd already produced
                         g.copy_(p.grad)
                     p.grad = g
+                views.append(p.grad)
                 off += n
+            bk["views"] = views
             bk["pending"] = len(bk["params"])
         self._next_launch = 0
 
     def zero_grad(self):
+        """One fill per bucket.  The p.grad views are re-created only if something replaced them (e.g. an
+        optimizer.zero_grad(set_to_none=True)): rebuilding 300+ views every step cost milliseconds of host time in a step that
+        is host-launch-bound."""
+        intact = True
         for bk in self.buckets:
             bk["flat"].zero_()
             bk["work"] = None
-        self.attach()
+            bk["pending"] = len(bk["params"])
+            views = bk["views"]
+            if views is None or any(p.grad is not v for p, v in zip(bk["params"], views)):
+                intact = False
+        self._next_launch = 0
+        if not intact:
+            self.attach()
+
+    def clip_grad_norm_(self, max_norm, eps=1e-6):
+        """torch.nn.utils.clip_grad_norm_ (2-norm) over all parameters, on the bucket arena: a handful of launches instead of a
+        multi-tensor pass over every parameter.  Same formula: coef = max_norm / (total + 1e-6), clamped to 1.  Returns the
+        total norm (a 0-dim tensor; no host synchronisation)."""
+        norms = torch.stack([torch.linalg.vector_norm(bk["flat"].float()) for bk in self.buckets])
+        total = torch.linalg.vector_norm(norms)
+        coef = torch.clamp(max_norm / (total + eps), max=1.0)
+        for bk in self.buckets:
+            bk["flat"].mul_(coef.to(bk["flat"].dtype))
+        return total
 
     def _launch_ready(self, force=False):
         while self._next_launch < len(self.buckets):
@@ -293,11 +317,14 @@ class P2PArena:
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD if group is None else group
         enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
-        if enable is not None:
-            try:
-                enable(group.group_name)
-            except Exception:
-                pass
+        if enable is not None:  # needed by older torch releases, a deprecated no-op on current ones
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", FutureWarning)
+                try:
+                    enable(group.group_name)
+                except Exception:
+                    pass
         self.buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)

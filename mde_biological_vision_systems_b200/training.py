@@ -37,7 +37,9 @@ class TrainStep:
             params = [{"params": model.get_1x_lr_params(), "lr": lr / 10}, {"params": model.get_10x_lr_params(), "lr": lr}]
         # DDP construction semantics (train.py:298-299): every replica starts from rank 0's parameters and buffers
         broadcast_module_state(model)
-        self.optimizer = torch.optim.AdamW(params, weight_decay=wd, lr=lr)
+        # fused multi-tensor AdamW on CUDA (same update rule, a few launches instead of dozens: the step is host-launch-bound)
+        on_cuda = all(p.is_cuda for p in model.parameters())
+        self.optimizer = torch.optim.AdamW(params, weight_decay=wd, lr=lr, **({"fused": True} if on_cuda else {}))
         # train.py:364: OneCycleLR(optimizer, args.lr, ...) -- a SCALAR max_lr, which overrides the per-group learning rates:
         # encoder and decoder both peak at ``lr`` in the reference (the lr/10 of :351 only survives as initial value until the
         # scheduler's first step).  ``per_group_max_lr=True`` keeps the encoder at lr/10 instead (a deviation, off by default).
@@ -70,7 +72,7 @@ class TrainStep:
                 loss = self.criterion_ueff(pred, depth, mask=mask.to(torch.bool), interpolate=True)
         loss.backward()
         self.averager.reduce()
-        nn.utils.clip_grad_norm_(self.model.parameters(), 0.1)
+        self.averager.clip_grad_norm_(0.1)  # train.py:427 nn.utils.clip_grad_norm_(model.parameters(), 0.1), on the gradient arena
         self.optimizer.step()
         self.scheduler.step()
         return loss.detach()

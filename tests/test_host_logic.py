@@ -220,3 +220,32 @@ def test_torch_library_ops_registered_with_fake_impls():
         assert s.shape == () and c.shape == ()
     with pytest.raises(_lib.MdeError):
         torch.ops.mde.split_bf16(torch.zeros(1, 8, 4, 4))
+
+
+def test_gradient_arena_clip_matches_torch_clip():
+    """GradientAverager.clip_grad_norm_ (norm of the bucket norms, one scale per bucket) == nn.utils.clip_grad_norm_ (train.py:427),
+    and zero_grad keeps the p.grad views (re-attaching only when something replaced them)."""
+    from mde_biological_vision_systems_b200.parallel import GradientAverager
+    torch.manual_seed(11)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 1), torch.nn.Flatten(),
+                              torch.nn.Linear(4 * 6 * 6, 5))
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    avg = GradientAverager(net.parameters(), bucket_mb=0.0005)  # several buckets
+    assert len(avg.buckets) > 1
+    x = torch.randn(2, 3, 8, 8)
+    for mx in (0.1, 1e6):  # clipping active / inactive
+        avg.zero_grad()
+        views = [p.grad for p in net.parameters()]
+        (net(x) ** 2).sum().backward()
+        assert all(p.grad is v for p, v in zip(net.parameters(), views))
+        for r, p in zip(ref, net.parameters()):
+            r.grad = p.grad.detach().clone()
+        t_ref = torch.nn.utils.clip_grad_norm_(ref, mx)
+        t_ours = avg.clip_grad_norm_(mx)
+        assert torch.allclose(t_ours, t_ref, rtol=1e-6)
+        for r, p in zip(ref, net.parameters()):
+            assert torch.allclose(p.grad, r.grad, rtol=1e-6, atol=1e-12)
+    for p in net.parameters():  # something replaces the gradients: the next zero_grad re-attaches
+        p.grad = None
+    avg.zero_grad()
+    assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in net.parameters())
