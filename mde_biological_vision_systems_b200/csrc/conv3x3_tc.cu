@@ -25,7 +25,12 @@
 // MMAs of the next.  Epilogue: tcgen05.ld -> affine / LeakyReLU -> swizzled shared staging -> TMA tensor store (edge
 // tiles are clipped by the hardware; no predicates anywhere).  Persistent, 1 CTA / SM, warp-specialised: warp 0 TMA
 // producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 3-6 epilogue.
-// Measured (B200, head conv 128 -> 128 at B = 16, 208 x 272, TF32 form): 0.327 ms = 816 TFLOP/s, tensor pipe 80 % active.
+// PREC_BF16 (model.precision = "bf16"): the hi planes only, one bf16 product per K step; the TMA boxes carry one plane.
+// Measured (B200, B = 16): head conv 128 -> 128 at 208 x 272, x3 form: 0.516 ms = 1.55 PFLOP/s of issued bf16 products = 0.96 of
+// the measured bf16 peak (the TF32 form of the same kernel: 0.327 ms).  The decoder convs reach 0.57-0.87: the 26 x 34 / 52 x 68
+// maps pad to whole 128-pixel tiles (69 % / 79 % useful), C_out = 80 runs an N = 80 MMA at the shared-memory operand rate, and
+// operand rows must start on 64-byte boundaries (callers pad the channel pitch to 32: a 680- or 344-channel pitch put every other
+// row at a 16-byte offset and cost 25-30 % of the kernel).
 #include <stdlib.h>
 
 #include "common.cuh"
