@@ -191,6 +191,11 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
  *   per-(image, slab, channel) sums partial[B][slabs][C] of y (slabs = mde_pool_slabs(B, HW)); fixed summation order.
  * mde_se_gate: gate[b][c] = sigmoid(w2[c][:] . silu(w1 . mean_b + b1) + b2[c]) with mean_b = inv_hw * sum_s partial[b][s][:];
  *   w1 [R][C], w2 [C][R] (the 1x1 conv_reduce / conv_expand filters of geffnet's SqueezeExcite). */
+/* mde_stem_conv3x3s2_nhwc: the encoder stem in exact fp32 -- 3x3 / stride 2 convolution (geffnet conv_stem, TensorFlow-SAME
+ * padding as pad_top / pad_left + bounds), folded-BatchNorm bias and SiLU (act = 1): x [B][Hi][Wi][Cin] fp32 NHWC, Cin % 4 == 0;
+ * w_tcc [9][Cin][Cout] (tap = dy*3 + dx, C_out innermost); y [B][Ho][Wo][Cout]; Cout in {32, 48}. */
+int mde_stem_conv3x3s2_nhwc(const float* x, const float* w_tcc, const float* bias, float* y, int B, int Hi, int Wi, int Cin, int Cout,
+                            int pad_top, int pad_left, int Ho, int Wo, int act, mde_stream_t stream);
 int mde_pool_slabs(int B, int64_t HW);
 /* mde_depthwise_bias_act_pool_nhwc: the depthwise k x k convolution (k = 3 / 5, stride 1 / 2, zero padding pad_top / pad_left and
  * whatever the output size implies at the far edges -- TensorFlow-SAME included), its folded-BatchNorm bias, SiLU (act = 1) and

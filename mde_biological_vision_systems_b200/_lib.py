@@ -45,6 +45,7 @@ SIGNATURES = {
     "mde_upsample_concat_nhwc_pair_fwd": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_pointwise_x3_fwd": (_i32, [_p, _p, _i64, _p, _p, _i32, _p, _p, _i64, _i32, _i32, _i64, _i64, _p, _p]),
     "mde_pool_slabs": (_i32, [_i32, _i64]),
+    "mde_stem_conv3x3s2_nhwc": (_i32, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "mde_depthwise_bias_act_pool_nhwc": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                                 _i32, _p]),
     "mde_bias_act_pool_nhwc": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _p]),

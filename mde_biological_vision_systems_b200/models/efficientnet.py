@@ -190,6 +190,21 @@ def conv_bn(conv, bn, x, act=None, residual=None, out_pads=None, prepadded=False
                                       gate=gate, out_pads=out_pads))
     if gate is not None:
         x = x * gate[:, :, None, None]
+    if (not torch.backends.cudnn.allow_tf32 and residual is None and out_pads is None and not pool and conv.groups == 1
+            and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.dilation == (1, 1)
+            and (act is None or isinstance(act, nn.SiLU)) and isinstance(conv, SamePadConv2d)
+            and ops.stem_conv_supported(x, conv.in_channels, conv.out_channels)):
+        # the stem in exact mode: the library's exact-fp32 NHWC engine takes 0.83 ms for this one layer at config 2; a direct fp32
+        # kernel of ours (ops.stem_conv3x3s2: bias + SiLU in the epilogue, SAME padding by bounds) does it in a fraction
+        h_in, w_in = x.shape[-2:]
+        pt, pb, pl, pr = (0, 0, 0, 0) if prepadded else conv.same_pads(h_in, w_in)
+        out_hw = ((h_in + pt + pb - 3) // 2 + 1, (w_in + pl + pr - 3) // 2 + 1)
+        key = conv._mde_fold[0]
+        cached = getattr(conv, "_mde_fold_tcc", None)
+        if cached is None or cached[0] != key:
+            cached = (key, ops.prepare_stem_weight(w))
+            conv._mde_fold_tcc = cached
+        return ops.stem_conv3x3s2(x, cached[1], b, 1 if act is not None else 0, pt, pl, out_hw)
     if pool and residual is None and gate is None and out_pads is None and _depthwise_ours(conv, x, act):
         # the depthwise convolution of an MBConv block: convolution + folded bias + SiLU + the squeeze-excite pooling in one
         # pass of our own fp32 kernel (ops.depthwise_bias_act_pool) instead of the library kernel, a bias/activation pass and a

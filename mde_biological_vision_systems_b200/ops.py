@@ -760,6 +760,32 @@ def bias_act_pool_nhwc_(x_cl, bias, act):
     return x_cl, partial
 
 
+def stem_conv_supported(x, cin, cout):
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == cin and cin % 4 == 0 and cout in (32, 48)
+                and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def prepare_stem_weight(weight):
+    """Conv filter [Cout,Cin,3,3] -> fp32 [9,Cin,Cout] (tap-major, C_out innermost: what stem_conv3x3s2 stages in shared memory)."""
+    return weight.detach().float().permute(2, 3, 1, 0).reshape(9, weight.shape[1], weight.shape[0]).contiguous()
+
+
+def stem_conv3x3s2(x_cl, w_tcc, bias, act, pad_top, pad_left, out_hw):
+    """act(conv3x3 stride 2 (x) + bias) in exact fp32 on channels_last x [B,Cin,Hi,Wi]; zero padding pad_top / pad_left (and what
+    out_hw implies at the bottom / right); w_tcc from prepare_stem_weight.  Returns channels_last [B,Cout,Ho,Wo]."""
+    lib = _lib.load()
+    _need_cuda(x_cl, w_tcc)
+    b, cin, hi, wi = x_cl.shape
+    cout = w_tcc.shape[2]
+    ho, wo = (int(v) for v in out_hw)
+    y = torch.empty((b, cout, ho, wo), dtype=torch.float32, device=x_cl.device, memory_format=torch.channels_last)
+    with timing("stem_conv", work=2.0 * b * ho * wo * cout * 9 * cin):
+        rc = lib.mde_stem_conv3x3s2_nhwc(_p(x_cl), _p(w_tcc), _p(bias), _p(y), b, hi, wi, cin, cout, int(pad_top), int(pad_left), ho,
+                                         wo, int(act), _s())
+    _lib.check(rc, "mde_stem_conv3x3s2_nhwc")
+    return y
+
+
 def depthwise_supported(x, channels, kernel_size, stride, dilation=(1, 1)):
     return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == channels and channels % 4 == 0
                 and x.is_contiguous(memory_format=torch.channels_last) and tuple(kernel_size) in ((3, 3), (5, 5))

@@ -480,6 +480,35 @@ def test_depthwise_bias_act_pool(cfg):
     assert float((partial.cpu().double().sum(1) - ref.sum((2, 3))).abs().max()) < 1e-4 * max(1.0, float(ref.sum((2, 3)).abs().max()))
 
 
+@pytest.mark.parametrize("cfg", [dict(shape=(2, 28, 47, 63), cout=32), dict(shape=(1, 76, 32, 40), cout=32, prepad=True),
+                                 dict(shape=(2, 4, 33, 34), cout=48, act=0)])
+def test_stem_conv3x3s2(cfg):
+    """ops.stem_conv3x3s2 (exact-fp32 3x3 / stride-2 stem with bias + SiLU, TensorFlow-SAME padding by bounds or pre-padded input)
+    vs float64 torch; odd sizes exercise the asymmetric padding and the single-pixel tail of a row."""
+    rng = np.random.default_rng(184)
+    b, c, h, w = cfg["shape"]
+    cout, act = cfg["cout"], cfg.get("act", 1)
+    x = torch.from_numpy(rng.standard_normal((b, c, h, w)).astype(np.float32))
+    wt = torch.from_numpy((rng.standard_normal((cout, c, 3, 3)) / np.sqrt(9 * c)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32))
+    th, tw = max((-(-h // 2) - 1) * 2 + 3 - h, 0), max((-(-w // 2) - 1) * 2 + 3 - w, 0)
+    pt, pb, pl, pr = th // 2, th - th // 2, tw // 2, tw - tw // 2
+    xp = torch.nn.functional.pad(x, (pl, pr, pt, pb))
+    ref = torch.nn.functional.conv2d(xp.double(), wt.double(), bias.double(), stride=2)
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    wk = ops.prepare_stem_weight(wt.to(DEV))
+    if cfg.get("prepad"):
+        xin = xp.to(DEV).contiguous(memory_format=torch.channels_last)
+        out = ops.stem_conv3x3s2(xin, wk, bias.to(DEV), act, 0, 0, ref.shape[-2:])
+    else:
+        xin = x.to(DEV).contiguous(memory_format=torch.channels_last)
+        assert ops.stem_conv_supported(xin, c, cout)
+        out = ops.stem_conv3x3s2(xin, wk, bias.to(DEV), act, pt, pl, ref.shape[-2:])
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert float((out.cpu().double() - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.gpu
 def test_encoder_inference_walk_matches_generic_walk():
     """Encoder._forward_inference (folded stem, squeeze-excite gate inside the projection GEMM, padded expansion output,
