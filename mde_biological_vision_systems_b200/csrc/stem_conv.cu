@@ -15,6 +15,8 @@
 
 namespace mde {
 
+constexpr int STEM_ROWS = 4;
+
 template <int COUT>
 __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __restrict__ x, const float* __restrict__ w_tcc,
                                                              const float* __restrict__ bias, float* __restrict__ y, int Hi,
@@ -22,11 +24,13 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
   extern __shared__ __align__(16) float sw[];  // [9][Cin][COUT]
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) sw[i] = w_tcc[i];
   __syncthreads();
-  const int b = blockIdx.z, oy = blockIdx.y;
+  const int b = blockIdx.z;
   const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;  // this thread's two output columns: ox0, ox0 + 1
   if (ox0 >= Wo) return;
   const bool two = ox0 + 1 < Wo;
   const float* xb = x + (long long)b * Hi * Wi * Cin;
+  // a block walks STEM_ROWS consecutive output rows: staging the 32 KB filter costs about as much as one row of outputs
+  for (int oy = blockIdx.y * STEM_ROWS; oy < min(Ho, (int)(blockIdx.y + 1) * STEM_ROWS); ++oy) {
   float acc[2][COUT];
 #pragma unroll
   for (int co = 0; co < COUT; ++co) {
@@ -83,6 +87,7 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
       *reinterpret_cast<float4*>(yo + p * COUT + co) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
+  }  // rows of this block
 }
 
 }  // namespace mde
@@ -105,7 +110,7 @@ extern "C" int mde_stem_conv3x3s2_nhwc(const float* x, const float* w_tcc, const
   // one block per output row when the row's column pairs fit 256 threads (whole warps), else several
   const int pairs = (Wo + 1) / 2;
   const int threads = pairs >= 256 ? 256 : ((pairs + 31) / 32) * 32;
-  const dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)Ho, (unsigned)B);
+  const dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)((Ho + STEM_ROWS - 1) / STEM_ROWS), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
 #define MDE_STEM(CO)                                                                                                       \
   {                                                                                                                        \
