@@ -480,27 +480,54 @@ def run_infer(cfg, ctx, steps, warmup, batch, detail=True):
     return out
 
 
-def run_train(cfg, ctx, steps, batch, sync_bn="kernels"):
+def run_train(cfg, ctx, steps, batch, sync_bn="kernels", launch="graph"):
     """Training iteration with the reference's semantics (train.py:387-455): forward + SILog + 0.1 chamfer + backward +
-    gradient mean all-reduce over ranks (NCCL, overlapped with backward) + clip 0.1 + AdamW + OneCycle, `batch` per GPU
-    (weak scaling, --use_new_batching), SyncBatchNorm when N > 1 (train.py:296).  Inputs come from pinned host memory."""
+    gradient mean all-reduce over ranks (NCCL) + clip 0.1 + AdamW + OneCycle, `batch` per GPU (weak scaling,
+    --use_new_batching), SyncBatchNorm when N > 1 (train.py:296).  Inputs come from pinned host memory.
+    launch = "graph": zero_grad + loaders + forward + losses + backward replayed as ONE CUDA graph (training.GraphedTrainStep;
+    the all-reduce is one collective on the gradient arena after the replay); "eager": ~2400 launches per step with the
+    all-reduce overlapped bucket by bucket.  A capture that fails falls back to the eager launch of the same kernels and says so."""
     import torch
     from mde_biological_vision_systems_b200 import ops, parallel
-    from mde_biological_vision_systems_b200.training import TrainStep
-    model, sem_loader, inst_loader = build_gpu(cfg, ctx)
-    if ctx.world > 1 and sync_bn == "stock":
-        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-    elif ctx.world > 1 and sync_bn:
-        # global-batch statistics on the B200 kernels (csrc/bn_sync.cu), exchanged by the kernels themselves over NVLink
-        # peer memory ("allreduce": one NCCL all-reduce per layer and direction instead)
-        model = parallel.convert_sync_batchnorm(model, p2p=(sync_bn != "allreduce"))
-    model.train()
+    from mde_biological_vision_systems_b200.training import GraphedTrainStep, TrainStep
+    launch = os.environ.get("MDE_TRAIN_LAUNCH", launch)
+
+    def make_model():
+        model, sem_loader, inst_loader = build_gpu(cfg, ctx)
+        if ctx.world > 1 and sync_bn == "stock":
+            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        elif ctx.world > 1 and sync_bn:
+            # global-batch statistics on the B200 kernels (csrc/bn_sync.cu), exchanged by the kernels themselves over NVLink
+            # peer memory ("allreduce": one NCCL all-reduce per layer and direction instead)
+            model = parallel.convert_sync_batchnorm(model, p2p=(sync_bn != "allreduce"))
+        model.train()
+        return model, sem_loader, inst_loader
+
     autocast = torch.bfloat16 if cfg["autocast"] == "bf16" else None
-    stepper = TrainStep(model, semantics_loader=sem_loader, instance_loader=inst_loader, total_steps=1000, autocast=autocast)
     host = host_batch(cfg, batch, ctx.rank, pin=True)
     steps = max(2, min(steps, 5))
-    for _ in range(3):
-        stepper(host, ctx.dev)
+    stepper, note = None, None
+    model, sem_loader, inst_loader = make_model()
+    # nn.SyncBatchNorm / the NCCL flavour of SyncBatchNorm2d call collectives inside forward and backward: not capturable
+    if launch == "graph" and (ctx.world == 1 or sync_bn in ("kernels", False, None)):
+        try:
+            stepper = GraphedTrainStep(model, host, ctx.dev, semantics_loader=sem_loader, instance_loader=inst_loader,
+                                       total_steps=1000, autocast=autocast)
+            for _ in range(2):
+                stepper(host, ctx.dev)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001 -- the same kernels are then launched eagerly; the line says so
+            note = f"{type(exc).__name__}: {str(exc)[:160]}"
+            sys.stderr.write(f"[bench] training graph capture failed, eager launch instead: {note}\n")
+            stepper = None
+            del model
+            torch.cuda.empty_cache()
+            model, sem_loader, inst_loader = make_model()
+    graphed = stepper is not None
+    if stepper is None:
+        stepper = TrainStep(model, semantics_loader=sem_loader, instance_loader=inst_loader, total_steps=1000, autocast=autocast)
+        for _ in range(3):
+            stepper(host, ctx.dev)
     l0 = ops.launch_count()
     box = {}
 
@@ -516,7 +543,10 @@ def run_train(cfg, ctx, steps, batch, sync_bn="kernels"):
     lib.mde_bn_wait_stats(ctypes.byref(wait_ns), ctypes.byref(waits), 1)
     res = {"config": cfg["name"].split(":")[0].replace("BASELINE config ", "cfg"), "imgs_s": round(ctx.world * batch / (ms * 1e-3), 1),
            "ms": round(ms, 2), "batch_per_gpu": batch, "loss": round(float(box["loss"].item()), 4),
-           "launches": int((ops.launch_count() - l0) / steps), "dtype": cfg["autocast"] or "f32"}
+           "launches": int((ops.launch_count() - l0) / steps) + (stepper.captured_launches if graphed else 0),
+           "dtype": cfg["autocast"] or "f32", "launch": "cuda_graph(fwd+bwd)" if graphed else "eager"}
+    if note:
+        res["graph_error"] = note
     if ctx.world > 1:
         res["sync_bn"] = sync_bn
         w = stepper.averager.last_exposed_wait_ms()

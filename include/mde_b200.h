@@ -461,6 +461,12 @@ int mde_bn_bwd_reduce_p2p_nhwc(const float* x, const float* dy, int64_t N, int C
 int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_t N, int C, const float* mean,
                               const float* invstd, const float* weight, uint64_t my_base, int64_t slot_off, int64_t flag_off,
                               int world, uint64_t epoch, double count, mde_stream_t stream);
+/* CUDA-graph replay of a training step (training.GraphedTrainStep): kernel arguments are frozen at capture, but SyncBatchNorm's
+ * epoch must advance by one per step.  While a replay counter is set (device address of a uint64 that the graph's first node
+ * increments once per replay), the *_p2p launches take `epoch` as a BASE that the kernels add to the counter's current value,
+ * and slot_off / flag_off as the parity-0 offsets of the direction (the kernels add (epoch & 1) * world * 2C * 8 resp.
+ * world * 8 bytes themselves).  NULL restores the eager meaning.  Host-side state of the process (one process per GPU). */
+int mde_bn_p2p_set_epoch_counter(const uint64_t* counter);
 /* Bound of the peer-flag wait inside the *_p2p kernels (seconds, default 600: all ranks must enter every BatchNorm layer
  * within it -- the role NCCL's collective timeout plays for the reference's nn.SyncBatchNorm, train.py:296).  The wait backs
  * off with __nanosleep; on expiry the rank counts the event (mde_bn_peer_timeouts) and traps.  Both calls synchronise. */

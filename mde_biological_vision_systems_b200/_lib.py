@@ -94,6 +94,7 @@ SIGNATURES = {
     "mde_bn_bwd_reduce_p2p_nhwc": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _i32, _i64, _i64, ctypes.c_uint64, _p]),
     "mde_bn_bwd_apply_p2p_nhwc": (_i32, [_p, _p, _p, _i64, _i32, _p, _p, _p, ctypes.c_uint64, _i64, _i64, _i32,
                                          ctypes.c_uint64, ctypes.c_double, _p]),
+    "mde_bn_p2p_set_epoch_counter": (_i32, [_p]),
     "mde_bn_set_peer_timeout_seconds": (_i32, [ctypes.c_double]),
     "mde_bn_peer_timeouts": (_i32, []),
     "mde_bn_wait_stats": (_i32, [_p, _p, _i32]),

@@ -257,6 +257,19 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// CUDA-graph replay: kernel arguments are frozen at capture, but the epoch (and with it the parity of the slots / flags) must
+// advance by one per step.  With a device-resident replay counter (mde_bn_p2p_set_epoch_counter) the `epoch` argument is a BASE
+// to which the counter's current value is added, and slot_off / flag_off address parity 0 of the direction: the kernel derives
+// the parity offsets itself (slot rows are world * 2C doubles, flag rows world uint64 -- the layout the host uses).
+__device__ __forceinline__ void bn_resolve_epoch(const unsigned long long* ctr, unsigned long long& epoch, long long& slot_off,
+                                                 long long& flag_off, int world, int C) {
+  if (ctr == nullptr) return;
+  epoch += __ldcg(ctr);
+  const long long par = (long long)(epoch & 1ULL);
+  slot_off += par * (long long)world * 2 * C * 8;
+  flag_off += par * (long long)world * 8;
+}
+
 // Called by every block after its atomics into `local` [2C] (+ ticket at index 2C): the last block publishes.
 __device__ __forceinline__ void bn_publish_if_last(double* local, int C, const BnPeers& peers, long long slot_off,
                                                    long long flag_off, unsigned long long epoch) {
@@ -329,7 +342,8 @@ __device__ __forceinline__ void bn_wait_peers(unsigned long long my_base, long l
 __global__ void __launch_bounds__(256) bn_stats_p2p_kernel(const float* __restrict__ x, long long N, int C,
                                                            double* __restrict__ local, double* __restrict__ zero_next,
                                                            int cl_log2, BnPeers peers, long long slot_off, long long flag_off,
-                                                           unsigned long long epoch) {
+                                                           unsigned long long epoch, const unsigned long long* epoch_ctr) {
+  bn_resolve_epoch(epoch_ctr, epoch, slot_off, flag_off, peers.world, C);
   if (zero_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
     for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) zero_next[i] = 0.0;
   const int c4 = C >> 2;
@@ -369,7 +383,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_p2p_kernel(const float* __r
                                                                 const float* __restrict__ invstd, double* __restrict__ local,
                                                                 double* __restrict__ zero_next, int cl_log2, BnPeers peers,
                                                                 long long slot_off, long long flag_off,
-                                                                unsigned long long epoch) {
+                                                                unsigned long long epoch, const unsigned long long* epoch_ctr) {
+  bn_resolve_epoch(epoch_ctr, epoch, slot_off, flag_off, peers.world, C);
   if (zero_next != nullptr && blockIdx.x == 0 && blockIdx.y == 0)
     for (int i = threadIdx.x; i < 2 * C + 1; i += blockDim.x) zero_next[i] = 0.0;
   const int c4 = C >> 2;
@@ -423,7 +438,8 @@ __global__ void __launch_bounds__(256) bn_apply_p2p_kernel(const float* __restri
                                                            const float* __restrict__ bias, float eps,
                                                            float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                                            float* running_mean, float* running_var, float momentum,
-                                                           int cl_log2) {
+                                                           int cl_log2, const unsigned long long* epoch_ctr) {
+  bn_resolve_epoch(epoch_ctr, epoch, slot_off, flag_off, world, C);
   bn_wait_peers(my_base, flag_off, world, epoch);
   const int c4 = C >> 2;
   const int cl = 1 << cl_log2, npl = 256 >> cl_log2, ci = threadIdx.x & (cl - 1);
@@ -464,7 +480,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_p2p_kernel(const float* __re
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                const float* __restrict__ weight, unsigned long long my_base,
                                                                long long slot_off, long long flag_off, int world,
-                                                               unsigned long long epoch, double count, int cl_log2) {
+                                                               unsigned long long epoch, double count, int cl_log2,
+                                                               const unsigned long long* epoch_ctr) {
+  bn_resolve_epoch(epoch_ctr, epoch, slot_off, flag_off, world, C);
   bn_wait_peers(my_base, flag_off, world, epoch);
   const int c4 = C >> 2;
   const int cl = 1 << cl_log2, npl = 256 >> cl_log2, ci = threadIdx.x & (cl - 1);
@@ -493,6 +511,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_p2p_kernel(const float* __re
   }
 }
 
+// device address of the replay counter (null: eager launches, `epoch` is the epoch).  One process per GPU: process-global.
+static const unsigned long long* g_bn_epoch_ctr = nullptr;
+
 static bool fill_peers(BnPeers& p, const uint64_t* bases, int world, int rank) {
   if (!bases || world < 1 || world > 8 || rank < 0 || rank >= world) return false;
   for (int i = 0; i < 8; ++i) p.base[i] = i < world ? bases[i] : 0ULL;
@@ -513,7 +534,7 @@ int mde_bn_stats_p2p_nhwc(const float* x, int64_t N, int C, double* local, doubl
   BnPeers p;
   if (!fill_peers(p, peer_bases, world, rank)) return MDE_ERR_BAD_SHAPE;
   bn_stats_p2p_kernel<<<bn_grid(N, C), 256, 0, (cudaStream_t)stream>>>(x, N, C, local, zero_next, bn_cl_log2(C), p, slot_off,
-                                                                       flag_off, epoch);
+                                                                       flag_off, epoch, g_bn_epoch_ctr);
   return check_launch();
 }
 
@@ -526,7 +547,8 @@ int mde_bn_apply_p2p_nhwc(const float* x, float* y, int64_t N, int C, uint64_t m
   if (C % 4 != 0 || !aligned(x, 16) || !aligned(y, 16)) return MDE_ERR_UNSUPPORTED;
   bn_apply_p2p_kernel<<<bn_grid(N, C), 256, 0, (cudaStream_t)stream>>>(x, y, N, C, my_base, slot_off, flag_off, world, epoch,
                                                                        count, weight, bias, eps, save_mean, save_invstd,
-                                                                       running_mean, running_var, momentum, bn_cl_log2(C));
+                                                                       running_mean, running_var, momentum, bn_cl_log2(C),
+                                                                       g_bn_epoch_ctr);
   return check_launch();
 }
 
@@ -539,7 +561,8 @@ int mde_bn_bwd_reduce_p2p_nhwc(const float* x, const float* dy, int64_t N, int C
   BnPeers p;
   if (!fill_peers(p, peer_bases, world, rank)) return MDE_ERR_BAD_SHAPE;
   bn_bwd_reduce_p2p_kernel<<<bn_grid(N, C), 256, 0, (cudaStream_t)stream>>>(x, dy, N, C, mean, invstd, local, zero_next,
-                                                                            bn_cl_log2(C), p, slot_off, flag_off, epoch);
+                                                                            bn_cl_log2(C), p, slot_off, flag_off, epoch,
+                                                                            g_bn_epoch_ctr);
   return check_launch();
 }
 
@@ -551,8 +574,16 @@ int mde_bn_bwd_apply_p2p_nhwc(const float* x, const float* dy, float* dx, int64_
   if (C % 4 != 0 || !aligned(x, 16) || !aligned(dy, 16) || !aligned(dx, 16)) return MDE_ERR_UNSUPPORTED;
   bn_bwd_apply_p2p_kernel<<<bn_grid(N, C), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, N, C, mean, invstd, weight, my_base,
                                                                            slot_off, flag_off, world, epoch, count,
-                                                                           bn_cl_log2(C));
+                                                                           bn_cl_log2(C), g_bn_epoch_ctr);
   return check_launch();
+}
+
+// CUDA-graph capture of a training step: while `counter` (device address of a uint64 the graph's first node increments once
+// per replay) is set, the *_p2p launches above take `epoch` as a base added to the counter's value on the device and slot_off /
+// flag_off as the parity-0 offsets of the direction.  NULL restores eager semantics.  Host-side state only (no stream work).
+int mde_bn_p2p_set_epoch_counter(const uint64_t* counter) {
+  g_bn_epoch_ctr = reinterpret_cast<const unsigned long long*>(counter);
+  return MDE_OK;
 }
 
 // Bound of the peer-flag wait of the *_p2p kernels (seconds; default 600).  Synchronous (cudaMemcpyToSymbol).

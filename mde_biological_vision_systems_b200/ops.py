@@ -236,9 +236,36 @@ def gather_embed(labels, table, background=None, write_back=False, out=None, tab
                                          h * w, rows, d, -1 if background is None else int(background),
                                          0 if table.dtype == torch.float32 else 1, int(table_image_stride), _p(flag), _s())
     _lib.check(rc, "mde_gather_embed_labels")
-    if flag is not None and int(flag.item()) != 0:
-        raise IndexError("index out of range in label gather (table has %d rows)" % rows)
+    if flag is not None:
+        if _DEFERRED is not None and torch.cuda.is_current_stream_capturing():
+            _DEFERRED.append((flag, rows))  # a captured launch cannot raise: the owner of the graph reads the flag after a replay
+        elif int(flag.item()) != 0:
+            raise IndexError("index out of range in label gather (table has %d rows)" % rows)
     return out
+
+
+_DEFERRED = None
+
+
+def begin_deferred_checks():
+    """CUDA-graph capture of a step that contains un-clamped gathers (150-class table): collect their out-of-range flags instead
+    of reading them (a device -> host read is illegal during capture).  Pair with end_deferred_checks()."""
+    global _DEFERRED
+    _DEFERRED = []
+
+
+def end_deferred_checks():
+    """-> list of (flag tensor, table rows) recorded since begin_deferred_checks(); the flags are rewritten by every replay."""
+    global _DEFERRED
+    out, _DEFERRED = (_DEFERRED or []), None
+    return out
+
+
+def raise_deferred_checks(deferred):
+    """IndexError (like the reference's index_select) if a replayed gather met an out-of-range label.  Synchronises."""
+    for flag, rows in deferred:
+        if int(flag.item()) != 0:
+            raise IndexError("index out of range in label gather (table has %d rows)" % rows)
 
 
 def gather_embed_nhwc(labels, table, background, c_before, c_after=0, pads=(0, 0, 0, 0), labels_out=None, image=None):

@@ -328,14 +328,35 @@ class P2PArena:
         self.buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.graph_owned = False
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
         if self.world > 8:
             raise RuntimeError("P2PArena supports at most 8 ranks (one NVSwitch domain)")
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.ptrs = (ctypes.c_uint64 * 8)(*(ptrs + [0] * (8 - len(ptrs))))
         self.my_base = ptrs[self.rank]
+        # CUDA-graph replay (training.GraphedTrainStep): a device-resident step counter the graph's first node increments; the
+        # SyncBatchNorm kernels add it to the epoch base frozen into the graph (csrc/bn_sync.cu: bn_resolve_epoch)
+        self.replay_counter = torch.zeros(1, dtype=torch.int64, device=self.buf.device)
+        self.capture_base = None  # counter value + 1 at capture (None: eager launches)
         torch.cuda.synchronize()
         dist.barrier(group=group)  # every arena is zeroed before anyone publishes into it
+
+    def begin_capture(self):
+        """Call right before capturing a training step (host-synchronising): from here on `_P2PRegion.next` hands the kernels
+        epoch BASES and parity-0 offsets, and the launches read the step counter on the device."""
+        from . import _lib
+        if self.graph_owned:
+            raise RuntimeError("P2PArena: a training graph was already captured over this arena")
+        self.capture_base = int(self.replay_counter.item()) + 1
+        _lib.check(_lib.load().mde_bn_p2p_set_epoch_counter(self.replay_counter.data_ptr()), "mde_bn_p2p_set_epoch_counter")
+
+    def end_capture(self, captured=True):
+        from . import _lib
+        _lib.check(_lib.load().mde_bn_p2p_set_epoch_counter(None), "mde_bn_p2p_set_epoch_counter")
+        self.capture_base = None
+        if captured:
+            self.graph_owned = True  # eager SyncBatchNorm calls would now reuse epochs the replays consume
 
 
 class _P2PRegion:
@@ -354,8 +375,17 @@ class _P2PRegion:
         return (4 * world * 2 * channels * 8 + 4 * world * 8 + 255) // 256 * 256
 
     def next(self, direction):
+        base = getattr(self.arena, "capture_base", None)
+        if getattr(self.arena, "graph_owned", False) and base is None:
+            raise RuntimeError("SyncBatchNorm2d: the peer-memory epochs of this model belong to a captured training graph; "
+                               "eager training-mode calls after the capture are not supported")
         self.epochs[direction] += 1
         e = self.epochs[direction]
+        if base is not None:
+            # captured launch: epoch = base + device step counter (== e at the first replay), parity resolved by the kernel
+            k = 2 * direction
+            return self.arena, e - base, self.slots0 + k * self.slot_bytes, \
+                self.flags0 + k * self.arena.world * 8
         k = 2 * direction + (e & 1)
         return self.arena, e, self.slots0 + k * self.slot_bytes, self.flags0 + k * self.arena.world * 8
 
@@ -391,12 +421,20 @@ class _BnScratch:
     def next_forward(self, c, device):
         self.fwd = self._rows(self.fwd, c, device)
         self.fi ^= 1
-        return self.fwd[self.fi], self.fwd[self.fi ^ 1]
+        return self._take(self.fwd, self.fi)
 
     def next_backward(self, c, device):
         self.bwd = self._rows(self.bwd, c, device)
         self.bi ^= 1
-        return self.bwd[self.bi], self.bwd[self.bi ^ 1]
+        return self._take(self.bwd, self.bi)
+
+    @staticmethod
+    def _take(rows, i):
+        if rows.is_cuda and torch.cuda.is_current_stream_capturing():
+            # a replayed graph accumulates into the SAME row every step (the alternation is frozen at capture): zero it inside
+            # the graph instead of relying on the previous call
+            rows[i].zero_()
+        return rows[i], rows[i ^ 1]
 
 
 # every rank of this path holds the same per-GPU batch (weak scaling, train.py:286-287), so the global pixel count is

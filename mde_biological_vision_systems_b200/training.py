@@ -10,6 +10,7 @@ not a re-implementation of train.py's logging / validation / checkpoint code (ou
 import torch
 import torch.nn as nn
 
+from . import ops
 from .loss import BinsChamferLoss, DepthLosses, SILogLoss
 from .parallel import GradientAverager, broadcast_module_state
 
@@ -17,7 +18,7 @@ from .parallel import GradientAverager, broadcast_module_state
 class TrainStep:
     def __init__(self, model, semantics_loader=None, instance_loader=None, lr=0.000357, wd=0.1, w_chamfer=0.1,
                  min_depth=1e-3, total_steps=1000, div_factor=25, final_div_factor=100, same_lr=False, bucket_mb=25.0,
-                 cudnn_benchmark=True, per_group_max_lr=False, autocast=None):
+                 cudnn_benchmark=True, per_group_max_lr=False, autocast=None, overlap=True):
         # the stock torch bodies (encoder, decoder convolutions in training mode) run fixed shapes every step: let cuDNN
         # pick its kernels by measurement (64.2 -> 58.4 ms per step on B200; the reference leaves the flag off)
         if cudnn_benchmark:
@@ -47,9 +48,21 @@ class TrainStep:
         self.scheduler = torch.optim.lr_scheduler.OneCycleLR(
             self.optimizer, max_lr, total_steps=total_steps, cycle_momentum=True, base_momentum=0.85, max_momentum=0.95,
             div_factor=div_factor, final_div_factor=final_div_factor)
-        self.averager = GradientAverager(model.parameters(), bucket_mb=bucket_mb)
+        self.averager = GradientAverager(model.parameters(), bucket_mb=bucket_mb, overlap=overlap)
 
     def __call__(self, batch, device):
+        loss = self.forward_backward(batch, device)
+        self.update()
+        return loss
+
+    def update(self):
+        """[gradient mean all-reduce] -> clip 0.1 -> AdamW -> OneCycle (train.py:426-430)."""
+        self.averager.reduce()
+        self.averager.clip_grad_norm_(0.1)  # train.py:427 nn.utils.clip_grad_norm_(model.parameters(), 0.1), on the gradient arena
+        self.optimizer.step()
+        self.scheduler.step()
+
+    def forward_backward(self, batch, device):
         self.averager.zero_grad()  # gradients live in the averager's bucket arena (views); one fill per bucket
         img = batch["image"].to(device, non_blocking=True)
         depth = batch["depth"].to(device, non_blocking=True)
@@ -71,8 +84,96 @@ class TrainStep:
                 mask = depth > self.min_depth
                 loss = self.criterion_ueff(pred, depth, mask=mask.to(torch.bool), interpolate=True)
         loss.backward()
-        self.averager.reduce()
-        self.averager.clip_grad_norm_(0.1)  # train.py:427 nn.utils.clip_grad_norm_(model.parameters(), 0.1), on the gradient arena
-        self.optimizer.step()
-        self.scheduler.step()
         return loss.detach()
+
+
+class GraphedTrainStep(TrainStep):
+    """TrainStep with zero_grad + loaders + forward + losses + backward replayed as ONE CUDA graph per iteration.
+
+    The eager iteration is ~2400 kernel launches: 56 ms of host time to enqueue 58 ms of GPU work on one B200, so at N GPUs the
+    step pays for every microsecond of host contention and rank skew (8 processes + NCCL proxy threads on the box's cores:
+    weak-scaling efficiency 0.86 at N = 8).  Replayed as a graph the host issues one launch; what stays
+    eager is what must: the gradient all-reduce (NCCL, ONE in-place collective on the gradient arena -- nothing inside the
+    graph talks to NCCL), the clip on the arena, fused AdamW and the OneCycle schedule (its learning rate and momentum are
+    host scalars that change every step, train.py:364-368).
+
+    What makes the iteration capturable:
+      * every kernel of this package launches on the current stream without host synchronisation (include/mde_b200.h);
+      * gradients accumulate in place into the averager's arena (p.grad are views; the arena fill is the graph's first node);
+      * inputs are copied into static device buffers before each replay;
+      * SyncBatchNorm's peer-memory exchange takes its epoch from a device-resident step counter that the graph's first node
+        increments (parallel.P2PArena.begin_capture; csrc/bn_sync.cu bn_resolve_epoch), and its float64 scratch rows are zeroed
+        inside the graph.  The NCCL all-reduce flavour of SyncBatchNorm2d cannot be captured: use the peer-memory one.
+    Shapes, modes and the set of inputs must not change after construction; dropout keeps drawing fresh masks (torch registers
+    the generator with the graph).  After the capture the model's SyncBatchNorm epochs belong to the graph."""
+
+    def __init__(self, model, example_batch, device, warmup=3, check_labels_every=1, **kwargs):
+        kwargs.setdefault("bucket_mb", 1 << 20)  # one bucket: one collective after the replay
+        super().__init__(model, overlap=False, **kwargs)
+        device = torch.device(device)
+        self.device = device
+        self.check_labels_every = check_labels_every
+        self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in example_batch.items()
+                       if torch.is_tensor(v)}
+        self.extra = {k: v for k, v in example_batch.items() if not torch.is_tensor(v)}
+        self.arena = self._p2p_arena(model)
+        self.replays = 0
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # cuDNN plans, cached operands, shared-memory attributes: everything lazy, outside the capture
+                self._load(example_batch)
+                self.forward_backward(dict(self.extra, **self.static), device)
+                self.update()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self._load(example_batch)
+        if self.arena is not None:
+            self.arena.begin_capture()
+        self.graph = torch.cuda.CUDAGraph()
+        captured = False
+        launches0 = ops.launch_count()
+        ops.begin_deferred_checks()
+        try:
+            with torch.cuda.graph(self.graph):
+                if self.arena is not None:
+                    self.arena.replay_counter.add_(1)
+                self.static_loss = self.forward_backward(dict(self.extra, **self.static), device)
+            captured = True
+        finally:
+            self.deferred = ops.end_deferred_checks()
+            self.captured_launches = ops.launch_count() - launches0  # C-ABI launches of this package inside one replay
+            if self.arena is not None:
+                self.arena.end_capture(captured)
+
+    @staticmethod
+    def _p2p_arena(model):
+        import torch.distributed as dist
+        from .parallel import SyncBatchNorm2d
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        arena = None
+        for m in model.modules():
+            if isinstance(m, SyncBatchNorm2d):
+                if m._p2p is not None:
+                    arena = m._p2p.arena
+                elif world > 1 and m.training:
+                    raise RuntimeError("GraphedTrainStep: SyncBatchNorm2d without the peer-memory exchange issues NCCL calls "
+                                       "inside forward / backward and cannot be captured (convert_sync_batchnorm(p2p=True))")
+            elif world > 1 and isinstance(m, nn.SyncBatchNorm):
+                raise RuntimeError("GraphedTrainStep: nn.SyncBatchNorm cannot be captured; use parallel.convert_sync_batchnorm")
+        return arena
+
+    def _load(self, batch):
+        for k, buf in self.static.items():
+            buf.copy_(batch[k], non_blocking=True)
+
+    def __call__(self, batch, device=None):
+        self._load(batch)
+        self.graph.replay()
+        self.replays += 1
+        self.update()
+        if self.deferred and self.check_labels_every and self.replays % self.check_labels_every == 0:
+            # the reference's index_select raises on an out-of-range label (150-class table, SemanticsLoader.py:125); a captured
+            # gather cannot raise, so its flag is read here, after the whole iteration has been enqueued
+            ops.raise_deferred_checks(self.deferred)
+        return self.static_loss

@@ -1450,6 +1450,45 @@ def test_training_step_with_own_conv_kernels_matches_cudnn():
         assert float((a - b).abs().max()) <= 3e-2 * float(b.abs().max()) + 1e-8  # train-mode BatchNorm at batch 2 (see above)
 
 
+def test_graphed_train_step_matches_eager():
+    """training.GraphedTrainStep (zero_grad + loader gather + forward + SILog / chamfer + backward replayed as ONE CUDA graph,
+    then the eager all-reduce / clip / AdamW / OneCycle) follows the eager TrainStep: same loss trajectory over several
+    iterations from the same initial weights (dropout off: the two launch modes draw different masks), weights really
+    change between replays, and the captured step contains this package's launches."""
+    from argparse import Namespace
+    from mde_biological_vision_systems_b200.training import GraphedTrainStep, TrainStep
+    mode = "glove-25d-ade20k-places"
+    b, h, w = 2, 352, 384
+    lab, _ = sem_labels(mode, b, h, w, seed=201, n_rect=(20, 40))
+    batch = {"image": synthetic.image(b, h, w, seed=200).pin_memory(), "depth": synthetic.depth(b, h, w, seed=202).pin_memory(),
+             "semantics": lab.pin_memory()}
+    losses = {}
+    for kind in ("eager", "graph"):
+        torch.manual_seed(0)
+        m = make_model(insertion_point="input", semantics_mode=mode, instance_segmentation_mode=None).to(DEV).channels_last_()
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.MultiheadAttention):
+                mod.dropout = 0.0
+        loader = SemanticsLoader(Namespace(use_semantics=mode), device=DEV)
+        loader.bind_encoder_input(m)
+        kw = dict(semantics_loader=loader, total_steps=100, cudnn_benchmark=False)
+        if kind == "eager":
+            st = TrainStep(m, **kw)
+            losses[kind] = [float(st(batch, DEV)) for _ in range(5)]
+        else:
+            st = GraphedTrainStep(m, batch, DEV, warmup=2, **kw)   # two eager iterations inside, then the capture
+            assert st.captured_launches > 20
+            w0 = m.conv_out[0].weight.detach().clone()
+            losses[kind] = [None, None] + [float(st(batch)) for _ in range(3)]
+            assert not torch.equal(w0, m.conv_out[0].weight.detach())
+    for i in range(2, 5):  # iterations 3..5 of both runs (the graphed run's first two were its eager warm-up)
+        assert abs(losses["graph"][i] - losses["eager"][i]) <= 2e-3 * abs(losses["eager"][i]), losses
+    assert losses["eager"][4] != losses["eager"][2]
+
+
 def test_depthwise_engine_is_exact():
     """models/efficientnet.py leaves cuDNN's TF32 switch on for DEPTHWISE convolutions inside the exact-fp32 region (it only
     selects the NHWC engine; depthwise math is fp32 FMAs either way): the two settings must give bit-identical outputs."""

@@ -153,3 +153,23 @@ def test_p2p_region_layout_and_epochs():
     assert len(set(slots)) == 4 and len(set(flags)) == 4
     assert all(b - a >= Arena.world * 2 * c * 8 for a, b in zip(slots, slots[1:]))   # slot sets do not overlap
     assert all(b - a >= Arena.world * 8 for a, b in zip(flags, flags[1:])) and flags[0] >= slots[-1] + Arena.world * 2 * c * 8
+    # captured launches (training.GraphedTrainStep): the region hands out an epoch BASE and the parity-0 offsets; what the kernel
+    # derives from them and the device step counter (csrc/bn_sync.cu bn_resolve_epoch) continues the eager sequence exactly
+    eager = _P2PRegion(Arena(), 1024, c)
+    for _ in range(3):   # three eager warm-up iterations
+        eager.next(0), eager.next(1)
+    cap = _P2PRegion(Arena(), 1024, c)
+    cap.epochs = list(eager.epochs)
+    arena = cap.arena
+    arena.capture_base, arena.graph_owned = 0 + 1, False   # replay counter 0 at capture
+    frozen = [cap.next(d)[1:] for d in (0, 1)]
+    arena.capture_base, arena.graph_owned = None, True
+    for replay in range(1, 6):
+        for d in (0, 1):
+            _, e_ref, slot_ref, flag_ref = eager.next(d)
+            base, slot0, flag0 = frozen[d]
+            e = base + replay
+            par = e & 1
+            assert (e, slot0 + par * Arena.world * 2 * c * 8, flag0 + par * Arena.world * 8) == (e_ref, slot_ref, flag_ref)
+    with pytest.raises(RuntimeError):
+        cap.next(0)   # eager call after the capture: the epochs belong to the graph
