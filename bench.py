@@ -532,7 +532,11 @@ def run_train(cfg, ctx, steps, batch, sync_bn="kernels", launch="graph"):
     box = {}
 
     def one():
-        box["loss"] = stepper(host, ctx.dev)
+        if graphed:  # the next batch's H2D copy runs on a side stream under this iteration's replay
+            box["loss"] = stepper() if stepper._staged else stepper(host)
+            stepper.prefetch(host)
+        else:
+            box["loss"] = stepper(host, ctx.dev)
 
     import ctypes
     from mde_biological_vision_systems_b200 import _lib

@@ -201,7 +201,11 @@ class GradientAverager:
             bk["work"].wait()
             bk["flat"].div_(world)
             bk["work"] = None
+            bk["pending"] = len(bk["params"])
             total += bk["flat"].numel()
+        # ready for the next backward pass even if zero_grad() is not called in between on the host (a replayed CUDA graph
+        # performs the fill on the device: training.GraphedTrainStep)
+        self._next_launch = 0
         if cuda:
             t1.record()
             self._wait_events = (t0, t1)

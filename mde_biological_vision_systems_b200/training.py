@@ -118,6 +118,7 @@ class GraphedTrainStep(TrainStep):
         self.extra = {k: v for k, v in example_batch.items() if not torch.is_tensor(v)}
         self.arena = self._p2p_arena(model)
         self.replays = 0
+        self._stage, self._staged = None, False
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -167,8 +168,36 @@ class GraphedTrainStep(TrainStep):
         for k, buf in self.static.items():
             buf.copy_(batch[k], non_blocking=True)
 
-    def __call__(self, batch, device=None):
-        self._load(batch)
+    def prefetch(self, batch):
+        """Start the NEXT iteration's host -> device copy on a side stream while the current one computes; the following
+        ``step()`` call (no batch argument) moves it into the graph's static buffers with a device-to-device copy.  Without it the
+        87 MB of a config-2 batch cross PCIe in front of every replay (1.6 ms of a 55 ms step)."""
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(v) for k, v in self.static.items()}
+            self._h2d = torch.cuda.Stream(self.device)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = None
+        if self._stage_free is not None:
+            self._h2d.wait_event(self._stage_free)  # the previous copy OUT of the staging buffers
+        with torch.cuda.stream(self._h2d):
+            for k, buf in self._stage.items():
+                buf.copy_(batch[k], non_blocking=True)
+            self._stage_ready.record(self._h2d)
+        self._staged = True
+
+    def __call__(self, batch=None, device=None):
+        if batch is None:
+            if not self._staged:
+                raise RuntimeError("GraphedTrainStep(): no batch given and none prefetched")
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(self._stage_ready)
+            for k, buf in self.static.items():
+                buf.copy_(self._stage[k], non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(cur)
+            self._staged = False
+        else:
+            self._load(batch)
         self.graph.replay()
         self.replays += 1
         self.update()

@@ -21,6 +21,9 @@ def main():
     batch = int(os.environ.get("BATCH", "8"))
     steps = int(os.environ.get("STEPS", "4"))
     host = bench.host_batch(cfg, batch, ctx.rank, pin=True)
+    if ctx.world > 1:  # a protocol bug must end this check in seconds, not after the production bound of 600 s
+        from mde_biological_vision_systems_b200 import _lib
+        _lib.load().mde_bn_set_peer_timeout_seconds(20.0)
     out = {"world": ctx.world, "batch_per_gpu": batch}
     for kind in ("eager", "graph"):
         torch.manual_seed(0)
@@ -40,7 +43,14 @@ def main():
         else:
             st = GraphedTrainStep(model, host, ctx.dev, warmup=3, **kw)
             losses = [None] * 3 + [float(st(host)) for _ in range(steps)]
-        ms = ctx.timed(lambda: st(host, ctx.dev), 5) / 5
+        if kind == "graph":  # with the next batch's H2D copy overlapped (GraphedTrainStep.prefetch), as bench.py runs it
+            def one():
+                st() if st._staged else st(host)
+                st.prefetch(host)
+            ms = ctx.timed(one, 5) / 5
+            out["graph_no_prefetch_ms"] = round(ctx.timed(lambda: st(host), 5) / 5, 2)
+        else:
+            ms = ctx.timed(lambda: st(host, ctx.dev), 5) / 5
         # replicas must stay identical: compare a parameter checksum across ranks
         chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()

@@ -1484,6 +1484,9 @@ def test_graphed_train_step_matches_eager():
             w0 = m.conv_out[0].weight.detach().clone()
             losses[kind] = [None, None] + [float(st(batch)) for _ in range(3)]
             assert not torch.equal(w0, m.conv_out[0].weight.detach())
+            st.prefetch(batch)   # the overlapped host -> device copy of the next batch, consumed by a call without arguments
+            staged = float(st())
+            assert abs(staged - losses["eager"][4]) <= 2e-2 * abs(losses["eager"][4]) and staged != losses[kind][4]
     for i in range(2, 5):  # iterations 3..5 of both runs (the graphed run's first two were its eager warm-up)
         assert abs(losses["graph"][i] - losses["eager"][i]) <= 2e-3 * abs(losses["eager"][i]), losses
     assert losses["eager"][4] != losses["eager"][2]

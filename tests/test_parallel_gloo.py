@@ -52,6 +52,14 @@ def _worker(rank, world, port, tmp):
             avg.reduce()
             assert all(p.grad is not None and p.grad.data_ptr() >= 0 for p in net.parameters())
         torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(tmp, f"h{rank}.pt"))
+        # --- the form a replayed CUDA graph uses (training.GraphedTrainStep): no hooks, one bucket, the arena is filled "on the
+        # device" (here: by hand) and reduce() is called step after step WITHOUT a host-side zero_grad() in between
+        one = parallel.GradientAverager(net.parameters(), bucket_mb=1 << 20, overlap=False)
+        assert len(one.buckets) == 1 and not one._hooks
+        for step in range(3):
+            one.buckets[0]["flat"].fill_(float(rank + 1 + step))
+            assert one.reduce() == one.buckets[0]["flat"].numel()
+            assert torch.all(one.buckets[0]["flat"] == (1 + 2) / 2 + step)
     finally:
         dist.destroy_process_group()
 
