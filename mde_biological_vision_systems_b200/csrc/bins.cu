@@ -10,11 +10,37 @@
 namespace mde {
 
 // ------------------------------------------------------------------------------------------------------------
-// regressor + bins: one 256-thread CTA per image.  Warp-per-output-row dot products (coalesced weight reads).
+// regressor + bins: one 1024-thread CTA per image.  Four output rows per warp pass, 16-byte coalesced weight reads.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const float* __restrict__ bias,
                                             const float* in, float* out, int n_out, int n_in, bool leaky) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if ((n_in & 127) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(in)) & 15) == 0) {
+    // FOUR output rows per warp pass, 16-byte weight loads: the layer is a chain of L2 round trips (640 KB of weights, 16 CTAs),
+    // so what counts is how many loads a warp has in flight -- the one-row, 4-byte form had 8 dependent-free but un-unrolled
+    // loads and a 5-step shuffle tree per row, 32 rows per warp: 73 us for the whole regressor at B = 16
+    for (int r0 = warp * 4; r0 < n_out; r0 += nw * 4) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = lane * 4; k < n_in; k += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(in + k);
+        float4 w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // rows beyond n_out re-read the last row (discarded below): no branch around the loads
+          w[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)min(r0 + j, n_out - 1) * n_in + k));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(w[j].x, x.x, fmaf(w[j].y, x.y, fmaf(w[j].z, x.z, fmaf(w[j].w, x.w, a[j]))));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] = warp_sum(a[j]);
+      if (lane < 4 && r0 + lane < n_out) {
+        float v = lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3];
+        v += bias[r0 + lane];
+        out[r0 + lane] = leaky ? (v > 0.f ? v : 0.01f * v) : v;
+      }
+    }
+    __syncthreads();
+    return;
+  }
   for (int r = warp; r < n_out; r += nw) {
     const float* wr = W + (long long)r * n_in;
     float a = 0.f;
@@ -28,7 +54,7 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ W, const f
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) regressor_bins_kernel(const float* __restrict__ t0, long long t0_stride,
+__global__ void __launch_bounds__(1024) regressor_bins_kernel(const float* __restrict__ t0, long long t0_stride,
                                                              const float* __restrict__ w1, const float* __restrict__ b1,
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const float* __restrict__ w3, const float* __restrict__ b3,
@@ -36,7 +62,7 @@ __global__ void __launch_bounds__(256) regressor_bins_kernel(const float* __rest
                                                              float max_val, float* __restrict__ y_raw,
                                                              float* __restrict__ widths_normed, float* __restrict__ edges,
                                                              float* __restrict__ centers) {
-  extern __shared__ double smd[];  // scan[n_bins+2] (double) | in[E] | h1[H] | h2[H] | y[n_bins]
+  extern __shared__ __align__(16) double smd[];  // scan[n_bins+2] (double) | in[E] | h1[H] | h2[H] | y[n_bins]
   double* scan = smd;
   float* sin = reinterpret_cast<float*>(smd + n_bins + 2);
   float* h1 = sin + E;
@@ -55,7 +81,7 @@ __global__ void __launch_bounds__(256) regressor_bins_kernel(const float* __rest
     __syncthreads();
   }
   // normalisation (miniViT.py:36-44)
-  __shared__ float red[8];
+  __shared__ float red[32];
   __shared__ float bcast;
   if (norm_mode == MDE_NORM_SOFTMAX) {
     float m = -INFINITY;
@@ -96,12 +122,24 @@ __global__ void __launch_bounds__(256) regressor_bins_kernel(const float* __rest
     widths_normed[(long long)b * n_bins + i] = wn;
   }
   __syncthreads();
-  // edges = cumsum(pad(widths, (1,0), min_val)); float64 running sum, rounded to fp32 per element
-  if (threadIdx.x == 0) {
-    double run = (double)min_val;
-    scan[0] = run;
+  // edges = cumsum(pad(widths, (1,0), min_val)); float64 running sum, rounded to fp32 per element.  One warp: every lane sums
+  // its run of consecutive widths, a shuffle scan turns the lane totals into offsets (a single thread walking all n_bins
+  // dependent fp64 adds was a third of this kernel)
+  if (threadIdx.x < 32) {
     const float range = max_val - min_val;
-    for (int i = 0; i < n_bins; ++i) {
+    const int per = (n_bins + 31) >> 5;
+    const int i0 = min((int)threadIdx.x * per, n_bins), i1 = min(i0 + per, n_bins);
+    double run = 0.0;
+    for (int i = i0; i < i1; ++i) run += (double)(range * y[i]);
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)threadIdx.x >= o) incl += u;
+    }
+    run = (double)min_val + (incl - run);  // exclusive offset of this lane's run
+    if (threadIdx.x == 0) scan[0] = run;
+    for (int i = i0; i < i1; ++i) {
       run += (double)(range * y[i]);
       scan[i + 1] = run;
     }
@@ -335,7 +373,7 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
   if (B <= 0 || E <= 0 || H <= 0 || n_bins <= 0 || n_bins > 4096 || E > 4096 || H > 4096) return MDE_ERR_BAD_SHAPE;
   if (norm_mode < 0 || norm_mode > 2) return MDE_ERR_UNSUPPORTED;
   const size_t sm = sizeof(float) * (size_t)(E + 2 * H + n_bins) + sizeof(double) * (size_t)(n_bins + 2);
-  regressor_bins_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(t0, t0_stride, w1, b1, w2, b2, w3, b3, E, H, n_bins,
+  regressor_bins_kernel<<<B, 1024, sm, (cudaStream_t)stream>>>(t0, t0_stride, w1, b1, w2, b2, w3, b3, E, H, n_bins,
                                                               norm_mode, min_val, max_val, y_raw, widths_normed, edges,
                                                               centers);
   return check_launch();

@@ -87,28 +87,35 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
   }
 }
 
-// qkv [S*NB, 3E] (row = s*NB + n); out rows have pitch out_ld.  grid (NB*heads, y splits over the query rows).
-// One CTA per (image, head, row range): K and V of the (image, head) resident in shared memory ([S][HD+1], conflict-free);
-// each warp processes FOUR query rows per pass so that every K / V word read from shared memory feeds four FMAs (the
-// one-row-per-warp form was bound by the shared-memory port: 666 warp-wide loads per row, now 222):
-//   scores : lane = key j, q of the four rows broadcast as one float4 per head-dim channel
-//   softmax: probabilities kept interleaved [j][4 rows] in shared memory
-//   P V    : lane = head-dim channel, one float4 broadcast of the four rows' p_j + one V word per key
+// qkv [S*NB, 3E] (row = s*NB + n); out rows have pitch out_ld.  grid (NB*heads, y splits over the query rows), 4 / 8 / 16 warps.
+// One CTA per (image, head, row range): K ([S][HD+1], conflict-free for lane == key) and V ([S][HD]) of the (image, head) are
+// resident in shared memory; a warp owns EIGHT query rows per pass.  The kernel lives on the shared-memory pipe (one wavefront
+// per clock and SM), so every phase is shaped to feed >= 4 FMAs per shared-memory instruction:
+//   scores : lane = key, TWO key blocks (j, j + 32) per pass; per head-dim channel two 16-byte broadcasts of the eight rows' q
+//            and two K words feed 16 FMAs;
+//   softmax: probabilities kept interleaved [j][8 rows] in shared memory (un-normalised; 1 / sum is applied to the output);
+//   P V    : a half-warp owns four of the rows, lane = a PAIR of head-dim channels: one 16-byte broadcast of the four rows' p_j
+//            and one 8-byte V load feed 8 FMAs.
+// (History: one row per warp -- 666 shared-memory loads per row; four rows with q hoisted into registers -- 162 registers, one
+// 256-thread CTA per SM, and a grid of 320 CTAs = three waves on 148 SMs: 42 us per layer at B = 16 for 0.4 GFLOP.)
 // split3 != 0 writes each output row as [v | v - trunc_tf32(v) | v] (the 3xTF32 A operand form).
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
+constexpr int ATT_ROWS = 8;  // query rows per warp pass
+
+__host__ __device__ inline size_t attention_kv_floats(int S, int HD) { return (((size_t)S * (HD + 1) + 3) & ~(size_t)3) + (size_t)S * HD; }
+__host__ __device__ inline size_t attention_warp_floats(int S, int HD) { return (size_t)ATT_ROWS * (HD + S); }
+
 template <int HD>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int S,
+__global__ void __launch_bounds__(512, 1) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int S,
                                                         int NB, int E, int heads, float scale, int out_ld, int split3) {
-  static_assert(HD == 32, "lane == head-dim channel");
+  static_assert(HD == 32, "lane == head-dim channel when q is staged; a half-warp covers HD as channel pairs");
   extern __shared__ __align__(16) float smem_att[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* sk = smem_att;                               // [S][HD+1]
-  float* sv = sk + (size_t)S * (HD + 1);              // [S][HD+1]
-  size_t off = (size_t)2 * S * (HD + 1);
-  off = (off + 3) & ~(size_t)3;                       // float4 alignment of the per-warp areas
-  float* sq = smem_att + off + (size_t)warp * (4 * HD + 4 * S);  // [HD][4]  q of the four rows, channel-major
-  float* sp = sq + 4 * HD;                                       // [S][4]   scores / probabilities of the four rows
+  float* sk = smem_att;                                                    // [S][HD+1]
+  float* sv = smem_att + (((size_t)S * (HD + 1) + 3) & ~(size_t)3);        // [S][HD]
+  float* sq = smem_att + attention_kv_floats(S, HD) + (size_t)warp * attention_warp_floats(S, HD);  // [HD][8]
+  float* sp = sq + ATT_ROWS * HD;                                          // [S][8] scores / exponentials of the eight rows
   const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
   const int ld = 3 * E;
   {
@@ -133,9 +140,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         if (i < total) {
           const int s = i / V4, d4 = i - s * V4;
           float* kd = sk + s * (HD + 1) + d4 * 4;
-          float* vd = sv + s * (HD + 1) + d4 * 4;
           kd[0] = kv[u].x; kd[1] = kv[u].y; kd[2] = kv[u].z; kd[3] = kv[u].w;
-          vd[0] = vv[u].x; vd[1] = vv[u].y; vd[2] = vv[u].z; vd[3] = vv[u].w;
+          *reinterpret_cast<float4*>(sv + s * HD + d4 * 4) = vv[u];
         }
       }
     }
@@ -143,72 +149,138 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   __syncthreads();
   const int rows_per_cta = (S + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(S, r0 + rows_per_cta);
-  for (int i0 = r0 + 4 * warp; i0 < r1; i0 += 4 * nwarps) {
-    // (1) the four (pre-scaled, as torch does: q / sqrt(hd)) query rows -> sq[d][r]
-    float4 qv;
+  const int half = lane >> 4, cp = lane & 15;
+  for (int i0 = r0 + ATT_ROWS * warp; i0 < r1; i0 += ATT_ROWS * nwarps) {
+    // (1) the eight (pre-scaled, as torch does: q / sqrt(hd)) query rows -> sq[d][r]; lane = channel
     {
-      float t[4];
+      float t[ATT_ROWS];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < ATT_ROWS; ++r) {
         const int i = min(i0 + r, S - 1);
-        t[r] = qkv[((long long)i * NB + n) * ld + hh * HD + lane] * scale;
+        t[r] = __ldg(qkv + ((long long)i * NB + n) * ld + hh * HD + lane) * scale;
       }
-      qv = make_float4(t[0], t[1], t[2], t[3]);
+      reinterpret_cast<float4*>(sq)[2 * lane] = make_float4(t[0], t[1], t[2], t[3]);
+      reinterpret_cast<float4*>(sq)[2 * lane + 1] = make_float4(t[4], t[5], t[6], t[7]);
     }
-    reinterpret_cast<float4*>(sq)[lane] = qv;
     __syncwarp();
-    // (2) scores, lane = key
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    for (int j0 = 0; j0 < S; j0 += 32) {
-      const int j = j0 + lane;
-      const float* kr = sk + (size_t)min(j, S - 1) * (HD + 1);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // (2) scores, lane = key, two key blocks per pass
+    float mx[ATT_ROWS];
+#pragma unroll
+    for (int r = 0; r < ATT_ROWS; ++r) mx[r] = -INFINITY;
+#pragma unroll 1
+    for (int j0 = 0; j0 < S; j0 += 64) {
+      const int ja = j0 + lane, jb = ja + 32;
+      const float* ka = sk + (size_t)min(ja, S - 1) * (HD + 1);
+      const float* kb = sk + (size_t)min(jb, S - 1) * (HD + 1);
+      float a[ATT_ROWS], b[ATT_ROWS];
+#pragma unroll
+      for (int r = 0; r < ATT_ROWS; ++r) a[r] = b[r] = 0.f;
+      // q is re-read from shared memory (broadcast loads) in every key-block pass: hoisting the 256 loop-invariant words out of
+      // this loop is what the compiler would do otherwise -- and spill them.  The empty asm makes the address opaque per pass.
+      int opaque = 0;
+      asm volatile("" : "+r"(opaque));  // (an offset, not the pointer: the loads must stay ld.shared)
+      const float4* sq4 = reinterpret_cast<const float4*>(sq) + opaque;
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        const float4 q4 = reinterpret_cast<const float4*>(sq)[d];
-        const float kd = kr[d];
-        a0 = fmaf(q4.x, kd, a0); a1 = fmaf(q4.y, kd, a1); a2 = fmaf(q4.z, kd, a2); a3 = fmaf(q4.w, kd, a3);
+        const float4 q0 = sq4[2 * d], q1 = sq4[2 * d + 1];
+        const float q[ATT_ROWS] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        const float kda = ka[d], kdb = kb[d];
+#pragma unroll
+        for (int r = 0; r < ATT_ROWS; ++r) {
+          a[r] = fmaf(q[r], kda, a[r]);
+          b[r] = fmaf(q[r], kdb, b[r]);
+        }
       }
-      if (j < S) {
-        reinterpret_cast<float4*>(sp)[j] = make_float4(a0, a1, a2, a3);
-        mx[0] = fmaxf(mx[0], a0); mx[1] = fmaxf(mx[1], a1); mx[2] = fmaxf(mx[2], a2); mx[3] = fmaxf(mx[3], a3);
+      if (ja < S) {
+        reinterpret_cast<float4*>(sp)[2 * ja] = make_float4(a[0], a[1], a[2], a[3]);
+        reinterpret_cast<float4*>(sp)[2 * ja + 1] = make_float4(a[4], a[5], a[6], a[7]);
+#pragma unroll
+        for (int r = 0; r < ATT_ROWS; ++r) mx[r] = fmaxf(mx[r], a[r]);
+      }
+      if (jb < S) {
+        reinterpret_cast<float4*>(sp)[2 * jb] = make_float4(b[0], b[1], b[2], b[3]);
+        reinterpret_cast<float4*>(sp)[2 * jb + 1] = make_float4(b[4], b[5], b[6], b[7]);
+#pragma unroll
+        for (int r = 0; r < ATT_ROWS; ++r) mx[r] = fmaxf(mx[r], b[r]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) mx[r] = warp_max(mx[r]);
-    // (3) exponentials and their sums
-    float sum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = lane; j < S; j += 32) {
-      float4 a = reinterpret_cast<float4*>(sp)[j];
-      a.x = expf(a.x - mx[0]); a.y = expf(a.y - mx[1]); a.z = expf(a.z - mx[2]); a.w = expf(a.w - mx[3]);
-      sum[0] += a.x; sum[1] += a.y; sum[2] += a.z; sum[3] += a.w;
-      reinterpret_cast<float4*>(sp)[j] = a;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) sum[r] = warp_sum(sum[r]);
+    for (int r = 0; r < ATT_ROWS; ++r) mx[r] = warp_max(mx[r]);
     __syncwarp();
-    // (4) P V, lane = head-dim channel
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    for (int j = 0; j < S; ++j) {
-      const float4 p4 = reinterpret_cast<const float4*>(sp)[j];
-      const float vj = sv[(size_t)j * (HD + 1) + lane];
-      o0 = fmaf(p4.x, vj, o0); o1 = fmaf(p4.y, vj, o1); o2 = fmaf(p4.z, vj, o2); o3 = fmaf(p4.w, vj, o3);
+    // (3) exponentials and their sums
+    float sum[ATT_ROWS];
+#pragma unroll
+    for (int r = 0; r < ATT_ROWS; ++r) sum[r] = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      float4 u = reinterpret_cast<float4*>(sp)[2 * j], v = reinterpret_cast<float4*>(sp)[2 * j + 1];
+      u.x = expf(u.x - mx[0]); u.y = expf(u.y - mx[1]); u.z = expf(u.z - mx[2]); u.w = expf(u.w - mx[3]);
+      v.x = expf(v.x - mx[4]); v.y = expf(v.y - mx[5]); v.z = expf(v.z - mx[6]); v.w = expf(v.w - mx[7]);
+      sum[0] += u.x; sum[1] += u.y; sum[2] += u.z; sum[3] += u.w;
+      sum[4] += v.x; sum[5] += v.y; sum[6] += v.z; sum[7] += v.w;
+      reinterpret_cast<float4*>(sp)[2 * j] = u;
+      reinterpret_cast<float4*>(sp)[2 * j + 1] = v;
     }
-    const float ov[4] = {o0 / sum[0], o1 / sum[1], o2 / sum[2], o3 / sum[3]};
+#pragma unroll
+    for (int r = 0; r < ATT_ROWS; ++r) sum[r] = warp_sum(sum[r]);
+    __syncwarp();
+    // (4) P V: this half-warp's four rows x this lane's two channels
+    float o[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[r][0] = o[r][1] = 0.f;
+    const float* pj = sp + 4 * half;
+    const float* vj = sv + 2 * cp;
+#pragma unroll 4
+    for (int j = 0; j < S; ++j) {
+      const float4 p4 = *reinterpret_cast<const float4*>(pj + (size_t)j * ATT_ROWS);
+      const float2 v2 = *reinterpret_cast<const float2*>(vj + (size_t)j * HD);
+      o[0][0] = fmaf(p4.x, v2.x, o[0][0]); o[0][1] = fmaf(p4.x, v2.y, o[0][1]);
+      o[1][0] = fmaf(p4.y, v2.x, o[1][0]); o[1][1] = fmaf(p4.y, v2.y, o[1][1]);
+      o[2][0] = fmaf(p4.z, v2.x, o[2][0]); o[2][1] = fmaf(p4.z, v2.y, o[2][1]);
+      o[3][0] = fmaf(p4.w, v2.x, o[3][0]); o[3][1] = fmaf(p4.w, v2.y, o[3][1]);
+    }
+    const float den[4] = {half ? sum[4] : sum[0], half ? sum[5] : sum[1], half ? sum[6] : sum[2], half ? sum[7] : sum[3]};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int i = i0 + r;
+      const int i = i0 + 4 * half + r;
       if (i < r1) {
-        float* orow = out + ((long long)i * NB + n) * out_ld + hh * HD + lane;
-        orow[0] = ov[r];
+        const float v0 = o[r][0] / den[r], v1 = o[r][1] / den[r];
+        float* orow = out + ((long long)i * NB + n) * out_ld + hh * HD + 2 * cp;
+        *reinterpret_cast<float2*>(orow) = make_float2(v0, v1);
         if (split3) {
-          orow[E] = tf32_lo(ov[r]);
-          orow[2 * E] = ov[r];
+          *reinterpret_cast<float2*>(orow + E) = make_float2(tf32_lo(v0), tf32_lo(v1));
+          *reinterpret_cast<float2*>(orow + 2 * E) = make_float2(v0, v1);
         }
       }
     }
     __syncwarp();
   }
+}
+
+// Launch geometry: the widest CTA (16 / 8 / 4 warps) whose K, V and per-warp score areas fit the SM's shared memory and that
+// still yields at least one CTA per SM; the query rows of an (image, head) are split over at most SMs / (images * heads) CTAs so
+// that the grid is a single resident wave (one CTA per SM: registers and shared memory), never finer than one pass per warp.
+static int launch_attention(const float* qkv, float* out, int S, int NB, int E, int heads, int out_ld, int split3,
+                            cudaStream_t st) {
+  constexpr int HD = 32;
+  const size_t limit = 227 * 1024;
+  auto smem_of = [&](int nw) { return sizeof(float) * (attention_kv_floats(S, HD) + (size_t)nw * attention_warp_floats(S, HD)); };
+  auto ctas_of = [&](int nw) { return (long long)NB * heads * ((S + ATT_ROWS * nw - 1) / (ATT_ROWS * nw)); };
+  int nw = 16;
+  while (nw > 4 && (smem_of(nw) > limit || ctas_of(nw) < MDE_NUM_SMS)) nw >>= 1;
+  if (smem_of(nw) > limit) return MDE_ERR_BAD_SHAPE;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit) != cudaSuccess)
+      return MDE_ERR_LAUNCH;
+    attr = true;
+  }
+  int ysplit = MDE_NUM_SMS / (NB * heads);
+  const int finest = (S + ATT_ROWS * nw - 1) / (ATT_ROWS * nw);
+  if (ysplit > finest) ysplit = finest;
+  if (ysplit < 1) ysplit = 1;
+  attention_kernel<HD><<<dim3(NB * heads, ysplit), 32 * nw, smem_of(nw), st>>>(qkv, out, S, NB, E, heads,
+                                                                              1.0f / sqrtf((float)HD), out_ld, split3);
+  return check_launch();
 }
 
 // out[m,:] = LayerNorm(x[m,:] + y[m,:]) * g + b ;  E == 128 (one float4 per lane)
@@ -308,21 +380,7 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
   float* ff = tmp + (size_t)M * E;
   int rc;
   if ((rc = launch_linear(x, E, in_w, E, in_b, qkv, 3 * E, M, 3 * E, E, 0, st))) return rc;
-  {
-    const int hd = E / heads;
-    const size_t sm = sizeof(float) * ((((size_t)2 * S * (hd + 1) + 3) & ~(size_t)3) + (size_t)8 * (4 * hd + 4 * S));
-    if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
-    int ysplit = (2 * MDE_NUM_SMS + NB * heads - 1) / (NB * heads);
-    if (ysplit < 1) ysplit = 1;
-    if (ysplit > (S + 7) / 8) ysplit = (S + 7) / 8;
-    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att, S, NB, E, heads, 1.0f / sqrtf((float)hd), E, 0);
-    if ((rc = check_launch())) return rc;
-  }
+  if ((rc = launch_attention(qkv, att, S, NB, E, heads, E, 0, st))) return rc;
   if ((rc = launch_linear(att, E, out_w, E, out_b, tmp, E, M, E, E, 0, st))) return rc;
   add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, tmp, ln1_w, ln1_b, att, M, eps);  // att := LN1(x + sa)
   if ((rc = check_launch())) return rc;
@@ -369,21 +427,7 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
   int rc;
   // qkv = x W_in^T + b_in
   if ((rc = mde_gemm_nt_tf32_ex(x3, E3, 0, in_w3, E3, 0, qkv, E3, 0, 1, M, E3, E3, 1, 1.0f, in_b, 0, 0, stream))) return rc;
-  {
-    const int hd = E / heads;
-    const size_t sm = sizeof(float) * ((((size_t)2 * S * (hd + 1) + 3) & ~(size_t)3) + (size_t)8 * (4 * hd + 4 * S));
-    if (sm > 200 * 1024) return MDE_ERR_BAD_SHAPE;
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
-    int ysplit = (2 * MDE_NUM_SMS + NB * heads - 1) / (NB * heads);
-    if (ysplit < 1) ysplit = 1;
-    if (ysplit > (S + 7) / 8) ysplit = (S + 7) / 8;
-    attention_kernel<32><<<dim3(NB * heads, ysplit), 256, sm, st>>>(qkv, att3, S, NB, E, heads, 1.0f / sqrtf((float)hd), E3, 1);
-    if ((rc = check_launch())) return rc;
-  }
+  if ((rc = launch_attention(qkv, att3, S, NB, E, heads, E3, 1, st))) return rc;
   // tmp = att W_out^T + b_out ; x1 = LN1(x + tmp)
   if ((rc = mde_gemm_nt_tf32_ex(att3, E3, 0, out_w3, E3, 0, tmp, E, 0, 1, M, E, E3, 1, 1.0f, out_b, 0, 0, stream))) return rc;
   add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x3, tmp, ln1_w, ln1_b, x13, M, eps, E3, E, E3, 1);

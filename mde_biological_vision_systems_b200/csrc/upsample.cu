@@ -305,46 +305,86 @@ __device__ __forceinline__ void store4(void* out, long long elem, long long plan
   }
 }
 
-// grid (ceil(W * C1/4 / 256), H, B): the row and the image come from the block index, so a thread needs one 32-bit division
-// (the 64-bit index arithmetic of a flat launch cost more than the interpolation itself)
+// eight channels at once: one 16-byte store per plane of a pair (two for fp32)
 template <bool PAIR>
+__device__ __forceinline__ void store8(void* out, long long elem, long long plane_elems, const float4& a, const float4& b) {
+  if constexpr (PAIR) {
+    uint4 hi, mid;
+    tc::split_bf16x2(a.x, a.y, hi.x, mid.x);
+    tc::split_bf16x2(a.z, a.w, hi.y, mid.y);
+    tc::split_bf16x2(b.x, b.y, hi.z, mid.z);
+    tc::split_bf16x2(b.z, b.w, hi.w, mid.w);
+    uint16_t* base = reinterpret_cast<uint16_t*>(out);
+    *reinterpret_cast<uint4*>(base + elem) = hi;
+    *reinterpret_cast<uint4*>(base + plane_elems + elem) = mid;
+  } else {
+    stg_stream(reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem), a);
+    stg_stream(reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + elem) + 1, b);
+  }
+}
+
+__device__ __forceinline__ float4 bilerp4(const float4& v00, const float4& v01, const float4& v10, const float4& v11, float ly0,
+                                          float ly1, float lx0, float lx1) {
+  float4 o;  // same association as ATen: ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * c + lx1 * d)
+  o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+  o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+  o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+  o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+  return o;
+}
+
+// grid (ceil(W * C1/(4V) / 256), H, B): the row and the image come from the block index, so a thread needs one 32-bit division
+// (the 64-bit index arithmetic of a flat launch cost more than the interpolation itself).  V = 2 (C1 % 8 == 0): a thread owns
+// EIGHT channels of one output pixel -- eight 16-byte tap loads in flight and 16-byte stores into each plane of the pair (the
+// four-channel form wrote 8 bytes per plane and thread and ran at 0.46-0.6 of the HBM rate).
+template <bool PAIR, int V>
 __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ x, void* __restrict__ out, int C1,
                                                             int Ctot, int h, int w, int H, int W, float sy, float sx,
                                                             long long plane_elems) {
-  const int c4 = C1 >> 2;
+  const int c4 = C1 >> 2;        // float4 groups per pixel
+  const int cgn = c4 / V;        // thread slots per pixel
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
-  if (t >= (unsigned)(W * c4)) return;
-  const int X = (int)(t / (unsigned)c4), cg = (int)(t - (unsigned)X * c4);
+  if (t >= (unsigned)(W * cgn)) return;
+  const int X = (int)(t / (unsigned)cgn), cg = (int)(t - (unsigned)X * cgn) * V;
   const int Y = blockIdx.y, b = blockIdx.z;
   int y0, y1, xa, xb;
   float ly0, ly1, lx0, lx1;
   up_src(Y, sy, h, y0, y1, ly0, ly1);
   up_src(X, sx, w, xa, xb, lx0, lx1);
   const float4* src = reinterpret_cast<const float4*>(x + (long long)b * h * w * C1) + cg;
-  const float4 v00 = __ldg(src + (y0 * w + xa) * c4), v01 = __ldg(src + (y0 * w + xb) * c4);
-  const float4 v10 = __ldg(src + (y1 * w + xa) * c4), v11 = __ldg(src + (y1 * w + xb) * c4);
-  float4 o;  // same association as ATen: ly0 * (lx0 * a + lx1 * b) + ly1 * (lx0 * c + lx1 * d)
-  o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
-  o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
-  o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
-  o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
-  store4<PAIR>(out, (((long long)b * H + Y) * W + X) * Ctot + 4 * cg, plane_elems, o);
+  const float4 *p00 = src + (y0 * w + xa) * c4, *p01 = src + (y0 * w + xb) * c4;
+  const float4 *p10 = src + (y1 * w + xa) * c4, *p11 = src + (y1 * w + xb) * c4;
+  const long long elem = (((long long)b * H + Y) * W + X) * Ctot + 4 * cg;
+  if constexpr (V == 2) {
+    const float4 a00 = __ldg(p00), a01 = __ldg(p01), a10 = __ldg(p10), a11 = __ldg(p11);
+    const float4 b00 = __ldg(p00 + 1), b01 = __ldg(p01 + 1), b10 = __ldg(p10 + 1), b11 = __ldg(p11 + 1);
+    store8<PAIR>(out, elem, plane_elems, bilerp4(a00, a01, a10, a11, ly0, ly1, lx0, lx1),
+                 bilerp4(b00, b01, b10, b11, ly0, ly1, lx0, lx1));
+  } else {
+    store4<PAIR>(out, elem, plane_elems, bilerp4(__ldg(p00), __ldg(p01), __ldg(p10), __ldg(p11), ly0, ly1, lx0, lx1));
+  }
 }
 
 // skip channels [C1, C1 + C2) of every pixel, then zeros up to the row pitch Ctot (>= C1 + C2: a pitch padded to whole
-// 64-byte groups keeps the conv's TMA boxes sector-aligned).  grid (ceil(P * (Ctot - C1)/4 / 256), B)
-template <bool PAIR>
+// 64-byte groups keeps the conv's TMA boxes sector-aligned).  grid (ceil(P * (Ctot - C1)/(4V) / 256), B)
+template <bool PAIR, int V>
 __global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __restrict__ skip, void* __restrict__ out,
                                                                  int C1, int C2, int Ctot, unsigned per_image,
                                                                  long long P, long long plane_elems) {
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
   if (t >= per_image) return;
-  const unsigned c4 = (unsigned)(Ctot - C1) >> 2;
-  const unsigned pl = t / c4, cg = t - pl * c4;
+  const unsigned cgn = ((unsigned)(Ctot - C1) >> 2) / V;
+  const unsigned pl = t / cgn, cg = (t - pl * cgn) * V;
   const long long p = (long long)blockIdx.y * P + pl;
-  const float4 v = 4 * cg < (unsigned)C2 ? ldg_stream(reinterpret_cast<const float4*>(skip + p * C2) + cg)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-  store4<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, v);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* sp = reinterpret_cast<const float4*>(skip + p * C2) + cg;
+  const float4 v = 4 * cg < (unsigned)C2 ? ldg_stream(sp) : z;
+  if constexpr (V == 2) {
+    const float4 u = 4 * (cg + 1) < (unsigned)C2 ? ldg_stream(sp + 1) : z;
+    store8<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, v, u);
+  } else {
+    store4<PAIR>(out, p * Ctot + C1 + 4 * cg, plane_elems, v);
+  }
 }
 }  // namespace mde
 
@@ -387,20 +427,30 @@ static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, i
   const long long plane = (long long)B * P * Ctot;
   if ((long long)W * (C1 / 4) > 0x7fffffffLL || (long long)h * w * (C1 / 4) > 0x7fffffffLL || P * ((Ctot - C1) / 4) > 0x7fffffffLL)
     return MDE_ERR_BAD_SHAPE;
-  const dim3 grid((unsigned)((W * (C1 / 4) + 255) / 256), (unsigned)H, (unsigned)B);
-  if (pair)
-    upsample_nhwc_kernel<true><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
-  else
-    upsample_nhwc_kernel<false><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+  // eight channels per thread where the widths allow it (every DecoderBN step: 1280 / 640 / 320 / 160 up-sampled channels)
+  const bool wide = C1 % 8 == 0 && Ctot % 8 == 0;
+  const int vv = wide ? 2 : 1;
+  const dim3 grid((unsigned)((W * (C1 / (4 * vv)) + 255) / 256), (unsigned)H, (unsigned)B);
+  if (pair) {
+    if (wide) upsample_nhwc_kernel<true, 2><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    else upsample_nhwc_kernel<true, 1><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+  } else {
+    if (wide) upsample_nhwc_kernel<false, 2><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    else upsample_nhwc_kernel<false, 1><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+  }
   int rc = check_launch();
   if (rc || Ctot == C1) return rc;
   if (skip_channels_last) {
-    const unsigned per_image = (unsigned)(P * ((Ctot - C1) / 4));
+    const bool wide2 = (Ctot - C1) % 8 == 0 && C2 % 8 == 0 && C1 % 8 == 0;
+    const unsigned per_image = (unsigned)(P * ((Ctot - C1) / (wide2 ? 8 : 4)));
     const dim3 g2((per_image + 255) / 256, (unsigned)B);
-    if (pair)
-      copy_channels_nhwc_kernel<true><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
-    else
-      copy_channels_nhwc_kernel<false><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+    if (pair) {
+      if (wide2) copy_channels_nhwc_kernel<true, 2><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+      else copy_channels_nhwc_kernel<true, 1><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+    } else {
+      if (wide2) copy_channels_nhwc_kernel<false, 2><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+      else copy_channels_nhwc_kernel<false, 1><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+    }
   } else {
     dim3 grid2((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);
     nchw_to_nhwc_kernel<<<grid2, 256, 0, st>>>(skip, reinterpret_cast<float*>(out) + C1, C2, P, Ctot);
