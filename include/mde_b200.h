@@ -45,6 +45,15 @@ const char* mde_error_string(int code);
 int mde_check_device(void);
 /* Number of kernels launched through this library since load (the bench's "gpu_launches" evidence). */
 int64_t mde_launch_count(void);
+/* Programmatic dependent launch (csrc/common.cuh: launch_pdl / pdl_sync): kernels of the inference step can be launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization; they wait for their predecessor on the device (griddepcontrol.wait) before
+ * their first global-memory access, so a kernel's launch latency and prologue overlap the previous kernel's execution.
+ * mask: bit 0 = chains of small kernels (transformer GEMMs / attention / LayerNorm, regressor, query fold), bit 1 = persistent
+ * tcgen05 kernels (conv3x3, point-wise GEMM, patch embedding, fused chain), bit 2 = streaming kernels (bias / SiLU / pooling,
+ * squeeze-excite gate, resize + concat, stem); 0 = off; mask < 0 queries.  Returns the mask in effect (default: environment
+ * MDE_PDL, else 0 -- measured on B200: a gain for eagerly launched steps only, none under CUDA-graph replay).
+ * Results are identical either way.  Host-side state of the process. */
+int mde_set_pdl(int mask);
 
 /* ---- K3: label -> embedding gather -------------------------------------------------------------------
  * Replaces SemanticsLoader.get_semantics (ExternalInfoLoaders/SemanticsLoader.py:102-145) and

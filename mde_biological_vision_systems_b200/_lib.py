@@ -19,6 +19,7 @@ SIGNATURES = {
     "mde_error_string": (ctypes.c_char_p, [_i32]),
     "mde_check_device": (_i32, []),
     "mde_launch_count": (_i64, []),
+    "mde_set_pdl": (_i32, [_i32]),
     "mde_gather_embed": (_i32, [_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     "mde_gather_embed_labels": (_i32, [_p, _i32, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _p, _p]),
     "mde_gather_embed_nhwc": (_i32, [_p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(256) bias_act_pool_nhwc_kernel(const float* __
                                                                  float* __restrict__ y, float* __restrict__ partial,
                                                                  long long HW, int c4, long long rows_per_slab, int act) {
   __shared__ float4 red[256];
+  pdl_sync();
   const long long b = blockIdx.y, slab = blockIdx.x;
   const long long r0 = slab * rows_per_slab;
   const long long r1 = r0 + rows_per_slab < HW ? r0 + rows_per_slab : HW;
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w2, const float* __restrict__ b2,
                                                       float* __restrict__ gate, int C, int R) {
   extern __shared__ __align__(16) float se_sm[];  // mean[C] | h[R]
+  pdl_sync();
   float* mean = se_sm;
   float* h = se_sm + C;
   const int b = blockIdx.y;
@@ -458,8 +460,8 @@ extern "C" int mde_bias_act_pool_nhwc(const float* x, const float* bias, float* 
   if (C % 4 != 0 || !aligned(x, 16) || !aligned(y, 16) || !aligned(bias, 16) || !aligned(partial, 16)) return MDE_ERR_UNSUPPORTED;
   const int slabs = mde_pool_slabs(B, HW);
   const long long rps = (HW + slabs - 1) / slabs;
-  bias_act_pool_nhwc_kernel<<<dim3((unsigned)slabs, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(x, bias, y, partial, HW, C / 4,
-                                                                                                 rps, act);
+  launch_pdl(PDL_STREAM, bias_act_pool_nhwc_kernel, dim3((unsigned)slabs, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, x, bias, y, partial,
+             HW, C / 4, rps, act);
   return check_launch();
 }
 
@@ -471,7 +473,7 @@ extern "C" int mde_se_gate(const float* partial, int slabs, float inv_hw, const 
   const size_t sm = (size_t)(C + R) * sizeof(float);
   if (sm > 48 * 1024) return MDE_ERR_UNSUPPORTED;
   const int splits = C >= 512 ? 8 : (C >= 128 ? 4 : 1);
-  se_gate_kernel<<<dim3((unsigned)splits, (unsigned)B), 256, sm, (cudaStream_t)stream>>>(partial, slabs, inv_hw, w1, b1, w2, b2,
-                                                                                         gate, C, R);
+  launch_pdl(PDL_STREAM, se_gate_kernel, dim3((unsigned)splits, (unsigned)B), dim3(256), sm, (cudaStream_t)stream, partial, slabs, inv_hw, w1,
+             b1, w2, b2, gate, C, R);
   return check_launch();
 }

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(1024) regressor_bins_kernel(const float* __res
   float* h2 = h1 + H;
   float* y = h2 + H;
   const int b = blockIdx.x;
+  pdl_sync();
   if (w1 != nullptr) {
     for (int i = threadIdx.x; i < E; i += blockDim.x) sin[i] = t0[(long long)b * t0_stride + i];
     __syncthreads();
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(256) pixel_gemm_kernel(const float* __restrict
                                                          float out_scale) {
   __shared__ __align__(16) float sx[16][128];
   __shared__ float sw[16][64 + 1];
+  pdl_sync();
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 128;
   const int n0 = blockIdx.y * 64;
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(256) chain_bias_kernel(const float* __restrict
   const int b = blockIdx.y;
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_sync();
   if (j >= n_bins) return;
   float a = 0.f;
   if (feat_bias) {
@@ -373,9 +376,8 @@ int mde_regressor_bins_fwd(const float* t0, int64_t t0_stride, const float* w1, 
   if (B <= 0 || E <= 0 || H <= 0 || n_bins <= 0 || n_bins > 4096 || E > 4096 || H > 4096) return MDE_ERR_BAD_SHAPE;
   if (norm_mode < 0 || norm_mode > 2) return MDE_ERR_UNSUPPORTED;
   const size_t sm = sizeof(float) * (size_t)(E + 2 * H + n_bins) + sizeof(double) * (size_t)(n_bins + 2);
-  regressor_bins_kernel<<<B, 1024, sm, (cudaStream_t)stream>>>(t0, t0_stride, w1, b1, w2, b2, w3, b3, E, H, n_bins,
-                                                              norm_mode, min_val, max_val, y_raw, widths_normed, edges,
-                                                              centers);
+  launch_pdl(PDL_CHAIN, regressor_bins_kernel, dim3(B), dim3(1024), sm, (cudaStream_t)stream, t0, (long long)t0_stride, w1, b1, w2, b2, w3, b3,
+             E, H, n_bins, norm_mode, min_val, max_val, y_raw, widths_normed, edges, centers);
   return check_launch();
 }
 
@@ -439,12 +441,16 @@ int mde_fold_queries(const float* w_out, const float* bias, const float* q, int6
   cudaStream_t st = (cudaStream_t)stream;
   const float LOG2E = 1.4426950408889634f;
   dim3 grid((unsigned)((K + 127) / 128), (unsigned)((n_bins + 63) / 64), (unsigned)B);
-  if (round_tf32) pixel_gemm_kernel<1><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
-  else pixel_gemm_kernel<2><<<grid, 256, 0, st>>>(q, w_out, 0, nullptr, wf, N, n_bins, K, LOG2E * operand_scale);
+  if (round_tf32)
+    launch_pdl(PDL_CHAIN, pixel_gemm_kernel<1>, grid, dim3(256), 0, st, q, w_out, 0LL, (const float*)nullptr, wf, N, n_bins, (long long)K,
+               LOG2E * operand_scale);
+  else
+    launch_pdl(PDL_CHAIN, pixel_gemm_kernel<2>, grid, dim3(256), 0, st, q, w_out, 0LL, (const float*)nullptr, wf, N, n_bins, (long long)K,
+               LOG2E * operand_scale);
   int rc = check_launch();
   if (rc) return rc;
-  chain_bias_kernel<<<dim3((unsigned)((n_bins + 7) / 8), (unsigned)B), 256, 0, st>>>(bias, wf, feat_bias, biasf, n_bins, K,
-                                                                                       LOG2E, 1.f / operand_scale);
+  launch_pdl(PDL_CHAIN, chain_bias_kernel, dim3((unsigned)((n_bins + 7) / 8), (unsigned)B), dim3(256), 0, st, bias, wf, feat_bias, biasf,
+             n_bins, K, LOG2E, 1.f / operand_scale);
   return check_launch();
 }
 

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // the prologue above overlaps the previous kernel of the stream (common.cuh); global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -501,7 +502,7 @@ int conv3x3_launch(const void* x, const void* w_prep, const float* scale, const 
         return MDE_ERR_LAUNCH;                                                                                         \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    tc::conv3x3_kernel<NT, TW, PREC><<<grid, tc::CV_THREADS, smem, st>>>(mx, mw, my, scale, shift, g);                 \
+    launch_pdl(PDL_TC, tc::conv3x3_kernel<NT, TW, PREC>, dim3(grid), dim3(tc::CV_THREADS), smem, st, mx, mw, my, scale, shift, g); \
   }
   switch (nt * 100 + tw) {
     case 216: MDE_CV_LAUNCH(2, 16) break;

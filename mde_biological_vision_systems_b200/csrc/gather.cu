@@ -6,11 +6,22 @@
 // Layout: one thread owns 4 consecutive pixels -> one 32 B label read and one 16 B store per channel plane,
 // so a warp writes 512 contiguous bytes per plane (fully coalesced); the table sits in shared memory with an odd
 // row pitch (D = 25 or 3) so distinct labels in a warp hit distinct banks.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mde {
 
 unsigned long long g_launch_count = 0;
+
+static int g_pdl = -1;  // mask of kernel classes (common.cuh); -1: not read yet
+bool pdl_enabled(int cls) {
+  if (g_pdl < 0) {
+    const char* e = getenv("MDE_PDL");
+    g_pdl = e != nullptr ? (atoi(e) & 7) : 0;
+  }
+  return (g_pdl & cls) != 0;
+}
 
 template <typename T>
 struct Vec4;
@@ -357,6 +368,15 @@ extern "C" {
 int mde_version(void) { return 100; }
 
 int64_t mde_launch_count(void) { return (int64_t)g_launch_count; }
+
+// Programmatic dependent launch of the kernels that support it (common.cuh): a mask of kernel classes (1 chains of small
+// kernels, 2 persistent tcgen05 kernels, 4 streaming kernels), 0 off, < 0 query only.  Returns the setting
+// in effect (default: the MDE_PDL environment variable, else off).  Host-side state of the process.
+int mde_set_pdl(int mask) {
+  (void)mde::pdl_enabled(0);
+  if (mask >= 0) mde::g_pdl = mask & 7;
+  return mde::g_pdl;
+}
 
 const char* mde_error_string(int code) {
   switch (code) {

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // the prologue above overlaps the previous kernel; operands and C are touched from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -305,7 +306,11 @@ static int gemm_nt_launch(const float* A, int64_t lda, int64_t a_batch, const fl
     attr = true;
   }
   dim3 grid((unsigned)(m_tiles * g.n_tiles), (unsigned)splits, (unsigned)batch);
-  tc::gemm_nt_kernel<<<grid, tc::GM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, C, g);
+  if (splits > 1 && g.atomic) {  // preceded by the caller's memset of C: an ordinary launch
+    tc::gemm_nt_kernel<<<grid, tc::GM_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, C, g);
+  } else {
+    launch_pdl(PDL_CHAIN, tc::gemm_nt_kernel, grid, dim3(tc::GM_THREADS), smem, (cudaStream_t)stream, ma, mb, C, g);
+  }
   return check_launch();
 }
 

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // the prologue above overlaps the previous kernel of the stream (common.cuh); global memory from here on
 
   if (warp == 0) {
     // ================= activation producer =================
@@ -490,8 +491,8 @@ static int launch_chain(const uint16_t* x_pair, const uint16_t* w_pair, const fl
       return MDE_ERR_LAUNCH;
     attr_set = true;
   }
-  head_chain_kernel<NB, EPI, PROF><<<grid, CHAIN_THREADS, Plan::TOTAL, st>>>(mx, mw, biasf, centers, out, tiles_per_img,
-                                                                             (int)total, P, g_prof, tr);
+  launch_pdl(PDL_TC, head_chain_kernel<NB, EPI, PROF>, dim3(grid), dim3(CHAIN_THREADS), Plan::TOTAL, st, mx, mw, biasf, centers, out,
+             tiles_per_img, (int)total, P, g_prof, tr);
   return check_launch();
 }
 

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // the prologue above overlaps the previous kernel of the stream (common.cuh); global memory from here on
   const uint32_t box_bytes = (uint32_t)(PE_KC * 2 * wp * pyt);  // OOB rows are zero-filled but still counted
 
   if (warp == 0) {
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(256) patch_reduce_kernel(const float* __restri
                                                            const float* __restrict__ pos, float* __restrict__ tokens,
                                                            long long SB, int B, int splits) {
   const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index over [S*B][128]
+  pdl_sync();
   if (idx4 >= SB * 32) return;
   const long long rowi = idx4 >> 5;
   const int e4 = (int)(idx4 & 31);
@@ -238,8 +240,8 @@ int mde_patch_embed_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const fl
         return MDE_ERR_LAUNCH;                                                                                          \
       attr = true;                                                                                                      \
     }                                                                                                                   \
-    tc::patch_embed_kernel<NT><<<grid, tc::PE_THREADS, smem, st>>>(mxh, mxm, mw, ws, B, hp, wp, pyt, chunks_per_row,   \
-                                                                    chunks_per_split, nstages);                         \
+    launch_pdl(PDL_TC, tc::patch_embed_kernel<NT>, grid, dim3(tc::PE_THREADS), smem, st, mxh, mxm, mw, ws, B, hp, wp, pyt,       \
+               chunks_per_row, chunks_per_split, nstages);                                                             \
   }
   switch (nt) {
     case 1: MDE_PE_LAUNCH(1) break;
@@ -251,7 +253,7 @@ int mde_patch_embed_fwd(const uint16_t* x_pair, const uint16_t* w_pair, const fl
   int rc = check_launch();
   if (rc) return rc;
   const long long SB = (long long)hp * wp * B;
-  tc::patch_reduce_kernel<<<(unsigned)((SB * 32 + 255) / 256), 256, 0, st>>>(ws, bias, pos, tokens, SB, B, splits);
+  launch_pdl(PDL_CHAIN, tc::patch_reduce_kernel, dim3((unsigned)((SB * 32 + 255) / 256)), dim3(256), 0, st, ws, bias, pos, tokens, SB, B, splits);
   return check_launch();
 }
 

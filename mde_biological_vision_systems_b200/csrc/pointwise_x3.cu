@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // the prologue above overlaps the previous kernel of the stream (common.cuh); global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -392,7 +393,7 @@ int mde_pointwise_x3_fwd(const float* x, const float* gate, int64_t rows_per_ima
     attr = true;
   }
   const long long grid = g.total_tiles < MDE_NUM_SMS ? g.total_tiles : MDE_NUM_SMS;
-  tc::pointwise_x3_kernel<<<(unsigned)grid, tc::PW_THREADS, smem, (cudaStream_t)stream>>>(mx, mw, y, g);
+  launch_pdl(PDL_TC, tc::pointwise_x3_kernel, dim3((unsigned)grid), dim3(tc::PW_THREADS), smem, (cudaStream_t)stream, mx, mw, y, g);
   return check_launch();
 }
 

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) stem_conv3x3s2_kernel(const float* __rest
                                                              const float* __restrict__ bias, float* __restrict__ y, int Hi,
                                                              int Wi, int Cin, int pad_t, int pad_l, int Ho, int Wo, int act) {
   extern __shared__ __align__(16) float sw[];  // [9][Cin][COUT]
+  pdl_sync();
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) sw[i] = w_tcc[i];
   __syncthreads();
   const int b = blockIdx.z;
@@ -120,7 +121,8 @@ extern "C" int mde_stem_conv3x3s2_nhwc(const float* x, const float* w_tcc, const
         return MDE_ERR_LAUNCH;                                                                                             \
       attr = true;                                                                                                         \
     }                                                                                                                      \
-    stem_conv3x3s2_kernel<CO><<<grid, threads, sm, st>>>(x, w_tcc, bias, y, Hi, Wi, Cin, pad_top, pad_left, Ho, Wo, act);       \
+    launch_pdl(PDL_STREAM, stem_conv3x3s2_kernel<CO>, grid, dim3(threads), sm, st, x, w_tcc, bias, y, Hi, Wi, Cin, pad_top, pad_left, Ho, Wo, \
+               act);                                                                                                        \
   }
   if (Cout == 32) MDE_STEM(32) else MDE_STEM(48)
 #undef MDE_STEM

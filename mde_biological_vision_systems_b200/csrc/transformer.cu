@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(512, 1) attention_kernel(const float* __restri
   float* sp = sq + ATT_ROWS * HD;                                          // [S][8] scores / exponentials of the eight rows
   const int n = blockIdx.x / heads, hh = blockIdx.x % heads;
   const int ld = 3 * E;
+  pdl_sync();  // qkv comes from the previous kernel of the stream
   {
     // K and V rows of this (image, head): float4 loads, four rows in flight per thread before the dependent smem stores
     constexpr int V4 = HD / 4;
@@ -278,8 +279,8 @@ static int launch_attention(const float* qkv, float* out, int S, int NB, int E, 
   const int finest = (S + ATT_ROWS * nw - 1) / (ATT_ROWS * nw);
   if (ysplit > finest) ysplit = finest;
   if (ysplit < 1) ysplit = 1;
-  attention_kernel<HD><<<dim3(NB * heads, ysplit), 32 * nw, smem_of(nw), st>>>(qkv, out, S, NB, E, heads,
-                                                                              1.0f / sqrtf((float)HD), out_ld, split3);
+  launch_pdl(PDL_CHAIN, attention_kernel<HD>, dim3(NB * heads, ysplit), dim3(32 * nw), smem_of(nw), st, qkv, out, S, NB, E, heads,
+             1.0f / sqrtf((float)HD), out_ld, split3);
   return check_launch();
 }
 
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(256) add_layernorm128_kernel(const float* __re
                                                                int y_planes = 1, long long y_plane_stride = 0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_sync();
   if (row >= M) return;
   const float4 a = reinterpret_cast<const float4*>(x + (long long)row * x_ld)[lane];
   float4 c = reinterpret_cast<const float4*>(y + (long long)row * y_ld)[lane];
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(256) add_layernorm128_kernel(const float* __re
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
                                                      int E) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_sync();
   if (i >= rows * E) return;
   const long long r = i / E;
   const int c = (int)(i - r * E);
@@ -382,11 +385,12 @@ int mde_encoder_layer_fwd(const float* x, float* y, const float* in_w, const flo
   if ((rc = launch_linear(x, E, in_w, E, in_b, qkv, 3 * E, M, 3 * E, E, 0, st))) return rc;
   if ((rc = launch_attention(qkv, att, S, NB, E, heads, E, 0, st))) return rc;
   if ((rc = launch_linear(att, E, out_w, E, out_b, tmp, E, M, E, E, 0, st))) return rc;
-  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, tmp, ln1_w, ln1_b, att, M, eps);  // att := LN1(x + sa)
+  launch_pdl(PDL_CHAIN, add_layernorm128_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x, tmp, ln1_w, ln1_b, att, M, eps, 128, 128, 128, 0, 1,
+             0LL);  // att := LN1(x + sa)
   if ((rc = check_launch())) return rc;
   if ((rc = launch_linear(att, E, l1_w, E, l1_b, ff, FF, M, FF, E, 1, st))) return rc;
   if ((rc = launch_linear(ff, FF, l2_w, FF, l2_b, tmp, E, M, E, FF, 0, st))) return rc;
-  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(att, tmp, ln2_w, ln2_b, y, M, eps);
+  launch_pdl(PDL_CHAIN, add_layernorm128_kernel, dim3((M + 7) / 8), dim3(256), 0, st, att, tmp, ln2_w, ln2_b, y, M, eps, 128, 128, 128, 0, 1, 0LL);
   return check_launch();
 }
 
@@ -403,7 +407,7 @@ int mde_split3_tf32(const float* in, float* out, int64_t rows, int E, mde_stream
   if (!in || !out) return MDE_ERR_BAD_POINTER;
   if (rows <= 0 || E <= 0) return MDE_ERR_BAD_SHAPE;
   const long long n = rows * E;
-  split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, rows, E);
+  launch_pdl(PDL_CHAIN, split3_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, in, out, (long long)rows, E);
   return check_launch();
 }
 
@@ -430,7 +434,7 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
   if ((rc = launch_attention(qkv, att3, S, NB, E, heads, E3, 1, st))) return rc;
   // tmp = att W_out^T + b_out ; x1 = LN1(x + tmp)
   if ((rc = mde_gemm_nt_tf32_ex(att3, E3, 0, out_w3, E3, 0, tmp, E, 0, 1, M, E, E3, 1, 1.0f, out_b, 0, 0, stream))) return rc;
-  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x3, tmp, ln1_w, ln1_b, x13, M, eps, E3, E, E3, 1);
+  launch_pdl(PDL_CHAIN, add_layernorm128_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x3, tmp, ln1_w, ln1_b, x13, M, eps, E3, E, E3, 1, 1, 0LL);
   if ((rc = check_launch())) return rc;
   // h = relu(x1 W_1^T + b_1), written in split form; tmp = h W_2^T + b_2: K' = 3 FF is split over 4 CTAs per output
   // tile, each writing its own partial plane (one CTA per tile: 31.7 us, atomics: 39 us); LN2 sums the planes
@@ -443,8 +447,8 @@ int mde_encoder_layer_tc_fwd(const float* x3, float* y, int y_split, const float
     return rc;
   const int cps = (kchunks + planes - 1) / planes;
   const int real_planes = (kchunks + cps - 1) / cps;
-  add_layernorm128_kernel<<<(M + 7) / 8, 256, 0, st>>>(x13, tmp, ln2_w, ln2_b, y, M, eps, E3, E, y_split ? E3 : E,
-                                                       y_split ? 1 : 0, real_planes, (long long)M * E);
+  launch_pdl(PDL_CHAIN, add_layernorm128_kernel, dim3((M + 7) / 8), dim3(256), 0, st, x13, tmp, ln2_w, ln2_b, y, M, eps, E3, E,
+             y_split ? E3 : E, y_split ? 1 : 0, real_planes, (long long)M * E);
   return check_launch();
 }
 

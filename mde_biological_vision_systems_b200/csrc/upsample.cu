@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restr
   const int c4 = C1 >> 2;        // float4 groups per pixel
   const int cgn = c4 / V;        // thread slots per pixel
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  pdl_sync();
   if (t >= (unsigned)(W * cgn)) return;
   const int X = (int)(t / (unsigned)cgn), cg = (int)(t - (unsigned)X * cgn) * V;
   const int Y = blockIdx.y, b = blockIdx.z;
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(256) copy_channels_nhwc_kernel(const float* __
                                                                  int C1, int C2, int Ctot, unsigned per_image,
                                                                  long long P, long long plane_elems) {
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  pdl_sync();
   if (t >= per_image) return;
   const unsigned cgn = ((unsigned)(Ctot - C1) >> 2) / V;
   const unsigned pl = t / cgn, cg = (t - pl * cgn) * V;
@@ -432,11 +434,11 @@ static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, i
   const int vv = wide ? 2 : 1;
   const dim3 grid((unsigned)((W * (C1 / (4 * vv)) + 255) / 256), (unsigned)H, (unsigned)B);
   if (pair) {
-    if (wide) upsample_nhwc_kernel<true, 2><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
-    else upsample_nhwc_kernel<true, 1><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    if (wide) launch_pdl(PDL_STREAM, upsample_nhwc_kernel<true, 2>, grid, dim3(256), 0, st, x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    else launch_pdl(PDL_STREAM, upsample_nhwc_kernel<true, 1>, grid, dim3(256), 0, st, x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
   } else {
-    if (wide) upsample_nhwc_kernel<false, 2><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
-    else upsample_nhwc_kernel<false, 1><<<grid, 256, 0, st>>>(x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    if (wide) launch_pdl(PDL_STREAM, upsample_nhwc_kernel<false, 2>, grid, dim3(256), 0, st, x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
+    else launch_pdl(PDL_STREAM, upsample_nhwc_kernel<false, 1>, grid, dim3(256), 0, st, x_nhwc, out, C1, Ctot, h, w, H, W, sy, sx, plane);
   }
   int rc = check_launch();
   if (rc || Ctot == C1) return rc;
@@ -445,11 +447,11 @@ static int upsample_concat_nhwc_launch(const float* x_nhwc, const float* skip, i
     const unsigned per_image = (unsigned)(P * ((Ctot - C1) / (wide2 ? 8 : 4)));
     const dim3 g2((per_image + 255) / 256, (unsigned)B);
     if (pair) {
-      if (wide2) copy_channels_nhwc_kernel<true, 2><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
-      else copy_channels_nhwc_kernel<true, 1><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+      if (wide2) launch_pdl(PDL_STREAM, copy_channels_nhwc_kernel<true, 2>, g2, dim3(256), 0, st, skip, out, C1, C2, Ctot, per_image, P, plane);
+      else launch_pdl(PDL_STREAM, copy_channels_nhwc_kernel<true, 1>, g2, dim3(256), 0, st, skip, out, C1, C2, Ctot, per_image, P, plane);
     } else {
-      if (wide2) copy_channels_nhwc_kernel<false, 2><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
-      else copy_channels_nhwc_kernel<false, 1><<<g2, 256, 0, st>>>(skip, out, C1, C2, Ctot, per_image, P, plane);
+      if (wide2) launch_pdl(PDL_STREAM, copy_channels_nhwc_kernel<false, 2>, g2, dim3(256), 0, st, skip, out, C1, C2, Ctot, per_image, P, plane);
+      else launch_pdl(PDL_STREAM, copy_channels_nhwc_kernel<false, 1>, g2, dim3(256), 0, st, skip, out, C1, C2, Ctot, per_image, P, plane);
     }
   } else {
     dim3 grid2((unsigned)((P + 63) / 64), (unsigned)((C2 + 63) / 64), (unsigned)B);

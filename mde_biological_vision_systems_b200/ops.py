@@ -460,10 +460,12 @@ def linear(x, weight, bias, act=0):
     return out
 
 
-def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=True):
+def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=False):
     """t0 [B,E] (rows may be strided) -> (widths_normed [B,n], edges [B,n+1], centers [B,n], y_raw [B,n]).
-    split=True runs the three dense layers as separate wide launches and a small finalise kernel (the single-CTA-per-
-    image variant is latency bound: 105 us at B = 16); split=False keeps everything in one launch."""
+    split=False (default): ONE launch, a 1024-thread CTA per image walks the three dense layers (four output rows per warp
+    pass, 16-byte weight loads), the normalisation and the edge scan.  split=True: the three layers as separate launches of
+    the generic SIMT linear kernel plus a finalise kernel (4 launches, 64 us at B = 16: M = 16 rows cannot fill a 64 x 64
+    tile grid; it used to be the faster form while the fused kernel computed one row per warp with 4-byte loads)."""
     lib = _lib.load()
     _need_cuda(t0, w1, w2, w3)
     t0 = _f32(t0)
@@ -483,10 +485,11 @@ def regressor_bins(t0, w1, b1, w2, b2, w3, b3, norm, min_val, max_val, split=Tru
         _lib.check(rc, "mde_bins_finalize_fwd")
         return wn, edges, centers, y_raw
     y_raw = torch.empty((b, n), dtype=torch.float32, device=dev)
-    rc = lib.mde_regressor_bins_fwd(_p(t0), t0.stride(0), _p(w1.contiguous()), _p(b1.contiguous()), _p(w2.contiguous()),
-                                    _p(b2.contiguous()), _p(w3.contiguous()), _p(b3.contiguous()), b, e, hdim, n,
-                                    _NORM.get(norm, 2), float(min_val), float(max_val), _p(y_raw), _p(wn), _p(edges),
-                                    _p(centers), _s())
+    with timing("regressor_bins"):
+        rc = lib.mde_regressor_bins_fwd(_p(t0), t0.stride(0), _p(w1.contiguous()), _p(b1.contiguous()), _p(w2.contiguous()),
+                                        _p(b2.contiguous()), _p(w3.contiguous()), _p(b3.contiguous()), b, e, hdim, n,
+                                        _NORM.get(norm, 2), float(min_val), float(max_val), _p(y_raw), _p(wn), _p(edges),
+                                        _p(centers), _s())
     _lib.check(rc, "mde_regressor_bins_fwd")
     return wn, edges, centers, y_raw
 

@@ -609,9 +609,9 @@ def test_regressor_bins(golden):
     m, sd = _head_state()
     tgt = torch.from_numpy(golden["head/tgt"])
     r = m.adaptive_bins_layer.regressor.to(DEV)
-    for norm in ("linear", "softmax", "sigmoid"):
+    for norm, split in [("linear", False), ("softmax", False), ("sigmoid", False), ("linear", True), ("softmax", True)]:
         wn, edges, centers, y_raw = ops.regressor_bins(tgt[0].to(DEV), r[0].weight, r[0].bias, r[2].weight, r[2].bias,
-                                                       r[4].weight, r[4].bias, norm, 1e-3, 10.0)
+                                                       r[4].weight, r[4].bias, norm, 1e-3, 10.0, split=split)
         y = oracle.regressor(tgt[0], sd)
         wn_ref = oracle.normalise_widths(y, norm)
         e_ref, c_ref = oracle.bins_from_widths(wn_ref, 1e-3, 10.0)
