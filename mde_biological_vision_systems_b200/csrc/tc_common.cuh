@@ -277,12 +277,13 @@ __device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& mid)
   mid = bf16_bits_rn(v - bf16_bits_to_f32(hi));
 }
 // two values -> packed (lo half = first value) hi and mid words
+// (the packed conversion cvt.rn.bf16x2.f32 d, x, y puts bf16(x) into the UPPER and bf16(y) into the lower half: one F2FP
+// instruction per pair on the fast pipe, where two scalar conversions are F2F instructions on the 16-lane XU pipe plus shifts
+// and ORs to pack -- the resize kernels spent 43 % of their issue slots there; same round-to-nearest-even results)
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& mid) {
-  uint16_t ah, am, bh, bm;
-  split_bf16(a, ah, am);
-  split_bf16(b, bh, bm);
-  hi = (uint32_t)ah | ((uint32_t)bh << 16);
-  mid = (uint32_t)am | ((uint32_t)bm << 16);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(rb), "f"(ra));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

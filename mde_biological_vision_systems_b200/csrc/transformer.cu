@@ -257,17 +257,25 @@ __global__ void __launch_bounds__(512, 1) attention_kernel(const float* __restri
   }
 }
 
-// Launch geometry: the widest CTA (16 / 8 / 4 warps) whose K, V and per-warp score areas fit the SM's shared memory and that
-// still yields at least one CTA per SM; the query rows of an (image, head) are split over at most SMs / (images * heads) CTAs so
-// that the grid is a single resident wave (one CTA per SM: registers and shared memory), never finer than one pass per warp.
+// Launch geometry.  One CTA is resident per SM (shared memory), so the grid should be ONE wave and every warp should make one
+// pass: the query rows of an (image, head) -- groups of ATT_ROWS rows, one per warp pass -- are split over
+// ysplit = SMs / (images * heads) CTAs (at least four groups each, so that the K / V load of a CTA is amortised), and the CTA gets
+// the smallest of 4 / 8 / 16 warps that covers its groups in one pass and fits the shared memory.  B = 16, S = 221: 28 groups per
+// (image, head), ysplit 2, 14 groups per CTA -> 128 CTAs of 16 warps, one pass.  (The first version of this heuristic preferred
+// more, narrower CTAs: 128 CTAs of 8 warps making two passes at 11 % of the SM's warp slots -- 28.6 us per layer under ncu.)
 static int launch_attention(const float* qkv, float* out, int S, int NB, int E, int heads, int out_ld, int split3,
                             cudaStream_t st) {
   constexpr int HD = 32;
   const size_t limit = 227 * 1024;
   auto smem_of = [&](int nw) { return sizeof(float) * (attention_kv_floats(S, HD) + (size_t)nw * attention_warp_floats(S, HD)); };
-  auto ctas_of = [&](int nw) { return (long long)NB * heads * ((S + ATT_ROWS * nw - 1) / (ATT_ROWS * nw)); };
-  int nw = 16;
-  while (nw > 4 && (smem_of(nw) > limit || ctas_of(nw) < MDE_NUM_SMS)) nw >>= 1;
+  const int groups = (S + ATT_ROWS - 1) / ATT_ROWS;
+  int ysplit = MDE_NUM_SMS / (NB * heads);
+  if (ysplit > (groups + 3) / 4) ysplit = (groups + 3) / 4;
+  if (ysplit < 1) ysplit = 1;
+  const int rows_per_cta = (S + ysplit - 1) / ysplit;
+  const int groups_per_cta = (rows_per_cta + ATT_ROWS - 1) / ATT_ROWS;
+  int nw = groups_per_cta <= 4 ? 4 : groups_per_cta <= 8 ? 8 : 16;
+  while (nw > 4 && smem_of(nw) > limit) nw >>= 1;
   if (smem_of(nw) > limit) return MDE_ERR_BAD_SHAPE;
   static bool attr = false;
   if (!attr) {
@@ -275,10 +283,6 @@ static int launch_attention(const float* qkv, float* out, int S, int NB, int E, 
       return MDE_ERR_LAUNCH;
     attr = true;
   }
-  int ysplit = MDE_NUM_SMS / (NB * heads);
-  const int finest = (S + ATT_ROWS * nw - 1) / (ATT_ROWS * nw);
-  if (ysplit > finest) ysplit = finest;
-  if (ysplit < 1) ysplit = 1;
   launch_pdl(PDL_CHAIN, attention_kernel<HD>, dim3(NB * heads, ysplit), dim3(32 * nw), smem_of(nw), st, qkv, out, S, NB, E, heads,
              1.0f / sqrtf((float)HD), out_ld, split3);
   return check_launch();
