@@ -2,12 +2,15 @@
 //
 // Reference: models/layers.py:8-9,23 (nn.TransformerEncoder of 4 default nn.TransformerEncoderLayer), eval semantics
 // (dropout is the identity).  Token layout is the reference's [S, N, E]: row index = s * N + n.
-// The sequence is short (S = 13*17 = 221 tokens/image) and the whole encoder is 0.68 GFLOP/image (3 % of the head),
-// so these are exact-fp32 SIMT kernels (the queries feed a softmax downstream, see DESIGN.md "precision"):
-//   linear_kernel      C = act(A W^T + b)            64x64x16 shared-memory tiles, 4x4 register blocking
-//   attention_kernel   softmax(Q K^T / sqrt(hd)) V   one CTA per (image, head), K and V resident in shared memory,
-//                                                    one warp per query row, lane == head-dim channel (hd = 32)
-//   add_layernorm_kernel  LN(x + y) * g + b          one warp per token row (E = 128 -> float4 per lane)
+// The sequence is short (S = 13*17 = 221 tokens/image) and the whole encoder is 0.68 GFLOP/image (3 % of the head): the layer is
+// latency-bound, not throughput-bound.  Two forms:
+//   mde_encoder_layer_tc_fwd (default): the four nn.Linear products on the tcgen05 NT GEMM (gemm_tc.cu) in 3xTF32 on split-form
+//                         operands (fp32-grade: the queries feed a softmax downstream, DESIGN.md "precision"), attention and
+//                         LayerNorm on the kernels below;
+//   mde_encoder_layer_fwd: everything exact fp32 SIMT (linear_kernel: 64x64x16 shared-memory tiles, 4x4 register blocking).
+//   attention_kernel      softmax(Q K^T / sqrt(hd)) V   one CTA per (image, head, row range), K and V resident in shared memory,
+//                                                    eight query rows per warp pass (see the kernel's comment)
+//   add_layernorm128_kernel  LN(x + y) * g + b       one warp per token row (E = 128 -> float4 per lane), sums split-K planes
 #include "common.cuh"
 
 namespace mde {

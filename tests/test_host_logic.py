@@ -249,3 +249,27 @@ def test_gradient_arena_clip_matches_torch_clip():
         p.grad = None
     avg.zero_grad()
     assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in net.parameters())
+
+
+def test_train_step_host_protocol_and_deferred_checks():
+    """Host-side pieces of training.GraphedTrainStep that need no GPU: TrainStep is split into forward_backward() (what the graph
+    replays) and update() (what stays eager), GraphedTrainStep refuses a SyncBatchNorm flavour that would call NCCL inside the
+    capture, and the deferred out-of-range check of a captured gather raises IndexError like the reference's index_select."""
+    import inspect
+    from mde_biological_vision_systems_b200 import ops, training
+    assert {"forward_backward", "update", "__call__"} <= set(vars(training.TrainStep))
+    src = inspect.getsource(training.TrainStep.__call__)
+    assert "forward_backward" in src and "update" in src
+    assert issubclass(training.GraphedTrainStep, training.TrainStep)
+    # nothing to capture around: a plain module passes, its peer-memory arena is None
+    assert training.GraphedTrainStep._p2p_arena(torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))) is None
+    # deferred label checks: flags collected between begin / end, read (and raised) afterwards
+    ops.begin_deferred_checks()
+    assert ops._DEFERRED == []
+    ops._DEFERRED.append((torch.zeros(1, dtype=torch.int32), 150))
+    flags = ops.end_deferred_checks()
+    assert ops._DEFERRED is None and len(flags) == 1
+    ops.raise_deferred_checks(flags)          # flag clear: passes
+    flags[0][0].fill_(1)                      # a replay met an out-of-range label
+    with pytest.raises(IndexError):
+        ops.raise_deferred_checks(flags)
