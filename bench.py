@@ -587,6 +587,8 @@ def roofline_from(cfg, r, batch):
         return {"kernel": "head_chain_kernel<256,softmax> (range-attention x conv_out fold + softmax + bins, bf16x3)",
                 "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
                 "algorithmic_bytes": alg, "peak_source": src, "ms_per_launch": ms,
+                "traffic_source": None if traffic is None else "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum "
+                                  "of one launch, ncu --set full capture of this round at the same batch and size",
                 "tensor": {"issued_tflops_bf16": 3 * fl / (ms * 1e-3) / 1e12, "peak_bf16_tflops": bf16,
                            "frac": 3 * fl / (ms * 1e-3) / 1e12 / bf16}}
     convs = {k: v for k, v in kt.items() if k.startswith("up") and "conv" in k}
