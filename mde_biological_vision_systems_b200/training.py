@@ -177,6 +177,9 @@ class GraphedTrainStep(TrainStep):
             self._h2d = torch.cuda.Stream(self.device)
             self._stage_ready = torch.cuda.Event()
             self._stage_free = None
+            # the staging buffers come from the consumer stream's allocator pool: whatever that stream still has in flight on
+            # a recycled block must finish before the side stream's first copy lands in it
+            self._h2d.wait_stream(torch.cuda.current_stream(self.device))
         if self._stage_free is not None:
             self._h2d.wait_event(self._stage_free)  # the previous copy OUT of the staging buffers
         with torch.cuda.stream(self._h2d):
