@@ -119,6 +119,40 @@ def test_chamfer_edge_cases(golden):
     assert torch.isnan(oracle.bins_chamfer(edges, depth))
 
 
+def test_chamfer_oracle_vs_independent_nearest_neighbour():
+    """pytorch3d (v0.6.1, environment.yml:104) is not installable here, so the restatement of its chamfer_distance is pinned from a
+    second side as well: the published definition -- per cloud, mean over x of the squared distance to the nearest y plus mean
+    over the VALID y of the squared distance to the nearest x, then the batch mean of each -- evaluated with scipy's cKDTree (an
+    independent nearest-neighbour search) on ragged, zero-padded clouds in float64."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(77)
+    n, p1, p2 = 3, 256, 5000
+    x = np.sort(rng.uniform(1e-3, 10.0, size=(n, p1, 1)), axis=1)
+    y = rng.uniform(1e-3, 10.0, size=(n, p2, 1))
+    lengths = np.array([p2, 1234, 17])
+    for i, li in enumerate(lengths):
+        y[i, li:] = 0.0   # pad_sequence's zero padding: must never match and never count
+    got, _ = oracle.chamfer_distance(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(lengths))
+    cx = cy = 0.0
+    for i, li in enumerate(lengths):
+        yi = y[i, :li]
+        cx += float((cKDTree(yi).query(x[i])[0] ** 2).mean())
+        cy += float((cKDTree(x[i]).query(yi)[0] ** 2).mean())
+    want = cx / n + cy / n
+    assert abs(float(got) - want) <= 1e-12 * abs(want)
+    # and the BinsChamferLoss wrapper (loss.py:33-46): centres from edges, targets >= 1e-3 only
+    edges = torch.from_numpy(np.concatenate([np.full((n, 1), 1e-3), np.sort(rng.uniform(1e-3, 10.0, size=(n, 256)), axis=1)], 1))
+    depth = torch.from_numpy(rng.uniform(0.0, 10.0, size=(n, 1, 24, 32)) * (rng.uniform(size=(n, 1, 24, 32)) > 0.2))
+    got = float(oracle.bins_chamfer(edges, depth))
+    c = 0.5 * (edges[:, 1:] + edges[:, :-1]).numpy()
+    want = 0.0
+    for i in range(n):
+        t = depth[i].flatten().numpy()
+        t = t[t >= 1e-3][:, None]
+        want += float((cKDTree(t).query(c[i][:, None])[0] ** 2).mean()) / n + float((cKDTree(c[i][:, None]).query(t)[0] ** 2).mean()) / n
+    assert abs(got - want) <= 1e-12 * abs(want)
+
+
 def test_eval_metrics_oracle_vs_reference_golden():
     """(f)2: oracle.compute_errors (float64 restatement) and oracle.eval_epilogue vs the reference's own
     utils.compute_errors outputs recorded by tests/golden/make_golden_eval.py."""
